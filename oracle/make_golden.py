@@ -1,0 +1,93 @@
+"""TEST INFRASTRUCTURE — mints tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the development container only (needs /root/reference):
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+The reference ships no golden vectors, so these fixtures — outputs of the
+reference itself on seeded synthetic inputs — are what pins the oracle and the CUDA path.
+Each fixture stores the input (cell-major CSR counts) and every stage output of
+alona/cell.py:224-255, alona/hvg.py:133-167, alona/clustering.py:82-113,179-240.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pandas as pd
+
+from . import synth_np, ref_shim, alona_port
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+PIPELINE_CASES = {
+    # name: (cells, genes, lbar, clusters, data_seed, hvg_n, pca_n, k, prune, seed)
+    'pipe_small': (600, 3000, 3000.0, 8, 1, 300, 12, 8, 0.067, 42),
+    'pipe_medium': (1500, 6000, 1500.0, 12, 7, 500, 30, 10, 0.067, 42),
+    'pipe_k20': (1200, 4000, 1200.0, 10, 11, 400, 20, 20, 0.067, 3),
+}
+
+
+def _counts_df(m):
+    genes = ['g%d' % i for i in range(m.shape[1])]
+    cells = ['c%d' % i for i in range(m.shape[0])]
+    return pd.DataFrame(m.T.toarray().astype(np.int64), index=genes, columns=cells)
+
+
+def make_pipeline_case(name, spec):
+    n, g, lbar, ncl, dseed, hvg_n, pca_n, k, prune, seed = spec
+    m, _ = synth_np.nb_counts(n, g, lbar=lbar, n_clusters=ncl, seed=dseed)
+    df = _counts_df(m)
+    ref = ref_shim.run_reference(df, hvg_n=hvg_n, pca_n=pca_n, nn_k=k, prune_snn=prune, seed=seed)
+    dn = ref['data_norm']
+    gene_pos = {gname: i for i, gname in enumerate(df.index)}
+    hvg_ranked = np.array([gene_pos[x] for x in ref['hvg']], dtype=np.int32)
+    _, counts = alona_port.snn(ref['nn_idx'], k, prune, return_counts=True)
+    np.random.seed(seed)
+    v0 = np.random.randn(m.shape[0])
+    np.savez_compressed(
+        os.path.join(OUT, name + '.npz'),
+        indptr=m.indptr.astype(np.int64), indices=m.indices.astype(np.int32),
+        data=m.data.astype(np.int32), shape=np.array(m.shape, dtype=np.int64),
+        hvg_n=hvg_n, pca_n=pca_n, k=k, prune=prune, seed=seed,
+        libsize=np.asarray(df.sum(axis=0).values, dtype=np.int64),
+        gene_mean=dn.mean(axis=1).values, gene_var=dn.var(axis=1).values,
+        hvg_ranked=hvg_ranked,
+        pca_components=ref['pca_components'], s=ref['lanczos']['s'],
+        U=ref['lanczos']['U'],
+        steps=ref['lanczos']['steps'], nmult=ref['lanczos']['nmult'], v0=v0,
+        nn_idx=ref['nn_idx'].astype(np.int32),
+        snn_graph=ref['snn_graph'].astype(np.int32), snn_overlap=counts.astype(np.int16))
+    print(name, m.shape, 'nnz', m.nnz, 'steps', ref['lanczos']['steps'], 'nmult',
+          ref['lanczos']['nmult'], 'edges', ref['snn_graph'].shape[0])
+
+
+def make_knn_case(name, n, d, k, seed, dup=0, quantise=None):
+    emb = synth_np.gaussian_mixture_embedding(n, d=d, seed=seed)
+    if quantise:
+        emb = np.round(emb * quantise) / quantise      # many exactly-equal distances
+    if dup:
+        emb[-dup:] = emb[:dup]                          # exact duplicate points
+    nn = ref_shim.reference_knn(emb, k)
+    edges = ref_shim.reference_snn(nn, k, 0.067)
+    _, counts = alona_port.snn(nn, k, 0.067, return_counts=True)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), emb=emb, k=k,
+                        nn_idx=nn.astype(np.int32), snn_graph=edges.astype(np.int32),
+                        snn_overlap=counts.astype(np.int16), prune=0.067)
+    print(name, emb.shape, 'k', k, 'edges', edges.shape[0])
+
+
+def main():
+    if not ref_shim.available():
+        sys.exit('reference tree not present; fixtures can only be minted in the dev container')
+    os.makedirs(OUT, exist_ok=True)
+    warnings.simplefilter('ignore')
+    for name, spec in PIPELINE_CASES.items():
+        make_pipeline_case(name, spec)
+    make_knn_case('knn_mix_3000x50_k20', 3000, 50, 20, seed=2)
+    make_knn_case('knn_mix_2000x50_k10', 2000, 50, 10, seed=5)
+    make_knn_case('knn_mix_1500x100_k30', 1500, 100, 30, seed=9)
+    make_knn_case('knn_mix_1000x50_k100', 1000, 50, 100, seed=4)
+    make_knn_case('knn_dup_800x50_k10', 800, 50, 10, seed=6, dup=5)
+
+
+if __name__ == '__main__':
+    main()

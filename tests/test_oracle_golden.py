@@ -1,0 +1,105 @@
+"""CPU tier (i): the oracle (port + restatements) against fixtures minted from the live
+reference (oracle/make_golden.py).  No GPU, no /root/reference needed."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES
+from oracle import alona_port as P, restate as R
+
+
+def _df(m):
+    return pd.DataFrame(m.T.toarray().astype(np.int64),
+                        index=['g%d' % i for i in range(m.shape[1])],
+                        columns=['c%d' % i for i in range(m.shape[0])])
+
+
+@pytest.mark.parametrize('case', PIPE_CASES)
+def test_port_pipeline_matches_reference_bitwise(case):
+    g = load_golden(case)
+    m = golden_csr(g)
+    out = P.run_pipeline(_df(m), int(g['hvg_n']), int(g['pca_n']), int(g['k']),
+                         float(g['prune']), int(g['seed']))
+    assert np.array_equal(out['data_norm'].mean(axis=1).values, g['gene_mean'])
+    hv = np.array([int(x[1:]) for x in out['hvg']])
+    assert set(hv.tolist()) == set(g['hvg_ranked'].tolist())
+    assert out['lanczos'].steps == int(g['steps']) and out['lanczos'].nmult == int(g['nmult'])
+    assert np.array_equal(out['pca_components'], g['pca_components'])
+    assert np.array_equal(out['nn_idx'], g['nn_idx'])
+    assert np.array_equal(out['snn_graph'], g['snn_graph'])
+
+
+@pytest.mark.parametrize('case', PIPE_CASES)
+def test_restated_normalise_moments_hvg(case):
+    g = load_golden(case)
+    m = golden_csr(g)
+    lib = R.libsize(m)
+    assert np.array_equal(lib, g['libsize'])
+    mean, var = R.gene_mean_var(m, lib)
+    assert np.max(np.abs(mean - g['gene_mean']) / g['gene_mean']) < 1e-14
+    assert np.max(np.abs(var - g['gene_var']) / g['gene_var']) < 1e-13
+    sx, sx2, _ = R.gene_moments(m, lib)
+    n = m.shape[0]
+    var1 = (sx2 - sx * sx / n) / (n - 1)
+    assert np.max(np.abs(var1 - g['gene_var']) / g['gene_var']) < 1e-11
+    for mu, vv in ((mean, var), (sx / n, var1)):
+        idx, _ = R.hvg_seurat_from_moments(mu, vv, int(g['hvg_n']))
+        assert set(idx.tolist()) == set(g['hvg_ranked'].tolist())
+
+
+@pytest.mark.parametrize('case', PIPE_CASES)
+@pytest.mark.parametrize('nshards', [1, 2, 8])
+def test_restated_sharded_irlb_follows_reference_trajectory(case, nshards):
+    g = load_golden(case)
+    m = golden_csr(g)
+    AH, _ = R.hvg_matrix(m, g['hvg_ranked'])
+    l = R.lanczos_csr(AH, int(g['pca_n']), seed=int(g['seed']), nshards=nshards)
+    assert l['steps'] == int(g['steps']) and l['nmult'] == int(g['nmult'])
+    err = R.column_rel_err(g['pca_components'], l['V'] * l['s'])
+    assert err.max() < 1e-9, err.max()
+    assert np.max(np.abs(l['s'] - g['s']) / g['s']) < 1e-12
+
+
+@pytest.mark.parametrize('case', PIPE_CASES)
+def test_bruteforce_knn_and_restated_snn_on_pipeline(case):
+    g = load_golden(case)
+    k = int(g['k'])
+    idx, rd = R.knn_bruteforce(g['pca_components'], k + 1)
+    ties = set(R.knn_tie_rows(rd).tolist())
+    same = np.all(idx[:, :k] + 1 == g['nn_idx'], axis=1)
+    assert all(r in ties for r in np.where(~same)[0])
+    e, c = R.snn_restated(g['nn_idx'].astype(np.int64) - 1, k, float(g['prune']))
+    assert np.array_equal(e, g['snn_graph'])
+    assert np.array_equal(c, g['snn_overlap'])
+
+
+@pytest.mark.parametrize('case', KNN_CASES)
+def test_bruteforce_knn_and_restated_snn_on_embeddings(case):
+    g = load_golden(case)
+    k = int(g['k'])
+    idx, rd = R.knn_bruteforce(g['emb'], k + 1)
+    ties = set(R.knn_tie_rows(rd).tolist())
+    same = np.all(idx[:, :k] + 1 == g['nn_idx'], axis=1)
+    assert all(r in ties for r in np.where(~same)[0])
+    assert same.mean() > 0.999
+    e, c = R.snn_restated(g['nn_idx'].astype(np.int64) - 1, k, float(g['prune']))
+    assert np.array_equal(e, g['snn_graph'])
+    assert np.array_equal(c, g['snn_overlap'])
+
+
+def test_snn_overlap_is_set_intersection():
+    g = load_golden('knn_mix_2000x50_k10')
+    nn0 = g['nn_idx'][:300].astype(np.int64) - 1
+    # restrict to a closed toy universe: remap to 0..299 by taking kNN of the first 300 points
+    idx, _ = R.knn_bruteforce(g['emb'][:300], 10)
+    dense = R.snn_overlap_bruteforce(idx)
+    e, c = R.snn_restated(idx, 10, 0.0, return_all=True)
+    assert np.array_equal(dense[e[:, 0], e[:, 1]], c)
+    assert (dense > 0).sum() == e.shape[0]
+
+
+def test_prune_threshold_matches_python_expression():
+    for k in (5, 10, 20, 30, 50, 100):
+        for p in (0.0, 0.067, 1 / 15, 0.2, 0.5, 1.0):
+            v = R.prune_threshold(k, p)
+            assert all((u / (k + (k - u)) > p) == (u >= v) for u in range(0, k + 1))
