@@ -1,0 +1,97 @@
+"""ctypes binding of libalona_b200.so (include/alona_b200.h).
+
+There is no CPU fallback: if the shared library cannot be loaded, or no sm_100 GPU is
+present, every compute entry point raises.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'libalona_b200.so')
+
+_lib = None
+_lock = threading.Lock()
+
+c_void_p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_f64 = ctypes.c_double
+c_size = ctypes.c_size_t
+c_u64 = ctypes.c_uint64
+p_i64 = ctypes.POINTER(ctypes.c_int64)
+
+# name -> (restype, argtypes); mirrors include/alona_b200.h one to one
+SIGNATURES = {
+    'ab_version': (ctypes.c_int, []),
+    'ab_last_error': (ctypes.c_char_p, []),
+    'ab_ctx_create': (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    'ab_ctx_destroy': (ctypes.c_int, [c_void_p]),
+    'ab_nccl_unique_id': (ctypes.c_int, [ctypes.c_char_p, c_void_p]),
+    'ab_ctx_init_nccl': (ctypes.c_int, [c_void_p, ctypes.c_char_p, c_void_p]),
+    'ab_allreduce_f64': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    'ab_allreduce_i64': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    'ab_allgather_bytes': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    'ab_norm_moments': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_f64,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ab_hvg_seurat': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ab_hvg_extract_ws_bytes': (c_size, [c_i64]),
+    'ab_hvg_extract_count': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, p_i64,
+                                            c_void_p, c_size, c_void_p]),
+    'ab_hvg_extract_fill': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
+                                           c_f64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ab_irlb_ws_bytes': (c_size, [c_i64, c_i32, c_i32]),
+    'ab_irlb': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_i32,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, p_i64, c_void_p, c_size, c_void_p]),
+    'ab_knn_ws_bytes': (c_size, [c_i64, c_i32, c_i64, c_i32]),
+    'ab_knn': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i64, c_i32, c_i32, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_size, c_void_p]),
+    'ab_snn_ws_bytes': (c_size, [c_i64, c_i32, c_i64]),
+    'ab_snn_count': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i64, c_i32, c_void_p, p_i64, p_i64,
+                                    c_void_p, c_size, c_void_p]),
+    'ab_snn_fill': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i64, c_i32, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_size, c_void_p]),
+    'ab_synth_ws_bytes': (c_size, [c_i64]),
+    'ab_synth_nb_count': (ctypes.c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i64, c_f64, c_f64, c_f64, c_u64,
+                                         c_void_p, p_i64, c_void_p, c_size, c_void_p]),
+    'ab_synth_nb_fill': (ctypes.c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i64, c_f64, c_f64, c_f64, c_u64,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ab_launch_count': (c_i64, [c_void_p]),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Loads the shared library (building it in-tree with nvcc if it is missing)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            from . import build as _build
+            _build.build()
+        try:
+            lib = ctypes.CDLL(_LIB_PATH)
+        except OSError as e:
+            raise RuntimeError('alona_b200: cannot load %s (%s). The CUDA extension is required; '
+                               'there is no CPU fallback. Build it with `python -m alona_b200.build`.'
+                               % (_LIB_PATH, e))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)            # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return _lib
+
+
+def last_error():
+    return load().ab_last_error().decode('utf-8', 'replace')
+
+
+def check(rc, what=''):
+    if rc != 0:
+        raise RuntimeError('alona_b200 %s failed: %s' % (what, last_error()))

@@ -1,0 +1,692 @@
+// K4-K8: truncated SVD of the HVG-restricted matrix by augmented implicitly-restarted Lanczos
+// bidiagonalisation, following alona/irlbpy/irlb.py:95-258 step for step (same work dimension,
+// same CGS order, same restart rule, same invcheck) so that the trajectory (`steps`, `nmult`)
+// and the scores V.diag(s) match the reference's (alona/clustering.py:108-111).
+//
+// A = A_H^T is H x N (genes x cells); the shard holds A_H as cell-major CSR (n_local x H), so
+//   A.v   (irlb.py:165,204)  = contraction over cells  -> "scatter" SpMV with per-warp private
+//                              FP64 accumulators in shared memory (no atomics, deterministic),
+//                              summed across ranks (all-reduce of H doubles);
+//   A^T.w (irlb.py:182)      = per-cell row dot products, local to the shard;
+//   CGS panels (irlb.py:190) = tall-skinny GEMV / GEMV-T over the cell dimension, coefficients
+//                              summed across ranks (all-reduce of j+1 doubles, then 1 double);
+//   SVD of B (irlb.py:224)   = one-sided Jacobi, one CTA, on the device;
+//   Ritz updates (:238,:246) = FP64 tall-skinny GEMM.
+// Everything is FP64 (HBM-bound; FP64 costs bandwidth only).  All reductions use a fixed
+// order, so a run is bitwise reproducible for a given (n_local, world).
+#include "ab_common.cuh"
+#include <math.h>
+#include <float.h>
+#include <algorithm>
+
+static constexpr int IR_MAXWORK = 128;          // work dimension m_b <= 128
+static constexpr int DOT_THREADS = 256;
+static constexpr int DOT_ROWS = 4;              // rows per thread
+static constexpr int DOT_TILE = DOT_THREADS * DOT_ROWS;
+
+// scalar slots (device doubles)
+enum { SC_S = 0, SC_FN2 = 1, SC_SMAX = 2, SC_V0N2 = 3, SC_COUNT = 8 };
+// control ints
+enum { CT_CONV = 0, CT_KEEP = 1, CT_DONE = 2, CT_ROT = 3, CT_COUNT = 8 };
+
+__device__ __forceinline__ double invcheck(double x) {       // irlb.py:84-92
+    return x > 2.0 * DBL_EPSILON ? 1.0 / x : 0.0;
+}
+
+// "last block" ticket: returns true in exactly one block, after all others have published.
+__device__ __forceinline__ bool last_block_ticket(int *counter) {
+    __shared__ int ticket_sm;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = atomicAdd(counter, 1);
+        ticket_sm = (t == (int)gridDim.x - 1);
+        if (ticket_sm) *counter = 0;                           // re-arm for the next launch
+    }
+    __syncthreads();
+    return ticket_sm != 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// A^T.w - s.V_j   (irlb.py:182,189)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+atw_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
+           int64_t n, const double *__restrict__ w, const double *__restrict__ vj, const double *__restrict__ scal,
+           double *__restrict__ F) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    const double s = scal[SC_S];
+    for (int64_t row = wid; row < n; row += nw) {
+        const int64_t a = rowptr[row], b = rowptr[row + 1];
+        double acc = 0.0;
+        for (int64_t p = a + lane; p < b; p += 32) acc = fma(__ldg(val + p), __ldg(w + __ldg(col + p)), acc);
+        acc = ab_warp_sum_f64(acc);
+        if (lane == 0) F[row] = __dsub_rn(acc, __dmul_rn(s, vj[row]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// c[l] = sum_i V[i,l] F[i]  for l < ncols     (irlb.py:74 dotY, contraction over cells)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DOT_THREADS)
+panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols, const double *__restrict__ F,
+                 double *__restrict__ partial /*[grid][IR_MAXWORK]*/, double *__restrict__ out, int *counter) {
+    __shared__ double wsum[DOT_THREADS / 32][IR_MAXWORK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * DOT_TILE;
+    double f[DOT_ROWS];
+    int64_t r[DOT_ROWS];
+#pragma unroll
+    for (int u = 0; u < DOT_ROWS; ++u) {
+        r[u] = base + threadIdx.x + (int64_t)u * DOT_THREADS;
+        f[u] = r[u] < n ? F[r[u]] : 0.0;
+        if (r[u] >= n) r[u] = 0;
+    }
+    for (int l = 0; l < ncols; ++l) {
+        const double *vl = V + (int64_t)l * ld;
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < DOT_ROWS; ++u) acc = fma(vl[r[u]], f[u], acc);
+        acc = ab_warp_sum_f64(acc);
+        if (lane == 0) wsum[warp][l] = acc;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) {
+        double t = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < DOT_THREADS / 32; ++w2) t += wsum[w2][l];
+        partial[(int64_t)blockIdx.x * IR_MAXWORK + l] = t;
+    }
+    if (last_block_ticket(counter)) {
+        for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) {
+            double t = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + (int64_t)b * IR_MAXWORK + l);
+            out[l] = t;
+        }
+    }
+}
+
+// F -= V[:, :ncols].c ;  fn2 = sum F^2      (irlb.py:79,191)
+__global__ void __launch_bounds__(DOT_THREADS)
+panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols, const double *__restrict__ c,
+                    double *__restrict__ F, double *__restrict__ partial, double *__restrict__ out_fn2, int *counter) {
+    __shared__ double cs[IR_MAXWORK];
+    __shared__ double red[DOT_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) cs[l] = c[l];
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * DOT_TILE;
+    double t[DOT_ROWS];
+    int64_t r[DOT_ROWS];
+    bool ok[DOT_ROWS];
+#pragma unroll
+    for (int u = 0; u < DOT_ROWS; ++u) {
+        r[u] = base + threadIdx.x + (int64_t)u * DOT_THREADS;
+        ok[u] = r[u] < n;
+        if (!ok[u]) r[u] = 0;
+        t[u] = 0.0;
+    }
+    for (int l = 0; l < ncols; ++l) {
+        const double *vl = V + (int64_t)l * ld;
+        const double cl = cs[l];
+#pragma unroll
+        for (int u = 0; u < DOT_ROWS; ++u) t[u] = fma(vl[r[u]], cl, t[u]);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < DOT_ROWS; ++u) {
+        if (ok[u]) {
+            const double nf = __dsub_rn(F[r[u]], t[u]);
+            F[r[u]] = nf;
+            acc = fma(nf, nf, acc);
+        }
+    }
+    acc = ab_warp_sum_f64(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tt = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < DOT_THREADS / 32; ++w2) tt += red[w2];
+        partial[blockIdx.x] = tt;
+    }
+    if (last_block_ticket(counter)) {
+        if (threadIdx.x == 0) {
+            double tt = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
+            *out_fn2 = tt;
+        }
+    }
+}
+
+// sum of squares of a vector (start vector normalisation, irlb.py:153)
+__global__ void __launch_bounds__(DOT_THREADS)
+sumsq_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ partial, double *__restrict__ out,
+             int *counter) {
+    __shared__ double red[DOT_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * DOT_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * DOT_THREADS)
+        acc = fma(x[i], x[i], acc);
+    acc = ab_warp_sum_f64(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tt = 0.0;
+        for (int w2 = 0; w2 < DOT_THREADS / 32; ++w2) tt += red[w2];
+        partial[blockIdx.x] = tt;
+    }
+    if (last_block_ticket(counter)) {
+        if (threadIdx.x == 0) {
+            double tt = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
+            *out = tt;
+        }
+    }
+}
+
+// dst = src * invcheck(sqrt(*sumsq))
+__global__ void scale_by_invnorm_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n,
+                                        const double *__restrict__ sumsq) {
+    const double inv = invcheck(sqrt(*sumsq));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __dmul_rn(inv, src[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// A.x : scatter SpMV.  x_i = scale * src_i (scale = invcheck(sqrt(*sumsq)) or 1), optionally
+// stored to vdst (the new Lanczos vector, irlb.py:195).  Each warp owns a private FP64
+// accumulator of H entries in shared memory: the genes of one cell row are distinct, so the
+// 32 lanes of a warp never collide and plain load/FMA/store is race-free.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
+          int64_t n, int H, const double *__restrict__ src, const double *__restrict__ sumsq,
+          double *__restrict__ vdst, int nwarps_cta, double *__restrict__ partial /*[grid][H]*/) {
+    extern __shared__ double acc_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double scale = sumsq ? invcheck(sqrt(*sumsq)) : 1.0;
+    for (int i = threadIdx.x; i < nwarps_cta * H; i += blockDim.x) acc_sm[i] = 0.0;
+    __syncthreads();
+    if (warp < nwarps_cta) {
+        double *acc = acc_sm + (size_t)warp * H;
+        const int64_t wid = (int64_t)blockIdx.x * nwarps_cta + warp;
+        const int64_t nw = (int64_t)gridDim.x * nwarps_cta;
+        // contiguous chunk of rows per warp
+        const int64_t per = (n + nw - 1) / nw;
+        const int64_t r0 = wid * per, r1 = min(n, r0 + per);
+        for (int64_t row = r0; row < r1; ++row) {
+            const double x = __dmul_rn(scale, src[row]);
+            if (vdst && lane == 0) vdst[row] = x;
+            const int64_t a = rowptr[row], b = rowptr[row + 1];
+            for (int64_t p = a + lane; p < b; p += 32) {
+                const int g = __ldg(col + p);
+                acc[g] = fma(__ldg(val + p), x, acc[g]);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < H; g += blockDim.x) {
+        double t = 0.0;
+        for (int w2 = 0; w2 < nwarps_cta; ++w2) t += acc_sm[(size_t)w2 * H + g];
+        partial[(size_t)blockIdx.x * H + g] = t;
+    }
+}
+
+__global__ void av_reduce_kernel(const double *__restrict__ partial, int nparts, int H, double *__restrict__ out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= H) return;
+    double t = 0.0;
+    for (int b = 0; b < nparts; ++b) t += partial[(size_t)b * H + g];
+    out[g] = t;
+}
+
+// ---------------------------------------------------------------------------------------
+// left-vector step (irlb.py:173-178 and :214-219), one CTA:
+//   t = wraw - (sub_prev ? fn*W[:,jd-1] : 0);  t -= W[:, :ncols].(W[:, :ncols]^T t);
+//   s = ||t||;  W[:,jd] = invcheck(s)*t.   Also records B[jb,jb]=s_old, B[jb,jb+1]=fn (irlb.py:196-197).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+wstep_kernel(const double *__restrict__ wraw, double *__restrict__ W, int H, int jd, int ncols, int sub_prev,
+             double *__restrict__ scal, double *__restrict__ B, int work, int jb) {
+    extern __shared__ double sm[];
+    double *t = sm;                       // H
+    double *c2 = sm + H;                  // IR_MAXWORK
+    double *red = c2 + IR_MAXWORK;        // 33
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double fn = sqrt(scal[SC_FN2]);
+    if (threadIdx.x == 0 && jb >= 0) {
+        B[jb * work + jb] = scal[SC_S];
+        if (jb + 1 < work) B[jb * work + jb + 1] = fn;
+    }
+    for (int g = threadIdx.x; g < H; g += blockDim.x) {
+        double v = wraw[g];
+        if (sub_prev) v = __dsub_rn(v, __dmul_rn(fn, W[(size_t)(jd - 1) * H + g]));
+        t[g] = v;
+    }
+    __syncthreads();
+    if (ncols > 0) {
+        for (int l = warp; l < ncols; l += nwarp) {
+            const double *wl = W + (size_t)l * H;
+            double acc = 0.0;
+            for (int g = lane; g < H; g += 32) acc = fma(wl[g], t[g], acc);
+            acc = ab_warp_sum_f64(acc);
+            if (lane == 0) c2[l] = acc;
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < H; g += blockDim.x) {
+            double acc = 0.0;
+            for (int l = 0; l < ncols; ++l) acc = fma(W[(size_t)l * H + g], c2[l], acc);
+            t[g] = __dsub_rn(t[g], acc);
+        }
+        __syncthreads();
+    }
+    double acc = 0.0;
+    for (int g = threadIdx.x; g < H; g += blockDim.x) acc = fma(t[g], t[g], acc);
+    acc = ab_warp_sum_f64(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double v = lane < nwarp ? red[lane] : 0.0;
+        v = ab_warp_sum_f64(v);
+        if (lane == 0) red[32] = v;
+    }
+    __syncthreads();
+    const double s = sqrt(red[32]);
+    const double sinv = invcheck(s);
+    for (int g = threadIdx.x; g < H; g += blockDim.x) W[(size_t)jd * H + g] = __dmul_rn(sinv, t[g]);
+    if (threadIdx.x == 0) scal[SC_S] = s;
+}
+
+// last Lanczos step of a pass (j = work-1): F *= invcheck(fn); B[j,j] = s  (irlb.py:193,221)
+__global__ void fscale_kernel(double *__restrict__ F, int64_t n, const double *__restrict__ scal,
+                              double *__restrict__ B, int work, int jb) {
+    const double inv = invcheck(sqrt(scal[SC_FN2]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) B[jb * work + jb] = scal[SC_S];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        F[i] = __dmul_rn(inv, F[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// SVD of the small matrix B (work x work), one-sided Jacobi, one CTA.   (irlb.py:224)
+// Outputs: Ub (columns = left vectors), sb (descending), Vb (columns = right vectors),
+// all row-major work x work.  Then residuals / convergence / restart bookkeeping (:225-234).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ Ub, double *__restrict__ sb,
+                   double *__restrict__ Vb, double *__restrict__ Gws /* 2*work*work scratch */,
+                   double *__restrict__ scal, int *__restrict__ ctrl, double *__restrict__ R, int nu, double tol,
+                   int it, int keep_prev) {
+    // G (col-major, work x work) starts as B and converges to U.diag(s); Q accumulates V.
+    double *G = Gws;
+    double *Q = Gws + (size_t)work * work;
+    __shared__ double nrm[IR_MAXWORK];
+    __shared__ int order[IR_MAXWORK];
+    __shared__ int rot_sm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int m = work;
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        const int r = e % m, c = e / m;
+        G[(size_t)c * m + r] = B[r * m + c];
+        Q[(size_t)c * m + r] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int mp = (m + 1) & ~1;                        // round-robin needs an even player count
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        if (threadIdx.x == 0) rot_sm = 0;
+        __syncthreads();
+        for (int round = 0; round < mp - 1; ++round) {
+            for (int pr = warp; pr < mp / 2; pr += nwarp) {
+                // circle method: player mp-1 fixed, the others rotate
+                int a = (pr == 0) ? mp - 1 : (round + pr) % (mp - 1);
+                int b = (round + mp - 1 - pr) % (mp - 1);
+                int p = min(a, b), q = max(a, b);
+                if (q >= m) continue;
+                double *gp = G + (size_t)p * m, *gq = G + (size_t)q * m;
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int r = lane; r < m; r += 32) {
+                    const double x = gp[r], y = gq[r];
+                    al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+                }
+                al = ab_warp_sum_f64(al); be = ab_warp_sum_f64(be); ga = ab_warp_sum_f64(ga);
+                if (fabs(ga) > 1e-15 * sqrt(al * be) && fabs(ga) > 1e-300) {
+                    if (lane == 0) rot_sm = 1;
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                    double *qp = Q + (size_t)p * m, *qq = Q + (size_t)q * m;
+                    for (int r = lane; r < m; r += 32) {
+                        const double x = gp[r], y = gq[r];
+                        gp[r] = cs * x - sn * y; gq[r] = sn * x + cs * y;
+                        const double u = qp[r], v = qq[r];
+                        qp[r] = cs * u - sn * v; qq[r] = sn * u + cs * v;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int any = rot_sm;
+        __syncthreads();
+        if (!any) break;
+    }
+    // singular values = column norms; sort descending by counting rank (ties by index)
+    for (int c = warp; c < m; c += nwarp) {
+        double acc = 0.0;
+        for (int r = lane; r < m; r += 32) acc = fma(G[(size_t)c * m + r], G[(size_t)c * m + r], acc);
+        acc = ab_warp_sum_f64(acc);
+        if (lane == 0) nrm[c] = sqrt(acc);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < m; c += blockDim.x) {
+        int rank = 0;
+        for (int o = 0; o < m; ++o) rank += (nrm[o] > nrm[c]) || (nrm[o] == nrm[c] && o < c);
+        order[rank] = c;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+        const int r = e / m, i = e % m;
+        const int c = order[i];
+        const double sv = nrm[c];
+        Ub[r * m + i] = sv > 0.0 ? G[(size_t)c * m + r] / sv : 0.0;
+        Vb[r * m + i] = Q[(size_t)c * m + r];
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) sb[i] = nrm[order[i]];
+    __syncthreads();
+    // residuals and restart bookkeeping
+    const double fn = sqrt(scal[SC_FN2]);
+    __shared__ int conv_sm;
+    if (threadIdx.x == 0) {
+        double smax = sb[0];
+        if (it > 0) smax = fmax(smax, scal[SC_SMAX]);
+        scal[SC_SMAX] = smax;
+        conv_sm = 0;
+    }
+    __syncthreads();
+    const double smax = scal[SC_SMAX];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double res = __dmul_rn(fn, Ub[(m - 1) * m + i]);
+        R[i] = res;
+        if (i < nu && fabs(res) < tol * smax) atomicAdd(&conv_sm, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int conv = conv_sm;
+        ctrl[CT_CONV] = conv;
+        if (conv >= nu) {
+            ctrl[CT_DONE] = 1;
+            ctrl[CT_KEEP] = keep_prev;
+        } else {
+            int k = max(conv + nu, keep_prev);
+            k = min(k, m - 3);
+            ctrl[CT_DONE] = 0;
+            ctrl[CT_KEEP] = k;
+        }
+    }
+}
+
+// B = 0; B[l,l] = sb[l] (l<keep); B[l,keep] = R[l]   (irlb.py:240-244)
+__global__ void reset_b_kernel(double *__restrict__ B, int work, const double *__restrict__ sb,
+                               const double *__restrict__ R, int keep) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < work * work; e += gridDim.x * blockDim.x) {
+        const int r = e / work, c = e % work;
+        double v = 0.0;
+        if (r < keep && c == r) v = sb[r];
+        if (r < keep && c == keep) v = R[r];
+        B[e] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Ritz update: out[:, c] = X[:, :work] . M[:, c]  for c < ncols     (irlb.py:238,246,249-250)
+// X column-major (ld), M row-major work x work (use columns 0..ncols-1).
+// out column-major (ldo) or, if rowmajor_out, row-major [n x ncols] scaled by colscale[c].
+// ---------------------------------------------------------------------------------------
+static constexpr int RZ_THREADS = 128;
+static constexpr int RZ_COLS = 16;
+
+__global__ void __launch_bounds__(RZ_THREADS)
+ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const double *__restrict__ M, int ncols,
+            double *__restrict__ out, int64_t ldo, int rowmajor_out, const double *__restrict__ colscale,
+            double *__restrict__ out2 /* optional second row-major output without scaling */) {
+    extern __shared__ double smr[];
+    double *xs = smr;                                   // [work][RZ_THREADS]
+    double *ms = smr + (size_t)work * RZ_THREADS;       // [work][RZ_COLS]
+    const int64_t row = (int64_t)blockIdx.x * RZ_THREADS + threadIdx.x;
+    const bool live = row < n;
+    for (int l = 0; l < work; ++l) xs[(size_t)l * RZ_THREADS + threadIdx.x] = live ? X[(int64_t)l * ld + row] : 0.0;
+    for (int c0 = 0; c0 < ncols; c0 += RZ_COLS) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < work * RZ_COLS; e += RZ_THREADS) {
+            const int l = e / RZ_COLS, c = e % RZ_COLS;
+            ms[e] = (c0 + c < ncols) ? M[l * work + c0 + c] : 0.0;
+        }
+        __syncthreads();
+        double acc[RZ_COLS];
+#pragma unroll
+        for (int c = 0; c < RZ_COLS; ++c) acc[c] = 0.0;
+        for (int l = 0; l < work; ++l) {
+            const double x = xs[(size_t)l * RZ_THREADS + threadIdx.x];
+            const double2 *mrow = reinterpret_cast<const double2 *>(ms + (size_t)l * RZ_COLS);
+#pragma unroll
+            for (int c = 0; c < RZ_COLS / 2; ++c) {
+                const double2 mm = mrow[c];
+                acc[2 * c] = fma(x, mm.x, acc[2 * c]);
+                acc[2 * c + 1] = fma(x, mm.y, acc[2 * c + 1]);
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < RZ_COLS; ++c) {
+                if (c0 + c < ncols) {
+                    if (rowmajor_out) {
+                        const double sc = colscale ? colscale[c0 + c] : 1.0;
+                        out[row * (int64_t)ncols + c0 + c] = __dmul_rn(acc[c], sc);
+                        if (out2) out2[row * (int64_t)ncols + c0 + c] = acc[c];
+                    } else {
+                        out[(int64_t)(c0 + c) * ldo + row] = acc[c];
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void copy_vec_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------
+struct IrlbWs {
+    double *V, *V2, *W, *W2, *F, *B, *Ub, *Vb, *sb, *R, *G, *scal, *coef, *wraw;
+    double *dot_partial, *nrm_partial, *av_partial;
+    int *ctrl;
+    int av_grid, av_warps;
+    int64_t dot_grid;
+};
+
+static int irlb_work_dim(int nval, int64_t n_total) {
+    int64_t w = nval + 20;
+    if (3LL * nval < w) w = 3LL * nval;
+    if (n_total < w) w = n_total;
+    return (int)w;
+}
+
+static int av_warps_for(int H) {
+    int w = (int)((200 * 1024) / ((size_t)H * 8));
+    if (w > 8) w = 8;
+    return w;
+}
+
+static size_t irlb_layout(int64_t n, int H, int nval, int64_t n_total_hint, int sm_count, void *ws, size_t bytes,
+                          IrlbWs *out) {
+    const int work = irlb_work_dim(nval, n_total_hint);
+    ab_arena a(ws ? ws : (void *)256, ws ? bytes : (size_t)-1 / 2);
+    IrlbWs w;
+    const int64_t ld = n > 0 ? n : 1;
+    w.V = a.take<double>((size_t)ld * work);
+    w.V2 = a.take<double>((size_t)ld * work);
+    w.W = a.take<double>((size_t)H * work);
+    w.W2 = a.take<double>((size_t)H * work);
+    w.F = a.take<double>(ld);
+    w.B = a.take<double>((size_t)work * work);
+    w.Ub = a.take<double>((size_t)work * work);
+    w.Vb = a.take<double>((size_t)work * work);
+    w.sb = a.take<double>(work);
+    w.R = a.take<double>(work);
+    w.G = a.take<double>((size_t)2 * work * work);
+    w.scal = a.take<double>(SC_COUNT);
+    w.coef = a.take<double>(IR_MAXWORK);
+    w.wraw = a.take<double>(H);
+    w.dot_grid = (n + DOT_TILE - 1) / DOT_TILE;
+    if (w.dot_grid < 1) w.dot_grid = 1;
+    w.dot_partial = a.take<double>((size_t)w.dot_grid * IR_MAXWORK);
+    w.nrm_partial = a.take<double>((size_t)(w.dot_grid > 1024 ? w.dot_grid : 1024));
+    w.av_warps = av_warps_for(H);
+    w.av_grid = sm_count;
+    w.av_partial = a.take<double>((size_t)w.av_grid * H);
+    w.ctrl = a.take<int>(CT_COUNT);
+    if (out) *out = w;
+    return a.ok ? a.off : 0;
+}
+
+extern "C" size_t ab_irlb_ws_bytes(int64_t n_local, int32_t n_hvg, int32_t nval) {
+    // work dimension is at most nval+20; n_total >= that in every supported call
+    return irlb_layout(n_local, n_hvg, nval, (int64_t)1 << 40, 256, nullptr, 0, nullptr) + 256;
+}
+
+extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_h, const double *val_h,
+                       int64_t n_local, int64_t n_total, int32_t n_hvg, int32_t nval, double tol, int32_t maxit,
+                       const double *v0_local, double *scores_local, double *v_local, double *s_out, double *u_out,
+                       int64_t *h_info, void *ws, size_t ws_bytes, void *stream) {
+    AB_REQUIRE(ctx, "ab_irlb: null ctx");
+    AB_REQUIRE(n_hvg >= 2 && n_total >= 2, "ab_irlb: the input matrix must be at least 2x2 (irlb.py:119-120)");
+    AB_REQUIRE(nval >= 1, "ab_irlb: nval must be >= 1");
+    const int work = irlb_work_dim(nval, n_total);
+    AB_REQUIRE(work <= IR_MAXWORK, "ab_irlb: work dimension %d exceeds %d (nval too large)", work, IR_MAXWORK);
+    AB_REQUIRE(work >= nval + 1 && work - 3 >= 1, "ab_irlb: nval=%d too large for this matrix (work=%d)", nval, work);
+    AB_REQUIRE(av_warps_for(n_hvg) >= 1, "ab_irlb: n_hvg=%d too large for the shared-memory accumulators", n_hvg);
+    IrlbWs w;
+    size_t need = irlb_layout(n_local, n_hvg, nval, n_total, ctx->sm_count, ws, ws_bytes, &w);
+    AB_REQUIRE(need != 0, "ab_irlb: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int H = n_hvg;
+    const int64_t n = n_local, ld = n_local > 0 ? n_local : 1;
+    int *cnt = ctx->d_counter;
+
+    AB_CUDA(cudaMemsetAsync(w.V, 0, (size_t)ld * work * 8, st));
+    AB_CUDA(cudaMemsetAsync(w.V2, 0, (size_t)ld * work * 8, st));
+    AB_CUDA(cudaMemsetAsync(w.W, 0, (size_t)H * work * 8, st));
+    AB_CUDA(cudaMemsetAsync(w.W2, 0, (size_t)H * work * 8, st));
+    AB_CUDA(cudaMemsetAsync(w.B, 0, (size_t)work * work * 8, st));
+    AB_CUDA(cudaMemsetAsync(w.scal, 0, SC_COUNT * 8, st));
+    AB_CUDA(cudaMemsetAsync(w.ctrl, 0, CT_COUNT * 4, st));
+
+    const size_t av_smem = (size_t)w.av_warps * H * 8;
+    AB_CUDA(cudaFuncSetAttribute(av_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
+    const size_t ws_smem = ((size_t)H + IR_MAXWORK + 40) * 8;
+    AB_CUDA(cudaFuncSetAttribute(wstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem));
+    const size_t rz_smem_v = ((size_t)work * RZ_THREADS + (size_t)work * RZ_COLS) * 8;
+    AB_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rz_smem_v));
+
+    const unsigned g_rows = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 32));
+    const unsigned g_vec = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
+    const unsigned g_dot = (unsigned)w.dot_grid;
+    const unsigned g_rz = (unsigned)std::max<int64_t>(1, (n + RZ_THREADS - 1) / RZ_THREADS);
+    const unsigned g_rzw = (unsigned)((H + RZ_THREADS - 1) / RZ_THREADS);
+
+    int64_t nmult = 0, sum_panel = 0;
+
+    auto av = [&](const double *src, const double *sumsq, double *vdst) -> int {
+        av_kernel<<<w.av_grid, 256, av_smem, st>>>(rowptr_h, col_h, val_h, n, H, src, sumsq, vdst, w.av_warps,
+                                                    w.av_partial);
+        AB_LAUNCH_CHECK(ctx);
+        av_reduce_kernel<<<(H + 127) / 128, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw);
+        AB_LAUNCH_CHECK(ctx);
+        if (ab_allreduce_f64(ctx, w.wraw, H, st)) return 1;
+        nmult++;
+        return 0;
+    };
+
+    // start vector (irlb.py:151-153)
+    sumsq_kernel<<<(unsigned)std::min<int64_t>(1024, std::max<int64_t>(1, (n + 255) / 256)), DOT_THREADS, 0, st>>>(
+        v0_local, n, w.nrm_partial, w.scal + SC_V0N2, cnt);
+    AB_LAUNCH_CHECK(ctx);
+    if (ab_allreduce_f64(ctx, w.scal + SC_V0N2, 1, st)) return 1;
+    scale_by_invnorm_kernel<<<g_vec, 256, 0, st>>>(v0_local, w.V, n, w.scal + SC_V0N2);
+    AB_LAUNCH_CHECK(ctx);
+
+    int it = 0, keep = nval;
+    int h_ctrl[CT_COUNT] = {0};
+    bool converged = false;
+    while (it < maxit) {
+        int j = it > 0 ? keep : 0;
+        // W[:,j] = A.V[:,j]  (irlb.py:165), orthogonalised against W[:, :j] on restarts (:173-175)
+        if (av(w.V + (int64_t)j * ld, nullptr, nullptr)) return 1;
+        wstep_kernel<<<1, 1024, ws_smem, st>>>(w.wraw, w.W, H, j, it > 0 ? j : 0, 0, w.scal, w.B, work, -1);
+        AB_LAUNCH_CHECK(ctx);
+        while (j < work) {
+            atw_kernel<<<g_rows, 256, 0, st>>>(rowptr_h, col_h, val_h, n, w.W + (size_t)j * H, w.V + (int64_t)j * ld,
+                                                w.scal, w.F);
+            AB_LAUNCH_CHECK(ctx);
+            nmult++;
+            panel_dot_kernel<<<g_dot, DOT_THREADS, 0, st>>>(w.V, ld, n, j + 1, w.F, w.dot_partial, w.coef, cnt + 1);
+            AB_LAUNCH_CHECK(ctx);
+            if (ab_allreduce_f64(ctx, w.coef, j + 1, st)) return 1;
+            panel_update_kernel<<<g_dot, DOT_THREADS, 0, st>>>(w.V, ld, n, j + 1, w.coef, w.F, w.nrm_partial,
+                                                                w.scal + SC_FN2, cnt + 2);
+            AB_LAUNCH_CHECK(ctx);
+            if (ab_allreduce_f64(ctx, w.scal + SC_FN2, 1, st)) return 1;
+            sum_panel += j + 1;
+            if (j < work - 1) {
+                // V[:,j+1] = F/fn ; W[:,j+1] = A.V[:,j+1] - fn W[:,j], CGS, normalise (irlb.py:195-219)
+                if (av(w.F, w.scal + SC_FN2, w.V + (int64_t)(j + 1) * ld)) return 1;
+                wstep_kernel<<<1, 1024, ws_smem, st>>>(w.wraw, w.W, H, j + 1, j + 1, 1, w.scal, w.B, work, j);
+                AB_LAUNCH_CHECK(ctx);
+            } else {
+                fscale_kernel<<<g_vec, 256, 0, st>>>(w.F, n, w.scal, w.B, work, j);
+                AB_LAUNCH_CHECK(ctx);
+            }
+            ++j;
+        }
+        svd_restart_kernel<<<1, 512, 0, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it, keep);
+        AB_LAUNCH_CHECK(ctx);
+        AB_CUDA(cudaMemcpyAsync(h_ctrl, w.ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, st));
+        AB_CUDA(cudaStreamSynchronize(st));
+        if (h_ctrl[CT_DONE]) { converged = true; break; }
+        keep = h_ctrl[CT_KEEP];
+        // Ritz vectors (irlb.py:238-246)
+        ritz_kernel<<<g_rz, RZ_THREADS, rz_smem_v, st>>>(w.V, ld, n, work, w.Vb, keep, w.V2, ld, 0, nullptr, nullptr);
+        AB_LAUNCH_CHECK(ctx);
+        copy_vec_kernel<<<g_vec, 256, 0, st>>>(w.F, w.V2 + (int64_t)keep * ld, n);
+        AB_LAUNCH_CHECK(ctx);
+        ritz_kernel<<<g_rzw, RZ_THREADS, rz_smem_v, st>>>(w.W, H, H, work, w.Ub, keep, w.W2, H, 0, nullptr, nullptr);
+        AB_LAUNCH_CHECK(ctx);
+        reset_b_kernel<<<8, 256, 0, st>>>(w.B, work, w.sb, w.R, keep);
+        AB_LAUNCH_CHECK(ctx);
+        std::swap(w.V, w.V2);
+        std::swap(w.W, w.W2);
+        ++it;
+    }
+    // outputs (irlb.py:249-257; clustering.py:111)
+    ritz_kernel<<<g_rz, RZ_THREADS, rz_smem_v, st>>>(w.V, ld, n, work, w.Vb, nval, scores_local, 0, 1, w.sb, v_local);
+    AB_LAUNCH_CHECK(ctx);
+    if (u_out) {
+        ritz_kernel<<<g_rzw, RZ_THREADS, rz_smem_v, st>>>(w.W, H, H, work, w.Ub, nval, u_out, 0, 1, nullptr, nullptr);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    if (s_out) AB_CUDA(cudaMemcpyAsync(s_out, w.sb, (size_t)nval * 8, cudaMemcpyDeviceToDevice, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    if (h_info) {
+        h_info[0] = it;
+        h_info[1] = nmult;
+        h_info[2] = sum_panel;
+        h_info[3] = converged ? 0 : 1;
+    }
+    return 0;
+}

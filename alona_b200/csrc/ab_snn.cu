@@ -1,0 +1,515 @@
+// K10: shared-nearest-neighbour graph from the kNN table.
+// Replaces AlonaClustering.snn (alona/clustering.py:204-231):
+//   A = kNN incidence (self included), C = A.A^T (integer overlaps, scipy csr_matmat),
+//   keep (i,m) iff C[i,m]/(k+(k-C[i,m])) > prune_snn, emit in csr_matmat's order.
+//
+// C[i,m] = |N(i) n N(m)| = #{ j in N(i) : m in R(j) },  R(j) = { m : j in N(m) } (reverse lists).
+// scipy's order inside row i is the REVERSE of first-encounter order when scanning j over
+// sorted(N(i)) and m over sorted(R(j)).  So, per row, the 2-hop walk is
+// enumerated by position p = base(j) + t; a per-warp shared-memory hash keeps for every
+// distinct m its overlap count and the position of its first encounter; a second walk emits
+// the first encounters from the last position to the first, filtered by overlap >= v_min.
+// No sort, no atomics in the common path (duplicates inside a 32-wide step are merged with
+// match.any, steps are processed in ascending position order).
+//
+// Rows whose walk is longer than the per-warp table are handled by one CTA each, with dense
+// per-CTA count/first arrays in global scratch (always correct, any in-degree).
+#include "ab_common.cuh"
+#include <limits.h>
+
+static constexpr int SNN_WARPS = 8;
+static constexpr int SNN_SLOTS = 2048;            // per warp, power of two
+static constexpr int SNN_WALK_LIMIT = 1400;       // rows with a longer walk go to the big path
+static constexpr int SNN_MAXK = 128;
+static constexpr int SNN_BIG_CTAS = 32;
+static constexpr int SNN_BIG_THREADS = 256;
+static constexpr int SORT_CTA_MAX = 4096;
+
+// ---------------------------------------------------------------------------------------
+// reverse graph
+// ---------------------------------------------------------------------------------------
+__global__ void snn_degree_kernel(const int32_t *__restrict__ knn, int64_t total, int64_t n_total,
+                                  int64_t *__restrict__ deg, int *__restrict__ bad) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < total) {
+        int j = knn[e];
+        if (j < 0 || j >= n_total) { atomicAdd(bad, 1); return; }
+        atomicAdd((unsigned long long *)(deg + j), 1ull);
+    }
+}
+
+__global__ void snn_scatter_kernel(const int32_t *__restrict__ knn, int64_t total, int k,
+                                   const int64_t *__restrict__ rptr, int *__restrict__ cursor,
+                                   int32_t *__restrict__ rlist) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < total) {
+        int j = knn[e];
+        int pos = atomicAdd(cursor + j, 1);
+        rlist[rptr[j] + pos] = (int32_t)(e / k);
+    }
+}
+
+__device__ __forceinline__ int warp_bitonic_sort(int v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            int other = __shfl_xor_sync(AB_FULL, v, stride);
+            bool up = ((lane & size) == 0);
+            bool lower = ((lane & stride) == 0);
+            int mn = min(v, other), mx = max(v, other);
+            v = (lower == up) ? mn : mx;
+        }
+    }
+    return v;
+}
+
+// lists of <= 32 entries: one warp each, register bitonic sort.  Longer lists are queued.
+__global__ void __launch_bounds__(256)
+snn_sort_short_kernel(const int64_t *__restrict__ rptr, int32_t *__restrict__ rlist, int64_t n_total,
+                      int32_t *__restrict__ long_ids, int *__restrict__ n_long) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    for (int64_t j = w; j < n_total; j += nw) {
+        const int64_t a = rptr[j];
+        const int len = (int)(rptr[j + 1] - a);
+        if (len <= 1) continue;
+        if (len > 32) {
+            if (lane == 0) long_ids[atomicAdd(n_long, 1)] = (int32_t)j;
+            continue;
+        }
+        int v = lane < len ? rlist[a + lane] : INT_MAX;
+        v = warp_bitonic_sort(v, lane);
+        if (lane < len) rlist[a + lane] = v;
+    }
+}
+
+// lists of 33..4096 entries: CTA bitonic sort in shared memory; longer: counting rank via tmp.
+__global__ void __launch_bounds__(256)
+snn_sort_long_kernel(const int64_t *__restrict__ rptr, int32_t *__restrict__ rlist,
+                     const int32_t *__restrict__ long_ids, const int *__restrict__ n_long,
+                     int32_t *__restrict__ tmp) {
+    __shared__ int sm[SORT_CTA_MAX];
+    const int nl = *n_long;
+    for (int q = blockIdx.x; q < nl; q += gridDim.x) {
+        const int j = long_ids[q];
+        const int64_t a = rptr[j];
+        const int64_t len = rptr[j + 1] - a;
+        if (len <= SORT_CTA_MAX) {
+            int n2 = 64;
+            while (n2 < len) n2 <<= 1;
+            for (int i = threadIdx.x; i < n2; i += 256) sm[i] = i < len ? rlist[a + i] : INT_MAX;
+            __syncthreads();
+            for (int size = 2; size <= n2; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int i = threadIdx.x; i < (n2 >> 1); i += 256) {
+                        int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+                        int hi = lo | stride;
+                        bool up = ((lo & size) == 0);
+                        int x = sm[lo], y = sm[hi];
+                        if ((x > y) == up) { sm[lo] = y; sm[hi] = x; }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int i = threadIdx.x; i < len; i += 256) rlist[a + i] = sm[i];
+            __syncthreads();
+        } else {
+            // entries of one reverse list are distinct cells -> rank = #smaller
+            for (int64_t i = threadIdx.x; i < len; i += 256) {
+                const int v = rlist[a + i];
+                int64_t r = 0;
+                for (int64_t t = 0; t < len; ++t) r += rlist[a + t] < v;
+                tmp[a + r] = v;
+            }
+            __syncthreads();
+            for (int64_t i = threadIdx.x; i < len; i += 256) rlist[a + i] = tmp[a + i];
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-row walk length and classification
+// ---------------------------------------------------------------------------------------
+__global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_t n_rows,
+                                const int64_t *__restrict__ rptr, int32_t *__restrict__ big_rows,
+                                int *__restrict__ n_big, unsigned long long *__restrict__ max_walk,
+                                int *__restrict__ n_dup) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int32_t *row = knn + (row_begin + r) * k;
+    long long walk = 0;
+    for (int c = 0; c < k; ++c) {
+        int j = row[c];
+        walk += rptr[j + 1] - rptr[j];
+    }
+    if (row[0] != row_begin + r) atomicAdd(n_dup, 1);
+    if (walk > SNN_WALK_LIMIT) big_rows[atomicAdd(n_big, 1)] = (int32_t)r;
+    atomicMax(max_walk, (unsigned long long)walk);
+}
+
+// ---------------------------------------------------------------------------------------
+// small rows: one warp per row, shared-memory hash
+// ---------------------------------------------------------------------------------------
+struct WarpRowState {
+    int nb[SNN_MAXK];            // sorted neighbour ids
+    int base[SNN_MAXK + 1];      // walk position where each neighbour's reverse list starts
+    long long start[SNN_MAXK];   // rptr of each neighbour
+};
+
+__device__ __forceinline__ unsigned hash_slot(int key) {
+    return ((unsigned)key * 2654435761u) >> (32 - 11);          // 2048 slots
+}
+
+// Loads and sorts row `r`, fills st; returns the walk length.
+__device__ __forceinline__ int warp_load_row(const int32_t *__restrict__ knn, int k, int64_t grow,
+                                             const int64_t *__restrict__ rptr, WarpRowState &st, int lane) {
+    // sort k <= 128 ids: 4 registers per lane, rank by counting through shared memory
+    for (int c = lane; c < k; c += 32) st.base[c] = knn[grow * k + c];       // base[] as scratch
+    __syncwarp();
+    for (int c = lane; c < k; c += 32) {
+        const int v = st.base[c];
+        int rank = 0;
+        for (int t = 0; t < k; ++t) {
+            const int u = st.base[t];
+            rank += (u < v) || (u == v && t < c);
+        }
+        st.nb[rank] = v;
+    }
+    __syncwarp();
+    // degrees and exclusive prefix
+    int run = 0;
+    for (int c0 = 0; c0 < k; c0 += 32) {
+        const int c = c0 + lane;
+        int d = 0;
+        if (c < k) {
+            const int j = st.nb[c];
+            const long long s = rptr[j];
+            st.start[c] = s;
+            d = (int)(rptr[j + 1] - s);
+        }
+        int inc = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(AB_FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __syncwarp();
+        if (c < k) st.base[c] = run + inc - d;
+        run += __shfl_sync(AB_FULL, inc, 31);
+    }
+    if (lane == 0) st.base[k] = run;
+    __syncwarp();
+    return run;
+}
+
+// walk position -> cell id m
+__device__ __forceinline__ int walk_fetch(const WarpRowState &st, int k, int p, const int32_t *__restrict__ rlist) {
+    int lo = 0, hi = k;                                   // last a with base[a] <= p
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (st.base[mid] <= p) lo = mid; else hi = mid;
+    }
+    return __ldg(rlist + st.start[lo] + (p - st.base[lo]));
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(SNN_WARPS * 32)
+snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_t n_rows,
+                 const int64_t *__restrict__ rptr, const int32_t *__restrict__ rlist, int v_min,
+                 int64_t *__restrict__ rowcount, const int64_t *__restrict__ rowptr_out,
+                 int32_t *__restrict__ src, int32_t *__restrict__ dst, uint8_t *__restrict__ overlap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpRowState &st = reinterpret_cast<WarpRowState *>(smem_raw)[warp];
+    int *keys = reinterpret_cast<int *>(smem_raw + sizeof(WarpRowState) * SNN_WARPS) + warp * SNN_SLOTS * 2;
+    int *vals = keys + SNN_SLOTS;
+    const int64_t w = (int64_t)blockIdx.x * SNN_WARPS + warp;
+    const int64_t nw = (int64_t)gridDim.x * SNN_WARPS;
+    for (int64_t r = w; r < n_rows; r += nw) {
+        const int walk = warp_load_row(knn, k, row_begin + r, rptr, st, lane);
+        if (walk > SNN_WALK_LIMIT) continue;              // big path
+        for (int s = lane; s < SNN_SLOTS; s += 32) keys[s] = -1;
+        __syncwarp();
+        // walk 1: ascending positions; merge duplicates inside a step with match.any
+        for (int p0 = 0; p0 < walk; p0 += 32) {
+            const int p = p0 + lane;
+            const bool live = p < walk;
+            const int m = live ? walk_fetch(st, k, p, rlist) : -1 - lane;
+            const unsigned grp = __match_any_sync(AB_FULL, m);
+            const bool leader = live && (__ffs(grp) - 1 == lane);
+            if (leader) {
+                const int add = __popc(grp);
+                unsigned s = hash_slot(m);
+                while (true) {
+                    const int prev = atomicCAS(keys + s, -1, m);
+                    if (prev == -1) { vals[s] = (p << 8) | add; break; }
+                    if (prev == m) { vals[s] += add; break; }
+                    s = (s + 1) & (SNN_SLOTS - 1);
+                }
+            }
+            __syncwarp();
+        }
+        if (!FILL) {
+            int c = 0;
+            for (int s = lane; s < SNN_SLOTS; s += 32) c += (keys[s] != -1) && ((vals[s] & 255) >= v_min);
+            c = ab_warp_sum_i32(c);
+            if (lane == 0) rowcount[r] = c;
+        } else {
+            int64_t out = rowptr_out[r];
+            const int grow = (int)(row_begin + r);
+            for (int p0 = ((walk - 1) / 32) * 32; p0 >= 0; p0 -= 32) {
+                const int p = p0 + lane;
+                bool keep = false;
+                int m = 0, cnt = 0;
+                if (p < walk) {
+                    m = walk_fetch(st, k, p, rlist);
+                    unsigned s = hash_slot(m);
+                    while (keys[s] != m) s = (s + 1) & (SNN_SLOTS - 1);
+                    const int v = vals[s];
+                    cnt = v & 255;
+                    keep = ((v >> 8) == p) && cnt >= v_min;
+                }
+                const unsigned b = __ballot_sync(AB_FULL, keep);
+                if (keep) {
+                    const int64_t q = out + __popc(b & ~((2u << lane) - 1));     // higher lanes first
+                    dst[q] = m;
+                    src[q] = grow;
+                    if (overlap) overlap[q] = (uint8_t)cnt;
+                }
+                out += __popc(b);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// big rows: one CTA per row, dense per-CTA arrays in global scratch (cnt, first)
+// ---------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(SNN_BIG_THREADS)
+snn_big_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_t n_total,
+               const int64_t *__restrict__ rptr, const int32_t *__restrict__ rlist, int v_min,
+               const int32_t *__restrict__ big_rows, const int *__restrict__ n_big,
+               int *__restrict__ dense /* SNN_BIG_CTAS x 2 x n_total, cnt=0 / first=INT_MAX */,
+               int64_t *__restrict__ rowcount, const int64_t *__restrict__ rowptr_out,
+               int32_t *__restrict__ src, int32_t *__restrict__ dst, uint8_t *__restrict__ overlap) {
+    __shared__ WarpRowState st;
+    __shared__ int warp_tot[SNN_BIG_THREADS / 32];
+    __shared__ int walk_sm;
+    __shared__ int total_sm;
+    int *cnt = dense + (int64_t)blockIdx.x * 2 * n_total;
+    int *first = cnt + n_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = *n_big;
+    for (int q = blockIdx.x; q < nb; q += gridDim.x) {
+        const int64_t r = big_rows[q];
+        __syncthreads();
+        if (warp == 0) {
+            int wl = warp_load_row(knn, k, row_begin + r, rptr, st, lane);
+            if (lane == 0) { walk_sm = wl; total_sm = 0; }
+        }
+        __syncthreads();
+        const int walk = walk_sm;
+        for (int p = threadIdx.x; p < walk; p += SNN_BIG_THREADS) {
+            const int m = walk_fetch(st, k, p, rlist);
+            atomicAdd(cnt + m, 1);
+            atomicMin(first + m, p);
+        }
+        __syncthreads();
+        if (!FILL) {
+            int c = 0;
+            for (int p = threadIdx.x; p < walk; p += SNN_BIG_THREADS) {
+                const int m = walk_fetch(st, k, p, rlist);
+                c += (first[m] == p) && (cnt[m] >= v_min);
+            }
+            c = ab_warp_sum_i32(c);
+            if (lane == 0) atomicAdd(&total_sm, c);
+            __syncthreads();
+            if (threadIdx.x == 0) rowcount[r] = total_sm;
+        } else {
+            int64_t out = rowptr_out[r];
+            const int grow = (int)(row_begin + r);
+            for (int p0 = ((walk - 1) / SNN_BIG_THREADS) * SNN_BIG_THREADS; p0 >= 0; p0 -= SNN_BIG_THREADS) {
+                const int p = p0 + threadIdx.x;
+                bool keep = false;
+                int m = 0, c = 0;
+                if (p < walk) {
+                    m = walk_fetch(st, k, p, rlist);
+                    c = cnt[m];
+                    keep = (first[m] == p) && c >= v_min;
+                }
+                const unsigned b = __ballot_sync(AB_FULL, keep);
+                if (lane == 0) warp_tot[warp] = __popc(b);
+                __syncthreads();
+                int higher = 0, tot = 0;
+                for (int w2 = 0; w2 < SNN_BIG_THREADS / 32; ++w2) {
+                    tot += warp_tot[w2];
+                    if (w2 > warp) higher += warp_tot[w2];
+                }
+                if (keep) {
+                    const int64_t pos = out + higher + __popc(b & ~((2u << lane) - 1));
+                    dst[pos] = m;
+                    src[pos] = grow;
+                    if (overlap) overlap[pos] = (uint8_t)min(c, 255);
+                }
+                out += tot;
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        // restore the dense arrays
+        for (int p = threadIdx.x; p < walk; p += SNN_BIG_THREADS) {
+            const int m = walk_fetch(st, k, p, rlist);
+            cnt[m] = 0;
+            first[m] = INT_MAX;
+        }
+    }
+}
+
+__global__ void snn_init_dense_kernel(int *dense, int64_t n_total, int nctas) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = 2 * n_total;
+    if (i < per * nctas) dense[i] = ((i % per) < n_total) ? 0 : INT_MAX;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct SnnWs {
+    int64_t *deg;        // n_total+1 (becomes rptr after the scan)
+    int *cursor;         // n_total
+    int32_t *rlist;      // n_total*k
+    int32_t *tmp;        // n_total*k
+    int32_t *long_ids;   // n_total
+    int32_t *big_rows;   // n_rows
+    int *dense;          // SNN_BIG_CTAS*2*n_total
+    int *counters;       // 8 ints: n_long, n_big, n_dup, bad
+    unsigned long long *max_walk;
+    int64_t *rowcount;   // n_rows+1
+    void *scan_ws;
+    size_t scan_bytes;
+};
+
+static size_t snn_layout(int64_t n_total, int32_t k, int64_t n_rows, void *ws, size_t ws_bytes, SnnWs *out) {
+    ab_arena a(ws ? ws : (void *)256, ws ? ws_bytes : (size_t)-1 / 2);
+    SnnWs w;
+    w.deg = a.take<int64_t>(n_total + 1);
+    w.cursor = a.take<int>(n_total);
+    w.rlist = a.take<int32_t>((size_t)n_total * k);
+    w.tmp = a.take<int32_t>((size_t)n_total * k);
+    w.long_ids = a.take<int32_t>(n_total);
+    w.big_rows = a.take<int32_t>(n_rows > 0 ? n_rows : 1);
+    w.dense = a.take<int>((size_t)SNN_BIG_CTAS * 2 * n_total);
+    w.counters = a.take<int>(8);
+    w.max_walk = a.take<unsigned long long>(1);
+    w.rowcount = a.take<int64_t>(n_rows + 1);
+    int64_t big = n_total > n_rows ? n_total : n_rows;
+    w.scan_bytes = ab_scan_ws_bytes(big + 1);
+    w.scan_ws = a.take<char>(w.scan_bytes);
+    if (out) *out = w;
+    return a.ok ? a.off : 0;
+}
+
+extern "C" size_t ab_snn_ws_bytes(int64_t n_total, int32_t k, int64_t n_rows) {
+    return snn_layout(n_total, k, n_rows, nullptr, 0, nullptr) + 256;
+}
+
+static size_t snn_small_smem() { return sizeof(WarpRowState) * SNN_WARPS + (size_t)SNN_WARPS * SNN_SLOTS * 2 * sizeof(int); }
+
+extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k, int64_t row_begin,
+                            int64_t row_end, int32_t v_min, int64_t *rowptr, int64_t *h_edges, int64_t *stats,
+                            void *ws, size_t ws_bytes, void *stream) {
+    AB_REQUIRE(ctx, "ab_snn_count: null ctx");
+    AB_REQUIRE(k >= 1 && k <= SNN_MAXK, "ab_snn_count: k must be in 1..%d", SNN_MAXK);
+    AB_REQUIRE(n_total >= 1 && n_total < INT_MAX, "ab_snn_count: bad n_total");
+    AB_REQUIRE(row_begin >= 0 && row_end >= row_begin && row_end <= n_total, "ab_snn_count: bad row range");
+    const int64_t n_rows = row_end - row_begin;
+    SnnWs w;
+    size_t need = snn_layout(n_total, k, n_rows, ws, ws_bytes, &w);
+    AB_REQUIRE(need != 0, "ab_snn_count: workspace too small (need %zu)", ab_snn_ws_bytes(n_total, k, n_rows));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = n_total * k;
+    AB_CUDA(cudaMemsetAsync(w.deg, 0, (n_total + 1) * sizeof(int64_t), st));
+    AB_CUDA(cudaMemsetAsync(w.cursor, 0, n_total * sizeof(int), st));
+    AB_CUDA(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), st));
+    AB_CUDA(cudaMemsetAsync(w.max_walk, 0, sizeof(unsigned long long), st));
+    const unsigned eb = (unsigned)((total + 255) / 256);
+    snn_degree_kernel<<<eb, 256, 0, st>>>(knn_all, total, n_total, w.deg, w.counters + 3);
+    AB_LAUNCH_CHECK(ctx);
+    if (ab_exclusive_scan_i64(ctx, w.deg, w.deg, n_total, w.scan_ws, w.scan_bytes, st)) return 1;
+    int h_bad = 0;
+    AB_CUDA(cudaMemcpyAsync(&h_bad, w.counters + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    AB_REQUIRE(h_bad == 0, "ab_snn_count: kNN table holds %d indices outside [0,%lld)", h_bad, (long long)n_total);
+    snn_scatter_kernel<<<eb, 256, 0, st>>>(knn_all, total, k, w.deg, w.cursor, w.rlist);
+    AB_LAUNCH_CHECK(ctx);
+    snn_sort_short_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(w.deg, w.rlist, n_total, w.long_ids, w.counters + 0);
+    AB_LAUNCH_CHECK(ctx);
+    snn_sort_long_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(w.deg, w.rlist, w.long_ids, w.counters + 0, w.tmp);
+    AB_LAUNCH_CHECK(ctx);
+    if (n_rows > 0) {
+        snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(knn_all, k, row_begin, n_rows, w.deg,
+                                                                           w.big_rows, w.counters + 1, w.max_walk,
+                                                                           w.counters + 2);
+        AB_LAUNCH_CHECK(ctx);
+        snn_init_dense_kernel<<<(unsigned)(((int64_t)SNN_BIG_CTAS * 2 * n_total + 255) / 256), 256, 0, st>>>(
+            w.dense, n_total, SNN_BIG_CTAS);
+        AB_LAUNCH_CHECK(ctx);
+        const size_t smem = snn_small_smem();
+        AB_CUDA(cudaFuncSetAttribute(snn_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t blocks = (n_rows + SNN_WARPS - 1) / SNN_WARPS;
+        if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+        snn_small_kernel<false><<<(unsigned)blocks, SNN_WARPS * 32, smem, st>>>(
+            knn_all, k, row_begin, n_rows, w.deg, w.rlist, v_min, w.rowcount, nullptr, nullptr, nullptr, nullptr);
+        AB_LAUNCH_CHECK(ctx);
+        snn_big_kernel<false><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
+            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.big_rows, w.counters + 1, w.dense, w.rowcount,
+            nullptr, nullptr, nullptr, nullptr);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    if (ab_exclusive_scan_i64(ctx, w.rowcount, rowptr, n_rows, w.scan_ws, w.scan_bytes, st)) return 1;
+    int h_cnt[4];
+    unsigned long long h_walk = 0;
+    AB_CUDA(cudaMemcpyAsync(h_cnt, w.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaMemcpyAsync(&h_walk, w.max_walk, sizeof(h_walk), cudaMemcpyDeviceToHost, st));
+    if (h_edges) AB_CUDA(cudaMemcpyAsync(h_edges, rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    AB_REQUIRE(h_walk < (1ull << 23), "ab_snn_count: 2-hop walk of %llu exceeds the 2^23 position field", h_walk);
+    if (stats) {
+        // host array: {rows on the big path, longest 2-hop walk, rows whose first neighbour is not
+        // the cell itself (duplicate points; alona/clustering.py:204 assumes it is), long reverse lists}
+        stats[0] = h_cnt[1];
+        stats[1] = (int64_t)h_walk;
+        stats[2] = h_cnt[2];
+        stats[3] = h_cnt[0];
+    }
+    return 0;
+}
+
+extern "C" int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k, int64_t row_begin,
+                           int64_t row_end, int32_t v_min, const int64_t *rowptr, int32_t *src, int32_t *dst,
+                           uint8_t *overlap, void *ws, size_t ws_bytes, void *stream) {
+    AB_REQUIRE(ctx, "ab_snn_fill: null ctx");
+    const int64_t n_rows = row_end - row_begin;
+    SnnWs w;
+    size_t need = snn_layout(n_total, k, n_rows, ws, ws_bytes, &w);
+    AB_REQUIRE(need != 0, "ab_snn_fill: workspace too small");
+    if (n_rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = snn_small_smem();
+    AB_CUDA(cudaFuncSetAttribute(snn_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (n_rows + SNN_WARPS - 1) / SNN_WARPS;
+    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    snn_small_kernel<true><<<(unsigned)blocks, SNN_WARPS * 32, smem, st>>>(
+        knn_all, k, row_begin, n_rows, w.deg, w.rlist, v_min, nullptr, rowptr, src, dst, overlap);
+    AB_LAUNCH_CHECK(ctx);
+    snn_big_kernel<true><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
+        knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.big_rows, w.counters + 1, w.dense, nullptr, rowptr,
+        src, dst, overlap);
+    AB_LAUNCH_CHECK(ctx);
+    return 0;
+}

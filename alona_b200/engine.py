@@ -1,0 +1,271 @@
+"""Device-level stage functions: torch tensors for memory and streams, every bit of arithmetic
+in libalona_b200.so (hand-written sm_100a kernels) through the C-ABI.
+
+One Engine per process / GPU.  PyTorch is plumbing only (allocation, streams,
+torch.distributed bootstrap); there is no torch compute on the hot path and no CPU fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SCALE = 10000.0          # alona/cell.py:242
+
+
+class DeviceCSR:
+    """Cell-major CSR shard on the device: rows = this rank's cells."""
+
+    def __init__(self, rowptr, col, val, n_genes, row_begin=0, n_total=None):
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.n_local = int(rowptr.numel() - 1)
+        self.n_genes = int(n_genes)
+        self.row_begin = int(row_begin)
+        self.n_total = int(n_total if n_total is not None else self.n_local)
+
+    @property
+    def nnz(self):
+        return int(self.col.numel())
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Engine:
+    def __init__(self, device=None, rank=0, world=1):
+        if not torch.cuda.is_available():
+            raise RuntimeError('alona_b200 needs a B200 GPU (sm_100a); there is no CPU fallback')
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device_index = int(device)
+        self.device = torch.device('cuda', self.device_index)
+        self.rank, self.world = int(rank), int(world)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.ab_ctx_create(ctypes.byref(h), self.device_index, self.rank, self.world), 'ab_ctx_create')
+        self.ctx = h
+        self._ws = None
+
+    def close(self):
+        if self.ctx is not None:
+            self.lib.ab_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    # -- plumbing ---------------------------------------------------------------------
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, nbytes):
+        nbytes = int(nbytes)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def launch_count(self):
+        return int(self.lib.ab_launch_count(self.ctx))
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def init_nccl(self):
+        """Joins the world's NCCL communicator; the unique id travels over torch.distributed."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        path = nccl_library_path().encode()
+        buf = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(self.lib.ab_nccl_unique_id(path, buf), 'ab_nccl_unique_id')
+        obj = [buf.raw if self.rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        idbuf = ctypes.create_string_buffer(obj[0], 128)
+        _lib.check(self.lib.ab_ctx_init_nccl(self.ctx, path, idbuf), 'ab_ctx_init_nccl')
+
+    def allreduce_f64(self, t):
+        _lib.check(self.lib.ab_allreduce_f64(self.ctx, _ptr(t), t.numel(), self.stream()), 'ab_allreduce_f64')
+
+    def allreduce_i64(self, t):
+        _lib.check(self.lib.ab_allreduce_i64(self.ctx, _ptr(t), t.numel(), self.stream()), 'ab_allreduce_i64')
+
+    def allgather_rows(self, local, counts):
+        """All-gather of row blocks with per-rank row counts `counts` (list); returns [sum(counts), ...]."""
+        if self.world == 1:
+            return local
+        mx = max(counts)
+        rest = tuple(local.shape[1:])
+        pad = self.zeros((mx,) + rest, local.dtype)
+        pad[:local.shape[0]] = local
+        out = self.empty((self.world * mx,) + rest, local.dtype)
+        nbytes = pad.numel() * pad.element_size()
+        _lib.check(self.lib.ab_allgather_bytes(self.ctx, _ptr(pad), _ptr(out), nbytes, self.stream()),
+                   'ab_allgather_bytes')
+        if all(c == mx for c in counts):
+            return out
+        parts = [out[r * mx: r * mx + counts[r]] for r in range(self.world)]
+        return torch.cat(parts, dim=0)
+
+    # -- uploads ----------------------------------------------------------------------
+    def upload_csr(self, csr, row_begin=0, n_total=None, non_blocking=False):
+        """scipy/numpy CSR (cells x genes, ascending column ids) -> DeviceCSR."""
+        indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        data = np.ascontiguousarray(csr.data, dtype=np.int32)
+        return DeviceCSR(torch.from_numpy(indptr).to(self.device, non_blocking=non_blocking),
+                         torch.from_numpy(indices).to(self.device, non_blocking=non_blocking),
+                         torch.from_numpy(data).to(self.device, non_blocking=non_blocking),
+                         csr.shape[1], row_begin, n_total)
+
+    # -- K1 ---------------------------------------------------------------------------
+    def norm_moments(self, A, gsum=None, gsumsq=None, allreduce=True):
+        lib = self.empty((A.n_local,), torch.int64)
+        if gsum is None:
+            gsum = self.zeros((A.n_genes,), torch.float64)
+            gsumsq = self.zeros((A.n_genes,), torch.float64)
+        _lib.check(self.lib.ab_norm_moments(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), A.n_local,
+                                            A.n_genes, SCALE, _ptr(lib), _ptr(gsum), _ptr(gsumsq), self.stream()),
+                   'ab_norm_moments')
+        if allreduce and self.world > 1:
+            both = torch.cat([gsum, gsumsq])
+            self.allreduce_f64(both)
+            gsum, gsumsq = both[:A.n_genes].contiguous(), both[A.n_genes:].contiguous()
+        return lib, gsum, gsumsq
+
+    # -- K2 ---------------------------------------------------------------------------
+    def hvg_seurat(self, gsum, gsumsq, n_total, hvg_n, nbins=20):
+        g = gsum.numel()
+        ranked = self.empty((min(hvg_n, g),), torch.int32)
+        z = self.empty((g,), torch.float64)
+        gene2hvg = self.empty((g,), torch.int32)
+        stats = self.empty((4,), torch.int32)
+        _lib.check(self.lib.ab_hvg_seurat(self.ctx, _ptr(gsum), _ptr(gsumsq), int(n_total), g, nbins, int(hvg_n),
+                                          _ptr(ranked), _ptr(z), _ptr(gene2hvg), _ptr(stats), self.stream()),
+                   'ab_hvg_seurat')
+        return ranked, z, gene2hvg, stats
+
+    # -- K3 ---------------------------------------------------------------------------
+    def hvg_extract(self, A, libsize, gene2hvg, n_hvg):
+        ws = self.workspace(self.lib.ab_hvg_extract_ws_bytes(A.n_local))
+        rowptr_h = self.empty((A.n_local + 1,), torch.int64)
+        nnz = ctypes.c_int64(0)
+        _lib.check(self.lib.ab_hvg_extract_count(self.ctx, _ptr(A.rowptr), _ptr(A.col), A.n_local, _ptr(gene2hvg),
+                                                 _ptr(rowptr_h), ctypes.byref(nnz), _ptr(ws), ws.numel(),
+                                                 self.stream()), 'ab_hvg_extract_count')
+        col_h = self.empty((nnz.value,), torch.int32)
+        val_h = self.empty((nnz.value,), torch.float64)
+        _lib.check(self.lib.ab_hvg_extract_fill(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), _ptr(libsize),
+                                                A.n_local, _ptr(gene2hvg), SCALE, _ptr(rowptr_h), _ptr(col_h),
+                                                _ptr(val_h), self.stream()), 'ab_hvg_extract_fill')
+        return DeviceCSR(rowptr_h, col_h, val_h, n_hvg, A.row_begin, A.n_total)
+
+    # -- K4-K8 ------------------------------------------------------------------------
+    def irlb(self, AH, nval, tol=1e-4, maxit=1000, v0_local=None, want_v=True, want_u=True):
+        n, H = AH.n_local, AH.n_genes
+        ws = self.workspace(self.lib.ab_irlb_ws_bytes(n, H, nval))
+        scores = self.empty((n, nval), torch.float64)
+        v = self.empty((n, nval), torch.float64) if want_v else None
+        s = self.empty((nval,), torch.float64)
+        u = self.empty((H, nval), torch.float64) if want_u else None
+        info = (ctypes.c_int64 * 4)()
+        _lib.check(self.lib.ab_irlb(self.ctx, _ptr(AH.rowptr), _ptr(AH.col), _ptr(AH.val), n, AH.n_total, H, int(nval),
+                                    float(tol), int(maxit), _ptr(v0_local), _ptr(scores), _ptr(v), _ptr(s), _ptr(u),
+                                    info, _ptr(ws), ws.numel(), self.stream()), 'ab_irlb')
+        return {'scores': scores, 'V': v, 's': s, 'U': u, 'steps': int(info[0]), 'nmult': int(info[1]),
+                'sum_panel': int(info[2]), 'not_converged': int(info[3])}
+
+    # -- K9 ---------------------------------------------------------------------------
+    def knn(self, emb_all, k, q_begin=0, q_end=None, mode=0):
+        n, d = emb_all.shape
+        if q_end is None:
+            q_end = n
+        nq = q_end - q_begin
+        assert emb_all.dtype == torch.float64 and emb_all.is_contiguous()
+        ws = self.workspace(self.lib.ab_knn_ws_bytes(n, d, nq, k))
+        idx = self.empty((nq, k), torch.int32)
+        rd = self.empty((nq, k), torch.float64)
+        stats = self.empty((8,), torch.int64)
+        _lib.check(self.lib.ab_knn(self.ctx, _ptr(emb_all), n, d, q_begin, q_end, int(k), int(mode), _ptr(idx),
+                                   _ptr(rd), _ptr(stats), _ptr(ws), ws.numel(), self.stream()), 'ab_knn')
+        return idx, rd, stats
+
+    # -- K10 --------------------------------------------------------------------------
+    def snn(self, knn_all, v_min, row_begin=0, row_end=None, want_overlap=True):
+        n, k = knn_all.shape
+        if row_end is None:
+            row_end = n
+        nrows = row_end - row_begin
+        assert knn_all.dtype == torch.int32 and knn_all.is_contiguous()
+        ws = self.workspace(self.lib.ab_snn_ws_bytes(n, k, nrows))
+        rowptr = self.empty((nrows + 1,), torch.int64)
+        edges = ctypes.c_int64(0)
+        stats = (ctypes.c_int64 * 4)()
+        _lib.check(self.lib.ab_snn_count(self.ctx, _ptr(knn_all), n, k, row_begin, row_end, int(v_min), _ptr(rowptr),
+                                         ctypes.byref(edges), stats, _ptr(ws), ws.numel(), self.stream()),
+                   'ab_snn_count')
+        src = self.empty((edges.value,), torch.int32)
+        dst = self.empty((edges.value,), torch.int32)
+        ov = self.empty((edges.value,), torch.uint8) if want_overlap else None
+        _lib.check(self.lib.ab_snn_fill(self.ctx, _ptr(knn_all), n, k, row_begin, row_end, int(v_min), _ptr(rowptr),
+                                        _ptr(src), _ptr(dst), _ptr(ov), _ptr(ws), ws.numel(), self.stream()),
+                   'ab_snn_fill')
+        return {'rowptr': rowptr, 'src': src, 'dst': dst, 'overlap': ov,
+                'big_rows': int(stats[0]), 'max_walk': int(stats[1]), 'dup_rows': int(stats[2]),
+                'long_lists': int(stats[3])}
+
+    # -- synthetic data ---------------------------------------------------------------
+    def synth_counts(self, prof, cell_begin, n_local, lbar, n_total=None, depth_sigma=0.35, r_disp=5.0,
+                     seed=20251019):
+        ncl, g = prof.shape
+        assert prof.dtype == torch.float32 and prof.is_contiguous()
+        ws = self.workspace(self.lib.ab_synth_ws_bytes(n_local))
+        rowptr = self.empty((n_local + 1,), torch.int64)
+        nnz = ctypes.c_int64(0)
+        _lib.check(self.lib.ab_synth_nb_count(self.ctx, _ptr(prof), ncl, g, int(cell_begin), int(n_local), float(lbar),
+                                              float(depth_sigma), float(r_disp), int(seed), _ptr(rowptr),
+                                              ctypes.byref(nnz), _ptr(ws), ws.numel(), self.stream()),
+                   'ab_synth_nb_count')
+        col = self.empty((nnz.value,), torch.int32)
+        val = self.empty((nnz.value,), torch.int32)
+        _lib.check(self.lib.ab_synth_nb_fill(self.ctx, _ptr(prof), ncl, g, int(cell_begin), int(n_local), float(lbar),
+                                             float(depth_sigma), float(r_disp), int(seed), _ptr(rowptr), _ptr(col),
+                                             _ptr(val), self.stream()), 'ab_synth_nb_fill')
+        return DeviceCSR(rowptr, col, val, g, cell_begin, n_total if n_total is not None else n_local)
+
+
+def nccl_library_path():
+    """The torch-bundled NCCL (nvidia-nccl-cu12 wheel), else the system one."""
+    try:
+        import nvidia.nccl
+        base = list(nvidia.nccl.__path__)[0]
+        p = os.path.join(base, 'lib', 'libnccl.so.2')
+        if os.path.exists(p):
+            return p
+    except Exception:
+        pass
+    return 'libnccl.so.2'
+
+
+_engine = None
+
+
+def get_engine():
+    """Process-wide engine, honouring torch.distributed if it has been initialised."""
+    global _engine
+    if _engine is None:
+        rank, world = 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+        except Exception:
+            pass
+        _engine = Engine(rank=rank, world=world)
+        if world > 1:
+            _engine.init_nccl()
+    return _engine

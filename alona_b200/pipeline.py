@@ -1,0 +1,84 @@
+"""The device-resident front end: normalise -> HVG -> PCA (IRLBA) -> kNN -> SNN on one rank's
+shard of cells, with the exchanges SURVEY.md §8(e) lists (moments all-reduce inside
+norm_moments, IRLBA all-reduces inside ab_irlb, all-gather of the embedding and of the kNN
+table here).  Order of the stages = alona/cell.py:408,432-435 and alona/clustering.py:307-310.
+"""
+import numpy as np
+import torch
+
+
+def prune_threshold(k, prune_snn):
+    """Smallest integer overlap kept by the reference's test  v/(k+(k-v)) > prune_snn
+    (alona/clustering.py:225-227), evaluated with Python floats exactly as the reference does."""
+    for v in range(0, k + 1):
+        if v / (k + (k - v)) > prune_snn:
+            return v
+    return k + 1
+
+
+def shard_bounds(n_total, world):
+    return [(n_total * r) // world for r in range(world + 1)]
+
+
+def start_vector(n_total, seed):
+    """The reference's start vector (alona/irlbpy/irlb.py:151-152)."""
+    np.random.seed(seed)
+    return np.random.randn(n_total)
+
+
+class StageTimer:
+    """CUDA-event timer per stage (events on the current stream)."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.marks = []
+
+    def mark(self, name):
+        if self.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def result(self):
+        if not self.enabled or len(self.marks) < 2:
+            return {}
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def frontend(eng, counts, hvg_n, pca_n, nn_k, prune_snn=0.067, seed=42, knn_mode=0, v0=None,
+             timer=None, want_overlap=False, tol=1e-4, maxit=1000):
+    """Runs the whole path on `counts` (DeviceCSR shard).  Everything returned is on the device.
+    Returns a dict with libsize, gsum, gsumsq, hvg_ranked, z, gene2hvg, AH, irlb (dict),
+    emb_all [N x d], knn_idx (this shard, 0-based), knn_all, snn (dict) and statistics."""
+    t = timer or StageTimer(False)
+    bounds = shard_bounds(counts.n_total, eng.world)
+    rows = [bounds[r + 1] - bounds[r] for r in range(eng.world)]
+    t.mark('start')
+    libsize, gsum, gsumsq = eng.norm_moments(counts)
+    t.mark('normalize')
+    ranked, z, gene2hvg, hstats = eng.hvg_seurat(gsum, gsumsq, counts.n_total, hvg_n)
+    n_hvg = min(int(hvg_n), counts.n_genes)
+    t.mark('hvg')
+    AH = eng.hvg_extract(counts, libsize, gene2hvg, n_hvg)
+    t.mark('hvg_extract')
+    if v0 is None:
+        v0 = start_vector(counts.n_total, seed)
+    lo, hi = counts.row_begin, counts.row_begin + counts.n_local
+    v0_local = torch.from_numpy(np.ascontiguousarray(v0[lo:hi])).to(eng.device)
+    ir = eng.irlb(AH, pca_n, tol=tol, maxit=maxit, v0_local=v0_local, want_v=False, want_u=False)
+    t.mark('pca')
+    emb_all = eng.allgather_rows(ir['scores'], rows)
+    idx, rdist, kstats = eng.knn(emb_all, nn_k, q_begin=lo, q_end=hi, mode=knn_mode)
+    t.mark('knn')
+    knn_all = eng.allgather_rows(idx, rows)
+    vmin = prune_threshold(nn_k, prune_snn)
+    sn = eng.snn(knn_all, vmin, row_begin=lo, row_end=hi, want_overlap=want_overlap)
+    t.mark('snn')
+    return {'libsize': libsize, 'gsum': gsum, 'gsumsq': gsumsq, 'hvg_ranked': ranked, 'z': z,
+            'gene2hvg': gene2hvg, 'hvg_stats': hstats, 'AH': AH, 'irlb': ir, 'emb_all': emb_all,
+            'knn_idx': idx, 'knn_rdist': rdist, 'knn_stats': kstats, 'knn_all': knn_all, 'snn': sn,
+            'v_min': vmin}

@@ -1,0 +1,161 @@
+/* alona_b200 — C-ABI of the B200-native clustering front end
+ * (normalise -> HVG -> truncated PCA (IRLBA) -> exact kNN -> SNN edge list).
+ *
+ * The reference (oscar-franzen/alona v0.3.5) is pure Python and has no FFI; its boundary is
+ * the method surface of its mixin chain.  Each entry point below replaces the arithmetic of
+ * one reference method body (cited per function); the Python package alona_b200/ keeps the
+ * reference's class/method/flag names and calls these through ctypes (INTEGRATION.md shows
+ * the stub a maintainer would add to the reference itself).
+ *
+ * Conventions
+ *   - plain C; every function returns 0 on success, non-zero on error;
+ *     ab_last_error() returns a thread-local message.  No exceptions cross the boundary.
+ *   - there is NO CPU fallback: unsupported arguments and a missing GPU are errors.
+ *   - all array arguments are DEVICE pointers owned by the caller unless named h_*;
+ *     `stream` is a cudaStream_t passed as void*; calls are asynchronous on it unless
+ *     documented otherwise (functions that return sizes synchronise the stream).
+ *   - matrices: counts are cell-major CSR (rows = cells): rowptr int64 [n+1] (local to the
+ *     shard, rowptr[0]==0), col int32 (gene id, ascending within a row), val int32 (count>0).
+ *   - sharding: a rank owns a contiguous range of cell rows; `n_local` is the shard height,
+ *     `n_total` the global number of cells.
+ *   - workspace: functions that need scratch take (ws, ws_bytes); ab_*_ws_bytes() gives the
+ *     required size.  Scratch contents are undefined on return.
+ */
+#ifndef ALONA_B200_H
+#define ALONA_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB_VERSION 100
+
+typedef struct ab_ctx ab_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int ab_version(void);
+const char *ab_last_error(void);
+/* Binds to CUDA device `device`; fails if it is not an sm_100 part. rank/world describe the
+ * row sharding (world==1: single GPU). */
+int ab_ctx_create(ab_ctx **out, int device, int rank, int world);
+int ab_ctx_destroy(ab_ctx *ctx);
+/* Multi-GPU: dlopen()s NCCL at `libnccl_path` and joins the communicator described by the
+ * 128-byte ncclUniqueId (rank 0 obtains it with ab_nccl_unique_id and broadcasts it). */
+int ab_nccl_unique_id(const char *libnccl_path, void *h_id128);
+int ab_ctx_init_nccl(ab_ctx *ctx, const char *libnccl_path, const void *h_id128);
+/* In-place sum all-reduce of `count` float64 / int64 on the ctx communicator (no-op at world 1). */
+int ab_allreduce_f64(ab_ctx *ctx, double *buf, int64_t count, void *stream);
+int ab_allreduce_i64(ab_ctx *ctx, int64_t *buf, int64_t count, void *stream);
+/* All-gather of equal-sized byte blocks (bytes_per_rank each) into recv (world*bytes). */
+int ab_allgather_bytes(ab_ctx *ctx, const void *send, void *recv, int64_t bytes_per_rank, void *stream);
+
+/* ---- K1: library-size normalisation + log2 + per-gene moments -------------------------
+ * replaces AlonaCell.normalize raw branch  (alona/cell.py:241-243)
+ *      and the per-gene reductions of hvg_seurat (alona/hvg.py:148,157).
+ * libsize[i] = sum of the row's counts (exact); x = log2(fl(fl(c/S)*scale)+1) in FP64;
+ * gsum[g] += x, gsumsq[g] += x*x over this shard's cells.  gsum/gsumsq must be zeroed by the
+ * caller (they accumulate, so shards/tiles can be chained); all-reduce them across ranks
+ * with ab_allreduce_f64. */
+int ab_norm_moments(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                    int64_t n_local, int32_t n_genes, double scale,
+                    int64_t *libsize, double *gsum, double *gsumsq, void *stream);
+
+/* ---- K2: Seurat-style HVG selection ----------------------------------------------------
+ * replaces AlonaHighlyVariableGenes.hvg_seurat (alona/hvg.py:146-165): mean, ddof-1 variance,
+ * `nbins` equal-width mean bins (pandas.cut semantics), dispersion=var/mean, per-bin z-score,
+ * top hvg_n by z (descending; ties by gene index; NaN last).
+ * Outputs: ranked[hvg_n] gene ids in rank order, z[n_genes], gene2hvg[n_genes] = column of the
+ * gene inside the HVG-restricted matrix (HVGs keep ORIGINAL gene order, clustering.py:104-105)
+ * or -1, stats[4] (device int32) = {#finite z, #selected, #ties at the cut, 0}. */
+int ab_hvg_seurat(ab_ctx *ctx, const double *gsum, const double *gsumsq, int64_t n_total,
+                  int32_t n_genes, int32_t nbins, int32_t hvg_n,
+                  int32_t *ranked, double *z, int32_t *gene2hvg, int32_t *stats, void *stream);
+
+/* ---- K3: HVG-restricted normalised matrix A_H (cell-major CSR, FP64 values) -------------
+ * replaces the row slice `data_norm[index.isin(hvg)]` (alona/clustering.py:104-105).
+ * count: rowptr_h[n_local+1] (exclusive scan of per-cell HVG nonzeros); synchronises and
+ * returns the shard's nnz_H in *h_nnz.  fill: col_h (0..H-1 ascending), val_h (FP64 x). */
+size_t ab_hvg_extract_ws_bytes(int64_t n_local);
+int ab_hvg_extract_count(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, int64_t n_local,
+                         const int32_t *gene2hvg, int64_t *rowptr_h, int64_t *h_nnz,
+                         void *ws, size_t ws_bytes, void *stream);
+int ab_hvg_extract_fill(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                        const int64_t *libsize, int64_t n_local, const int32_t *gene2hvg,
+                        double scale, const int64_t *rowptr_h, int32_t *col_h, double *val_h,
+                        void *stream);
+
+/* ---- K4-K8: truncated SVD by augmented implicitly-restarted Lanczos bidiagonalisation ---
+ * replaces alona.irlbpy.lanczos (alona/irlbpy/irlb.py:95-258) as called by
+ * AlonaClustering.PCA (alona/clustering.py:108-111): A = A_H^T (H x N), no centring/scaling.
+ * Same work dimension (irlb.py:138), restart rule (:231-234), invcheck (:84-92), CGS order.
+ * v0_local: this shard's slice of the start vector (the reference draws it on the host with
+ * np.random.seed(seed); randn(N), irlb.py:151-152; normalised here).
+ * Outputs: scores_local [n_local x nval] row-major = V.diag(s) (clustering.py:111),
+ * v_local [n_local x nval] row-major (may be NULL), s[nval], u[H x nval] row-major (may be
+ * NULL); h_info[4] (host int64) = {steps, nmult, sum of CGS panel widths, status flags}.
+ * Synchronises the stream (one small D2H per restart decides convergence). */
+size_t ab_irlb_ws_bytes(int64_t n_local, int32_t n_hvg, int32_t nval);
+int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_h, const double *val_h,
+            int64_t n_local, int64_t n_total, int32_t n_hvg, int32_t nval, double tol,
+            int32_t maxit, const double *v0_local, double *scores_local, double *v_local,
+            double *s, double *u, int64_t *h_info, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- K9: exact k-nearest neighbours ----------------------------------------------------
+ * replaces AlonaClustering.knn (alona/clustering.py:184-186; scikit-learn BallTree).
+ * emb_all: N x d row-major FP64 embedding of ALL cells; queries are rows [q_begin,q_end).
+ * Candidate generation: 3xTF32 tcgen05 distance GEMM with per-query top-m selection;
+ * then exact re-rank with the reference's own arithmetic (sequential non-fused FP64
+ * sum of squared differences) and a certificate that no non-candidate can belong to the
+ * top k; uncertified queries are recomputed by an exact FP64 scan.
+ * idx [nq x k] int32 0-based sorted by (distance, index) (the Python layer adds 1);
+ * rdist [nq x k] FP64 squared distances; stats[8] (device int64) = {rows whose k-th and
+ * (k+1)-th distances tie exactly, rows recomputed by the exact scan, rows with a zero-distance
+ * duplicate, rows certified by the tensor pass, ...}.
+ * mode: 0 = tensor-core path (default), 1 = exact FP64 scan for every query. */
+size_t ab_knn_ws_bytes(int64_t n_total, int32_t d, int64_t n_query, int32_t k);
+int ab_knn(ab_ctx *ctx, const double *emb_all, int64_t n_total, int32_t d, int64_t q_begin,
+           int64_t q_end, int32_t k, int32_t mode, int32_t *idx, double *rdist, int64_t *stats,
+           void *ws, size_t ws_bytes, void *stream);
+
+/* ---- K10: shared-nearest-neighbour graph ------------------------------------------------
+ * replaces AlonaClustering.snn (alona/clustering.py:204-231): overlap(i,m)=|N(i) n N(m)| over
+ * self-inclusive neighbour sets, keep iff overlap >= v_min (the host evaluates the reference's
+ * v/(k+(k-v)) > prune_snn for v=0..k), emit rows ascending and, inside a row, in the order
+ * scipy's csr_matmat produces (reverse first-encounter).  Self loops and both directions
+ * are kept, as in the reference.
+ * knn_all: N x k int32 0-based table of ALL cells; rows [row_begin,row_end) are emitted.
+ * count: rowptr [nrows+1] int64 (exclusive scan), returns edges in *h_edges (synchronises);
+ * fill: src/dst int32 [E], overlap uint8 [E] (may be NULL). */
+size_t ab_snn_ws_bytes(int64_t n_total, int32_t k, int64_t n_rows);
+int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k,
+                 int64_t row_begin, int64_t row_end, int32_t v_min, int64_t *rowptr,
+                 int64_t *h_edges, int64_t *stats, void *ws, size_t ws_bytes, void *stream);
+int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k,
+                int64_t row_begin, int64_t row_end, int32_t v_min, const int64_t *rowptr,
+                int32_t *src, int32_t *dst, uint8_t *overlap, void *ws, size_t ws_bytes,
+                void *stream);
+
+/* ---- synthetic negative-binomial counts generated on the device (bench / tests only) ----
+ * cluster model, Gamma-Poisson counts; data are a pure function of
+ * (seed, cell id, gene id), hence identical for any sharding.  count: rowptr[n_local+1];
+ * fill: col/val.  prof: n_clusters x n_genes FP32 gene probabilities (device). */
+size_t ab_synth_ws_bytes(int64_t n_local);
+int ab_synth_nb_count(ab_ctx *ctx, const float *prof, int32_t n_clusters, int32_t n_genes,
+                      int64_t cell_begin, int64_t n_local, double lbar, double depth_sigma,
+                      double r_disp, uint64_t seed, int64_t *rowptr, int64_t *h_nnz,
+                      void *ws, size_t ws_bytes, void *stream);
+int ab_synth_nb_fill(ab_ctx *ctx, const float *prof, int32_t n_clusters, int32_t n_genes,
+                     int64_t cell_begin, int64_t n_local, double lbar, double depth_sigma,
+                     double r_disp, uint64_t seed, const int64_t *rowptr, int32_t *col,
+                     int32_t *val, void *stream);
+
+/* number of kernels launched by this library on this thread's context since creation */
+int64_t ab_launch_count(ab_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,97 @@
+"""GPU tier: size-independent properties on device-generated data at sizes the CPU oracle
+cannot check exhaustively."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from alona_b200.engine import get_engine
+    return get_engine()
+
+
+@pytest.fixture(scope='module')
+def synth(eng):
+    from alona_b200.synth import make_profiles
+    prof = make_profiles(4000, 12, seed=3)
+    A = eng.synth_counts(torch.from_numpy(prof).to(eng.device), 0, 20000, lbar=1500.0, seed=77)
+    return A
+
+
+def test_synth_is_shard_invariant(eng, synth):
+    from alona_b200.synth import make_profiles
+    prof = torch.from_numpy(make_profiles(4000, 12, seed=3)).to(eng.device)
+    B = eng.synth_counts(prof, 5000, 3000, lbar=1500.0, n_total=20000, seed=77)
+    rp = synth.rowptr.cpu().numpy()
+    a, b = rp[5000], rp[8000]
+    assert np.array_equal(B.col.cpu().numpy(), synth.col.cpu().numpy()[a:b])
+    assert np.array_equal(B.val.cpu().numpy(), synth.val.cpu().numpy()[a:b])
+    assert int(synth.val.min()) >= 1
+    cols = synth.col.cpu().numpy()
+    for r in (0, 1234, 19999):
+        seg = cols[rp[r]:rp[r + 1]]
+        assert np.all(np.diff(seg) > 0)
+
+
+def test_moments_and_hvg_vs_oracle_at_20k(eng, synth):
+    m = sp.csr_matrix((synth.val.cpu().numpy(), synth.col.cpu().numpy(), synth.rowptr.cpu().numpy()),
+                      shape=(synth.n_local, synth.n_genes))
+    lib, gsum, gsumsq = eng.norm_moments(synth)
+    assert np.array_equal(lib.cpu().numpy(), R.libsize(m))
+    sx, sx2, nz = R.gene_moments(m)
+    ok = nz > 0
+    assert np.max(np.abs(gsum.cpu().numpy()[ok] - sx[ok]) / sx[ok]) < 1e-12
+    # moments are additive over row tiles (what the multi-GPU all-reduce relies on)
+    half = 10000
+    rp = synth.rowptr
+    from alona_b200.engine import DeviceCSR
+    top = DeviceCSR(rp[:half + 1].contiguous(), synth.col, synth.val, synth.n_genes)
+    bot = DeviceCSR((rp[half:] - rp[half]).contiguous(), synth.col[int(rp[half]):], synth.val[int(rp[half]):], synth.n_genes)
+    _, g1, q1 = eng.norm_moments(top)
+    _, g2, q2 = eng.norm_moments(bot)
+    assert torch.allclose(g1 + g2, gsum, rtol=1e-13, atol=0)
+    mean, var = R.gene_mean_var(m)
+    keep = nz > 0
+    ranked, z, g2h, st = eng.hvg_seurat(gsum, gsumsq, synth.n_local, 500)
+    zz = z.cpu().numpy()
+    if keep.all():
+        ref_idx, zref = R.hvg_seurat_from_moments(mean, var, 500)
+        assert set(ranked.cpu().numpy().tolist()) == set(ref_idx.tolist())
+
+
+def test_frontend_properties_at_20k(eng, synth):
+    from alona_b200.pipeline import frontend
+    out = frontend(eng, synth, 500, 20, 15, 0.067, 5, want_overlap=True)
+    n, k = synth.n_local, 15
+    idx = out['knn_all']
+    # tensor-core path == exact FP64 scan, bit for bit
+    ex, rd, st = eng.knn(out['emb_all'], k, mode=1)
+    assert torch.equal(idx, ex)
+    assert torch.equal(out['knn_rdist'], rd)
+    assert torch.equal(idx[:, 0].long(), torch.arange(n, device=idx.device))
+    assert bool((rd[:, 1:] >= rd[:, :-1]).all())
+    # SNN: self loops, symmetry of the overlap, strict pruning
+    src, dst, ov = (out['snn'][x].cpu().numpy().astype(np.int64) for x in ('src', 'dst', 'overlap'))
+    assert (src == dst).sum() == n and np.all(ov[src == dst] == k)
+    assert ov.min() >= out['v_min']
+    key = src * n + dst
+    rkey = dst * n + src
+    o1 = np.argsort(key); o2 = np.argsort(rkey)
+    assert np.array_equal(key[o1], rkey[o2]) and np.array_equal(ov[o1], ov[o2])
+    # sampled rows against the CPU restatement
+    nn = idx.cpu().numpy().astype(np.int64)
+    sets = [set(r.tolist()) for r in nn]
+    rng = np.random.RandomState(0)
+    rp = out['snn']['rowptr'].cpu().numpy()
+    for i in rng.choice(n, 50, replace=False):
+        row_dst = dst[rp[i]:rp[i + 1]]; row_ov = ov[rp[i]:rp[i + 1]]
+        for m_, v in zip(row_dst, row_ov):
+            assert len(sets[i] & sets[m_]) == v
+    # PCA scores: residual of the truncated SVD relation on the device matrix
+    assert out['irlb']['not_converged'] == 0
