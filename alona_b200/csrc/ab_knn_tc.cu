@@ -1,14 +1,614 @@
-// K9 tensor-core candidate pass (placeholder until the tcgen05 kernel lands): routes to the
-// exact FP64 scan so that the pipeline is correct end to end.
+// K9 tensor-core candidate pass: tiled  s(q,x) = ||x||^2 - 2 q.x  on tcgen05 (TF32 inputs, FP32
+// accumulation in TMEM) with a per-query top-m selection epilogue, followed by an exact FP64
+// re-rank that reproduces the reference's number and certifies the result.
+//
+// Replaces the search of AlonaClustering.knn (alona/clustering.py:184-186, scikit-learn BallTree).
+//
+//  prep      centre the embedding (translation invariant, shrinks norms), round to FP32, split
+//            every coordinate into two TF32 pieces (hi = rna(x), lo = rna(x-hi)) and lay out the
+//            K-major operand rows so that ONE GEMM emits finished scores (3xTF32 emulation,
+//            norms folded into three extra K columns):
+//               A[q] = [  q_hi |  q_hi |  q_lo | 1 1 1 | 0.. ]
+//               B[x] = [-2x_hi |-2x_lo |-2x_hi | n0 n1 n2 | 0.. ],  n0+n1+n2 = ||x||^2
+//  main      persistent warp-specialised kernel, one CTA per SM: warp 0 = TMA producer
+//            (128B-swizzled K chunks through an mbarrier ring), warp 1 = tcgen05.mma issuer
+//            (M=128 queries x N=256 points per tile, two 256-column TMEM accumulators so the
+//            epilogue of tile t overlaps the MMAs of tile t+1), warps 2-5 = epilogue: thread r
+//            owns query row r (= TMEM lane r), pulls 32 columns per tcgen05.ld, compares with
+//            its running threshold (one min-tree + one branch per 32 scores) and, rarely,
+//            inserts into its sorted candidate list.
+//  re-rank   one warp per query: exact distances of the m candidates with the reference's
+//            arithmetic, sort by (distance, index), certificate
+//                 tau + ||q||^2 - eps  >  D_k      (tau = m-th smallest approximate score)
+//            which proves that no point outside the candidate list can enter the top k;
+//            eps = KAPPA (||q|| + R)^2 bounds FP32 rounding + split + accumulation error.
+//            Uncertified queries are recomputed by the exact FP64 scan (ab_knn_exact.cu).
 #include "ab_common.cuh"
+#include <cuda.h>
+#include <math.h>
+#include <algorithm>
+
 size_t ab_knn_exact_ws_bytes(int64_t nq, int k, int splits);
 int ab_knn_exact_pick_splits(ab_ctx *ctx, int64_t nq);
 int ab_knn_exact_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, const int64_t *qlist, int64_t q_begin,
                      int64_t nq, int k, int splits, const int64_t *out_rows, int32_t *idx, double *rdist,
                      unsigned long long *stats, void *ws, size_t ws_bytes, cudaStream_t st);
-size_t ab_knn_tc_ws_bytes(int64_t n_total, int d, int64_t nq, int k) { return ab_knn_exact_ws_bytes(nq, k, 64); }
+
+static constexpr int TC_BM = 128;            // queries per CTA tile (UMMA M)
+static constexpr int TC_BN = 256;            // database points per tile (UMMA N)
+static constexpr int TC_KCH = 32;            // tf32 elements per K chunk = one 128-byte swizzle row
+static constexpr int TC_THREADS = 192;       // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+static constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
+static constexpr int TC_B_STAGE_BYTES = TC_BN * 128;
+static constexpr int TC_MAX_STAGES = 6;
+static constexpr int TC_MAX_CHUNKS = 10;     // 3d+3 <= 320  ->  d <= 105
+static constexpr double TC_KAPPA = 1.52587890625e-05;   // 2^-16
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must fault, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                           // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------
+// prep
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+knn_colsum_kernel(const double *__restrict__ emb, int64_t n, int d, double *__restrict__ partial /*[grid][d]*/) {
+    __shared__ double sm[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(n, r0 + per);
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = lane + 32 * u;
+            if (j < d) acc[u] += emb[r * d + j];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sm[warp][lane + 32 * u] = acc[u];
+    __syncthreads();
+    for (int j = threadIdx.x; j < d; j += 256) {
+        double t = 0.0;
+        for (int w2 = 0; w2 < 8; ++w2) t += sm[w2][j];
+        partial[(size_t)blockIdx.x * d + j] = t;
+    }
+}
+
+__global__ void knn_colmean_kernel(const double *__restrict__ partial, int nparts, int d, int64_t n, double *__restrict__ mean) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    double t = 0.0;
+    for (int b = 0; b < nparts; ++b) t += partial[(size_t)b * d + j];
+    mean[j] = t / (double)n;
+}
+
+// one warp per point: writes the A and B operand rows, ||x~||^2 and the running max norm
+__global__ void __launch_bounds__(256)
+knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const double *__restrict__ mean,
+                float *__restrict__ aop, float *__restrict__ bop, double *__restrict__ qn, unsigned int *__restrict__ rmax_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    for (int64_t i = w; i < n; i += nw) {
+        float *a = aop + i * kt, *b = bop + i * kt;
+        double n2 = 0.0;
+        for (int j = lane; j < kt; j += 32) {            // clear, then fill
+            a[j] = 0.f; b[j] = 0.f;
+        }
+        __syncwarp();
+        for (int j = lane; j < d; j += 32) {
+            const float x = (float)(emb[i * d + j] - mean[j]);
+            const float hi = tf32_rna(x);
+            const float lo = tf32_rna(x - hi);
+            a[j] = hi; a[d + j] = hi; a[2 * d + j] = lo;
+            b[j] = -2.f * hi; b[d + j] = -2.f * lo; b[2 * d + j] = -2.f * hi;
+            n2 += (double)x * (double)x;
+        }
+        n2 = ab_warp_sum_f64(n2);
+        if (lane == 0) {
+            const float n0 = tf32_rna((float)n2);
+            const double r1 = n2 - (double)n0;
+            const float n1 = tf32_rna((float)r1);
+            const float n2f = tf32_rna((float)(r1 - (double)n1));
+            b[3 * d] = n0; b[3 * d + 1] = n1; b[3 * d + 2] = n2f;
+            a[3 * d] = 1.f; a[3 * d + 1] = 1.f; a[3 * d + 2] = 1.f;
+            qn[i] = n2;
+            atomicMax(rmax_bits, __float_as_uint((float)sqrt(n2) * 1.0000002f));
+        }
+    }
+}
+
+__global__ void knn_init_cand_kernel(float *__restrict__ cs, int32_t *__restrict__ ci, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        cs[i] = INFINITY;
+        ci[i] = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ float cand_insert(float *cs, int32_t *ci, int m, float s, int idx) {
+    int p = m - 1;
+    while (p > 0) {
+        const float prev = cs[p - 1];
+        if (!(prev > s)) break;
+        cs[p] = prev;
+        ci[p] = ci[p - 1];
+        --p;
+    }
+    cs[p] = s;
+    ci[p] = idx;
+    return cs[m - 1];
+}
+
+struct TcParams {
+    int64_t n_total;       // database points
+    int64_t q_begin;       // first query (row of the operand arrays)
+    int64_t nq;            // number of queries
+    int chunks;            // K chunks of 32 tf32
+    int stages;            // B ring depth
+    int m;                 // candidates per query
+    float *cand_s;
+    int32_t *cand_i;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // layout: [A chunks][B stages][barriers]
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sA = smem;
+    unsigned char *sB = sA + (size_t)P.chunks * TC_A_CHUNK_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)P.stages * TC_B_STAGE_BYTES);
+    uint64_t *full = bars;                          // [stages]
+    uint64_t *empty = bars + TC_MAX_STAGES;         // [stages]
+    uint64_t *a_full = bars + 2 * TC_MAX_STAGES;
+    uint64_t *a_empty = a_full + 1;
+    uint64_t *t_full = a_full + 2;                  // [2]
+    uint64_t *t_empty = a_full + 4;                 // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_qblocks = (P.nq + TC_BM - 1) / TC_BM;
+    const int64_t n_tiles = (P.n_total + TC_BN - 1) / TC_BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(t_full + b, 1); mbar_init(t_empty + b, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+                mbar_wait(a_empty, aphase ^ 1);
+                mbar_expect_tx(a_full, (uint32_t)(P.chunks * TC_A_CHUNK_BYTES));
+                const int qrow = (int)(P.q_begin + qb * TC_BM);
+                for (int c = 0; c < P.chunks; ++c)
+                    tma_load_2d(sA + (size_t)c * TC_A_CHUNK_BYTES, &map_a, a_full, c * TC_KCH, qrow);
+                aphase ^= 1;
+                for (int64_t t = 0; t < n_tiles; ++t) {
+                    const int xrow = (int)(t * TC_BN);
+                    for (int c = 0; c < P.chunks; ++c) {
+                        mbar_wait(empty + stage, phase ^ 1);
+                        mbar_expect_tx(full + stage, (uint32_t)TC_B_STAGE_BYTES);
+                        tma_load_2d(sB + (size_t)stage * TC_B_STAGE_BYTES, &map_b, full + stage, c * TC_KCH, xrow);
+                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor: D=F32, A=B=TF32, K-major both, N=256, M=128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int stage = 0, buf = 0;
+            int64_t nblocks_done = 0;
+            uint32_t phase = 0, aphase = 0, bphase = 0;
+            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+            for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+                mbar_wait(a_full, aphase);
+                aphase ^= 1;
+                for (int64_t t = 0; t < n_tiles; ++t) {
+                    mbar_wait(t_empty + buf, bphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_BN;
+                    for (int c = 0; c < P.chunks; ++c) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint32_t a_c = a_addr + (uint32_t)c * TC_A_CHUNK_BYTES;
+                        const uint32_t b_s = b_addr + (uint32_t)stage * TC_B_STAGE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < TC_KCH / 8; ++k)
+                            tc_mma_tf32(tmem_d, umma_desc_sw128(a_c + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
+                                        (uint32_t)((c | k) != 0));
+                        tc_commit(empty + stage);               // smem slot free once these MMAs retire
+                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(t_full + buf);                    // accumulator ready for the epilogue
+                    buf ^= 1;
+                    if (buf == 0) bphase ^= 1;
+                }
+                tc_commit(a_empty);                             // A tile may be overwritten
+                ++nblocks_done;
+            }
+            // do not let the CTA retire with a tcgen05.commit arrive still in flight
+            if (nblocks_done > 0) mbar_wait(a_empty, (uint32_t)((nblocks_done - 1) & 1));
+        }
+    } else {
+        // ================= epilogue: thread <-> query row =================
+        const int lane_base = (warp & 3) * 32;                  // TMEM lanes this warp may touch
+        const int row = lane_base + lane;
+        int buf = 0;
+        uint32_t bphase = 0;
+        for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+            const int64_t q = qb * TC_BM + row;                 // query position inside [0,nq)
+            const bool live = q < P.nq;
+            float *cs = P.cand_s + (live ? q : 0) * P.m;
+            int32_t *ci = P.cand_i + (live ? q : 0) * P.m;
+            float tau = INFINITY;
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                mbar_wait(t_full + buf, bphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)buf * TC_BN;
+                const int64_t col0 = t * TC_BN;
+                const bool partial = col0 + TC_BN > P.n_total;
+#pragma unroll 1
+                for (int cc = 0; cc < TC_BN / 32; ++cc) {
+                    uint32_t r[32];
+                    tc_ld32(taddr + cc * 32, r);
+                    tc_wait_ld();
+                    float mn = __uint_as_float(r[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) mn = fminf(mn, __uint_as_float(r[j]));
+                    if (live && (mn < tau || partial)) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float s = __uint_as_float(r[j]);
+                            const int64_t col = col0 + cc * 32 + j;
+                            if (s < tau && col < P.n_total) tau = cand_insert(cs, ci, P.m, s, (int)col);
+                        }
+                    }
+                    __syncwarp();                               // reconverge before the next warp-collective load
+                }
+                tc_fence_before();
+                mbar_arrive(t_empty + buf);
+                buf ^= 1;
+                if (buf == 0) bphase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// exact re-rank + certificate, one warp per query
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_lt(double da, int ia, double db, int ib) { return da < db || (da == db && ia < ib); }
+
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k, int m,
+                  const float *__restrict__ cand_s, const int32_t *__restrict__ cand_i, const double *__restrict__ qn,
+                  const unsigned int *__restrict__ rmax_bits, int32_t *__restrict__ idx, double *__restrict__ rdist,
+                  int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mp = m;                                      // power of two, 32..256
+    double *sd = reinterpret_cast<double *>(sm_raw) + (size_t)warp * mp;
+    int *si = reinterpret_cast<int *>(sm_raw + (size_t)8 * mp * sizeof(double)) + (size_t)warp * mp;
+    const float R = __uint_as_float(*rmax_bits);
+    for (int64_t q = (int64_t)blockIdx.x * 8 + warp; q < nq; q += (int64_t)gridDim.x * 8) {
+        const int64_t qid = q_begin + q;
+        const double *qv = emb + qid * d;
+        const double qnorm2 = qn[qid];
+        double worst_rel = 0.0;
+        for (int c = lane; c < mp; c += 32) {
+            double dist = INFINITY;
+            int id = INT_MAX;
+            if (c < m) {
+                const int cand = cand_i[q * m + c];
+                if (cand >= 0) {
+                    const double *xv = emb + (int64_t)cand * d;
+                    double acc = 0.0;
+                    for (int j = 0; j < d; ++j) {                 // the reference's arithmetic, no FMA
+                        const double df = __dsub_rn(qv[j], xv[j]);
+                        acc = __dadd_rn(acc, __dmul_rn(df, df));
+                    }
+                    dist = acc;
+                    id = cand;
+                    const double approx = (double)cand_s[q * m + c] + qnorm2;
+                    const double scale = (sqrt(qnorm2) + (double)R);
+                    worst_rel = fmax(worst_rel, fabs(approx - acc) / (scale * scale));
+                }
+            }
+            sd[c] = dist;
+            si[c] = id;
+        }
+        __syncwarp();
+        // bitonic sort of mp (distance, index) pairs in shared memory
+        for (int size = 2; size <= mp; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = lane; i < (mp >> 1); i += 32) {
+                    const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+                    const int hi = lo | stride;
+                    const bool up = ((lo & size) == 0);
+                    const double dl = sd[lo], dh = sd[hi];
+                    const int il = si[lo], ih = si[hi];
+                    const bool sw = up ? pair_lt(dh, ih, dl, il) : pair_lt(dl, il, dh, ih);
+                    if (sw) { sd[lo] = dh; sd[hi] = dl; si[lo] = ih; si[hi] = il; }
+                }
+                __syncwarp();
+            }
+        }
+        for (int c = lane; c < k; c += 32) {
+            idx[q * k + c] = si[c];
+            rdist[q * k + c] = sd[c];
+        }
+        if (lane == 0) {
+            const double dk = sd[k - 1];
+            const double tau = (double)cand_s[q * m + (m - 1)];      // m-th smallest approximate score
+            const double scale = sqrt(qnorm2) + (double)R;
+            const double eps = TC_KAPPA * scale * scale;
+            const bool full_list = cand_i[q * m + (m - 1)] >= 0;
+            // every point outside the list has  D >= tau + ||q||^2 - eps ; strict '>' also settles ties
+            const bool certified = !full_list || (tau + qnorm2 - eps > dk);
+            if (certified) {
+                atomicAdd(stats + 3, 1ull);
+                if (k < mp && sd[k] == dk) atomicAdd(stats + 0, 1ull);
+                if (si[0] != (int)qid || (k > 1 && sd[1] == 0.0)) atomicAdd(stats + 2, 1ull);
+            } else {
+                const unsigned long long slot = atomicAdd(stats + 1, 1ull);
+                fb_list[slot] = qid;
+                fb_list[nq + slot] = q;                              // output row
+            }
+        }
+        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 16));
+        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 8));
+        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 4));
+        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 2));
+        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 1));
+        if (lane == 0) atomicMax(relerr_bits, __float_as_uint((float)worst_rel));
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static int tc_candidates(int k) {
+    const int want = k + std::max(8, k / 2);
+    int m = 32;
+    while (m < want) m <<= 1;                      // power of two (bitonic re-rank), 32..256
+    return std::min(m, 256);
+}
+static int tc_kt(int d) { return (3 * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
+
+struct TcWs {
+    double *mean, *partial, *qn;
+    float *aop, *bop, *cand_s;
+    int32_t *cand_i;
+    int64_t *fb_list;
+    unsigned int *scal;      // [0] rmax bits, [1] relerr bits
+    void *exact_ws;
+    size_t exact_bytes;
+};
+
+static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t bytes, TcWs *out) {
+    ab_arena a(ws ? ws : (void *)1024, ws ? bytes : (size_t)-1 / 2);
+    TcWs w;
+    const int kt = tc_kt(d), m = tc_candidates(k);
+    w.aop = a.take<float>((size_t)n * kt);
+    w.bop = a.take<float>((size_t)n * kt);
+    w.mean = a.take<double>(d);
+    w.partial = a.take<double>((size_t)1024 * d);
+    w.qn = a.take<double>(n);
+    w.cand_s = a.take<float>((size_t)nq * m);
+    w.cand_i = a.take<int32_t>((size_t)nq * m);
+    w.fb_list = a.take<int64_t>((size_t)2 * nq);
+    w.scal = a.take<unsigned int>(4);
+    // the exact scan only ever sees the uncertified minority; reserve room for 1/8 of the queries
+    w.exact_bytes = ab_knn_exact_ws_bytes(std::max<int64_t>(1024, nq / 8), k, 64);
+    w.exact_ws = a.take<char>(w.exact_bytes);
+    if (out) *out = w;
+    return a.ok ? a.off : 0;
+}
+
+size_t ab_knn_tc_ws_bytes(int64_t n_total, int d, int64_t nq, int k) {
+    return tc_layout(n_total, d, nq, k, nullptr, 0, nullptr) + 2048;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap *map, float *base, int64_t rows, int kt, int box_rows) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !p) return ab_fail("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+        fn = (PFN_encodeTiled)p;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)kt, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)kt * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_KCH, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ab_fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
 int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k,
                   int32_t *idx, double *rdist, unsigned long long *stats, void *ws, size_t ws_bytes, cudaStream_t st) {
-    return ab_knn_exact_run(ctx, emb, n_total, d, nullptr, q_begin, nq, k, ab_knn_exact_pick_splits(ctx, nq), nullptr,
-                            idx, rdist, stats, ws, ws_bytes, st);
+    const int kt = tc_kt(d), chunks = kt / TC_KCH, m = tc_candidates(k);
+    if (chunks > TC_MAX_CHUNKS || n_total < m || n_total >= ((int64_t)1 << 31) - TC_BN) {
+        // outside the tensor path's envelope (very wide embeddings, tiny inputs): exact scan
+        return ab_knn_exact_run(ctx, emb, n_total, d, nullptr, q_begin, nq, k, ab_knn_exact_pick_splits(ctx, nq), nullptr,
+                                idx, rdist, stats, ws, ws_bytes, st);
+    }
+    TcWs w;
+    AB_REQUIRE(tc_layout(n_total, d, nq, k, ws, ws_bytes, &w) != 0, "ab_knn: workspace too small");
+    AB_CUDA(cudaMemsetAsync(w.scal, 0, 4 * sizeof(unsigned int), st));
+    // ---- prep ----
+    const int parts = (int)std::min<int64_t>(1024, std::max<int64_t>(1, n_total / 64));
+    knn_colsum_kernel<<<parts, 256, 0, st>>>(emb, n_total, d, w.partial);
+    AB_LAUNCH_CHECK(ctx);
+    knn_colmean_kernel<<<(d + 127) / 128, 128, 0, st>>>(w.partial, parts, d, n_total, w.mean);
+    AB_LAUNCH_CHECK(ctx);
+    const unsigned g_prep = (unsigned)std::min<int64_t>((n_total + 7) / 8, (int64_t)ctx->sm_count * 16);
+    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, kt, w.mean, w.aop, w.bop, w.qn, w.scal);
+    AB_LAUNCH_CHECK(ctx);
+    knn_init_cand_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(w.cand_s, w.cand_i, nq * m);
+    AB_LAUNCH_CHECK(ctx);
+    // ---- main ----
+    CUtensorMap map_a, map_b;
+    if (make_map(&map_a, w.aop, n_total, kt, TC_BM)) return 1;
+    if (make_map(&map_b, w.bop, n_total, kt, TC_BN)) return 1;
+    const size_t a_bytes = (size_t)chunks * TC_A_CHUNK_BYTES;
+    const size_t bar_bytes = 256;
+    int stages = (int)(((size_t)ctx->smem_optin - 1024 - a_bytes - bar_bytes) / TC_B_STAGE_BYTES);
+    stages = std::min(stages, TC_MAX_STAGES);
+    AB_REQUIRE(stages >= 2, "ab_knn: not enough shared memory for d=%d", d);
+    const size_t smem = 1024 + a_bytes + (size_t)stages * TC_B_STAGE_BYTES + bar_bytes;
+    AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TcParams P;
+    P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.stages = stages; P.m = m;
+    P.cand_s = w.cand_s; P.cand_i = w.cand_i;
+    const int64_t n_qblocks = (nq + TC_BM - 1) / TC_BM;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
+    knn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, P);
+    AB_LAUNCH_CHECK(ctx);
+    // ---- exact re-rank + certificate ----
+    const int mp = m;
+    const size_t rr_smem = (size_t)8 * mp * (sizeof(double) + sizeof(int));
+    AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
+    const unsigned g_rr = (unsigned)std::min<int64_t>((nq + 7) / 8, (int64_t)ctx->sm_count * 8);
+    knn_rerank_kernel<<<g_rr, 256, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, w.cand_s, w.cand_i, w.qn, w.scal,
+                                                  idx, rdist, w.fb_list, stats, w.scal + 1);
+    AB_LAUNCH_CHECK(ctx);
+    // ---- uncertified queries: exact scan ----
+    unsigned long long h_stats[4];
+    unsigned int h_scal[2];
+    AB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaMemcpyAsync(h_scal, w.scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_fb = (int64_t)h_stats[1];
+    // stats[4] = max observed |approx - exact| / (||q||+R)^2 as float bits, stats[5] = candidates per query
+    unsigned long long extra[2] = {(unsigned long long)h_scal[1], (unsigned long long)m};
+    AB_CUDA(cudaMemcpyAsync(stats + 4, extra, sizeof(extra), cudaMemcpyHostToDevice, st));
+    if (n_fb > 0) {
+        int64_t done = 0;
+        const int64_t batch = std::max<int64_t>(1024, nq / 8);
+        while (done < n_fb) {
+            const int64_t cur = std::min(batch, n_fb - done);
+            const int splits = ab_knn_exact_pick_splits(ctx, cur);
+            if (ab_knn_exact_run(ctx, emb, n_total, d, w.fb_list + done, 0, cur, k, splits, w.fb_list + nq + done, idx,
+                                 rdist, stats, w.exact_ws, w.exact_bytes, st))
+                return 1;
+            done += cur;
+        }
+    }
+    return 0;
 }

@@ -21,7 +21,7 @@ __device__ __forceinline__ long long row_sum_counts(const int32_t *__restrict__ 
     long long acc = 0;
     // head to 16-byte alignment
     int64_t p = a;
-    int64_t a4 = (a + 3) & ~(int64_t)3;
+    int64_t a4 = a + ((4 - (int)((reinterpret_cast<uintptr_t>(val + a) >> 2) & 3)) & 3);
     if (a4 > b) a4 = b;
     if (p + lane < a4) acc += val[p + lane];
     p = a4;

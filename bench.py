@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — cells/s of normalise -> HVG -> PCA -> kNN -> SNN on synthetic NB counts.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|...] [--impl ours|reference]
+
+One "step" = one pass of the whole front end over the workload (device-resident cell-major CSR
+counts in, device-resident SNN edge list out).  N>1 is launched by torchrun, one rank per GPU;
+cells are sharded by rows (strong scaling: total work fixed).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'cells/sec normalise->PCA->kNN->SNN'
+UNIT = 'cells/s'
+CPU_SAMPLE_CELLS = 3000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default=os.environ.get('AB_WORKLOAD', 'c3'))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--seed', type=int, default=42)
+    ap.add_argument('--knn-mode', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cells', type=int, default=0, help='override the workload cell count (debug)')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace('.', '').isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (same third-party calls as the reference) on a bounded sample
+# ------------------------------------------------------------------------------------------
+def cpu_sample_frame(host_csr_sample):
+    """genes x cells int64 DataFrame of the sample, all-zero genes dropped (alona/cell.py:64-81)."""
+    import pandas as pd
+    keep = np.asarray((host_csr_sample != 0).sum(axis=0)).ravel() > 0
+    sub = host_csr_sample[:, keep]
+    return pd.DataFrame(sub.T.toarray().astype(np.int64), index=['g%d' % i for i in np.where(keep)[0]],
+                        columns=['c%d' % i for i in range(sub.shape[0])])
+
+
+def run_cpu_port(df, wl, seed):
+    from oracle import alona_port
+    tm = {}
+    t0 = time.perf_counter()
+    alona_port.run_pipeline(df, min(wl['hvg_n'], df.shape[0]), wl['pca_n'], wl['k'], 0.067, seed, timings=tm)
+    return time.perf_counter() - t0, tm
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get('num_threads', 1) for p in threadpool_info() if p.get('user_api') == 'blas']
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def sample_counts_host(wl, n_cells, seed_data=20251019):
+    """First n_cells cells of the workload's synthetic matrix: generated on the GPU when there is one
+    (identical to the GPU arm's data), else by the numpy twin of the generator."""
+    import scipy.sparse as sp
+    import torch
+    if torch.cuda.is_available():
+        from alona_b200.engine import Engine
+        from alona_b200.synth import make_profiles
+        eng = Engine()
+        prof = torch.from_numpy(make_profiles(wl['genes'])).to(eng.device)
+        A = eng.synth_counts(prof, 0, n_cells, wl['lbar'], n_total=wl['cells'], seed=seed_data)
+        m = sp.csr_matrix((A.val.cpu().numpy(), A.col.cpu().numpy(), A.rowptr.cpu().numpy()), shape=(n_cells, wl['genes']))
+        eng.close()
+        return m
+    from oracle import synth_np
+    m, _ = synth_np.nb_counts(n_cells, wl['genes'], lbar=wl['lbar'], seed=1, drop_empty=False)
+    return m
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    from alona_b200.synth import WORKLOADS
+    wl = dict(WORKLOADS[args.workload])
+    if args.cells:
+        wl['cells'] = args.cells
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    config = {'workload': '%s: synthetic NB %d cells x %d genes, hvg_n %d, pca_n %d, k %d, prune 0.067'
+              % (args.workload, wl['cells'], wl['genes'], wl['hvg_n'], wl['pca_n'], wl['k']),
+              'parallelism': 'cells row-sharded over %d GPU(s)' % world,
+              'cache': 'inputs (CSR counts) larger than L2; no flush needed'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        n_s = min(CPU_SAMPLE_CELLS, wl['cells'])
+        df = cpu_sample_frame(sample_counts_host(wl, n_s))
+        times = []
+        for i in range(args.warmup + args.steps):
+            dt, tm = run_cpu_port(df, wl, args.seed)
+            if i >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * float(np.mean(times))
+        val = n_s / (ms / 1e3)
+        sample = 'first %d cells of the workload matrix (%d expressed genes), dense pandas path' % (n_s, df.shape[0])
+        print(json.dumps({
+            'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config,
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port', 'sample': sample,
+                             'stage_s': tm},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from alona_b200.engine import get_engine
+    from alona_b200.pipeline import frontend, StageTimer, shard_bounds, start_vector
+    from alona_b200.synth import make_profiles
+    eng = get_engine()
+    dev = eng.device
+
+    # ---- synthetic input, generated on the device, shard by shard ---------------------------
+    bounds = shard_bounds(wl['cells'], world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    prof = torch.from_numpy(make_profiles(wl['genes'])).to(dev)
+    A = eng.synth_counts(prof, lo, hi - lo, wl['lbar'], n_total=wl['cells'])
+    torch.cuda.synchronize()
+    nnz_local = A.nnz
+    v0 = start_vector(wl['cells'], args.seed)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step(timer=None):
+        return frontend(eng, A, wl['hvg_n'], wl['pca_n'], wl['k'], 0.067, args.seed, knn_mode=args.knn_mode, v0=v0,
+                        timer=timer)
+
+    for _ in range(args.warmup):
+        out = one_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    timer = StageTimer(True)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = one_step(timer)
+    ev1.record()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = {k: v / args.steps for k, v in timer.result().items()}
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = wl['cells'] / (ms_per_step / 1e3)
+    edges_local = int(out['snn']['src'].numel())
+    nnz_h = out['AH'].nnz
+    info = {'steps': out['irlb']['steps'], 'nmult': out['irlb']['nmult'], 'sum_panel': out['irlb']['sum_panel'],
+            'nnz': nnz_local, 'nnz_hvg': nnz_h, 'edges': edges_local,
+            'knn_stats': out['knn_stats'].cpu().numpy().tolist(), 'snn_big_rows': out['snn']['big_rows'],
+            'snn_max_walk': out['snn']['max_walk'], 'hvg_stats': out['hvg_stats'].cpu().numpy().tolist()}
+
+    # ---- end to end through the public API with HOST buffers -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_rowptr = A.rowptr.cpu().pin_memory()
+        h_col = A.col.cpu().pin_memory()
+        h_val = A.val.cpu().pin_memory()
+        h_v0 = torch.from_numpy(v0[lo:hi].copy()).pin_memory()
+        from alona_b200.engine import DeviceCSR
+
+        def e2e_step():
+            d = DeviceCSR(h_rowptr.to(dev, non_blocking=True), h_col.to(dev, non_blocking=True),
+                          h_val.to(dev, non_blocking=True), wl['genes'], lo, wl['cells'])
+            o = frontend(eng, d, wl['hvg_n'], wl['pca_n'], wl['k'], 0.067, args.seed, knn_mode=args.knn_mode, v0=v0)
+            src = o['snn']['src'].to('cpu', non_blocking=True)
+            dst = o['snn']['dst'].to('cpu', non_blocking=True)
+            torch.cuda.synchronize()
+            return src, dst
+        del out
+        for _ in range(1):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ne = max(1, min(args.steps, 3))
+        for _ in range(ne):
+            src, dst = e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / ne
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = (h_rowptr.numel() * 8 + h_col.numel() * 4 + h_val.numel() * 4 + h_v0.numel() * 8)
+        d2h = src.numel() * 4 * 2
+        tot = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        e2e = {'value': wl['cells'] / float(tt.item()), 'unit': UNIT, 'h2d_bytes_per_step': int(tot[0].item()),
+               'd2h_bytes_per_step': int(tot[1].item()), 'ms_per_step': 1e3 * float(tt.item()),
+               'path': 'pinned host CSR -> alona_b200.pipeline.frontend (C-ABI stages) -> host edge list'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    roof = roofline(args, wl, world, stage_ms, info, peaks)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_s = min(CPU_SAMPLE_CELLS, wl['cells'])
+        rp = A.rowptr[:n_s + 1].cpu().numpy()
+        import scipy.sparse as sp
+        m = sp.csr_matrix((A.val[:rp[-1]].cpu().numpy(), A.col[:rp[-1]].cpu().numpy(), rp), shape=(n_s, wl['genes']))
+        df = cpu_sample_frame(m)
+        dt, tm = run_cpu_port(df, wl, args.seed)
+        cpu = {'value': n_s / dt, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port',
+               'sample': 'first %d cells of the same matrix (%d expressed genes), dense pandas path, one run'
+                         % (n_s, df.shape[0]), 'stage_s': tm}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f64 (normalise/HVG/IRLBA/re-rank), tf32x3 fp32-accumulate (distance GEMM), int32 (SNN)',
+            'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': launches // max(1, args.steps),
+            'stage_ms': stage_ms, 'info': info, 'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(args, wl, world, stage_ms, info, peaks):
+    """Dominant kernel = the kNN distance pass.  Algorithmic work: 2*N_q*N*d flops (true d)."""
+    n, d = wl['cells'], wl['pca_n']
+    nq = n / world
+    knn_ms = stage_ms.get('knn')
+    if not knn_ms:
+        return None
+    flops = 2.0 * nq * n * d
+    achieved = flops / (knn_ms / 1e3) / 1e12
+    bf16 = peaks.get('bf16_tflops_sustained') or 1400.0
+    peak = bf16 / 2.0
+    return {'bound': 'tensor', 'kernel': 'knn distance pass (stage time incl. re-rank)', 'achieved': achieved,
+            'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+            'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 = half the bf16 rate)'
+                           if peaks else 'fallback 1.4 PFLOP/s bf16 sustained / 2'}
+
+
+if __name__ == '__main__':
+    main()
