@@ -26,6 +26,8 @@
 #include "ab_common.cuh"
 #include <cuda.h>
 #include <math.h>
+#include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 
 size_t ab_knn_exact_ws_bytes(int64_t nq, int k, int splits);
@@ -37,7 +39,6 @@ int ab_knn_exact_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, con
 static constexpr int TC_BM = 128;            // queries per CTA tile (UMMA M)
 static constexpr int TC_BN = 256;            // database points per tile (UMMA N)
 static constexpr int TC_KCH = 32;            // tf32 elements per K chunk = one 128-byte swizzle row
-static constexpr int TC_THREADS = 192;       // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 static constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
 static constexpr int TC_B_STAGE_BYTES = TC_BN * 128;
 static constexpr int TC_MAX_STAGES = 6;
@@ -198,28 +199,35 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const 
     }
 }
 
-__global__ void knn_init_cand_kernel(float *__restrict__ cs, int32_t *__restrict__ ci, int64_t total) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        cs[i] = INFINITY;
-        ci[i] = -1;
-    }
-}
 
 // ---------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ float cand_insert(float *cs, int32_t *ci, int m, float s, int idx) {
-    int p = m - 1;
-    while (p > 0) {
-        const float prev = cs[p - 1];
-        if (!(prev > s)) break;
-        cs[p] = prev;
-        ci[p] = ci[p - 1];
-        --p;
-    }
-    cs[p] = s;
-    ci[p] = idx;
-    return cs[m - 1];
+static constexpr int TC_EPI_WARPS = 8;                       // two groups of four warps
+static constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+static constexpr int TC_NTHREADS = 64 + TC_EPI_THREADS;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+static constexpr int TC_BUF = 16;                            // per-thread append buffer (entries)
+static constexpr unsigned long long TC_KEY_MAX = 0xFFFFFFFFFFFFFFFFull;
+
+// candidate key = order-preserving bits of the FP32 score in the high word, point id in the low word
+__device__ __forceinline__ unsigned long long cand_key(float s, int idx) {
+    const uint32_t b = __float_as_uint(s);
+    const uint32_t o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ((unsigned long long)o << 32) | (uint32_t)idx;
+}
+__host__ __device__ __forceinline__ float key_score(unsigned long long key) {
+    const uint32_t o = (uint32_t)(key >> 32);
+    const uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+    return key == TC_KEY_MAX ? INFINITY : __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return key == TC_KEY_MAX ? INFINITY : f;
+#endif
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 
 struct TcParams {
@@ -228,19 +236,101 @@ struct TcParams {
     int64_t nq;            // number of queries
     int chunks;            // K chunks of 32 tf32
     int stages;            // B ring depth
-    int m;                 // candidates per query
-    float *cand_s;
-    int32_t *cand_i;
+    int m;                 // candidates kept per (query, epilogue group)
+    int sortp;             // power of two >= m + TC_BUF (prune sort size)
+    unsigned long long *cand;   // [2 groups][nq][m] sorted keys
+    unsigned long long *dbg;    // optional [grid][16] cycle counters (AB_KNN_DEBUG=1), else NULL
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// 32-wide bitonic sort across the warp, descending (lane 0 ends with the largest key)
+__device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(AB_FULL, v, stride);
+            const bool up = ((lane & size) == 0);            // this block sorts descending when `up`
+            const bool lower = ((lane & stride) == 0);
+            const unsigned long long mx = v > o ? v : o, mn = v > o ? o : v;
+            v = (lower == up) ? mx : mn;
+        }
+    }
+    return v;
+}
+
+// Warp-cooperative prune: for every lane in `lanes`, merge its append buffer (<= TC_BUF unsorted
+// keys in shared memory) into its sorted m-list (global memory, m = 32*E keys, element i lives in
+// register x[i/32] of lane i%32), keep the m smallest, refresh the lane's threshold.
+// Bitonic split + merge entirely in registers/shuffles.  Warp-uniform call.
+template <int E>
+__device__ __noinline__ void warp_prune_t(unsigned lanes, unsigned long long *cand_group, int64_t q_lane, int &cnt,
+                                          float &tau, const unsigned long long *bufcol, int lane) {
+    while (lanes) {
+        const int L = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
+        const int cntL = __shfl_sync(AB_FULL, cnt, L);
+        const long long qL = __shfl_sync(AB_FULL, (long long)q_lane, L);
+        const unsigned long long *colL = (const unsigned long long *)__shfl_sync(AB_FULL, (unsigned long long)bufcol, L);
+        unsigned long long *list = cand_group + (size_t)qL * (32 * E);
+        unsigned long long x[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = list[e * 32 + lane];
+        unsigned long long b = lane < cntL ? colL[(size_t)lane * TC_EPI_THREADS] : TC_KEY_MAX;
+        b = warp_sort_desc(b, lane);
+        // bitonic split against the (virtual) upper half [MAX.. , b descending]: only the top 32 slots matter
+        x[E - 1] = x[E - 1] < b ? x[E - 1] : b;
+        // bitonic merge of the lower half (length 32*E)
+#pragma unroll
+        for (int stride = 16 * E; stride >= 32; stride >>= 1) {
+            const int se = stride / 32;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if ((e & se) == 0) {
+                    const unsigned long long lo = x[e], hi = x[e + se];
+                    x[e] = lo < hi ? lo : hi;
+                    x[e + se] = lo < hi ? hi : lo;
+                }
+            }
+        }
+#pragma unroll
+        for (int stride = 16; stride > 0; stride >>= 1) {
+            const bool lower = ((lane & stride) == 0);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const unsigned long long o = __shfl_xor_sync(AB_FULL, x[e], stride);
+                const unsigned long long mn = x[e] < o ? x[e] : o, mx = x[e] < o ? o : x[e];
+                x[e] = lower ? mn : mx;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) list[e * 32 + lane] = x[e];
+        const unsigned long long kth = __shfl_sync(AB_FULL, x[E - 1], 31);
+        if (lane == L) { tau = key_score(kth); cnt = 0; }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, int group, int64_t q_lane, int &cnt,
+                                           float &tau, const unsigned long long *bufcol, int lane) {
+    unsigned long long *cg = P.cand + (size_t)group * P.nq * P.m;
+    switch (P.m) {
+        case 32: warp_prune_t<1>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
+        case 64: warp_prune_t<2>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
+        case 128: warp_prune_t<4>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
+        default: warp_prune_t<8>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
+    }
+}
+
+__global__ void __launch_bounds__(TC_NTHREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: [A chunks][B stages][barriers]
+    // layout: [A chunks][B stages][append buffers][prune scratch][barriers]
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sA = smem;
     unsigned char *sB = sA + (size_t)P.chunks * TC_A_CHUNK_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)P.stages * TC_B_STAGE_BYTES);
+    unsigned long long *sBuf = reinterpret_cast<unsigned long long *>(sB + (size_t)P.stages * TC_B_STAGE_BYTES);
+    unsigned long long *sScratch = sBuf + (size_t)TC_BUF * TC_EPI_THREADS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sScratch + (size_t)TC_EPI_WARPS * P.sortp);
     uint64_t *full = bars;                          // [stages]
     uint64_t *empty = bars + TC_MAX_STAGES;         // [stages]
     uint64_t *a_full = bars + 2 * TC_MAX_STAGES;
@@ -252,6 +342,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_qblocks = (P.nq + TC_BM - 1) / TC_BM;
     const int64_t n_tiles = (P.n_total + TC_BN - 1) / TC_BN;
+    // q-blocks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int64_t my_blocks = n_qblocks > blockIdx.x ? (n_qblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t my_tiles = my_blocks * n_tiles;   // global tile counter `it` runs over [0, my_tiles)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -274,6 +367,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, aphase = 0;
+            long long dbg_prod = 0;
+            const long long tstart = clock64();
             for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
                 mbar_wait(a_empty, aphase ^ 1);
                 mbar_expect_tx(a_full, (uint32_t)(P.chunks * TC_A_CHUNK_BYTES));
@@ -284,32 +379,41 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 for (int64_t t = 0; t < n_tiles; ++t) {
                     const int xrow = (int)(t * TC_BN);
                     for (int c = 0; c < P.chunks; ++c) {
+                        const long long t0 = clock64();
                         mbar_wait(empty + stage, phase ^ 1);
+                        dbg_prod += clock64() - t0;
                         mbar_expect_tx(full + stage, (uint32_t)TC_B_STAGE_BYTES);
                         tma_load_2d(sB + (size_t)stage * TC_B_STAGE_BYTES, &map_b, full + stage, c * TC_KCH, xrow);
                         if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
+            if (P.dbg) { P.dbg[blockIdx.x * 16 + 0] = dbg_prod; P.dbg[blockIdx.x * 16 + 1] = clock64() - tstart; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
             // instruction descriptor: D=F32, A=B=TF32, K-major both, N=256, M=128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            int stage = 0, buf = 0;
-            int64_t nblocks_done = 0;
-            uint32_t phase = 0, aphase = 0, bphase = 0;
+            int stage = 0;
+            int64_t it = 0, nblocks_done = 0;
+            long long dbg_tempty = 0, dbg_full = 0;
+            uint32_t phase = 0, aphase = 0;
             const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
             for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
                 mbar_wait(a_full, aphase);
                 aphase ^= 1;
-                for (int64_t t = 0; t < n_tiles; ++t) {
-                    mbar_wait(t_empty + buf, bphase ^ 1);
+                for (int64_t t = 0; t < n_tiles; ++t, ++it) {
+                    const int buf = (int)(it & 1);
+                    long long t0 = clock64();
+                    mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
+                    dbg_tempty += clock64() - t0;
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_BN;
                     for (int c = 0; c < P.chunks; ++c) {
+                        t0 = clock64();
                         mbar_wait(full + stage, phase);
+                        dbg_full += clock64() - t0;
                         tc_fence_after();
                         const uint32_t a_c = a_addr + (uint32_t)c * TC_A_CHUNK_BYTES;
                         const uint32_t b_s = b_addr + (uint32_t)stage * TC_B_STAGE_BYTES;
@@ -321,56 +425,109 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
                     tc_commit(t_full + buf);                    // accumulator ready for the epilogue
-                    buf ^= 1;
-                    if (buf == 0) bphase ^= 1;
                 }
                 tc_commit(a_empty);                             // A tile may be overwritten
                 ++nblocks_done;
             }
             // do not let the CTA retire with a tcgen05.commit arrive still in flight
             if (nblocks_done > 0) mbar_wait(a_empty, (uint32_t)((nblocks_done - 1) & 1));
+            if (P.dbg) { P.dbg[blockIdx.x * 16 + 2] = dbg_tempty; P.dbg[blockIdx.x * 16 + 3] = dbg_full; }
         }
     } else {
-        // ================= epilogue: thread <-> query row =================
+        // ================= epilogue: two groups alternate tiles; thread <-> query row =================
+        const int ew = warp - 2;                                // 0..7
+        const int group = ew >> 2;                              // tiles with (it & 1) == group, TMEM buffer = group
         const int lane_base = (warp & 3) * 32;                  // TMEM lanes this warp may touch
         const int row = lane_base + lane;
-        int buf = 0;
-        uint32_t bphase = 0;
-        for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
-            const int64_t q = qb * TC_BM + row;                 // query position inside [0,nq)
-            const bool live = q < P.nq;
-            float *cs = P.cand_s + (live ? q : 0) * P.m;
-            int32_t *ci = P.cand_i + (live ? q : 0) * P.m;
-            float tau = INFINITY;
-            for (int64_t t = 0; t < n_tiles; ++t) {
-                mbar_wait(t_full + buf, bphase);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)buf * TC_BN;
-                const int64_t col0 = t * TC_BN;
-                const bool partial = col0 + TC_BN > P.n_total;
-#pragma unroll 1
-                for (int cc = 0; cc < TC_BN / 32; ++cc) {
-                    uint32_t r[32];
-                    tc_ld32(taddr + cc * 32, r);
-                    tc_wait_ld();
-                    float mn = __uint_as_float(r[0]);
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) mn = fminf(mn, __uint_as_float(r[j]));
-                    if (live && (mn < tau || partial)) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float s = __uint_as_float(r[j]);
-                            const int64_t col = col0 + cc * 32 + j;
-                            if (s < tau && col < P.n_total) tau = cand_insert(cs, ci, P.m, s, (int)col);
-                        }
-                    }
-                    __syncwarp();                               // reconverge before the next warp-collective load
-                }
-                tc_fence_before();
-                mbar_arrive(t_empty + buf);
-                buf ^= 1;
-                if (buf == 0) bphase ^= 1;
+        const int etid = ew * 32 + lane;
+        unsigned long long *bufcol = sBuf + etid;               // entry e at bufcol[e * TC_EPI_THREADS]
+        const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)group * TC_BN;
+        int64_t cur_block = -1, q = 0;
+        bool live = false;
+        float tau = INFINITY;
+        int cnt = 0;
+        long long dbg_wait = 0, dbg_slow = 0, dbg_prune = 0, dbg_nslow = 0, dbg_nprune = 0;
+        const long long tstart = clock64();
+        for (int64_t it = group; it < my_tiles; it += 2) {
+            const int64_t blk = it / n_tiles, t = it - blk * n_tiles;
+            if (blk != cur_block) {
+                if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, group, q, cnt, tau, bufcol, lane);
+                cur_block = blk;
+                q = (blockIdx.x + blk * gridDim.x) * TC_BM + row;     // query position inside [0,nq)
+                live = q < P.nq;
+                tau = INFINITY;
+                cnt = 0;
             }
+            long long t0 = clock64();
+            mbar_wait(t_full + group, (uint32_t)((it >> 1) & 1));
+            dbg_wait += clock64() - t0;
+            tc_fence_after();
+            const int64_t col0 = t * TC_BN;
+#pragma unroll 1
+            for (int cc = 0; cc < TC_BN / 32; ++cc) {
+                uint32_t r[32];
+                tc_ld32(taddr + cc * 32, r);
+                tc_wait_ld();
+                float gmin[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float v = fmin3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+                    v = fmin3(v, __uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]));
+                    v = fmin3(v, __uint_as_float(r[8 * g + 5]), __uint_as_float(r[8 * g + 6]));
+                    gmin[g] = fminf(v, __uint_as_float(r[8 * g + 7]));
+                }
+                const float mn = fminf(fmin3(gmin[0], gmin[1], gmin[2]), gmin[3]);
+                bool active = live && mn < tau;
+                if (__any_sync(AB_FULL, active)) {
+                    const long long ts = clock64();
+                    ++dbg_nslow;
+                    // rare path: append passing scores; a lane whose buffer fills stops at `jnext`, is pruned
+                    // (warp-cooperatively) and resumes from there with its tightened threshold
+                    const int64_t cbase = col0 + cc * 32;
+                    int jnext = 0;
+                    while (true) {
+                        if (active) {
+                            bool stopped = false;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (gmin[g] < tau) {
+#pragma unroll
+                                    for (int jj = 0; jj < 8; ++jj) {
+                                        const int j = 8 * g + jj;
+                                        const float s = __uint_as_float(r[j]);
+                                        if (!stopped && j >= jnext && s < tau && cbase + j < P.n_total) {
+                                            if (cnt < TC_BUF) {
+                                                bufcol[(size_t)cnt * TC_EPI_THREADS] = cand_key(s, (int)(cbase + j));
+                                                ++cnt;
+                                            } else {
+                                                jnext = j;
+                                                stopped = true;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                            active = stopped;
+                        }
+                        const unsigned fullm = __ballot_sync(AB_FULL, cnt >= TC_BUF);
+                        if (fullm) {
+                            const long long tp = clock64();
+                            warp_prune(fullm, P, group, q, cnt, tau, bufcol, lane);
+                            dbg_prune += clock64() - tp;
+                            dbg_nprune += __popc(fullm);
+                        }
+                        if (!__any_sync(AB_FULL, active)) break;
+                    }
+                    dbg_slow += clock64() - ts;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(t_empty + group);
+        }
+        if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, group, q, cnt, tau, bufcol, lane);
+        if (P.dbg && ew == 0 && lane == 0) {
+            unsigned long long *o = P.dbg + blockIdx.x * 16 + 4;
+            o[0] = dbg_wait; o[1] = dbg_slow; o[2] = dbg_prune; o[3] = dbg_nslow; o[4] = dbg_nprune; o[5] = clock64() - tstart;
         }
     }
     tc_fence_before();
@@ -388,12 +545,12 @@ __device__ __forceinline__ bool pair_lt(double da, int ia, double db, int ib) { 
 
 __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k, int m,
-                  const float *__restrict__ cand_s, const int32_t *__restrict__ cand_i, const double *__restrict__ qn,
+                  const unsigned long long *__restrict__ cand, const double *__restrict__ qn,
                   const unsigned int *__restrict__ rmax_bits, int32_t *__restrict__ idx, double *__restrict__ rdist,
                   int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mp = m;                                      // power of two, 32..256
+    const int mp = 2 * m;                                  // both epilogue groups' lists; power of two
     double *sd = reinterpret_cast<double *>(sm_raw) + (size_t)warp * mp;
     int *si = reinterpret_cast<int *>(sm_raw + (size_t)8 * mp * sizeof(double)) + (size_t)warp * mp;
     const float R = __uint_as_float(*rmax_bits);
@@ -401,31 +558,30 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         const int64_t qid = q_begin + q;
         const double *qv = emb + qid * d;
         const double qnorm2 = qn[qid];
+        const double scale = sqrt(qnorm2) + (double)R;
         double worst_rel = 0.0;
         for (int c = lane; c < mp; c += 32) {
+            const int g = c / m, e = c - g * m;
+            const unsigned long long key = cand[((size_t)g * nq + q) * m + e];
             double dist = INFINITY;
             int id = INT_MAX;
-            if (c < m) {
-                const int cand = cand_i[q * m + c];
-                if (cand >= 0) {
-                    const double *xv = emb + (int64_t)cand * d;
-                    double acc = 0.0;
-                    for (int j = 0; j < d; ++j) {                 // the reference's arithmetic, no FMA
-                        const double df = __dsub_rn(qv[j], xv[j]);
-                        acc = __dadd_rn(acc, __dmul_rn(df, df));
-                    }
-                    dist = acc;
-                    id = cand;
-                    const double approx = (double)cand_s[q * m + c] + qnorm2;
-                    const double scale = (sqrt(qnorm2) + (double)R);
-                    worst_rel = fmax(worst_rel, fabs(approx - acc) / (scale * scale));
+            if (key != TC_KEY_MAX) {
+                const int cnd = (int)(uint32_t)(key & 0xFFFFFFFFull);
+                const double *xv = emb + (int64_t)cnd * d;
+                double acc = 0.0;
+                for (int j = 0; j < d; ++j) {                 // the reference's arithmetic, no FMA
+                    const double df = __dsub_rn(qv[j], xv[j]);
+                    acc = __dadd_rn(acc, __dmul_rn(df, df));
                 }
+                dist = acc;
+                id = cnd;
+                const double approx = (double)key_score(key) + qnorm2;
+                worst_rel = fmax(worst_rel, fabs(approx - acc) / (scale * scale));
             }
             sd[c] = dist;
             si[c] = id;
         }
         __syncwarp();
-        // bitonic sort of mp (distance, index) pairs in shared memory
         for (int size = 2; size <= mp; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
                 for (int i = lane; i < (mp >> 1); i += 32) {
@@ -446,12 +602,15 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         }
         if (lane == 0) {
             const double dk = sd[k - 1];
-            const double tau = (double)cand_s[q * m + (m - 1)];      // m-th smallest approximate score
-            const double scale = sqrt(qnorm2) + (double)R;
+            // a group whose list is not full holds every point it saw -> no outside point there
+            double tau = INFINITY;
+            for (int g = 0; g < 2; ++g) {
+                const unsigned long long last = cand[((size_t)g * nq + q) * m + (m - 1)];
+                if (last != TC_KEY_MAX) tau = fmin(tau, (double)key_score(last));
+            }
             const double eps = TC_KAPPA * scale * scale;
-            const bool full_list = cand_i[q * m + (m - 1)] >= 0;
-            // every point outside the list has  D >= tau + ||q||^2 - eps ; strict '>' also settles ties
-            const bool certified = !full_list || (tau + qnorm2 - eps > dk);
+            // every point outside the lists has  D >= tau + ||q||^2 - eps ; strict '>' also settles ties
+            const bool certified = (tau + qnorm2 - eps > dk);
             if (certified) {
                 atomicAdd(stats + 3, 1ull);
                 if (k < mp && sd[k] == dk) atomicAdd(stats + 0, 1ull);
@@ -462,11 +621,8 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                 fb_list[nq + slot] = q;                              // output row
             }
         }
-        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 16));
-        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 8));
-        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 4));
-        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 2));
-        worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, 1));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst_rel = fmax(worst_rel, ab_shfl_xor_f64(worst_rel, o));
         if (lane == 0) atomicMax(relerr_bits, __float_as_uint((float)worst_rel));
         __syncwarp();
     }
@@ -485,10 +641,11 @@ static int tc_kt(int d) { return (3 * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
 
 struct TcWs {
     double *mean, *partial, *qn;
-    float *aop, *bop, *cand_s;
-    int32_t *cand_i;
+    float *aop, *bop;
+    unsigned long long *cand;
     int64_t *fb_list;
     unsigned int *scal;      // [0] rmax bits, [1] relerr bits
+    unsigned long long *dbg; // [256][16]
     void *exact_ws;
     size_t exact_bytes;
 };
@@ -502,10 +659,10 @@ static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t by
     w.mean = a.take<double>(d);
     w.partial = a.take<double>((size_t)1024 * d);
     w.qn = a.take<double>(n);
-    w.cand_s = a.take<float>((size_t)nq * m);
-    w.cand_i = a.take<int32_t>((size_t)nq * m);
+    w.cand = a.take<unsigned long long>((size_t)2 * nq * m);
     w.fb_list = a.take<int64_t>((size_t)2 * nq);
     w.scal = a.take<unsigned int>(4);
+    w.dbg = a.take<unsigned long long>(256 * 16);
     // the exact scan only ever sees the uncertified minority; reserve room for 1/8 of the queries
     w.exact_bytes = ab_knn_exact_ws_bytes(std::max<int64_t>(1024, nq / 8), k, 64);
     w.exact_ws = a.take<char>(w.exact_bytes);
@@ -560,32 +717,36 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     const unsigned g_prep = (unsigned)std::min<int64_t>((n_total + 7) / 8, (int64_t)ctx->sm_count * 16);
     knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, kt, w.mean, w.aop, w.bop, w.qn, w.scal);
     AB_LAUNCH_CHECK(ctx);
-    knn_init_cand_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(w.cand_s, w.cand_i, nq * m);
-    AB_LAUNCH_CHECK(ctx);
+    AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)2 * nq * m * sizeof(unsigned long long), st));
     // ---- main ----
     CUtensorMap map_a, map_b;
     if (make_map(&map_a, w.aop, n_total, kt, TC_BM)) return 1;
     if (make_map(&map_b, w.bop, n_total, kt, TC_BN)) return 1;
     const size_t a_bytes = (size_t)chunks * TC_A_CHUNK_BYTES;
     const size_t bar_bytes = 256;
-    int stages = (int)(((size_t)ctx->smem_optin - 1024 - a_bytes - bar_bytes) / TC_B_STAGE_BYTES);
+    const int sortp = 0;                       // prune works in registers; no shared scratch
+    const size_t epi_bytes = (size_t)TC_BUF * TC_EPI_THREADS * 8 + (size_t)TC_EPI_WARPS * sortp * 8;
+    int stages = (int)(((size_t)ctx->smem_optin - 1024 - a_bytes - bar_bytes - epi_bytes) / TC_B_STAGE_BYTES);
     stages = std::min(stages, TC_MAX_STAGES);
-    AB_REQUIRE(stages >= 2, "ab_knn: not enough shared memory for d=%d", d);
-    const size_t smem = 1024 + a_bytes + (size_t)stages * TC_B_STAGE_BYTES + bar_bytes;
+    AB_REQUIRE(stages >= 2, "ab_knn: not enough shared memory for d=%d k=%d", d, k);
+    const size_t smem = 1024 + a_bytes + (size_t)stages * TC_B_STAGE_BYTES + epi_bytes + bar_bytes;
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcParams P;
     P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.stages = stages; P.m = m;
-    P.cand_s = w.cand_s; P.cand_i = w.cand_i;
+    P.sortp = sortp; P.cand = w.cand;
+    const bool debug = getenv("AB_KNN_DEBUG") != nullptr;
+    P.dbg = debug ? w.dbg : nullptr;
+    if (debug) AB_CUDA(cudaMemsetAsync(w.dbg, 0, 256 * 16 * 8, st));
     const int64_t n_qblocks = (nq + TC_BM - 1) / TC_BM;
     const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
-    knn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, P);
+    knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, map_b, P);
     AB_LAUNCH_CHECK(ctx);
     // ---- exact re-rank + certificate ----
-    const int mp = m;
+    const int mp = 2 * m;
     const size_t rr_smem = (size_t)8 * mp * (sizeof(double) + sizeof(int));
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     const unsigned g_rr = (unsigned)std::min<int64_t>((nq + 7) / 8, (int64_t)ctx->sm_count * 8);
-    knn_rerank_kernel<<<g_rr, 256, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, w.cand_s, w.cand_i, w.qn, w.scal,
+    knn_rerank_kernel<<<g_rr, 256, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, w.cand, w.qn, w.scal,
                                                   idx, rdist, w.fb_list, stats, w.scal + 1);
     AB_LAUNCH_CHECK(ctx);
     // ---- uncertified queries: exact scan ----
@@ -594,6 +755,17 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaMemcpyAsync(h_scal, w.scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaStreamSynchronize(st));
+    if (debug) {
+        static unsigned long long h_dbg[256 * 16];
+        AB_CUDA(cudaMemcpy(h_dbg, w.dbg, sizeof(h_dbg), cudaMemcpyDeviceToHost));
+        const char *names[10] = {"prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "epi_wait_tfull",
+                                 "epi_slow", "epi_prune", "epi_nslow", "epi_nprune", "epi_total"};
+        for (int c = 0; c < 10; ++c) {
+            double sum = 0;
+            for (unsigned b = 0; b < grid; ++b) sum += (double)h_dbg[b * 16 + c];
+            fprintf(stderr, "[knn dbg] %-16s avg/CTA %.3e\n", names[c], sum / grid);
+        }
+    }
     const int64_t n_fb = (int64_t)h_stats[1];
     // stats[4] = max observed |approx - exact| / (||q||+R)^2 as float bits, stats[5] = candidates per query
     unsigned long long extra[2] = {(unsigned long long)h_scal[1], (unsigned long long)m};
