@@ -12,10 +12,13 @@
 // No sort, no atomics in the common path (duplicates inside a 32-wide step are merged with
 // match.any, steps are processed in ascending position order).
 //
-// Rows whose walk is longer than the per-warp table are handled by one CTA each, with dense
-// per-CTA count/first arrays in global scratch (always correct, any in-degree).
+// Rows are classified by walk length: short walks take one warp with a per-warp table, longer
+// ones one CTA with a shared-memory table sized to the walk (the common case at scale: kNN graphs
+// in 50 dimensions have hubs), and anything beyond shared memory one CTA with dense count/first
+// arrays in global scratch (always correct, any in-degree).
 #include "ab_common.cuh"
 #include <limits.h>
+#include <algorithm>
 
 static constexpr int SNN_WARPS = 8;
 static constexpr int SNN_SLOTS = 2048;            // per warp, power of two
@@ -132,26 +135,51 @@ snn_sort_long_kernel(const int64_t *__restrict__ rptr, int32_t *__restrict__ rli
 
 // ---------------------------------------------------------------------------------------
 // per-row walk length and classification
+//   class 0: walk <= SNN_WALK_LIMIT          one warp per row, 2048-slot table per warp
+//   class 1: walk <= 0.7 * SNN_MID_SLOTS     one CTA (256 threads) per row, 4096-slot table
+//   class 2: walk <= 0.7 * large slots       one CTA (512 threads) per row, 16384 (k<=32) / 8192 slots
+//   class 3: anything longer                 one CTA per row, dense arrays in global scratch
+// High-dimensional kNN graphs have hubs (in-degrees in the thousands), so classes 1-2 are the
+// common case at scale, not the exception.
 // ---------------------------------------------------------------------------------------
+static constexpr int SNN_MID_SLOTS = 4096;
+static constexpr int SNN_MID_THREADS = 256;
+static constexpr int SNN_LARGE_THREADS = 512;
+static inline int snn_large_slots(int k) { return k <= 32 ? 16384 : 8192; }
+static inline int snn_walk_cap(int slots) { return slots / 10 * 7; }
+
 __global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_t n_rows,
-                                const int64_t *__restrict__ rptr, int32_t *__restrict__ big_rows,
-                                int *__restrict__ n_big, unsigned long long *__restrict__ max_walk,
+                                const int64_t *__restrict__ rptr, int32_t *__restrict__ cls_rows /*[4][n_rows]*/,
+                                int *__restrict__ n_cls /*[4]*/, int lim1, int lim2,
+                                unsigned long long *__restrict__ max_walk, unsigned long long *__restrict__ sum_walk,
                                 int *__restrict__ n_dup) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    const int32_t *row = knn + (row_begin + r) * k;
     long long walk = 0;
-    for (int c = 0; c < k; ++c) {
-        int j = row[c];
-        walk += rptr[j + 1] - rptr[j];
+    if (r < n_rows) {
+        const int32_t *row = knn + (row_begin + r) * k;
+        for (int c = 0; c < k; ++c) {
+            int j = row[c];
+            walk += rptr[j + 1] - rptr[j];
+        }
+        if (row[0] != row_begin + r) atomicAdd(n_dup, 1);
+        const int cls = walk <= SNN_WALK_LIMIT ? 0 : (walk <= lim1 ? 1 : (walk <= lim2 ? 2 : 3));
+        cls_rows[(int64_t)cls * n_rows + atomicAdd(n_cls + cls, 1)] = (int32_t)r;
     }
-    if (row[0] != row_begin + r) atomicAdd(n_dup, 1);
-    if (walk > SNN_WALK_LIMIT) big_rows[atomicAdd(n_big, 1)] = (int32_t)r;
-    atomicMax(max_walk, (unsigned long long)walk);
+    // block-level max / sum before touching the global atomics
+    unsigned long long wmax = (unsigned long long)walk, wsum = (unsigned long long)walk;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wmax = max(wmax, __shfl_xor_sync(AB_FULL, wmax, o));
+        wsum += __shfl_xor_sync(AB_FULL, wsum, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(max_walk, wmax);
+        atomicAdd(sum_walk, wsum);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
-// small rows: one warp per row, shared-memory hash
+// shared row state: sorted neighbours, their reverse-list extents and walk positions
 // ---------------------------------------------------------------------------------------
 struct WarpRowState {
     int nb[SNN_MAXK];            // sorted neighbour ids
@@ -162,11 +190,12 @@ struct WarpRowState {
 __device__ __forceinline__ unsigned hash_slot(int key) {
     return ((unsigned)key * 2654435761u) >> (32 - 11);          // 2048 slots
 }
+__device__ __forceinline__ unsigned hash_slot_lg(int key, int lg) { return ((unsigned)key * 2654435761u) >> (32 - lg); }
 
-// Loads and sorts row `r`, fills st; returns the walk length.
+// Loads and sorts row `r`, fills st; returns the walk length.  One warp.
 __device__ __forceinline__ int warp_load_row(const int32_t *__restrict__ knn, int k, int64_t grow,
                                              const int64_t *__restrict__ rptr, WarpRowState &st, int lane) {
-    // sort k <= 128 ids: 4 registers per lane, rank by counting through shared memory
+    // sort k <= 128 ids: rank by counting through shared memory
     for (int c = lane; c < k; c += 32) st.base[c] = knn[grow * k + c];       // base[] as scratch
     __syncwarp();
     for (int c = lane; c < k; c += 32) {
@@ -215,12 +244,16 @@ __device__ __forceinline__ int walk_fetch(const WarpRowState &st, int k, int p, 
     return __ldg(rlist + st.start[lo] + (p - st.base[lo]));
 }
 
+// ---------------------------------------------------------------------------------------
+// class 0: one warp per row, shared-memory hash  (value = first position << 8 | count)
+// ---------------------------------------------------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(SNN_WARPS * 32)
-snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_t n_rows,
-                 const int64_t *__restrict__ rptr, const int32_t *__restrict__ rlist, int v_min,
-                 int64_t *__restrict__ rowcount, const int64_t *__restrict__ rowptr_out,
-                 int32_t *__restrict__ src, int32_t *__restrict__ dst, uint8_t *__restrict__ overlap) {
+snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const int32_t *__restrict__ rows,
+                 const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
+                 const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
+                 const int64_t *__restrict__ rowptr_out, int32_t *__restrict__ src, int32_t *__restrict__ dst,
+                 uint8_t *__restrict__ overlap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpRowState &st = reinterpret_cast<WarpRowState *>(smem_raw)[warp];
@@ -228,9 +261,10 @@ snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int6
     int *vals = keys + SNN_SLOTS;
     const int64_t w = (int64_t)blockIdx.x * SNN_WARPS + warp;
     const int64_t nw = (int64_t)gridDim.x * SNN_WARPS;
-    for (int64_t r = w; r < n_rows; r += nw) {
+    const int64_t n_rows = *n_rows_ptr;
+    for (int64_t q = w; q < n_rows; q += nw) {
+        const int64_t r = rows[q];
         const int walk = warp_load_row(knn, k, row_begin + r, rptr, st, lane);
-        if (walk > SNN_WALK_LIMIT) continue;              // big path
         for (int s = lane; s < SNN_SLOTS; s += 32) keys[s] = -1;
         __syncwarp();
         // walk 1: ascending positions; merge duplicates inside a step with match.any
@@ -274,10 +308,10 @@ snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int6
                 }
                 const unsigned b = __ballot_sync(AB_FULL, keep);
                 if (keep) {
-                    const int64_t q = out + __popc(b & ~((2u << lane) - 1));     // higher lanes first
-                    dst[q] = m;
-                    src[q] = grow;
-                    if (overlap) overlap[q] = (uint8_t)cnt;
+                    const int64_t o = out + __popc(b & ~((2u << lane) - 1));     // higher lanes first
+                    dst[o] = m;
+                    src[o] = grow;
+                    if (overlap) overlap[o] = (uint8_t)cnt;
                 }
                 out += __popc(b);
             }
@@ -287,7 +321,186 @@ snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int6
 }
 
 // ---------------------------------------------------------------------------------------
-// big rows: one CTA per row, dense per-CTA arrays in global scratch (cnt, first)
+// classes 1-2: one CTA per row.  The walk is cut into chunks of <= 32 consecutive entries of ONE
+// reverse list (coalesced 128-byte reads, no binary search, no duplicate cell inside a chunk) that
+// the warps take round-robin.  Table value = bitmask over the row's sorted neighbours a that
+// contain the cell: overlap = popcount, first encounter = lowest set bit (the walk visits the
+// lists in ascending a and each list in ascending cell id, so the first encounter of m is at
+// (lowest a, rank of m in R(nb[a]))); atomicOr makes the insertion order irrelevant.
+// ---------------------------------------------------------------------------------------
+struct CtaRowState {
+    WarpRowState w;
+    int chunk0[SNN_MAXK + 1];    // first chunk of each neighbour's list
+    int walk, chunks;
+};
+
+template <int SLOTS, int W, int THREADS, bool FILL>
+__global__ void __launch_bounds__(THREADS)
+snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const int32_t *__restrict__ rows,
+               const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
+               const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
+               const int64_t *__restrict__ rowptr_out, int32_t *__restrict__ src, int32_t *__restrict__ dst,
+               uint8_t *__restrict__ overlap) {
+    static_assert(SLOTS / 10 * 7 / 32 + SNN_MAXK + 1 <= THREADS, "chunk table must fit one scan pass");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *keys = reinterpret_cast<int *>(smem_raw);
+    unsigned *masks = reinterpret_cast<unsigned *>(keys + SLOTS);
+    CtaRowState &st = *reinterpret_cast<CtaRowState *>(masks + (size_t)SLOTS * W);
+    int *chunk_tab = reinterpret_cast<int *>(&st + 1);                 // [THREADS]
+    unsigned *ballots = reinterpret_cast<unsigned *>(chunk_tab + THREADS);   // [THREADS]
+    int *choff = reinterpret_cast<int *>(ballots + THREADS);           // [THREADS]
+    __shared__ int red[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = THREADS / 32;
+    const int n_rows = *n_rows_ptr;
+    for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
+        const int64_t r = rows[q];
+        __syncthreads();                                               // previous row fully retired
+        if (warp == 0) {
+            const int walk = warp_load_row(knn, k, row_begin + r, rptr, st.w, lane);
+            int run = 0;
+            for (int c0 = 0; c0 < k; c0 += 32) {
+                const int c = c0 + lane;
+                const int nch = c < k ? (st.w.base[c + 1] - st.w.base[c] + 31) >> 5 : 0;
+                int inc = nch;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(AB_FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (c < k) st.chunk0[c] = run + inc - nch;
+                run += __shfl_sync(AB_FULL, inc, 31);
+            }
+            if (lane == 0) { st.chunk0[k] = run; st.walk = walk; st.chunks = run; }
+        }
+        __syncthreads();
+        const int walk = st.walk, C = st.chunks;
+        int lg = 6;
+        while ((1 << lg) < 2 * walk && (1 << lg) < SLOTS) ++lg;
+        const int S = 1 << lg;
+        for (int s = threadIdx.x; s < S; s += THREADS) keys[s] = -1;
+        for (int s = threadIdx.x; s < S * W; s += THREADS) masks[s] = 0u;
+        for (int a = warp; a < k; a += NW) {
+            const int c0 = st.chunk0[a], nch = st.chunk0[a + 1] - c0;
+            for (int c = lane; c < nch; c += 32) chunk_tab[c0 + c] = (a << 24) | c;
+        }
+        __syncthreads();
+        // ---- walk: insert ----
+        for (int c = warp; c < C; c += NW) {
+            const int e = chunk_tab[c];
+            const int a = e >> 24, t = ((e & 0xFFFFFF) << 5) + lane;
+            const int len = st.w.base[a + 1] - st.w.base[a];
+            if (t < len) {
+                const int m = __ldg(rlist + st.w.start[a] + t);
+                unsigned s = hash_slot_lg(m, lg);
+                while (true) {
+                    const int prev = atomicCAS(keys + s, -1, m);
+                    if (prev == -1 || prev == m) break;
+                    s = (s + 1) & (S - 1);
+                }
+                atomicOr(masks + (size_t)s * W + (a >> 5), 1u << (a & 31));
+            }
+        }
+        __syncthreads();
+        if (!FILL) {
+            int c = 0;
+            for (int s = threadIdx.x; s < S; s += THREADS) {
+                if (keys[s] != -1) {
+                    int pc = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; ++w2) pc += __popc(masks[(size_t)s * W + w2]);
+                    c += pc >= v_min;
+                }
+            }
+            c = ab_warp_sum_i32(c);
+            if (lane == 0) red[warp] = c;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+                for (int w2 = 0; w2 < NW; ++w2) tot += red[w2];
+                rowcount[r] = tot;
+            }
+        } else {
+            // ---- pass A: which entries of each chunk are kept first encounters ----
+            for (int c = warp; c < C; c += NW) {
+                const int e = chunk_tab[c];
+                const int a = e >> 24, t = ((e & 0xFFFFFF) << 5) + lane;
+                const int len = st.w.base[a + 1] - st.w.base[a];
+                bool keep = false;
+                if (t < len) {
+                    const int m = __ldg(rlist + st.w.start[a] + t);
+                    unsigned s = hash_slot_lg(m, lg);
+                    while (keys[s] != m) s = (s + 1) & (S - 1);
+                    int pc = 0, first = -1;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; ++w2) {
+                        const unsigned mk = masks[(size_t)s * W + w2];
+                        if (first < 0 && mk) first = 32 * w2 + __ffs(mk) - 1;
+                        pc += __popc(mk);
+                    }
+                    keep = (first == a) && pc >= v_min;
+                }
+                const unsigned b = __ballot_sync(AB_FULL, keep);
+                if (lane == 0) ballots[c] = b;
+            }
+            __syncthreads();
+            // ---- suffix sums over chunks: output runs from the LAST walk position to the first ----
+            {
+                const int cidx = C - 1 - (int)threadIdx.x;                 // thread i owns chunk C-1-i
+                const int v = cidx >= 0 ? __popc(ballots[cidx]) : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(AB_FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) red[warp] = inc;
+                __syncthreads();
+                if (warp == 0) {
+                    int x = lane < NW ? red[lane] : 0;
+                    int xi = x;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int t = __shfl_up_sync(AB_FULL, xi, o);
+                        if (lane >= o) xi += t;
+                    }
+                    red[lane] = xi - x;
+                }
+                __syncthreads();
+                if (cidx >= 0) choff[cidx] = red[warp] + inc - v;      // entries emitted before this chunk
+            }
+            __syncthreads();
+            // ---- pass B: emit ----
+            const int64_t out = rowptr_out[r];
+            const int grow = (int)(row_begin + r);
+            for (int c = warp; c < C; c += NW) {
+                const unsigned b = ballots[c];
+                if ((b >> lane) & 1u) {
+                    const int e = chunk_tab[c];
+                    const int a = e >> 24, t = ((e & 0xFFFFFF) << 5) + lane;
+                    const int m = __ldg(rlist + st.w.start[a] + t);
+                    unsigned s = hash_slot_lg(m, lg);
+                    while (keys[s] != m) s = (s + 1) & (S - 1);
+                    int pc = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; ++w2) pc += __popc(masks[(size_t)s * W + w2]);
+                    const int64_t o = out + choff[c] + __popc(b & ~((2u << lane) - 1));   // higher lanes first
+                    dst[o] = m;
+                    src[o] = grow;
+                    if (overlap) overlap[o] = (uint8_t)pc;
+                }
+            }
+        }
+    }
+}
+
+template <int SLOTS, int W, int THREADS>
+static size_t snn_cta_smem() {
+    return (size_t)SLOTS * 4 * (1 + W) + sizeof(CtaRowState) + (size_t)THREADS * 12 + 64;
+}
+
+// ---------------------------------------------------------------------------------------
+// class 3: one CTA per row, dense per-CTA arrays in global scratch (cnt, first); any in-degree
 // ---------------------------------------------------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(SNN_BIG_THREADS)
@@ -385,10 +598,10 @@ struct SnnWs {
     int32_t *rlist;      // n_total*k
     int32_t *tmp;        // n_total*k
     int32_t *long_ids;   // n_total
-    int32_t *big_rows;   // n_rows
+    int32_t *cls_rows;   // 4*n_rows
     int *dense;          // SNN_BIG_CTAS*2*n_total
-    int *counters;       // 8 ints: n_long, n_big, n_dup, bad
-    unsigned long long *max_walk;
+    int *counters;       // 16 ints: [0] n_long, [2] n_dup, [3] bad, [4..7] rows per class
+    unsigned long long *walk_stats;   // [0] max walk, [1] sum of walks
     int64_t *rowcount;   // n_rows+1
     void *scan_ws;
     size_t scan_bytes;
@@ -402,10 +615,10 @@ static size_t snn_layout(int64_t n_total, int32_t k, int64_t n_rows, void *ws, s
     w.rlist = a.take<int32_t>((size_t)n_total * k);
     w.tmp = a.take<int32_t>((size_t)n_total * k);
     w.long_ids = a.take<int32_t>(n_total);
-    w.big_rows = a.take<int32_t>(n_rows > 0 ? n_rows : 1);
+    w.cls_rows = a.take<int32_t>((size_t)4 * (n_rows > 0 ? n_rows : 1));
     w.dense = a.take<int>((size_t)SNN_BIG_CTAS * 2 * n_total);
-    w.counters = a.take<int>(8);
-    w.max_walk = a.take<unsigned long long>(1);
+    w.counters = a.take<int>(16);
+    w.walk_stats = a.take<unsigned long long>(2);
     w.rowcount = a.take<int64_t>(n_rows + 1);
     int64_t big = n_total > n_rows ? n_total : n_rows;
     w.scan_bytes = ab_scan_ws_bytes(big + 1);
@@ -419,6 +632,49 @@ extern "C" size_t ab_snn_ws_bytes(int64_t n_total, int32_t k, int64_t n_rows) {
 }
 
 static size_t snn_small_smem() { return sizeof(WarpRowState) * SNN_WARPS + (size_t)SNN_WARPS * SNN_SLOTS * 2 * sizeof(int); }
+
+// launches the four per-class kernels (count or fill)
+template <bool FILL>
+static int snn_launch_rows(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, int64_t n_total, int k, int64_t row_begin,
+                           int64_t n_rows, int v_min, const int64_t *rowptr, int32_t *src, int32_t *dst,
+                           uint8_t *overlap, cudaStream_t st) {
+    int64_t *rowcount = FILL ? nullptr : w.rowcount;
+    const int32_t *rows0 = w.cls_rows, *rows1 = w.cls_rows + n_rows, *rows2 = w.cls_rows + 2 * n_rows,
+                  *rows3 = w.cls_rows + 3 * n_rows;
+    const int *ncls = w.counters + 4;
+    {
+        const size_t smem = snn_small_smem();
+        AB_CUDA(cudaFuncSetAttribute(snn_small_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t blocks = std::min<int64_t>((n_rows + SNN_WARPS - 1) / SNN_WARPS, (int64_t)ctx->sm_count * 4);
+        snn_small_kernel<FILL><<<(unsigned)blocks, SNN_WARPS * 32, smem, st>>>(
+            knn_all, k, row_begin, rows0, ncls + 0, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    const int64_t cap = std::max<int64_t>(1, n_rows);
+#define AB_SNN_CTA(SLOTS, W, THREADS, ROWS, NPTR, PER_SM)                                                        \
+    do {                                                                                                       \
+        const size_t smem = snn_cta_smem<SLOTS, W, THREADS>();                                                 \
+        AB_CUDA(cudaFuncSetAttribute(snn_cta_kernel<SLOTS, W, THREADS, FILL>,                                  \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        const unsigned grid = (unsigned)std::min<int64_t>(cap, (int64_t)ctx->sm_count * (PER_SM));             \
+        snn_cta_kernel<SLOTS, W, THREADS, FILL><<<grid, THREADS, smem, st>>>(                                  \
+            knn_all, k, row_begin, ROWS, NPTR, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap);    \
+        AB_LAUNCH_CHECK(ctx);                                                                                  \
+    } while (0)
+    if (k <= 32) {
+        AB_SNN_CTA(SNN_MID_SLOTS, 1, SNN_MID_THREADS, rows1, ncls + 1, 6);
+        AB_SNN_CTA(16384, 1, SNN_LARGE_THREADS, rows2, ncls + 2, 1);
+    } else {
+        AB_SNN_CTA(SNN_MID_SLOTS, 4, SNN_MID_THREADS, rows1, ncls + 1, 2);
+        AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows2, ncls + 2, 1);
+    }
+#undef AB_SNN_CTA
+    snn_big_kernel<FILL><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
+        knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, rows3, ncls + 3, w.dense, rowcount, rowptr, src, dst,
+        overlap);
+    AB_LAUNCH_CHECK(ctx);
+    return 0;
+}
 
 extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k, int64_t row_begin,
                             int64_t row_end, int32_t v_min, int64_t *rowptr, int64_t *h_edges, int64_t *stats,
@@ -435,8 +691,8 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     const int64_t total = n_total * k;
     AB_CUDA(cudaMemsetAsync(w.deg, 0, (n_total + 1) * sizeof(int64_t), st));
     AB_CUDA(cudaMemsetAsync(w.cursor, 0, n_total * sizeof(int), st));
-    AB_CUDA(cudaMemsetAsync(w.counters, 0, 8 * sizeof(int), st));
-    AB_CUDA(cudaMemsetAsync(w.max_walk, 0, sizeof(unsigned long long), st));
+    AB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), st));
+    AB_CUDA(cudaMemsetAsync(w.walk_stats, 0, 2 * sizeof(unsigned long long), st));
     const unsigned eb = (unsigned)((total + 255) / 256);
     snn_degree_kernel<<<eb, 256, 0, st>>>(knn_all, total, n_total, w.deg, w.counters + 3);
     AB_LAUNCH_CHECK(ctx);
@@ -452,40 +708,33 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     snn_sort_long_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(w.deg, w.rlist, w.long_ids, w.counters + 0, w.tmp);
     AB_LAUNCH_CHECK(ctx);
     if (n_rows > 0) {
-        snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(knn_all, k, row_begin, n_rows, w.deg,
-                                                                           w.big_rows, w.counters + 1, w.max_walk,
-                                                                           w.counters + 2);
+        snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
+            knn_all, k, row_begin, n_rows, w.deg, w.cls_rows, w.counters + 4, snn_walk_cap(SNN_MID_SLOTS),
+            snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2);
         AB_LAUNCH_CHECK(ctx);
         snn_init_dense_kernel<<<(unsigned)(((int64_t)SNN_BIG_CTAS * 2 * n_total + 255) / 256), 256, 0, st>>>(
             w.dense, n_total, SNN_BIG_CTAS);
         AB_LAUNCH_CHECK(ctx);
-        const size_t smem = snn_small_smem();
-        AB_CUDA(cudaFuncSetAttribute(snn_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int64_t blocks = (n_rows + SNN_WARPS - 1) / SNN_WARPS;
-        if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
-        snn_small_kernel<false><<<(unsigned)blocks, SNN_WARPS * 32, smem, st>>>(
-            knn_all, k, row_begin, n_rows, w.deg, w.rlist, v_min, w.rowcount, nullptr, nullptr, nullptr, nullptr);
-        AB_LAUNCH_CHECK(ctx);
-        snn_big_kernel<false><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
-            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.big_rows, w.counters + 1, w.dense, w.rowcount,
-            nullptr, nullptr, nullptr, nullptr);
-        AB_LAUNCH_CHECK(ctx);
+        if (snn_launch_rows<false>(ctx, w, knn_all, n_total, k, row_begin, n_rows, v_min, nullptr, nullptr, nullptr,
+                                   nullptr, st))
+            return 1;
     }
     if (ab_exclusive_scan_i64(ctx, w.rowcount, rowptr, n_rows, w.scan_ws, w.scan_bytes, st)) return 1;
-    int h_cnt[4];
-    unsigned long long h_walk = 0;
-    AB_CUDA(cudaMemcpyAsync(h_cnt, w.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    AB_CUDA(cudaMemcpyAsync(&h_walk, w.max_walk, sizeof(h_walk), cudaMemcpyDeviceToHost, st));
+    int h_cnt[8];
+    unsigned long long h_walk[2] = {0, 0};
+    AB_CUDA(cudaMemcpyAsync(h_cnt, w.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaMemcpyAsync(h_walk, w.walk_stats, sizeof(h_walk), cudaMemcpyDeviceToHost, st));
     if (h_edges) AB_CUDA(cudaMemcpyAsync(h_edges, rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaStreamSynchronize(st));
-    AB_REQUIRE(h_walk < (1ull << 23), "ab_snn_count: 2-hop walk of %llu exceeds the 2^23 position field", h_walk);
     if (stats) {
-        // host array: {rows on the big path, longest 2-hop walk, rows whose first neighbour is not
-        // the cell itself (duplicate points; alona/clustering.py:204 assumes it is), long reverse lists}
-        stats[0] = h_cnt[1];
-        stats[1] = (int64_t)h_walk;
+        // host array: {rows beyond the one-warp path (classes 1-3), longest 2-hop walk, rows whose first
+        // neighbour is not the cell itself (duplicate points; alona/clustering.py:204 assumes it is),
+        // rows on the dense global path (class 3), sum of all walk lengths (the gather traffic / 4 B)}
+        stats[0] = (int64_t)h_cnt[5] + h_cnt[6] + h_cnt[7];
+        stats[1] = (int64_t)h_walk[0];
         stats[2] = h_cnt[2];
-        stats[3] = h_cnt[0];
+        stats[3] = h_cnt[7];
+        stats[4] = (int64_t)h_walk[1];
     }
     return 0;
 }
@@ -499,17 +748,6 @@ extern "C" int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total,
     size_t need = snn_layout(n_total, k, n_rows, ws, ws_bytes, &w);
     AB_REQUIRE(need != 0, "ab_snn_fill: workspace too small");
     if (n_rows == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = snn_small_smem();
-    AB_CUDA(cudaFuncSetAttribute(snn_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (n_rows + SNN_WARPS - 1) / SNN_WARPS;
-    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
-    snn_small_kernel<true><<<(unsigned)blocks, SNN_WARPS * 32, smem, st>>>(
-        knn_all, k, row_begin, n_rows, w.deg, w.rlist, v_min, nullptr, rowptr, src, dst, overlap);
-    AB_LAUNCH_CHECK(ctx);
-    snn_big_kernel<true><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
-        knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.big_rows, w.counters + 1, w.dense, nullptr, rowptr,
-        src, dst, overlap);
-    AB_LAUNCH_CHECK(ctx);
-    return 0;
+    return snn_launch_rows<true>(ctx, w, knn_all, n_total, k, row_begin, n_rows, v_min, rowptr, src, dst, overlap,
+                                 (cudaStream_t)stream);
 }

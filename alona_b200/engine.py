@@ -204,7 +204,7 @@ class Engine:
         ws = self.workspace(self.lib.ab_snn_ws_bytes(n, k, nrows))
         rowptr = self.empty((nrows + 1,), torch.int64)
         edges = ctypes.c_int64(0)
-        stats = (ctypes.c_int64 * 4)()
+        stats = (ctypes.c_int64 * 8)()
         _lib.check(self.lib.ab_snn_count(self.ctx, _ptr(knn_all), n, k, row_begin, row_end, int(v_min), _ptr(rowptr),
                                          ctypes.byref(edges), stats, _ptr(ws), ws.numel(), self.stream()),
                    'ab_snn_count')
@@ -216,7 +216,7 @@ class Engine:
                    'ab_snn_fill')
         return {'rowptr': rowptr, 'src': src, 'dst': dst, 'overlap': ov,
                 'big_rows': int(stats[0]), 'max_walk': int(stats[1]), 'dup_rows': int(stats[2]),
-                'long_lists': int(stats[3])}
+                'dense_rows': int(stats[3]), 'sum_walk': int(stats[4])}
 
     # -- synthetic data ---------------------------------------------------------------
     def synth_counts(self, prof, cell_begin, n_local, lbar, n_total=None, depth_sigma=0.35, r_disp=5.0,

@@ -210,21 +210,41 @@ def test_snn_row_sharding_and_prune_levels(eng):
         assert np.array_equal(ov.astype(np.int64), ref_c)
 
 
-def test_snn_hub_rows_take_the_big_path(eng):
-    """A star-like table (every cell lists cell 0..k-2) forces huge reverse lists and long walks."""
-    n, k = 3000, 10
-    rng = np.random.RandomState(0)
+def _hub_table(n, k, plan, seed=0):
+    """kNN-like table with graded hubs: row i lists itself, the hubs `plan[i % len(plan)]` and random
+    non-hub cells.  A hub listed by a fraction f of the rows has in-degree f*n, so the 2-hop walk of a
+    row (sum of its neighbours' in-degrees) is controlled by which hubs it lists."""
+    rng = np.random.RandomState(seed)
+    n_hubs = 1 + max(max(p) for p in plan if p)
     nn = np.empty((n, k), dtype=np.int64)
-    nn[:, 0] = np.arange(n)
+    pool = np.arange(n_hubs, n)
     for i in range(n):
-        hubs = [h for h in range(6) if h != i][:5]
-        rest = rng.choice(np.setdiff1d(np.arange(6, n), [i]), k - 1 - len(hubs), replace=False)
-        nn[i, 1:] = np.concatenate([hubs, rest])
-    ref_e, ref_c = R.snn_restated(nn, k, 0.5)
-    res = eng.snn(torch.from_numpy(nn.astype(np.int32)).to(eng.device), R.prune_threshold(k, 0.5))
-    assert res['big_rows'] > 0 and res['long_lists'] > 0
+        hubs = [h for h in plan[i % len(plan)] if h != i]
+        rest = rng.choice(pool, k - 1 - len(hubs) + 1, replace=False)
+        rest = rest[rest != i][:k - 1 - len(hubs)]
+        nn[i] = np.concatenate([[i], hubs, rest])
+    return nn
+
+
+@pytest.mark.parametrize('n,k,plan,prune', [
+    # residues 0..7: walks ~14k (dense path), ~10k (large table), ~6k (large), ~2k (mid table), small x4
+    (16000, 10, [(0, 1, 2, 3), (0, 1), (0,), (4,), (), (), (), ()], 0.2),
+    # k > 32 uses the multi-word bitmask tables (8192/4096 slots): ~7.5k dense, ~4.5k large, ~1.5k mid
+    (6000, 40, [(0, 1, 2), (0,), (), ()], 0.03),
+])
+def test_snn_hub_rows_cover_every_walk_class(eng, n, k, plan, prune):
+    """Hub-heavy tables (every row class: one-warp, mid CTA table, large CTA table, dense global path)."""
+    nn = _hub_table(n, k, plan)
+    ref_e, ref_c = R.snn_restated(nn, k, prune)
+    t = torch.from_numpy(nn.astype(np.int32)).to(eng.device)
+    res = eng.snn(t, R.prune_threshold(k, prune))
+    assert 0 < res['dense_rows'] < res['big_rows'] <= n
     assert np.array_equal(np.stack([res['src'].cpu().numpy(), res['dst'].cpu().numpy()], 1), ref_e)
     assert np.array_equal(res['overlap'].cpu().numpy().astype(np.int64), ref_c)
+    # row sharding must not change anything
+    a = eng.snn(t, R.prune_threshold(k, prune), 0, n // 3)
+    b = eng.snn(t, R.prune_threshold(k, prune), n // 3, n)
+    assert np.array_equal(np.concatenate([a['dst'].cpu().numpy(), b['dst'].cpu().numpy()]), ref_e[:, 1])
 
 
 @pytest.mark.parametrize('case', PIPE_CASES)
