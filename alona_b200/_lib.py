@@ -58,6 +58,9 @@ SIGNATURES = {
     'ab_synth_nb_fill': (ctypes.c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i64, c_f64, c_f64, c_f64, c_u64,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     'ab_launch_count': (c_i64, [c_void_p]),
+    'ab_prof_set_level': (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    'ab_prof_slot_name': (ctypes.c_char_p, [ctypes.c_int]),
+    'ab_prof_read': (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_double), p_i64]),
 }
 
 

@@ -150,11 +150,92 @@ extern "C" int ab_ctx_destroy(ab_ctx *ctx) {
     if (!ctx) return 0;
     if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    for (int i = 0; i < AB_PROF_SLOTS; ++i) {
+        for (cudaEvent_t e : ctx->prof[i].begin) cudaEventDestroy(e);
+        for (cudaEvent_t e : ctx->prof[i].end) cudaEventDestroy(e);
+    }
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     delete ctx;
     return 0;
 }
 
 extern "C" int64_t ab_launch_count(ab_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------
+// CUDA-event profiling slots
+// ---------------------------------------------------------------------------------------
+static const char *const g_prof_names[AB_PROF_SLOTS] = {
+    "norm_moments", "hvg_extract", "irlb_av", "irlb_atw", "irlb_panel", "irlb_small", "knn_prep", "knn_main",
+    "knn_rerank", "snn_build", "snn_count", "snn_fill", "irlb_total", "knn_exact", "", ""};
+
+static bool prof_active(ab_ctx *ctx, int slot) {
+    if (!ctx || ctx->prof_level <= 0 || slot < 0 || slot >= AB_PROF_SLOTS) return false;
+    if (ctx->prof_level < 2 && ((AB_PROF_FINE_MASK >> slot) & 1)) return false;
+    return true;
+}
+static cudaEvent_t prof_event(ab_ctx *ctx) {
+    if (!ctx->prof_pool.empty()) {
+        cudaEvent_t e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void ab_prof_begin(ab_ctx *ctx, int slot, cudaStream_t st) {
+    if (!prof_active(ctx, slot)) return;
+    ab_prof_slot &s = ctx->prof[slot];
+    if (s.open) return;
+    cudaEvent_t e = prof_event(ctx);
+    if (!e) return;
+    cudaEventRecord(e, st);
+    s.begin.push_back(e);
+    s.open = true;
+}
+void ab_prof_end(ab_ctx *ctx, int slot, cudaStream_t st) {
+    if (!prof_active(ctx, slot)) return;
+    ab_prof_slot &s = ctx->prof[slot];
+    if (!s.open) return;
+    cudaEvent_t e = prof_event(ctx);
+    if (!e) { ctx->prof_pool.push_back(s.begin.back()); s.begin.pop_back(); s.open = false; return; }
+    cudaEventRecord(e, st);
+    s.end.push_back(e);
+    s.open = false;
+}
+
+extern "C" int ab_prof_set_level(ab_ctx *ctx, int level) {
+    AB_REQUIRE(ctx, "ab_prof_set_level: null ctx");
+    AB_REQUIRE(level >= 0 && level <= 2, "ab_prof_set_level: level must be 0, 1 or 2");
+    ctx->prof_level = level;
+    return 0;
+}
+
+extern "C" const char *ab_prof_slot_name(int slot) {
+    return (slot >= 0 && slot < AB_PROF_SLOTS) ? g_prof_names[slot] : "";
+}
+
+extern "C" int ab_prof_read(ab_ctx *ctx, int slot, double *h_ms_total, int64_t *h_count) {
+    AB_REQUIRE(ctx, "ab_prof_read: null ctx");
+    AB_REQUIRE(slot >= 0 && slot < AB_PROF_SLOTS, "ab_prof_read: bad slot %d", slot);
+    ab_prof_slot &s = ctx->prof[slot];
+    double total = 0.0;
+    const size_t n = s.end.size();
+    for (size_t i = 0; i < n; ++i) {
+        AB_CUDA(cudaEventSynchronize(s.end[i]));
+        float ms = 0.f;
+        AB_CUDA(cudaEventElapsedTime(&ms, s.begin[i], s.end[i]));
+        total += ms;
+        ctx->prof_pool.push_back(s.begin[i]);
+        ctx->prof_pool.push_back(s.end[i]);
+    }
+    if (s.open) { ctx->prof_pool.push_back(s.begin.back()); s.open = false; }
+    s.begin.clear();
+    s.end.clear();
+    if (h_ms_total) *h_ms_total = total;
+    if (h_count) *h_count = (int64_t)n;
+    return 0;
+}
 
 // ---------------------------------------------------------------------------------------
 // exclusive scan: block partials -> scan of partials (single block) -> block scan + offset

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <limits.h>
 #include <string>
+#include <vector>
 
 #include "../../include/alona_b200.h"
 
@@ -16,6 +17,23 @@
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
+// profiling slots: CUDA-event pairs recorded on the launching stream around the named kernels
+// (ab_prof_set_level: 0 = off, 1 = one pair per stage-level kernel, 2 = every launch incl. the
+// many small IRLBA launches).  bench.py reads them for the roofline fields.
+enum {
+    AB_PROF_NORM = 0, AB_PROF_HVG_EXTRACT = 1, AB_PROF_IRLB_AV = 2, AB_PROF_IRLB_ATW = 3, AB_PROF_IRLB_PANEL = 4,
+    AB_PROF_IRLB_SMALL = 5, AB_PROF_KNN_PREP = 6, AB_PROF_KNN_MAIN = 7, AB_PROF_KNN_RERANK = 8,
+    AB_PROF_SNN_BUILD = 9, AB_PROF_SNN_COUNT = 10, AB_PROF_SNN_FILL = 11, AB_PROF_IRLB_TOTAL = 12,
+    AB_PROF_KNN_EXACT = 13          // AB_PROF_SLOTS (16) comes from the public header
+};
+static const int AB_PROF_FINE_MASK = (1 << AB_PROF_IRLB_AV) | (1 << AB_PROF_IRLB_ATW) | (1 << AB_PROF_IRLB_PANEL) |
+                                     (1 << AB_PROF_IRLB_SMALL);
+
+struct ab_prof_slot {
+    std::vector<cudaEvent_t> begin, end;     // completed or in-flight pairs
+    bool open = false;
+};
+
 struct ab_nccl_api;   // resolved with dlopen, see ab_api.cu
 struct ab_ctx {
     int device = 0;
@@ -27,7 +45,13 @@ struct ab_ctx {
     ab_nccl_api *nccl = nullptr;
     void *comm = nullptr;          // ncclComm_t
     int *d_counter = nullptr;      // device scratch: "last block done" tickets (64 ints, kept 0)
+    int prof_level = 0;
+    ab_prof_slot prof[AB_PROF_SLOTS];
+    std::vector<cudaEvent_t> prof_pool;
 };
+
+void ab_prof_begin(ab_ctx *ctx, int slot, cudaStream_t st);
+void ab_prof_end(ab_ctx *ctx, int slot, cudaStream_t st);
 
 int ab_fail(const char *fmt, ...);                 // sets the thread-local message, returns 1
 const char *ab_cuda_err_name(cudaError_t e);

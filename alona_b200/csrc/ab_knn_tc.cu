@@ -1,23 +1,31 @@
-// K9 tensor-core candidate pass: tiled  s(q,x) = ||x||^2 - 2 q.x  on tcgen05 (TF32 inputs, FP32
+// K9 tensor-core candidate pass: tiled  s(q,x) = ||x||^2 - 2 q.x  on tcgen05 (FP16 inputs, FP32
 // accumulation in TMEM) with a per-query top-m selection epilogue, followed by an exact FP64
 // re-rank that reproduces the reference's number and certifies the result.
 //
 // Replaces the search of AlonaClustering.knn (alona/clustering.py:184-186, scikit-learn BallTree).
 //
-//  prep      centre the embedding (translation invariant, shrinks norms), round to FP32, split
-//            every coordinate into two TF32 pieces (hi = rna(x), lo = rna(x-hi)) and lay out the
-//            K-major operand rows so that ONE GEMM emits finished scores (3xTF32 emulation,
-//            norms folded into three extra K columns):
+//  prep      centre the embedding (translation invariant, shrinks norms), scale by a power of two
+//            so that the largest norm lies in [32,64) (keeps every operand inside FP16 range,
+//            exact), round to FP32 and split every coordinate into two FP16 pieces
+//            (hi = rn(x), lo = rn(x-hi): 22 significant bits, the same split a 3xTF32 scheme
+//            carries, at twice the tensor rate).  The operand rows are laid out so that ONE GEMM
+//            emits finished scores, norms folded into three extra K columns:
 //               A[q] = [  q_hi |  q_hi |  q_lo | 1 1 1 | 0.. ]
 //               B[x] = [-2x_hi |-2x_lo |-2x_hi | n0 n1 n2 | 0.. ],  n0+n1+n2 = ||x||^2
-//  main      persistent warp-specialised kernel, one CTA per SM: warp 0 = TMA producer
-//            (128B-swizzled K chunks through an mbarrier ring), warp 1 = tcgen05.mma issuer
-//            (M=128 queries x N=256 points per tile, two 256-column TMEM accumulators so the
-//            epilogue of tile t overlaps the MMAs of tile t+1), warps 2-5 = epilogue: thread r
-//            owns query row r (= TMEM lane r), pulls 32 columns per tcgen05.ld, compares with
-//            its running threshold (one min-tree + one branch per 32 scores) and, rarely,
-//            inserts into its sorted candidate list.
-//  re-rank   one warp per query: exact distances of the m candidates with the reference's
+//  main      persistent warp-specialised kernel, one CTA per SM:
+//              warp 0   TMA producer: 64-byte-swizzled K chunks (32 halves) through an mbarrier ring;
+//              warp 1   tcgen05.mma issuer (kind::f16, M=128, N=128): every B chunk is multiplied
+//                       against TWO resident 128-query A tiles (256 queries per CTA halve the L2->SMEM
+//                       operand traffic per flop); two 256-column TMEM buffers so the epilogue of
+//                       tile t overlaps the MMAs of tile t+1;
+//              warps 2-9 epilogue: thread <-> query row (= TMEM lane), 32 columns per tcgen05.ld,
+//                       two loads per wait; a min-tree + one
+//                       compare per 32 scores; on a hit the 32 scores are staged to shared memory,
+//                       a hit mask is built, and only the hits are appended to a per-thread buffer
+//                       that a warp-cooperative bitonic merge folds into the sorted m-list.
+//            For wide embeddings (A tiles of 256 queries do not fit) the same kernel runs with ONE
+//            query tile against 256-point B tiles (two lists per query, merged by the re-rank).
+//  re-rank   one warp per query: exact distances of the candidates with the reference's
 //            arithmetic, sort by (distance, index), certificate
 //                 tau + ||q||^2 - eps  >  D_k      (tau = m-th smallest approximate score)
 //            which proves that no point outside the candidate list can enter the top k;
@@ -25,6 +33,7 @@
 //            Uncertified queries are recomputed by the exact FP64 scan (ab_knn_exact.cu).
 #include "ab_common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -36,12 +45,10 @@ int ab_knn_exact_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, con
                      int64_t nq, int k, int splits, const int64_t *out_rows, int32_t *idx, double *rdist,
                      unsigned long long *stats, void *ws, size_t ws_bytes, cudaStream_t st);
 
-static constexpr int TC_BM = 128;            // queries per CTA tile (UMMA M)
-static constexpr int TC_BN = 256;            // database points per tile (UMMA N)
-static constexpr int TC_KCH = 32;            // tf32 elements per K chunk = one 128-byte swizzle row
-static constexpr int TC_A_CHUNK_BYTES = TC_BM * 128;
-static constexpr int TC_B_STAGE_BYTES = TC_BN * 128;
-static constexpr int TC_MAX_STAGES = 6;
+static constexpr int TC_TILE = 128;          // UMMA M and N
+static constexpr int TC_KCH = 32;            // halves per K chunk = one 64-byte swizzle row
+static constexpr int TC_SLAB = TC_TILE * 64; // bytes of one 128-row x 64-byte operand slab (8 KB)
+static constexpr int TC_MAX_STAGES = 12;
 static constexpr int TC_MAX_CHUNKS = 10;     // 3d+3 <= 320  ->  d <= 105
 static constexpr double TC_KAPPA = 1.52587890625e-05;   // 2^-16
 
@@ -88,11 +95,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -109,21 +116,33 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// pins the uses of registers filled by an asynchronous tcgen05.ld behind the wait that precedes this call
+__device__ __forceinline__ void tc_touch32(uint32_t (&r)[32]) {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+// K-major, 64-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// rows of 64 bytes, 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
     d |= (uint64_t)1 << 16;                           // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)(512 >> 4) << 32;                  // stride byte offset: 8 rows x 64 B
     d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    d |= (uint64_t)4 << 61;                           // SWIZZLE_64B
     return d;
 }
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+
+// power-of-two scale that puts the largest centred norm R into [32, 64)
+__device__ __forceinline__ double knn_scale_of(float R) {
+    if (!(R > 0.f) || !isfinite(R)) return 1.0;
+    return ldexp(1.0, 5 - ilogbf(R));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -163,47 +182,69 @@ __global__ void knn_colmean_kernel(const double *__restrict__ partial, int npart
     mean[j] = t / (double)n;
 }
 
-// one warp per point: writes the A and B operand rows, ||x~||^2 and the running max norm
+// largest centred norm (one warp per point), as float bits rounded up
 __global__ void __launch_bounds__(256)
-knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const double *__restrict__ mean,
-                float *__restrict__ aop, float *__restrict__ bop, double *__restrict__ qn, unsigned int *__restrict__ rmax_bits) {
+knn_rmax_kernel(const double *__restrict__ emb, int64_t n, int d, const double *__restrict__ mean,
+                unsigned int *__restrict__ rmax_bits) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * 8;
+    float best = 0.f;
     for (int64_t i = w; i < n; i += nw) {
-        float *a = aop + i * kt, *b = bop + i * kt;
         double n2 = 0.0;
-        for (int j = lane; j < kt; j += 32) {            // clear, then fill
-            a[j] = 0.f; b[j] = 0.f;
-        }
-        __syncwarp();
         for (int j = lane; j < d; j += 32) {
-            const float x = (float)(emb[i * d + j] - mean[j]);
-            const float hi = tf32_rna(x);
-            const float lo = tf32_rna(x - hi);
+            const double x = emb[i * d + j] - mean[j];
+            n2 += x * x;
+        }
+        n2 = ab_warp_sum_f64(n2);
+        best = fmaxf(best, (float)sqrt(n2) * 1.000001f);
+    }
+    if (lane == 0) atomicMax(rmax_bits, __float_as_uint(best));
+}
+
+// one warp per point: writes the FP16 A and B operand rows and ||x~||^2 (unscaled units)
+__global__ void __launch_bounds__(256)
+knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const double *__restrict__ mean,
+                const unsigned int *__restrict__ rmax_bits, __half *__restrict__ aop, __half *__restrict__ bop,
+                double *__restrict__ qn) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    const double sc = knn_scale_of(__uint_as_float(*rmax_bits));
+    const __half zero = __float2half_rn(0.f), one = __float2half_rn(1.f);
+    for (int64_t i = w; i < n; i += nw) {
+        __half *a = aop + i * kt, *b = bop + i * kt;
+        double n2 = 0.0;
+        for (int j = 3 * d + lane; j < kt; j += 32) {            // clear the tail (norm slots are rewritten below)
+            a[j] = zero; b[j] = zero;
+        }
+        for (int j = lane; j < d; j += 32) {
+            const float x = (float)((emb[i * d + j] - mean[j]) * sc);
+            const __half hi = __float2half_rn(x);
+            const __half lo = __float2half_rn(x - __half2float(hi));
+            const __half mhi = __float2half_rn(-2.f * __half2float(hi)), mlo = __float2half_rn(-2.f * __half2float(lo));
             a[j] = hi; a[d + j] = hi; a[2 * d + j] = lo;
-            b[j] = -2.f * hi; b[d + j] = -2.f * lo; b[2 * d + j] = -2.f * hi;
+            b[j] = mhi; b[d + j] = mlo; b[2 * d + j] = mhi;
             n2 += (double)x * (double)x;
         }
         n2 = ab_warp_sum_f64(n2);
+        __syncwarp();
         if (lane == 0) {
-            const float n0 = tf32_rna((float)n2);
-            const double r1 = n2 - (double)n0;
-            const float n1 = tf32_rna((float)r1);
-            const float n2f = tf32_rna((float)(r1 - (double)n1));
-            b[3 * d] = n0; b[3 * d + 1] = n1; b[3 * d + 2] = n2f;
-            a[3 * d] = 1.f; a[3 * d + 1] = 1.f; a[3 * d + 2] = 1.f;
-            qn[i] = n2;
-            atomicMax(rmax_bits, __float_as_uint((float)sqrt(n2) * 1.0000002f));
+            const __half n0 = __double2half(n2);
+            const double r1 = n2 - (double)__half2float(n0);
+            const __half n1 = __double2half(r1);
+            const __half n2h = __double2half(r1 - (double)__half2float(n1));
+            b[3 * d] = n0; b[3 * d + 1] = n1; b[3 * d + 2] = n2h;
+            a[3 * d] = one; a[3 * d + 1] = one; a[3 * d + 2] = one;
+            qn[i] = n2 / (sc * sc);
         }
     }
 }
 
-
 // ---------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------
-static constexpr int TC_EPI_WARPS = 8;                       // two groups of four warps
+static constexpr int TC_EPI_WARPS = 8;                       // two halves of four warps
 static constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 static constexpr int TC_NTHREADS = 64 + TC_EPI_THREADS;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 static constexpr int TC_BUF = 16;                            // per-thread append buffer (entries)
@@ -234,12 +275,12 @@ struct TcParams {
     int64_t n_total;       // database points
     int64_t q_begin;       // first query (row of the operand arrays)
     int64_t nq;            // number of queries
-    int chunks;            // K chunks of 32 tf32
+    int chunks;            // K chunks of 32 halves
+    int ksteps;            // UMMA K steps (16 halves) that carry data: ceil((3d+3)/16)
     int stages;            // B ring depth
-    int m;                 // candidates kept per (query, epilogue group)
-    int sortp;             // power of two >= m + TC_BUF (prune sort size)
-    unsigned long long *cand;   // [2 groups][nq][m] sorted keys
-    unsigned long long *dbg;    // optional [grid][16] cycle counters (AB_KNN_DEBUG=1), else NULL
+    int mt;                // 2: two query tiles x one 128-point B tile; 1: one query tile x 256-point B tile
+    int m;                 // candidates kept per list
+    unsigned long long *cand;   // [lists][nq][m] sorted keys, lists = 3 - mt
 };
 
 // 32-wide bitonic sort across the warp, descending (lane 0 ends with the largest key)
@@ -263,7 +304,7 @@ __device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long 
 // register x[i/32] of lane i%32), keep the m smallest, refresh the lane's threshold.
 // Bitonic split + merge entirely in registers/shuffles.  Warp-uniform call.
 template <int E>
-__device__ __noinline__ void warp_prune_t(unsigned lanes, unsigned long long *cand_group, int64_t q_lane, int &cnt,
+__device__ __noinline__ void warp_prune_t(unsigned lanes, unsigned long long *cand_list0, int64_t q_lane, int &cnt,
                                           float &tau, const unsigned long long *bufcol, int lane) {
     while (lanes) {
         const int L = __ffs(lanes) - 1;
@@ -271,7 +312,7 @@ __device__ __noinline__ void warp_prune_t(unsigned lanes, unsigned long long *ca
         const int cntL = __shfl_sync(AB_FULL, cnt, L);
         const long long qL = __shfl_sync(AB_FULL, (long long)q_lane, L);
         const unsigned long long *colL = (const unsigned long long *)__shfl_sync(AB_FULL, (unsigned long long)bufcol, L);
-        unsigned long long *list = cand_group + (size_t)qL * (32 * E);
+        unsigned long long *list = cand_list0 + (size_t)qL * (32 * E);
         unsigned long long x[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) x[e] = list[e * 32 + lane];
@@ -310,9 +351,9 @@ __device__ __noinline__ void warp_prune_t(unsigned lanes, unsigned long long *ca
     }
 }
 
-__device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, int group, int64_t q_lane, int &cnt,
+__device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, int list_id, int64_t q_lane, int &cnt,
                                            float &tau, const unsigned long long *bufcol, int lane) {
-    unsigned long long *cg = P.cand + (size_t)group * P.nq * P.m;
+    unsigned long long *cg = P.cand + (size_t)list_id * P.nq * P.m;
     switch (P.m) {
         case 32: warp_prune_t<1>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
         case 64: warp_prune_t<2>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
@@ -321,16 +362,71 @@ __device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, in
     }
 }
 
+// Rare path of the epilogue for one unit of 32 scores per lane (warp-uniform call): stage the
+// scores in shared memory (each lane only ever reads back its own row), build the per-lane hit
+// mask and append the hits; lanes whose buffer fills are pruned cooperatively and carry on with
+// the tightened threshold.
+__device__ __forceinline__ void epi_slow_path(const uint32_t (&r)[32], float *stage_row, int sw, bool hit, int nvalid,
+                                           int cbase, const TcParams &P, int list_id, int64_t q, int &cnt, float &tau,
+                                           unsigned long long *bufcol, int lane) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4 *>(stage_row + ((c ^ sw) << 2)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    unsigned mask = 0;
+    if (hit) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) < tau) ? (1u << j) : 0u;
+        if (nvalid < 32) mask &= (1u << nvalid) - 1u;           // columns past the end of the database
+    }
+    __syncwarp();
+    while (__any_sync(AB_FULL, mask != 0u)) {
+        if (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float s = stage_row[(((j >> 2) ^ sw) << 2) | (j & 3)];
+            if (s < tau) {
+                bufcol[(size_t)cnt * TC_EPI_THREADS] = cand_key(s, cbase + j);
+                ++cnt;
+            }
+        }
+        const unsigned fullm = __ballot_sync(AB_FULL, cnt >= TC_BUF);
+        if (fullm) warp_prune(fullm, P, list_id, q, cnt, tau, bufcol, lane);
+    }
+}
+
+// one unit = 32 consecutive scores of this thread's query row
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int64_t cbase, bool live, float *stage_row, int sw,
+                                         const TcParams &P, int list_id, int64_t q, int &cnt, float &tau,
+                                         unsigned long long *bufcol, int lane) {
+    float gmin[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float v = fmin3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+        v = fmin3(v, __uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]));
+        v = fmin3(v, __uint_as_float(r[8 * g + 5]), __uint_as_float(r[8 * g + 6]));
+        gmin[g] = fminf(v, __uint_as_float(r[8 * g + 7]));
+    }
+    const float mn = fminf(fmin3(gmin[0], gmin[1], gmin[2]), gmin[3]);
+    const bool hit = live && mn < tau;
+    if (__any_sync(AB_FULL, hit)) {
+        const int64_t left = P.n_total - cbase;
+        const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+        epi_slow_path(r, stage_row, sw, hit, nvalid, (int)cbase, P, list_id, q, cnt, tau, bufcol, lane);
+    }
+}
+
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: [A chunks][B stages][append buffers][prune scratch][barriers]
+    // layout: [A chunks][B stages][score staging][append buffers][barriers]
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_chunk_bytes = P.mt * TC_SLAB;             // 128*mt query rows x 64 B
+    const int b_stage_bytes = (3 - P.mt) * TC_SLAB;       // 128*(3-mt) database rows x 64 B
     unsigned char *sA = smem;
-    unsigned char *sB = sA + (size_t)P.chunks * TC_A_CHUNK_BYTES;
-    unsigned long long *sBuf = reinterpret_cast<unsigned long long *>(sB + (size_t)P.stages * TC_B_STAGE_BYTES);
-    unsigned long long *sScratch = sBuf + (size_t)TC_BUF * TC_EPI_THREADS;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sScratch + (size_t)TC_EPI_WARPS * P.sortp);
+    unsigned char *sB = sA + (size_t)P.chunks * a_chunk_bytes;
+    float *sStage = reinterpret_cast<float *>(sB + (size_t)P.stages * b_stage_bytes);       // [8 warps][32 rows][32]
+    unsigned long long *sBuf = reinterpret_cast<unsigned long long *>(sStage + TC_EPI_WARPS * 32 * 32);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sBuf + (size_t)TC_BUF * TC_EPI_THREADS);
     uint64_t *full = bars;                          // [stages]
     uint64_t *empty = bars + TC_MAX_STAGES;         // [stages]
     uint64_t *a_full = bars + 2 * TC_MAX_STAGES;
@@ -340,9 +436,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t n_qblocks = (P.nq + TC_BM - 1) / TC_BM;
-    const int64_t n_tiles = (P.n_total + TC_BN - 1) / TC_BN;
-    // q-blocks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int q_per_block = TC_TILE * P.mt;
+    const int x_per_tile = TC_TILE * (3 - P.mt);
+    const int64_t n_qblocks = (P.nq + q_per_block - 1) / q_per_block;
+    const int64_t n_tiles = (P.n_total + x_per_tile - 1) / x_per_tile;
     const int64_t my_blocks = n_qblocks > blockIdx.x ? (n_qblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t my_tiles = my_blocks * n_tiles;   // global tile counter `it` runs over [0, my_tiles)
 
@@ -350,7 +447,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(t_full + b, 1); mbar_init(t_empty + b, 128); }
+        for (int b = 0; b < 2; ++b) { mbar_init(t_full + b, 1); mbar_init(t_empty + b, TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -367,168 +464,113 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, aphase = 0;
-            long long dbg_prod = 0;
-            const long long tstart = clock64();
             for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
                 mbar_wait(a_empty, aphase ^ 1);
-                mbar_expect_tx(a_full, (uint32_t)(P.chunks * TC_A_CHUNK_BYTES));
-                const int qrow = (int)(P.q_begin + qb * TC_BM);
+                mbar_expect_tx(a_full, (uint32_t)(P.chunks * a_chunk_bytes));
+                const int qrow = (int)(P.q_begin + qb * q_per_block);
                 for (int c = 0; c < P.chunks; ++c)
-                    tma_load_2d(sA + (size_t)c * TC_A_CHUNK_BYTES, &map_a, a_full, c * TC_KCH, qrow);
+                    tma_load_2d(sA + (size_t)c * a_chunk_bytes, &map_a, a_full, c * TC_KCH, qrow);
                 aphase ^= 1;
                 for (int64_t t = 0; t < n_tiles; ++t) {
-                    const int xrow = (int)(t * TC_BN);
+                    const int xrow = (int)(t * x_per_tile);
                     for (int c = 0; c < P.chunks; ++c) {
-                        const long long t0 = clock64();
                         mbar_wait(empty + stage, phase ^ 1);
-                        dbg_prod += clock64() - t0;
-                        mbar_expect_tx(full + stage, (uint32_t)TC_B_STAGE_BYTES);
-                        tma_load_2d(sB + (size_t)stage * TC_B_STAGE_BYTES, &map_b, full + stage, c * TC_KCH, xrow);
+                        mbar_expect_tx(full + stage, (uint32_t)b_stage_bytes);
+                        tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, full + stage, c * TC_KCH, xrow);
                         if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            if (P.dbg) { P.dbg[blockIdx.x * 16 + 0] = dbg_prod; P.dbg[blockIdx.x * 16 + 1] = clock64() - tstart; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // instruction descriptor: D=F32, A=B=TF32, K-major both, N=256, M=128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // instruction descriptor: D=F32, A=B=F16, K-major both, N=128, M=128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
             int stage = 0;
             int64_t it = 0, nblocks_done = 0;
-            long long dbg_tempty = 0, dbg_full = 0;
             uint32_t phase = 0, aphase = 0;
             const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+            const uint32_t a_half = P.mt == 2 ? TC_SLAB : 0;          // second query tile
+            const uint32_t b_half = P.mt == 1 ? TC_SLAB : 0;          // second half of a 256-point B tile
             for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
                 mbar_wait(a_full, aphase);
                 aphase ^= 1;
                 for (int64_t t = 0; t < n_tiles; ++t, ++it) {
                     const int buf = (int)(it & 1);
-                    long long t0 = clock64();
                     mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
-                    dbg_tempty += clock64() - t0;
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)buf * TC_BN;
+                    const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
                     for (int c = 0; c < P.chunks; ++c) {
-                        t0 = clock64();
                         mbar_wait(full + stage, phase);
-                        dbg_full += clock64() - t0;
                         tc_fence_after();
-                        const uint32_t a_c = a_addr + (uint32_t)c * TC_A_CHUNK_BYTES;
-                        const uint32_t b_s = b_addr + (uint32_t)stage * TC_B_STAGE_BYTES;
-#pragma unroll
-                        for (int k = 0; k < TC_KCH / 8; ++k)
-                            tc_mma_tf32(tmem_d, umma_desc_sw128(a_c + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
-                                        (uint32_t)((c | k) != 0));
+                        const uint32_t a_c = a_addr + (uint32_t)c * a_chunk_bytes;
+                        const uint32_t b_s = b_addr + (uint32_t)stage * b_stage_bytes;
+                        const int nk = min(2, P.ksteps - 2 * c);
+                        for (int h = 0; h < 2; ++h) {
+                            for (int k = 0; k < nk; ++k)
+                                tc_mma_f16(tmem_d + (uint32_t)h * TC_TILE, umma_desc_sw64(a_c + h * a_half + k * 32),
+                                           umma_desc_sw64(b_s + h * b_half + k * 32), idesc, (uint32_t)((c | k) != 0));
+                        }
                         tc_commit(empty + stage);               // smem slot free once these MMAs retire
                         if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit(t_full + buf);                    // accumulator ready for the epilogue
+                    tc_commit(t_full + buf);                    // accumulators ready for the epilogue
                 }
-                tc_commit(a_empty);                             // A tile may be overwritten
+                tc_commit(a_empty);                             // A tiles may be overwritten
                 ++nblocks_done;
             }
             // do not let the CTA retire with a tcgen05.commit arrive still in flight
             if (nblocks_done > 0) mbar_wait(a_empty, (uint32_t)((nblocks_done - 1) & 1));
-            if (P.dbg) { P.dbg[blockIdx.x * 16 + 2] = dbg_tempty; P.dbg[blockIdx.x * 16 + 3] = dbg_full; }
         }
     } else {
-        // ================= epilogue: two groups alternate tiles; thread <-> query row =================
+        // ================= epilogue: thread <-> query row; warps 2-5 half 0, warps 6-9 half 1 =================
         const int ew = warp - 2;                                // 0..7
-        const int group = ew >> 2;                              // tiles with (it & 1) == group, TMEM buffer = group
+        const int half = ew >> 2;                               // accumulator columns [half*128, half*128+128)
         const int lane_base = (warp & 3) * 32;                  // TMEM lanes this warp may touch
         const int row = lane_base + lane;
         const int etid = ew * 32 + lane;
+        const int list_id = P.mt == 1 ? half : 0;
         unsigned long long *bufcol = sBuf + etid;               // entry e at bufcol[e * TC_EPI_THREADS]
-        const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)group * TC_BN;
+        float *stage_row = sStage + (size_t)(ew * 32 + lane) * 32;
+        const int sw = lane & 7;
+        const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)half * TC_TILE;
         int64_t cur_block = -1, q = 0;
         bool live = false;
         float tau = INFINITY;
         int cnt = 0;
-        long long dbg_wait = 0, dbg_slow = 0, dbg_prune = 0, dbg_nslow = 0, dbg_nprune = 0;
-        const long long tstart = clock64();
-        for (int64_t it = group; it < my_tiles; it += 2) {
+        for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t blk = it / n_tiles, t = it - blk * n_tiles;
+            const int buf = (int)(it & 1);
             if (blk != cur_block) {
-                if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, group, q, cnt, tau, bufcol, lane);
+                if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufcol, lane);
                 cur_block = blk;
-                q = (blockIdx.x + blk * gridDim.x) * TC_BM + row;     // query position inside [0,nq)
+                q = (blockIdx.x + blk * gridDim.x) * q_per_block + (P.mt == 2 ? half * TC_TILE : 0) + row;
                 live = q < P.nq;
                 tau = INFINITY;
                 cnt = 0;
             }
-            long long t0 = clock64();
-            mbar_wait(t_full + group, (uint32_t)((it >> 1) & 1));
-            dbg_wait += clock64() - t0;
+            mbar_wait(t_full + buf, (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            const int64_t col0 = t * TC_BN;
+            const int64_t col0 = t * x_per_tile + (P.mt == 1 ? half * TC_TILE : 0);
+            const uint32_t taddr = taddr0 + (uint32_t)buf * 256;
+            uint32_t ra[32], rb[32];
 #pragma unroll 1
-            for (int cc = 0; cc < TC_BN / 32; ++cc) {
-                uint32_t r[32];
-                tc_ld32(taddr + cc * 32, r);
+            for (int c2 = 0; c2 < TC_TILE / 64; ++c2) {
+                // two units per wait: no tcgen05.ld is in flight while the (call-heavy) rare path runs
+                tc_ld32(taddr + (2 * c2) * 32, ra);
+                tc_ld32(taddr + (2 * c2 + 1) * 32, rb);
                 tc_wait_ld();
-                float gmin[4];
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float v = fmin3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
-                    v = fmin3(v, __uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]));
-                    v = fmin3(v, __uint_as_float(r[8 * g + 5]), __uint_as_float(r[8 * g + 6]));
-                    gmin[g] = fminf(v, __uint_as_float(r[8 * g + 7]));
-                }
-                const float mn = fminf(fmin3(gmin[0], gmin[1], gmin[2]), gmin[3]);
-                bool active = live && mn < tau;
-                if (__any_sync(AB_FULL, active)) {
-                    const long long ts = clock64();
-                    ++dbg_nslow;
-                    // rare path: append passing scores; a lane whose buffer fills stops at `jnext`, is pruned
-                    // (warp-cooperatively) and resumes from there with its tightened threshold
-                    const int64_t cbase = col0 + cc * 32;
-                    int jnext = 0;
-                    while (true) {
-                        if (active) {
-                            bool stopped = false;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (gmin[g] < tau) {
-#pragma unroll
-                                    for (int jj = 0; jj < 8; ++jj) {
-                                        const int j = 8 * g + jj;
-                                        const float s = __uint_as_float(r[j]);
-                                        if (!stopped && j >= jnext && s < tau && cbase + j < P.n_total) {
-                                            if (cnt < TC_BUF) {
-                                                bufcol[(size_t)cnt * TC_EPI_THREADS] = cand_key(s, (int)(cbase + j));
-                                                ++cnt;
-                                            } else {
-                                                jnext = j;
-                                                stopped = true;
-                                            }
-                                        }
-                                    }
-                                }
-                            }
-                            active = stopped;
-                        }
-                        const unsigned fullm = __ballot_sync(AB_FULL, cnt >= TC_BUF);
-                        if (fullm) {
-                            const long long tp = clock64();
-                            warp_prune(fullm, P, group, q, cnt, tau, bufcol, lane);
-                            dbg_prune += clock64() - tp;
-                            dbg_nprune += __popc(fullm);
-                        }
-                        if (!__any_sync(AB_FULL, active)) break;
-                    }
-                    dbg_slow += clock64() - ts;
-                }
+                tc_touch32(ra);
+                tc_touch32(rb);
+                epi_unit(ra, col0 + (2 * c2) * 32, live, stage_row, sw, P, list_id, q, cnt, tau, bufcol, lane);
+                epi_unit(rb, col0 + (2 * c2 + 1) * 32, live, stage_row, sw, P, list_id, q, cnt, tau, bufcol, lane);
             }
             tc_fence_before();
-            mbar_arrive(t_empty + group);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty + buf);
         }
-        if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, group, q, cnt, tau, bufcol, lane);
-        if (P.dbg && ew == 0 && lane == 0) {
-            unsigned long long *o = P.dbg + blockIdx.x * 16 + 4;
-            o[0] = dbg_wait; o[1] = dbg_slow; o[2] = dbg_prune; o[3] = dbg_nslow; o[4] = dbg_nprune; o[5] = clock64() - tstart;
-        }
+        if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufcol, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -545,15 +587,17 @@ __device__ __forceinline__ bool pair_lt(double da, int ia, double db, int ib) { 
 
 __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k, int m,
-                  const unsigned long long *__restrict__ cand, const double *__restrict__ qn,
+                  int lists, const unsigned long long *__restrict__ cand, const double *__restrict__ qn,
                   const unsigned int *__restrict__ rmax_bits, int32_t *__restrict__ idx, double *__restrict__ rdist,
                   int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mp = 2 * m;                                  // both epilogue groups' lists; power of two
+    const int mp = lists * m;                              // all lists of the query; power of two
     double *sd = reinterpret_cast<double *>(sm_raw) + (size_t)warp * mp;
     int *si = reinterpret_cast<int *>(sm_raw + (size_t)8 * mp * sizeof(double)) + (size_t)warp * mp;
     const float R = __uint_as_float(*rmax_bits);
+    const double sc = knn_scale_of(R);
+    const double inv_sc2 = 1.0 / (sc * sc);                // scores are in scaled units
     for (int64_t q = (int64_t)blockIdx.x * 8 + warp; q < nq; q += (int64_t)gridDim.x * 8) {
         const int64_t qid = q_begin + q;
         const double *qv = emb + qid * d;
@@ -575,7 +619,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                 }
                 dist = acc;
                 id = cnd;
-                const double approx = (double)key_score(key) + qnorm2;
+                const double approx = (double)key_score(key) * inv_sc2 + qnorm2;
                 worst_rel = fmax(worst_rel, fabs(approx - acc) / (scale * scale));
             }
             sd[c] = dist;
@@ -602,11 +646,11 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         }
         if (lane == 0) {
             const double dk = sd[k - 1];
-            // a group whose list is not full holds every point it saw -> no outside point there
+            // a list that is not full holds every point it saw -> no outside point there
             double tau = INFINITY;
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < lists; ++g) {
                 const unsigned long long last = cand[((size_t)g * nq + q) * m + (m - 1)];
-                if (last != TC_KEY_MAX) tau = fmin(tau, (double)key_score(last));
+                if (last != TC_KEY_MAX) tau = fmin(tau, (double)key_score(last) * inv_sc2);
             }
             const double eps = TC_KAPPA * scale * scale;
             // every point outside the lists has  D >= tau + ||q||^2 - eps ; strict '>' also settles ties
@@ -638,14 +682,15 @@ static int tc_candidates(int k) {
     return std::min(m, 256);
 }
 static int tc_kt(int d) { return (3 * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
+// two resident query tiles when their A operand (256 rows x kt halves) leaves room for the B ring
+static int tc_mt(int d) { return tc_kt(d) * 2 * 256 <= 96 * 1024 ? 2 : 1; }
 
 struct TcWs {
     double *mean, *partial, *qn;
-    float *aop, *bop;
+    __half *aop, *bop;
     unsigned long long *cand;
     int64_t *fb_list;
     unsigned int *scal;      // [0] rmax bits, [1] relerr bits
-    unsigned long long *dbg; // [256][16]
     void *exact_ws;
     size_t exact_bytes;
 };
@@ -654,15 +699,14 @@ static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t by
     ab_arena a(ws ? ws : (void *)1024, ws ? bytes : (size_t)-1 / 2);
     TcWs w;
     const int kt = tc_kt(d), m = tc_candidates(k);
-    w.aop = a.take<float>((size_t)n * kt);
-    w.bop = a.take<float>((size_t)n * kt);
+    w.aop = a.take<__half>((size_t)n * kt);
+    w.bop = a.take<__half>((size_t)n * kt);
     w.mean = a.take<double>(d);
     w.partial = a.take<double>((size_t)1024 * d);
     w.qn = a.take<double>(n);
     w.cand = a.take<unsigned long long>((size_t)2 * nq * m);
     w.fb_list = a.take<int64_t>((size_t)2 * nq);
     w.scal = a.take<unsigned int>(4);
-    w.dbg = a.take<unsigned long long>(256 * 16);
     // the exact scan only ever sees the uncertified minority; reserve room for 1/8 of the queries
     w.exact_bytes = ab_knn_exact_ws_bytes(std::max<int64_t>(1024, nq / 8), k, 64);
     w.exact_ws = a.take<char>(w.exact_bytes);
@@ -678,7 +722,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap *map, float *base, int64_t rows, int kt, int box_rows) {
+static int make_map(CUtensorMap *map, __half *base, int64_t rows, int kt, int box_rows) {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -688,11 +732,11 @@ static int make_map(CUtensorMap *map, float *base, int64_t rows, int kt, int box
         fn = (PFN_encodeTiled)p;
     }
     cuuint64_t gdim[2] = {(cuuint64_t)kt, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)kt * sizeof(float)};
+    cuuint64_t gstr[1] = {(cuuint64_t)kt * sizeof(__half)};
     cuuint32_t box[2] = {(cuuint32_t)TC_KCH, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return ab_fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;
 }
@@ -700,7 +744,7 @@ static int make_map(CUtensorMap *map, float *base, int64_t rows, int kt, int box
 int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k,
                   int32_t *idx, double *rdist, unsigned long long *stats, void *ws, size_t ws_bytes, cudaStream_t st) {
     const int kt = tc_kt(d), chunks = kt / TC_KCH, m = tc_candidates(k);
-    if (chunks > TC_MAX_CHUNKS || n_total < m || n_total >= ((int64_t)1 << 31) - TC_BN) {
+    if (chunks > TC_MAX_CHUNKS || n_total < m || n_total >= ((int64_t)1 << 31) - 512) {
         // outside the tensor path's envelope (very wide embeddings, tiny inputs): exact scan
         return ab_knn_exact_run(ctx, emb, n_total, d, nullptr, q_begin, nq, k, ab_knn_exact_pick_splits(ctx, nq), nullptr,
                                 idx, rdist, stats, ws, ws_bytes, st);
@@ -708,67 +752,64 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     TcWs w;
     AB_REQUIRE(tc_layout(n_total, d, nq, k, ws, ws_bytes, &w) != 0, "ab_knn: workspace too small");
     AB_CUDA(cudaMemsetAsync(w.scal, 0, 4 * sizeof(unsigned int), st));
+    const int mt = tc_mt(d), lists = 3 - mt;
     // ---- prep ----
+    ab_prof_begin(ctx, AB_PROF_KNN_PREP, st);
     const int parts = (int)std::min<int64_t>(1024, std::max<int64_t>(1, n_total / 64));
     knn_colsum_kernel<<<parts, 256, 0, st>>>(emb, n_total, d, w.partial);
     AB_LAUNCH_CHECK(ctx);
     knn_colmean_kernel<<<(d + 127) / 128, 128, 0, st>>>(w.partial, parts, d, n_total, w.mean);
     AB_LAUNCH_CHECK(ctx);
     const unsigned g_prep = (unsigned)std::min<int64_t>((n_total + 7) / 8, (int64_t)ctx->sm_count * 16);
-    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, kt, w.mean, w.aop, w.bop, w.qn, w.scal);
+    knn_rmax_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, w.mean, w.scal);
     AB_LAUNCH_CHECK(ctx);
-    AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)2 * nq * m * sizeof(unsigned long long), st));
+    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, kt, w.mean, w.scal, w.aop, w.bop, w.qn);
+    AB_LAUNCH_CHECK(ctx);
+    AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)lists * nq * m * sizeof(unsigned long long), st));
+    ab_prof_end(ctx, AB_PROF_KNN_PREP, st);
     // ---- main ----
     CUtensorMap map_a, map_b;
-    if (make_map(&map_a, w.aop, n_total, kt, TC_BM)) return 1;
-    if (make_map(&map_b, w.bop, n_total, kt, TC_BN)) return 1;
-    const size_t a_bytes = (size_t)chunks * TC_A_CHUNK_BYTES;
+    if (make_map(&map_a, w.aop, n_total, kt, TC_TILE * mt)) return 1;
+    if (make_map(&map_b, w.bop, n_total, kt, TC_TILE * (3 - mt))) return 1;
+    const size_t a_bytes = (size_t)chunks * mt * TC_SLAB;
+    const size_t b_stage = (size_t)(3 - mt) * TC_SLAB;
     const size_t bar_bytes = 256;
-    const int sortp = 0;                       // prune works in registers; no shared scratch
-    const size_t epi_bytes = (size_t)TC_BUF * TC_EPI_THREADS * 8 + (size_t)TC_EPI_WARPS * sortp * 8;
-    int stages = (int)(((size_t)ctx->smem_optin - 1024 - a_bytes - bar_bytes - epi_bytes) / TC_B_STAGE_BYTES);
+    const size_t epi_bytes = (size_t)TC_EPI_WARPS * 32 * 32 * 4 + (size_t)TC_BUF * TC_EPI_THREADS * 8;
+    AB_REQUIRE((size_t)ctx->smem_optin > 1024 + a_bytes + bar_bytes + epi_bytes + 2 * b_stage,
+               "ab_knn: not enough shared memory for d=%d k=%d", d, k);
+    int stages = (int)(((size_t)ctx->smem_optin - 1024 - a_bytes - bar_bytes - epi_bytes) / b_stage);
     stages = std::min(stages, TC_MAX_STAGES);
-    AB_REQUIRE(stages >= 2, "ab_knn: not enough shared memory for d=%d k=%d", d, k);
-    const size_t smem = 1024 + a_bytes + (size_t)stages * TC_B_STAGE_BYTES + epi_bytes + bar_bytes;
+    const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + epi_bytes + bar_bytes;
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcParams P;
-    P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.stages = stages; P.m = m;
-    P.sortp = sortp; P.cand = w.cand;
-    const bool debug = getenv("AB_KNN_DEBUG") != nullptr;
-    P.dbg = debug ? w.dbg : nullptr;
-    if (debug) AB_CUDA(cudaMemsetAsync(w.dbg, 0, 256 * 16 * 8, st));
-    const int64_t n_qblocks = (nq + TC_BM - 1) / TC_BM;
+    P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (3 * d + 3 + 15) / 16;
+    P.stages = stages; P.mt = mt; P.m = m; P.cand = w.cand;
+    const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
     const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
+    ab_prof_begin(ctx, AB_PROF_KNN_MAIN, st);
     knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, map_b, P);
     AB_LAUNCH_CHECK(ctx);
+    ab_prof_end(ctx, AB_PROF_KNN_MAIN, st);
     // ---- exact re-rank + certificate ----
-    const int mp = 2 * m;
+    ab_prof_begin(ctx, AB_PROF_KNN_RERANK, st);
+    const int mp = lists * m;
     const size_t rr_smem = (size_t)8 * mp * (sizeof(double) + sizeof(int));
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     const unsigned g_rr = (unsigned)std::min<int64_t>((nq + 7) / 8, (int64_t)ctx->sm_count * 8);
-    knn_rerank_kernel<<<g_rr, 256, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, w.cand, w.qn, w.scal,
+    knn_rerank_kernel<<<g_rr, 256, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
                                                   idx, rdist, w.fb_list, stats, w.scal + 1);
     AB_LAUNCH_CHECK(ctx);
+    ab_prof_end(ctx, AB_PROF_KNN_RERANK, st);
     // ---- uncertified queries: exact scan ----
     unsigned long long h_stats[4];
     unsigned int h_scal[2];
     AB_CUDA(cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaMemcpyAsync(h_scal, w.scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaStreamSynchronize(st));
-    if (debug) {
-        static unsigned long long h_dbg[256 * 16];
-        AB_CUDA(cudaMemcpy(h_dbg, w.dbg, sizeof(h_dbg), cudaMemcpyDeviceToHost));
-        const char *names[10] = {"prod_wait_empty", "prod_total", "mma_wait_tempty", "mma_wait_full", "epi_wait_tfull",
-                                 "epi_slow", "epi_prune", "epi_nslow", "epi_nprune", "epi_total"};
-        for (int c = 0; c < 10; ++c) {
-            double sum = 0;
-            for (unsigned b = 0; b < grid; ++b) sum += (double)h_dbg[b * 16 + c];
-            fprintf(stderr, "[knn dbg] %-16s avg/CTA %.3e\n", names[c], sum / grid);
-        }
-    }
     const int64_t n_fb = (int64_t)h_stats[1];
-    // stats[4] = max observed |approx - exact| / (||q||+R)^2 as float bits, stats[5] = candidates per query
-    unsigned long long extra[2] = {(unsigned long long)h_scal[1], (unsigned long long)m};
+    // stats[4] = max observed |approx - exact| / (||q||+R)^2 as float bits, stats[5] = candidates per list,
+    // stats[6] = query tiles per CTA (2: 256-query blocks, 1: wide embeddings)
+    unsigned long long extra[3] = {(unsigned long long)h_scal[1], (unsigned long long)m, (unsigned long long)mt};
     AB_CUDA(cudaMemcpyAsync(stats + 4, extra, sizeof(extra), cudaMemcpyHostToDevice, st));
     if (n_fb > 0) {
         int64_t done = 0;

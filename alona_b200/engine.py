@@ -68,6 +68,25 @@ class Engine:
     def launch_count(self):
         return int(self.lib.ab_launch_count(self.ctx))
 
+    # -- measurement ------------------------------------------------------------------
+    def prof_set_level(self, level):
+        """0 = off, 1 = stage-level kernels, 2 = every IRLBA launch too (include/alona_b200.h)."""
+        _lib.check(self.lib.ab_prof_set_level(self.ctx, int(level)), 'ab_prof_set_level')
+
+    def prof_read(self):
+        """{slot name: (device ms since the last read, event pairs)} for the slots that recorded."""
+        out = {}
+        for slot in range(16):
+            name = self.lib.ab_prof_slot_name(slot).decode()
+            if not name:
+                continue
+            ms = ctypes.c_double(0.0)
+            cnt = ctypes.c_int64(0)
+            _lib.check(self.lib.ab_prof_read(self.ctx, slot, ctypes.byref(ms), ctypes.byref(cnt)), 'ab_prof_read')
+            if cnt.value:
+                out[name] = (ms.value, cnt.value)
+        return out
+
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 

@@ -33,6 +33,7 @@ def main():
     ap.add_argument('--snn', action='store_true')
     a = ap.parse_args()
     eng = get_engine()
+    eng.prof_set_level(1)
     emb = mixture(a.n, a.d, eng.device)
     for k in [int(x) for x in a.ks.split(',')]:
         for rep in range(a.reps):
@@ -40,10 +41,14 @@ def main():
             idx, rd, st = eng.knn(emb, k)
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
         s = st.cpu().numpy()
+        prof = eng.prof_read()
         relerr = float(np.array([s[4]], dtype=np.uint32).view(np.float32)[0])
         rec = {'n': a.n, 'd': a.d, 'k': k, 'knn_s': dt, 'tflops_alg': 2.0 * a.n * a.n * a.d / dt / 1e12,
                'tie_rows': int(s[0]), 'fallback_rows': int(s[1]), 'dup_rows': int(s[2]), 'certified': int(s[3]),
-               'max_rel_err': relerr, 'kappa': 2.0 ** -16, 'm': int(s[5])}
+               'max_rel_err': relerr, 'kappa': 2.0 ** -16, 'm': int(s[5]), 'mt': int(s[6]),
+               'kernel_ms': {k2: round(v[0] / v[1], 3) for k2, v in prof.items()},
+               'tflops_alg_main': 2.0 * a.n * a.n * a.d / (prof['knn_main'][0] / prof['knn_main'][1] / 1e3) / 1e12
+               if 'knn_main' in prof else None}
         if a.check:
             lo = (a.n // 2 // 128) * 128
             ex, exd, _ = eng.knn(emb, k, q_begin=lo, q_end=min(a.n, lo + a.check), mode=1)
