@@ -90,6 +90,16 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// exactly one lane of the (converged) warp gets true; ptxas keeps the code under it on uniform registers
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -460,69 +470,76 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, aphase = 0;
-            for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
-                mbar_wait(a_empty, aphase ^ 1);
+        // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
+        int stage = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+            mbar_wait(a_empty, aphase ^ 1);
+            const int qrow = (int)(P.q_begin + qb * q_per_block);
+            if (elect_one()) {
                 mbar_expect_tx(a_full, (uint32_t)(P.chunks * a_chunk_bytes));
-                const int qrow = (int)(P.q_begin + qb * q_per_block);
                 for (int c = 0; c < P.chunks; ++c)
                     tma_load_2d(sA + (size_t)c * a_chunk_bytes, &map_a, a_full, c * TC_KCH, qrow);
-                aphase ^= 1;
-                for (int64_t t = 0; t < n_tiles; ++t) {
-                    const int xrow = (int)(t * x_per_tile);
-                    for (int c = 0; c < P.chunks; ++c) {
-                        mbar_wait(empty + stage, phase ^ 1);
+            }
+            __syncwarp();
+            aphase ^= 1;
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const int xrow = (int)(t * x_per_tile);
+                for (int c = 0; c < P.chunks; ++c) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    if (elect_one()) {
                         mbar_expect_tx(full + stage, (uint32_t)b_stage_bytes);
                         tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, full + stage, c * TC_KCH, xrow);
-                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            // instruction descriptor: D=F32, A=B=F16, K-major both, N=128, M=128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
-            int stage = 0;
-            int64_t it = 0, nblocks_done = 0;
-            uint32_t phase = 0, aphase = 0;
-            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-            const uint32_t a_half = P.mt == 2 ? TC_SLAB : 0;          // second query tile
-            const uint32_t b_half = P.mt == 1 ? TC_SLAB : 0;          // second half of a 256-point B tile
-            for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
-                mbar_wait(a_full, aphase);
-                aphase ^= 1;
-                for (int64_t t = 0; t < n_tiles; ++t, ++it) {
-                    const int buf = (int)(it & 1);
-                    mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
+        // ================= MMA issuer (warp-uniform control flow, one elected lane issues) =================
+        // instruction descriptor: D=F32, A=B=F16, K-major both, N=128, M=128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+        int stage = 0;
+        int64_t it = 0, nblocks_done = 0;
+        uint32_t phase = 0, aphase = 0;
+        // descriptors: only the 14-bit start-address field changes; every offset used here is a multiple of 16
+        const uint64_t a_desc0 = umma_desc_sw64(smem_u32(sA)), b_desc0 = umma_desc_sw64(smem_u32(sB));
+        const uint32_t a_step = (uint32_t)a_chunk_bytes >> 4, b_step = (uint32_t)b_stage_bytes >> 4;
+        const uint32_t a_half = P.mt == 2 ? (TC_SLAB >> 4) : 0;       // second query tile
+        const uint32_t b_half = P.mt == 1 ? (TC_SLAB >> 4) : 0;       // second half of a 256-point B tile
+        for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+            mbar_wait(a_full, aphase);
+            aphase ^= 1;
+            for (int64_t t = 0; t < n_tiles; ++t, ++it) {
+                const int buf = (int)(it & 1);
+                mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
+                for (int c = 0; c < P.chunks; ++c) {
+                    mbar_wait(full + stage, phase);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
-                    for (int c = 0; c < P.chunks; ++c) {
-                        mbar_wait(full + stage, phase);
-                        tc_fence_after();
-                        const uint32_t a_c = a_addr + (uint32_t)c * a_chunk_bytes;
-                        const uint32_t b_s = b_addr + (uint32_t)stage * b_stage_bytes;
-                        const int nk = min(2, P.ksteps - 2 * c);
-                        for (int h = 0; h < 2; ++h) {
-                            for (int k = 0; k < nk; ++k)
-                                tc_mma_f16(tmem_d + (uint32_t)h * TC_TILE, umma_desc_sw64(a_c + h * a_half + k * 32),
-                                           umma_desc_sw64(b_s + h * b_half + k * 32), idesc, (uint32_t)((c | k) != 0));
-                        }
+                    if (elect_one()) {
+                        const uint64_t a_c = a_desc0 + (uint64_t)((uint32_t)c * a_step);
+                        const uint64_t b_s = b_desc0 + (uint64_t)((uint32_t)stage * b_step);
+                        const bool two = P.ksteps - 2 * c >= 2;
+                        tc_mma_f16(tmem_d, a_c, b_s, idesc, (uint32_t)(c != 0));
+                        if (two) tc_mma_f16(tmem_d, a_c + 2, b_s + 2, idesc, 1u);
+                        tc_mma_f16(tmem_d + TC_TILE, a_c + a_half, b_s + b_half, idesc, (uint32_t)(c != 0));
+                        if (two) tc_mma_f16(tmem_d + TC_TILE, a_c + a_half + 2, b_s + b_half + 2, idesc, 1u);
                         tc_commit(empty + stage);               // smem slot free once these MMAs retire
-                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                        if (c == P.chunks - 1) tc_commit(t_full + buf);   // accumulators ready for the epilogue
                     }
-                    tc_commit(t_full + buf);                    // accumulators ready for the epilogue
+                    __syncwarp();
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(a_empty);                             // A tiles may be overwritten
-                ++nblocks_done;
             }
-            // do not let the CTA retire with a tcgen05.commit arrive still in flight
-            if (nblocks_done > 0) mbar_wait(a_empty, (uint32_t)((nblocks_done - 1) & 1));
+            if (elect_one()) tc_commit(a_empty);                // A tiles may be overwritten
+            __syncwarp();
+            ++nblocks_done;
         }
+        // do not let the CTA retire with a tcgen05.commit arrive still in flight
+        if (nblocks_done > 0) mbar_wait(a_empty, (uint32_t)((nblocks_done - 1) & 1));
     } else {
         // ================= epilogue: thread <-> query row; warps 2-5 half 0, warps 6-9 half 1 =================
         const int ew = warp - 2;                                // 0..7
