@@ -13,7 +13,8 @@
 //               A[q] = [  q_hi |  q_hi |  q_lo | 1 1 1 | 0.. ]
 //               B[x] = [-2x_hi |-2x_lo |-2x_hi | n0 n1 n2 | 0.. ],  n0+n1+n2 = ||x||^2
 //  main      persistent warp-specialised kernel, one CTA per SM:
-//              warp 0   TMA producer: 64-byte-swizzled K chunks (32 halves) through an mbarrier ring;
+//              warp 0   TMA producer: B arrives as contiguous 8 KB bulk copies (one 128-point x 32-half K chunk,
+//                       stored pre-swizzled in HBM) through an mbarrier ring; A by 2-D tensor-map loads;
 //              warp 1   tcgen05.mma issuer (kind::f16, M=128, N=128): every B chunk is multiplied
 //                       against TWO resident 128-query A tiles (256 queries per CTA halve the L2->SMEM
 //                       operand traffic per flop); two 256-column TMEM buffers so the epilogue of
@@ -99,6 +100,13 @@ __device__ __forceinline__ bool elect_one() {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(pred));
     return pred != 0;
+}
+// 1-D bulk copy global -> shared (UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -212,9 +220,22 @@ knn_rmax_kernel(const double *__restrict__ emb, int64_t n, int d, const double *
     if (lane == 0) atomicMax(rmax_bits, __float_as_uint(best));
 }
 
-// one warp per point: writes the FP16 A and B operand rows and ||x~||^2 (unscaled units)
+// Position (in halves) of element (row i, K column j) of the B operand.  B is stored as the exact
+// shared-memory image the MMA reads: slabs of 128 rows, inside a slab one 8 KB block per K chunk
+// (128 rows x 64 B) with the 64-byte swizzle (16-byte unit index ^= (row>>1)&3) already applied, so
+// a pipeline stage is ONE contiguous 8 KB bulk copy instead of 128 strided 64-byte row requests
+// (a 2-D tensor-map load of such narrow rows is bound by the TMA's per-row request rate).
+__host__ __device__ __forceinline__ size_t knn_b_pos(int64_t i, int j, int chunks) {
+    const int64_t slab = i >> 7;
+    const int r = (int)(i & 127), c = j >> 5, jj = j & 31;
+    return ((size_t)slab * chunks + c) * 4096 + (size_t)r * 32 + ((((jj >> 3) ^ ((r >> 1) & 3)) << 3) | (jj & 7));
+}
+
+// one warp per point: writes the FP16 A and B operand rows and ||x~||^2 (unscaled units).
+// B has n_pad >= n rows (a whole number of tiles): padding rows are all zero except a norm of
+// 60000, larger than any real score (<= (2*64)^2), so padded columns never pass a threshold.
 __global__ void __launch_bounds__(256)
-knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const double *__restrict__ mean,
+knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d, int kt, const double *__restrict__ mean,
                 const unsigned int *__restrict__ rmax_bits, __half *__restrict__ aop, __half *__restrict__ bop,
                 double *__restrict__ qn) {
     const int lane = threadIdx.x & 31;
@@ -222,11 +243,12 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const 
     const int64_t nw = (int64_t)gridDim.x * 8;
     const double sc = knn_scale_of(__uint_as_float(*rmax_bits));
     const __half zero = __float2half_rn(0.f), one = __float2half_rn(1.f);
+    const int chunks = kt / TC_KCH;
     for (int64_t i = w; i < n; i += nw) {
-        __half *a = aop + i * kt, *b = bop + i * kt;
+        __half *a = aop + i * kt;
         double n2 = 0.0;
         for (int j = 3 * d + lane; j < kt; j += 32) {            // clear the tail (norm slots are rewritten below)
-            a[j] = zero; b[j] = zero;
+            a[j] = zero; bop[knn_b_pos(i, j, chunks)] = zero;
         }
         for (int j = lane; j < d; j += 32) {
             const float x = (float)((emb[i * d + j] - mean[j]) * sc);
@@ -234,7 +256,9 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const 
             const __half lo = __float2half_rn(x - __half2float(hi));
             const __half mhi = __float2half_rn(-2.f * __half2float(hi)), mlo = __float2half_rn(-2.f * __half2float(lo));
             a[j] = hi; a[d + j] = hi; a[2 * d + j] = lo;
-            b[j] = mhi; b[d + j] = mlo; b[2 * d + j] = mhi;
+            bop[knn_b_pos(i, j, chunks)] = mhi;
+            bop[knn_b_pos(i, d + j, chunks)] = mlo;
+            bop[knn_b_pos(i, 2 * d + j, chunks)] = mhi;
             n2 += (double)x * (double)x;
         }
         n2 = ab_warp_sum_f64(n2);
@@ -244,10 +268,15 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const 
             const double r1 = n2 - (double)__half2float(n0);
             const __half n1 = __double2half(r1);
             const __half n2h = __double2half(r1 - (double)__half2float(n1));
-            b[3 * d] = n0; b[3 * d + 1] = n1; b[3 * d + 2] = n2h;
+            bop[knn_b_pos(i, 3 * d, chunks)] = n0;
+            bop[knn_b_pos(i, 3 * d + 1, chunks)] = n1;
+            bop[knn_b_pos(i, 3 * d + 2, chunks)] = n2h;
             a[3 * d] = one; a[3 * d + 1] = one; a[3 * d + 2] = one;
             qn[i] = n2 / (sc * sc);
         }
+    }
+    for (int64_t i = n + w; i < n_pad; i += nw) {
+        for (int j = lane; j < kt; j += 32) bop[knn_b_pos(i, j, chunks)] = (j == 3 * d) ? __float2half_rn(60000.f) : zero;
     }
 }
 
@@ -257,7 +286,7 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int d, int kt, const 
 static constexpr int TC_EPI_WARPS = 8;                       // two halves of four warps
 static constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 static constexpr int TC_NTHREADS = 64 + TC_EPI_THREADS;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-static constexpr int TC_BUF = 16;                            // per-thread append buffer (entries)
+static constexpr int TC_BUF = 32;                            // per-thread append buffer (entries; one prune merges <= 32)
 static constexpr unsigned long long TC_KEY_MAX = 0xFFFFFFFFFFFFFFFFull;
 
 // candidate key = order-preserving bits of the FP32 score in the high word, point id in the low word
@@ -288,9 +317,12 @@ struct TcParams {
     int chunks;            // K chunks of 32 halves
     int ksteps;            // UMMA K steps (16 halves) that carry data: ceil((3d+3)/16)
     int stages;            // B ring depth
+    int group;             // chunks handled per barrier round (<= stages, <= 30)
     int mt;                // 2: two query tiles x one 128-point B tile; 1: one query tile x 256-point B tile
     int m;                 // candidates kept per list
     unsigned long long *cand;   // [lists][nq][m] sorted keys, lists = 3 - mt
+    const unsigned char *bop;   // tiled, pre-swizzled B operand (knn_b_pos)
+    int dbg;               // experiments only (AB_KNN_DBG): 1 = epilogue skips the score scan, 2 = no MMA issue
 };
 
 // 32-wide bitonic sort across the warp, descending (lane 0 ends with the largest key)
@@ -309,24 +341,35 @@ __device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long 
     return v;
 }
 
-// Warp-cooperative prune: for every lane in `lanes`, merge its append buffer (<= TC_BUF unsorted
-// keys in shared memory) into its sorted m-list (global memory, m = 32*E keys, element i lives in
-// register x[i/32] of lane i%32), keep the m smallest, refresh the lane's threshold.
+__device__ __forceinline__ void sts_b64(uint32_t addr, unsigned long long v) {
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds_b64(uint32_t addr) {
+    unsigned long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// Warp-cooperative prune: for every lane in `lanes`, merge its append buffer (cnt <= 32 unsorted
+// keys in shared memory, entry e of epilogue thread t at buf + (e*256 + t)*8) into its sorted m-list
+// (global memory, m = 32*E keys, element i lives in register x[i/32] of lane i%32), keep the m
+// smallest.  Returns, in each pruned lane, its refreshed threshold (the caller resets its count).
 // Bitonic split + merge entirely in registers/shuffles.  Warp-uniform call.
 template <int E>
-__device__ __noinline__ void warp_prune_t(unsigned lanes, unsigned long long *cand_list0, int64_t q_lane, int &cnt,
-                                          float &tau, const unsigned long long *bufcol, int lane) {
+__device__ __noinline__ float warp_prune_t(unsigned lanes, unsigned long long *cand_list0, long long q_lane, int cnt,
+                                           uint32_t bufaddr, int lane) {
+    float my_tau = 0.f;
     while (lanes) {
         const int L = __ffs(lanes) - 1;
         lanes &= lanes - 1;
         const int cntL = __shfl_sync(AB_FULL, cnt, L);
-        const long long qL = __shfl_sync(AB_FULL, (long long)q_lane, L);
-        const unsigned long long *colL = (const unsigned long long *)__shfl_sync(AB_FULL, (unsigned long long)bufcol, L);
+        const long long qL = __shfl_sync(AB_FULL, q_lane, L);
+        const uint32_t colL = __shfl_sync(AB_FULL, bufaddr, L);
         unsigned long long *list = cand_list0 + (size_t)qL * (32 * E);
         unsigned long long x[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) x[e] = list[e * 32 + lane];
-        unsigned long long b = lane < cntL ? colL[(size_t)lane * TC_EPI_THREADS] : TC_KEY_MAX;
+        unsigned long long b = lane < cntL ? lds_b64(colL + (uint32_t)lane * (TC_EPI_THREADS * 8)) : TC_KEY_MAX;
         b = warp_sort_desc(b, lane);
         // bitonic split against the (virtual) upper half [MAX.. , b descending]: only the top 32 slots matter
         x[E - 1] = x[E - 1] < b ? x[E - 1] : b;
@@ -356,58 +399,33 @@ __device__ __noinline__ void warp_prune_t(unsigned lanes, unsigned long long *ca
 #pragma unroll
         for (int e = 0; e < E; ++e) list[e * 32 + lane] = x[e];
         const unsigned long long kth = __shfl_sync(AB_FULL, x[E - 1], 31);
-        if (lane == L) { tau = key_score(kth); cnt = 0; }
+        if (lane == L) my_tau = key_score(kth);
         __syncwarp();
     }
+    return my_tau;
 }
 
-__device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, int list_id, int64_t q_lane, int &cnt,
-                                           float &tau, const unsigned long long *bufcol, int lane) {
+// prunes the lanes in `lanes` (warp-uniform mask), updating their (cnt, tau)
+__device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, int list_id, long long q_lane, int &cnt,
+                                           float &tau, uint32_t bufaddr, int lane) {
     unsigned long long *cg = P.cand + (size_t)list_id * P.nq * P.m;
+    float t;
     switch (P.m) {
-        case 32: warp_prune_t<1>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
-        case 64: warp_prune_t<2>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
-        case 128: warp_prune_t<4>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
-        default: warp_prune_t<8>(lanes, cg, q_lane, cnt, tau, bufcol, lane); break;
+        case 32: t = warp_prune_t<1>(lanes, cg, q_lane, cnt, bufaddr, lane); break;
+        case 64: t = warp_prune_t<2>(lanes, cg, q_lane, cnt, bufaddr, lane); break;
+        case 128: t = warp_prune_t<4>(lanes, cg, q_lane, cnt, bufaddr, lane); break;
+        default: t = warp_prune_t<8>(lanes, cg, q_lane, cnt, bufaddr, lane); break;
     }
+    if ((lanes >> lane) & 1u) { tau = t; cnt = 0; }
 }
 
-// Rare path of the epilogue for one unit of 32 scores per lane (warp-uniform call): stage the
-// scores in shared memory (each lane only ever reads back its own row), build the per-lane hit
-// mask and append the hits; lanes whose buffer fills are pruned cooperatively and carry on with
-// the tightened threshold.
-__device__ __forceinline__ void epi_slow_path(const uint32_t (&r)[32], float *stage_row, int sw, bool hit, int nvalid,
-                                           int cbase, const TcParams &P, int list_id, int64_t q, int &cnt, float &tau,
-                                           unsigned long long *bufcol, int lane) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4 *>(stage_row + ((c ^ sw) << 2)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-    unsigned mask = 0;
-    if (hit) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) < tau) ? (1u << j) : 0u;
-        if (nvalid < 32) mask &= (1u << nvalid) - 1u;           // columns past the end of the database
-    }
-    __syncwarp();
-    while (__any_sync(AB_FULL, mask != 0u)) {
-        if (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float s = stage_row[(((j >> 2) ^ sw) << 2) | (j & 3)];
-            if (s < tau) {
-                bufcol[(size_t)cnt * TC_EPI_THREADS] = cand_key(s, cbase + j);
-                ++cnt;
-            }
-        }
-        const unsigned fullm = __ballot_sync(AB_FULL, cnt >= TC_BUF);
-        if (fullm) warp_prune(fullm, P, list_id, q, cnt, tau, bufcol, lane);
-    }
-}
-
-// one unit = 32 consecutive scores of this thread's query row
-__device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int64_t cbase, bool live, float *stage_row, int sw,
-                                         const TcParams &P, int list_id, int64_t q, int &cnt, float &tau,
-                                         unsigned long long *bufcol, int lane) {
+// one unit = 32 consecutive scores of this thread's query row.  Common path: a min-tree and one
+// compare.  On a hit the unit is revisited in groups of 8: only groups that hold a score below the
+// lane's threshold are scanned, hits go straight to the lane's append buffer (room for a whole
+// group is guaranteed beforehand; lanes short of room are pruned first, which also tightens
+// their threshold).  Padding columns carry a huge score (see knn_prep_kernel) and never pass.
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, bool live, const TcParams &P, int list_id,
+                                         long long q, int &cnt, float &tau, uint32_t bufaddr, int lane) {
     float gmin[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -417,25 +435,36 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int64_t cbase,
         gmin[g] = fminf(v, __uint_as_float(r[8 * g + 7]));
     }
     const float mn = fminf(fmin3(gmin[0], gmin[1], gmin[2]), gmin[3]);
-    const bool hit = live && mn < tau;
-    if (__any_sync(AB_FULL, hit)) {
-        const int64_t left = P.n_total - cbase;
-        const int nvalid = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
-        epi_slow_path(r, stage_row, sw, hit, nvalid, (int)cbase, P, list_id, q, cnt, tau, bufcol, lane);
+    if (!__any_sync(AB_FULL, live && mn < tau)) return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (!__any_sync(AB_FULL, live && gmin[g] < tau)) continue;
+        const unsigned tight = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
+        if (tight) warp_prune(tight, P, list_id, q, cnt, tau, bufaddr, lane);
+        if (live && gmin[g] < tau) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float sc = __uint_as_float(r[8 * g + jj]);
+                if (sc < tau) {
+                    sts_b64(bufaddr + (uint32_t)cnt * (TC_EPI_THREADS * 8), cand_key(sc, cbase + 8 * g + jj));
+                    ++cnt;
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
-knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams P) {
+knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: [A chunks][B stages][score staging][append buffers][barriers]
+    // layout: [A chunks][B stages][append buffers][barriers]
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_chunk_bytes = P.mt * TC_SLAB;             // 128*mt query rows x 64 B
     const int b_stage_bytes = (3 - P.mt) * TC_SLAB;       // 128*(3-mt) database rows x 64 B
     unsigned char *sA = smem;
     unsigned char *sB = sA + (size_t)P.chunks * a_chunk_bytes;
-    float *sStage = reinterpret_cast<float *>(sB + (size_t)P.stages * b_stage_bytes);       // [8 warps][32 rows][32]
-    unsigned long long *sBuf = reinterpret_cast<unsigned long long *>(sStage + TC_EPI_WARPS * 32 * 32);
+    unsigned long long *sBuf = reinterpret_cast<unsigned long long *>(sB + (size_t)P.stages * b_stage_bytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(sBuf + (size_t)TC_BUF * TC_EPI_THREADS);
     uint64_t *full = bars;                          // [stages]
     uint64_t *empty = bars + TC_MAX_STAGES;         // [stages]
@@ -484,15 +513,33 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             __syncwarp();
             aphase ^= 1;
             for (int64_t t = 0; t < n_tiles; ++t) {
-                const int xrow = (int)(t * x_per_tile);
-                for (int c = 0; c < P.chunks; ++c) {
-                    mbar_wait(empty + stage, phase ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(full + stage, (uint32_t)b_stage_bytes);
-                        tma_load_2d(sB + (size_t)stage * b_stage_bytes, &map_b, full + stage, c * TC_KCH, xrow);
+                // slabs of this tile: one (mt = 2) or two (mt = 1) blocks of `chunks` x 8 KB
+                const unsigned char *slab0 = P.bop + (size_t)t * (3 - P.mt) * P.chunks * TC_SLAB;
+                for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
+                    const int gsz = min(P.group, P.chunks - c0);
+                    // lane l waits for the slot of chunk c0+l: the waits of a group overlap
+                    if (lane < gsz) {
+                        int sl = stage + lane;
+                        uint32_t ph = phase;
+                        if (sl >= P.stages) { sl -= P.stages; ph ^= 1; }
+                        mbar_wait(empty + sl, ph ^ 1);
                     }
                     __syncwarp();
-                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    if (elect_one()) {
+                        for (int l = 0; l < gsz; ++l) {
+                            int sl = stage + l;
+                            if (sl >= P.stages) sl -= P.stages;
+                            const int c = c0 + l;
+                            mbar_expect_tx(full + sl, (uint32_t)b_stage_bytes);
+                            unsigned char *dst = sB + (size_t)sl * b_stage_bytes;
+                            bulk_load(dst, slab0 + (size_t)c * TC_SLAB, TC_SLAB, full + sl);
+                            if (P.mt == 1)
+                                bulk_load(dst + TC_SLAB, slab0 + (size_t)(P.chunks + c) * TC_SLAB, TC_SLAB, full + sl);
+                        }
+                    }
+                    __syncwarp();
+                    stage += gsz;
+                    if (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
                 }
             }
         }
@@ -513,25 +560,40 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             aphase ^= 1;
             for (int64_t t = 0; t < n_tiles; ++t, ++it) {
                 const int buf = (int)(it & 1);
-                mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
-                tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
-                for (int c = 0; c < P.chunks; ++c) {
-                    mbar_wait(full + stage, phase);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t a_c = a_desc0 + (uint64_t)((uint32_t)c * a_step);
-                        const uint64_t b_s = b_desc0 + (uint64_t)((uint32_t)stage * b_step);
-                        const bool two = P.ksteps - 2 * c >= 2;
-                        tc_mma_f16(tmem_d, a_c, b_s, idesc, (uint32_t)(c != 0));
-                        if (two) tc_mma_f16(tmem_d, a_c + 2, b_s + 2, idesc, 1u);
-                        tc_mma_f16(tmem_d + TC_TILE, a_c + a_half, b_s + b_half, idesc, (uint32_t)(c != 0));
-                        if (two) tc_mma_f16(tmem_d + TC_TILE, a_c + a_half + 2, b_s + b_half + 2, idesc, 1u);
-                        tc_commit(empty + stage);               // smem slot free once these MMAs retire
-                        if (c == P.chunks - 1) tc_commit(t_full + buf);   // accumulators ready for the epilogue
+                for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
+                    const int gsz = min(P.group, P.chunks - c0);
+                    // lane l waits for chunk c0+l, lane 31 for the accumulator buffer: the waits overlap
+                    // (a serial try_wait per 8 KB stage costs more than the 256 tensor cycles the stage feeds)
+                    if (lane < gsz) {
+                        int sl = stage + lane;
+                        uint32_t ph = phase;
+                        if (sl >= P.stages) { sl -= P.stages; ph ^= 1; }
+                        mbar_wait(full + sl, ph);
+                    } else if (lane == 31 && c0 == 0) {
+                        mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
                     }
                     __syncwarp();
-                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        for (int l = 0; l < gsz; ++l) {
+                            int sl = stage + l;
+                            if (sl >= P.stages) sl -= P.stages;
+                            const int c = c0 + l;
+                            const uint64_t a_c = a_desc0 + (uint64_t)((uint32_t)c * a_step);
+                            const uint64_t b_s = b_desc0 + (uint64_t)((uint32_t)sl * b_step);
+                            const bool two = P.ksteps - 2 * c >= 2 && !(P.dbg & 2);
+                            tc_mma_f16(tmem_d, a_c, b_s, idesc, (uint32_t)(c != 0));
+                            if (two) tc_mma_f16(tmem_d, a_c + 2, b_s + 2, idesc, 1u);
+                            tc_mma_f16(tmem_d + TC_TILE, a_c + a_half, b_s + b_half, idesc, (uint32_t)(c != 0));
+                            if (two) tc_mma_f16(tmem_d + TC_TILE, a_c + a_half + 2, b_s + b_half + 2, idesc, 1u);
+                            tc_commit(empty + sl);              // smem slot free once these MMAs retire
+                        }
+                        if (c0 + gsz == P.chunks) tc_commit(t_full + buf);   // accumulators ready for the epilogue
+                    }
+                    __syncwarp();
+                    stage += gsz;
+                    if (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
                 }
             }
             if (elect_one()) tc_commit(a_empty);                // A tiles may be overwritten
@@ -548,11 +610,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         const int row = lane_base + lane;
         const int etid = ew * 32 + lane;
         const int list_id = P.mt == 1 ? half : 0;
-        unsigned long long *bufcol = sBuf + etid;               // entry e at bufcol[e * TC_EPI_THREADS]
-        float *stage_row = sStage + (size_t)(ew * 32 + lane) * 32;
-        const int sw = lane & 7;
+        const uint32_t bufaddr = smem_u32(sBuf + etid);         // entry e at bufaddr + e * TC_EPI_THREADS * 8
         const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)half * TC_TILE;
-        int64_t cur_block = -1, q = 0;
+        int64_t cur_block = -1;
+        long long q = 0;
         bool live = false;
         float tau = INFINITY;
         int cnt = 0;
@@ -560,7 +621,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const int64_t blk = it / n_tiles, t = it - blk * n_tiles;
             const int buf = (int)(it & 1);
             if (blk != cur_block) {
-                if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufcol, lane);
+                if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufaddr, lane);
                 cur_block = blk;
                 q = (blockIdx.x + blk * gridDim.x) * q_per_block + (P.mt == 2 ? half * TC_TILE : 0) + row;
                 live = q < P.nq;
@@ -573,21 +634,26 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const uint32_t taddr = taddr0 + (uint32_t)buf * 256;
             uint32_t ra[32], rb[32];
 #pragma unroll 1
-            for (int c2 = 0; c2 < TC_TILE / 64; ++c2) {
+            for (int c2 = 0; c2 < ((P.dbg & 4) ? 0 : ((P.dbg & 8) ? 1 : TC_TILE / 64)); ++c2) {
                 // two units per wait: no tcgen05.ld is in flight while the (call-heavy) rare path runs
                 tc_ld32(taddr + (2 * c2) * 32, ra);
                 tc_ld32(taddr + (2 * c2 + 1) * 32, rb);
                 tc_wait_ld();
                 tc_touch32(ra);
                 tc_touch32(rb);
-                epi_unit(ra, col0 + (2 * c2) * 32, live, stage_row, sw, P, list_id, q, cnt, tau, bufcol, lane);
-                epi_unit(rb, col0 + (2 * c2 + 1) * 32, live, stage_row, sw, P, list_id, q, cnt, tau, bufcol, lane);
+                if (P.dbg & 1) continue;
+                epi_unit(ra, (int)col0 + (2 * c2) * 32, live, P, list_id, q, cnt, tau, bufaddr, lane);
+                epi_unit(rb, (int)col0 + (2 * c2 + 1) * 32, live, P, list_id, q, cnt, tau, bufaddr, lane);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty + buf);
+            // prune AFTER handing the accumulator back: the merge (two L2 round trips + a bitonic network)
+            // then overlaps the MMAs of the next tiles instead of sitting on the MMA->epilogue handoff
+            const unsigned due = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
+            if (due) warp_prune(due, P, list_id, q, cnt, tau, bufaddr, lane);
         }
-        if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufcol, lane);
+        if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufaddr, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -626,8 +692,8 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
             const unsigned long long key = cand[((size_t)g * nq + q) * m + e];
             double dist = INFINITY;
             int id = INT_MAX;
-            if (key != TC_KEY_MAX) {
-                const int cnd = (int)(uint32_t)(key & 0xFFFFFFFFull);
+            const int cnd = (int)(uint32_t)(key & 0xFFFFFFFFull);
+            if (key != TC_KEY_MAX && cnd < n_total) {             // (padding columns can enter only while a list is short)
                 const double *xv = emb + (int64_t)cnd * d;
                 double acc = 0.0;
                 for (int j = 0; j < d; ++j) {                 // the reference's arithmetic, no FMA
@@ -698,6 +764,7 @@ static int tc_candidates(int k) {
     while (m < want) m <<= 1;                      // power of two (bitonic re-rank), 32..256
     return std::min(m, 256);
 }
+static int64_t tc_pad(int64_t n) { return (n + 255) / 256 * 256; }
 static int tc_kt(int d) { return (3 * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
 // two resident query tiles when their A operand (256 rows x kt halves) leaves room for the B ring
 static int tc_mt(int d) { return tc_kt(d) * 2 * 256 <= 96 * 1024 ? 2 : 1; }
@@ -717,7 +784,7 @@ static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t by
     TcWs w;
     const int kt = tc_kt(d), m = tc_candidates(k);
     w.aop = a.take<__half>((size_t)n * kt);
-    w.bop = a.take<__half>((size_t)n * kt);
+    w.bop = a.take<__half>((size_t)tc_pad(n) * kt);
     w.mean = a.take<double>(d);
     w.partial = a.take<double>((size_t)1024 * d);
     w.qn = a.take<double>(n);
@@ -780,18 +847,17 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     const unsigned g_prep = (unsigned)std::min<int64_t>((n_total + 7) / 8, (int64_t)ctx->sm_count * 16);
     knn_rmax_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, w.mean, w.scal);
     AB_LAUNCH_CHECK(ctx);
-    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, kt, w.mean, w.scal, w.aop, w.bop, w.qn);
+    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, tc_pad(n_total), d, kt, w.mean, w.scal, w.aop, w.bop, w.qn);
     AB_LAUNCH_CHECK(ctx);
     AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)lists * nq * m * sizeof(unsigned long long), st));
     ab_prof_end(ctx, AB_PROF_KNN_PREP, st);
     // ---- main ----
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a;
     if (make_map(&map_a, w.aop, n_total, kt, TC_TILE * mt)) return 1;
-    if (make_map(&map_b, w.bop, n_total, kt, TC_TILE * (3 - mt))) return 1;
     const size_t a_bytes = (size_t)chunks * mt * TC_SLAB;
     const size_t b_stage = (size_t)(3 - mt) * TC_SLAB;
     const size_t bar_bytes = 256;
-    const size_t epi_bytes = (size_t)TC_EPI_WARPS * 32 * 32 * 4 + (size_t)TC_BUF * TC_EPI_THREADS * 8;
+    const size_t epi_bytes = (size_t)TC_BUF * TC_EPI_THREADS * 8;
     AB_REQUIRE((size_t)ctx->smem_optin > 1024 + a_bytes + bar_bytes + epi_bytes + 2 * b_stage,
                "ab_knn: not enough shared memory for d=%d k=%d", d, k);
     int stages = (int)(((size_t)ctx->smem_optin - 1024 - a_bytes - bar_bytes - epi_bytes) / b_stage);
@@ -800,11 +866,12 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcParams P;
     P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (3 * d + 3 + 15) / 16;
-    P.stages = stages; P.mt = mt; P.m = m; P.cand = w.cand;
+    P.stages = stages; P.group = std::min(chunks, std::max(1, stages / 2)); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
+    P.dbg = getenv("AB_KNN_DBG") ? atoi(getenv("AB_KNN_DBG")) : 0;
     const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
     const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
     ab_prof_begin(ctx, AB_PROF_KNN_MAIN, st);
-    knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, map_b, P);
+    knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, P);
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_MAIN, st);
     // ---- exact re-rank + certificate ----
