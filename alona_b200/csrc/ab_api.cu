@@ -166,7 +166,7 @@ extern "C" int64_t ab_launch_count(ab_ctx *ctx) { return ctx ? ctx->launches : 0
 // ---------------------------------------------------------------------------------------
 static const char *const g_prof_names[AB_PROF_SLOTS] = {
     "norm_moments", "hvg_extract", "irlb_av", "irlb_atw", "irlb_panel", "irlb_small", "knn_prep", "knn_main",
-    "knn_rerank", "snn_build", "snn_count", "snn_fill", "irlb_total", "knn_exact", "", ""};
+    "knn_rerank", "snn_build", "snn_count", "snn_fill", "irlb_total", "knn_exact", "irlb_ritz", "irlb_svd"};
 
 static bool prof_active(ab_ctx *ctx, int slot) {
     if (!ctx || ctx->prof_level <= 0 || slot < 0 || slot >= AB_PROF_SLOTS) return false;

@@ -24,10 +24,10 @@ enum {
     AB_PROF_NORM = 0, AB_PROF_HVG_EXTRACT = 1, AB_PROF_IRLB_AV = 2, AB_PROF_IRLB_ATW = 3, AB_PROF_IRLB_PANEL = 4,
     AB_PROF_IRLB_SMALL = 5, AB_PROF_KNN_PREP = 6, AB_PROF_KNN_MAIN = 7, AB_PROF_KNN_RERANK = 8,
     AB_PROF_SNN_BUILD = 9, AB_PROF_SNN_COUNT = 10, AB_PROF_SNN_FILL = 11, AB_PROF_IRLB_TOTAL = 12,
-    AB_PROF_KNN_EXACT = 13          // AB_PROF_SLOTS (16) comes from the public header
+    AB_PROF_KNN_EXACT = 13, AB_PROF_IRLB_RITZ = 14, AB_PROF_IRLB_SVD = 15   // AB_PROF_SLOTS (16): public header
 };
 static const int AB_PROF_FINE_MASK = (1 << AB_PROF_IRLB_AV) | (1 << AB_PROF_IRLB_ATW) | (1 << AB_PROF_IRLB_PANEL) |
-                                     (1 << AB_PROF_IRLB_SMALL);
+                                     (1 << AB_PROF_IRLB_SMALL) | (1 << AB_PROF_IRLB_RITZ) | (1 << AB_PROF_IRLB_SVD);
 
 struct ab_prof_slot {
     std::vector<cudaEvent_t> begin, end;     // completed or in-flight pairs

@@ -17,6 +17,7 @@
 #include "ab_common.cuh"
 #include <math.h>
 #include <float.h>
+#include <limits.h>
 #include <algorithm>
 
 static constexpr int IR_MAXWORK = 128;          // work dimension m_b <= 128
@@ -69,35 +70,52 @@ atw_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, 
 
 // ---------------------------------------------------------------------------------------
 // c[l] = sum_i V[i,l] F[i]  for l < ncols     (irlb.py:74 dotY, contraction over cells)
+// Thread <-> cell row inside a 256-row tile, CTAs stride over the tiles; PD_CB columns are
+// accumulated in registers per pass, so every thread has PD_CB independent coalesced loads in
+// flight and the (shuffle-heavy) reductions happen once per CTA and column, not once per tile.
+// Fixed grid and fixed summation order: bitwise reproducible for a given n.
 // ---------------------------------------------------------------------------------------
+static constexpr int PD_CB = 16;
+
 __global__ void __launch_bounds__(DOT_THREADS)
 panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols, const double *__restrict__ F,
                  double *__restrict__ partial /*[grid][IR_MAXWORK]*/, double *__restrict__ out, int *counter) {
-    __shared__ double wsum[DOT_THREADS / 32][IR_MAXWORK];
+    __shared__ double wsum[DOT_THREADS / 32][PD_CB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * DOT_TILE;
-    double f[DOT_ROWS];
-    int64_t r[DOT_ROWS];
+    const int64_t stride = (int64_t)gridDim.x * DOT_THREADS;
+    for (int l0 = 0; l0 < ncols; l0 += PD_CB) {
+        double acc[PD_CB];
 #pragma unroll
-    for (int u = 0; u < DOT_ROWS; ++u) {
-        r[u] = base + threadIdx.x + (int64_t)u * DOT_THREADS;
-        f[u] = r[u] < n ? F[r[u]] : 0.0;
-        if (r[u] >= n) r[u] = 0;
-    }
-    for (int l = 0; l < ncols; ++l) {
-        const double *vl = V + (int64_t)l * ld;
-        double acc = 0.0;
+        for (int c = 0; c < PD_CB; ++c) acc[c] = 0.0;
+        const double *v0 = V + (int64_t)l0 * ld;
+        if (l0 + PD_CB <= ncols) {
+            for (int64_t row = (int64_t)blockIdx.x * DOT_THREADS + threadIdx.x; row < n; row += stride) {
+                const double f = F[row];
 #pragma unroll
-        for (int u = 0; u < DOT_ROWS; ++u) acc = fma(vl[r[u]], f[u], acc);
-        acc = ab_warp_sum_f64(acc);
-        if (lane == 0) wsum[warp][l] = acc;
-    }
-    __syncthreads();
-    for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) {
-        double t = 0.0;
+                for (int c = 0; c < PD_CB; ++c) acc[c] = fma(v0[(int64_t)c * ld + row], f, acc[c]);
+            }
+        } else {
+            const int nc = ncols - l0;
+            for (int64_t row = (int64_t)blockIdx.x * DOT_THREADS + threadIdx.x; row < n; row += stride) {
+                const double f = F[row];
 #pragma unroll
-        for (int w2 = 0; w2 < DOT_THREADS / 32; ++w2) t += wsum[w2][l];
-        partial[(int64_t)blockIdx.x * IR_MAXWORK + l] = t;
+                for (int c = 0; c < PD_CB; ++c)
+                    if (c < nc) acc[c] = fma(v0[(int64_t)c * ld + row], f, acc[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < PD_CB; ++c) {
+            const double t = ab_warp_sum_f64(acc[c]);
+            if (lane == 0) wsum[warp][c] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x < PD_CB && l0 + threadIdx.x < ncols) {
+            double t = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < DOT_THREADS / 32; ++w2) t += wsum[w2][threadIdx.x];
+            partial[(int64_t)blockIdx.x * IR_MAXWORK + l0 + threadIdx.x] = t;
+        }
+        __syncthreads();
     }
     if (last_block_ticket(counter)) {
         for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) {
@@ -108,7 +126,7 @@ panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols,
     }
 }
 
-// F -= V[:, :ncols].c ;  fn2 = sum F^2      (irlb.py:79,191)
+// F -= V[:, :ncols].c ;  fn2 = sum F^2      (irlb.py:79,191).  Thread <-> row, 8 loads in flight.
 __global__ void __launch_bounds__(DOT_THREADS)
 panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols, const double *__restrict__ c,
                     double *__restrict__ F, double *__restrict__ partial, double *__restrict__ out_fn2, int *counter) {
@@ -117,31 +135,23 @@ panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int nco
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) cs[l] = c[l];
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * DOT_TILE;
-    double t[DOT_ROWS];
-    int64_t r[DOT_ROWS];
-    bool ok[DOT_ROWS];
-#pragma unroll
-    for (int u = 0; u < DOT_ROWS; ++u) {
-        r[u] = base + threadIdx.x + (int64_t)u * DOT_THREADS;
-        ok[u] = r[u] < n;
-        if (!ok[u]) r[u] = 0;
-        t[u] = 0.0;
-    }
-    for (int l = 0; l < ncols; ++l) {
-        const double *vl = V + (int64_t)l * ld;
-        const double cl = cs[l];
-#pragma unroll
-        for (int u = 0; u < DOT_ROWS; ++u) t[u] = fma(vl[r[u]], cl, t[u]);
-    }
+    const int64_t stride = (int64_t)gridDim.x * DOT_THREADS;
     double acc = 0.0;
-#pragma unroll
-    for (int u = 0; u < DOT_ROWS; ++u) {
-        if (ok[u]) {
-            const double nf = __dsub_rn(F[r[u]], t[u]);
-            F[r[u]] = nf;
-            acc = fma(nf, nf, acc);
+    for (int64_t row = (int64_t)blockIdx.x * DOT_THREADS + threadIdx.x; row < n; row += stride) {
+        const double *vr = V + row;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        int l = 0;
+        for (; l + 7 < ncols; l += 8) {
+            const double a0 = vr[(int64_t)l * ld], a1 = vr[(int64_t)(l + 1) * ld], a2 = vr[(int64_t)(l + 2) * ld],
+                         a3 = vr[(int64_t)(l + 3) * ld], a4 = vr[(int64_t)(l + 4) * ld], a5 = vr[(int64_t)(l + 5) * ld],
+                         a6 = vr[(int64_t)(l + 6) * ld], a7 = vr[(int64_t)(l + 7) * ld];
+            t0 = fma(a0, cs[l], t0); t1 = fma(a1, cs[l + 1], t1); t2 = fma(a2, cs[l + 2], t2); t3 = fma(a3, cs[l + 3], t3);
+            t0 = fma(a4, cs[l + 4], t0); t1 = fma(a5, cs[l + 5], t1); t2 = fma(a6, cs[l + 6], t2); t3 = fma(a7, cs[l + 7], t3);
         }
+        for (; l < ncols; ++l) t0 = fma(vr[(int64_t)l * ld], cs[l], t0);
+        const double nf = __dsub_rn(F[row], (t0 + t1) + (t2 + t3));
+        F[row] = nf;
+        acc = fma(nf, nf, acc);
     }
     acc = ab_warp_sum_f64(acc);
     if (lane == 0) red[warp] = acc;
@@ -198,10 +208,18 @@ __global__ void scale_by_invnorm_kernel(const double *__restrict__ src, double *
 // ---------------------------------------------------------------------------------------
 // A.x : scatter SpMV.  x_i = scale * src_i (scale = invcheck(sqrt(*sumsq)) or 1), optionally
 // stored to vdst (the new Lanczos vector, irlb.py:195).  Each warp owns a private FP64
-// accumulator of H entries in shared memory: the genes of one cell row are distinct, so the
-// 32 lanes of a warp never collide and plain load/FMA/store is race-free.
+// accumulator of H entries in shared memory and a contiguous range of rows; it walks the
+// nonzeros of that range as ONE flat stream, AV_U steps of 32 nonzeros prefetched into
+// registers at a time (the loads of a whole batch are in flight together: with 16 KB of
+// accumulator per warp only ~12 warps fit an SM, so the bandwidth has to come from
+// memory-level parallelism inside a warp, not from occupancy).  A step is consumed in row
+// segments: the genes of one cell row are distinct, so the lanes of a segment never collide
+// and plain load/FMA/store is race-free and order-deterministic; __syncwarp separates rows.
+// Row metadata (row end, x) travels in registers, 32 rows per refill, read by shuffle.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+static constexpr int AV_U = 8;
+
+__global__ void __launch_bounds__(384)
 av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
           int64_t n, int H, const double *__restrict__ src, const double *__restrict__ sumsq,
           double *__restrict__ vdst, int nwarps_cta, double *__restrict__ partial /*[grid][H]*/) {
@@ -214,18 +232,92 @@ av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, c
         double *acc = acc_sm + (size_t)warp * H;
         const int64_t wid = (int64_t)blockIdx.x * nwarps_cta + warp;
         const int64_t nw = (int64_t)gridDim.x * nwarps_cta;
-        // contiguous chunk of rows per warp
         const int64_t per = (n + nw - 1) / nw;
-        const int64_t r0 = wid * per, r1 = min(n, r0 + per);
-        for (int64_t row = r0; row < r1; ++row) {
-            const double x = __dmul_rn(scale, src[row]);
-            if (vdst && lane == 0) vdst[row] = x;
-            const int64_t a = rowptr[row], b = rowptr[row + 1];
-            for (int64_t p = a + lane; p < b; p += 32) {
-                const int g = __ldg(col + p);
-                acc[g] = fma(__ldg(val + p), x, acc[g]);
+        const int64_t r0 = min(n, wid * per), r1 = min(n, r0 + per);
+        if (r0 < r1) {
+            const int64_t p0 = rowptr[r0];
+            const int len = (int)(rowptr[r1] - p0);              // a warp's share is far below 2^31 nonzeros
+            const int32_t *colw = col + p0;
+            const double *valw = val + p0;
+            // row metadata block: lane l holds the end offset (relative to p0) and x of row blk + l
+            int64_t blk = r0;
+            int rp_l;
+            double x_l;
+            {
+                const int64_t r = blk + lane;
+                const bool ok = r < r1;
+                rp_l = ok ? (int)(rowptr[r + 1] - p0) : INT_MAX;
+                x_l = ok ? __dmul_rn(scale, src[r]) : 0.0;
+                if (ok && vdst) vdst[r] = x_l;
             }
-            __syncwarp();
+            int ri = 0;                                          // current row = blk + ri
+            int rend = __shfl_sync(AB_FULL, rp_l, 0);
+            double xrow = ab_shfl_f64(x_l, 0);
+            // two register batches: the loads of batch b+1 are in flight while batch b is consumed
+            int cg[2][AV_U];
+            double vv[2][AV_U];
+#pragma unroll
+            for (int u = 0; u < AV_U; ++u) {
+                const int p = 32 * u + lane;
+                const bool ok = p < len;
+                cg[0][u] = ok ? __ldg(colw + p) : 0;
+                vv[0][u] = ok ? __ldg(valw + p) : 0.0;
+            }
+            for (int base2 = 0; base2 < len; base2 += 64 * AV_U) {
+#pragma unroll
+                for (int bb = 0; bb < 2; ++bb) {
+                    const int base = base2 + bb * 32 * AV_U;
+#pragma unroll
+                    for (int u = 0; u < AV_U; ++u) {
+                        const int p = base + 32 * AV_U + 32 * u + lane;
+                        const bool ok = p < len;
+                        cg[bb ^ 1][u] = ok ? __ldg(colw + p) : 0;
+                        vv[bb ^ 1][u] = ok ? __ldg(valw + p) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < AV_U; ++u) {
+                        const int s0 = base + 32 * u;
+                        if (s0 >= len) break;
+                        const int s1 = min(s0 + 32, len);
+                        const int p = s0 + lane;
+                        if (rend >= s1) {
+                            // the whole step lies inside the current row: no ordering needed against the
+                            // previous steps of this row (distinct genes), the chains overlap freely
+                            if (p < s1) acc[cg[bb][u]] = fma(vv[bb][u], xrow, acc[cg[bb][u]]);
+                        } else {
+                            int cur = s0;
+                            while (cur < s1) {
+                                if (rend <= cur) {
+                                    __syncwarp();                // row switch: order the two rows' updates
+                                    do {                         // advance to the row that owns `cur` (skips empty rows)
+                                        if (++ri == 32) {
+                                            blk += 32;
+                                            const int64_t r = blk + lane;
+                                            const bool ok = r < r1;
+                                            rp_l = ok ? (int)(rowptr[r + 1] - p0) : INT_MAX;
+                                            x_l = ok ? __dmul_rn(scale, src[r]) : 0.0;
+                                            if (ok && vdst) vdst[r] = x_l;
+                                            ri = 0;
+                                        }
+                                        rend = __shfl_sync(AB_FULL, rp_l, ri);
+                                        xrow = ab_shfl_f64(x_l, ri);
+                                    } while (rend <= cur);
+                                }
+                                const int seg = min(rend, s1);
+                                if (p >= cur && p < seg) acc[cg[bb][u]] = fma(vv[bb][u], xrow, acc[cg[bb][u]]);
+                                cur = seg;
+                            }
+                        }
+                    }
+                }
+            }
+            // rows after the last nonzero (empty tail rows) still need their x stored
+            if (vdst) {
+                for (int64_t b2 = blk + 32; b2 < r1; b2 += 32) {
+                    const int64_t r = b2 + lane;
+                    if (r < r1) vdst[r] = __dmul_rn(scale, src[r]);
+                }
+            }
         }
     }
     __syncthreads();
@@ -269,18 +361,34 @@ wstep_kernel(const double *__restrict__ wraw, double *__restrict__ W, int H, int
     }
     __syncthreads();
     if (ncols > 0) {
+        // four independent partial sums per lane keep four loads of the (L2-resident) panel in flight
         for (int l = warp; l < ncols; l += nwarp) {
             const double *wl = W + (size_t)l * H;
-            double acc = 0.0;
-            for (int g = lane; g < H; g += 32) acc = fma(wl[g], t[g], acc);
-            acc = ab_warp_sum_f64(acc);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int g = lane;
+            for (; g + 96 < H; g += 128) {
+                a0 = fma(wl[g], t[g], a0);
+                a1 = fma(wl[g + 32], t[g + 32], a1);
+                a2 = fma(wl[g + 64], t[g + 64], a2);
+                a3 = fma(wl[g + 96], t[g + 96], a3);
+            }
+            for (; g < H; g += 32) a0 = fma(wl[g], t[g], a0);
+            const double acc = ab_warp_sum_f64((a0 + a1) + (a2 + a3));
             if (lane == 0) c2[l] = acc;
         }
         __syncthreads();
         for (int g = threadIdx.x; g < H; g += blockDim.x) {
-            double acc = 0.0;
-            for (int l = 0; l < ncols; ++l) acc = fma(W[(size_t)l * H + g], c2[l], acc);
-            t[g] = __dsub_rn(t[g], acc);
+            const double *wg = W + g;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int l = 0;
+            for (; l + 3 < ncols; l += 4) {
+                a0 = fma(wg[(size_t)l * H], c2[l], a0);
+                a1 = fma(wg[(size_t)(l + 1) * H], c2[l + 1], a1);
+                a2 = fma(wg[(size_t)(l + 2) * H], c2[l + 2], a2);
+                a3 = fma(wg[(size_t)(l + 3) * H], c2[l + 3], a3);
+            }
+            for (; l < ncols; ++l) a0 = fma(wg[(size_t)l * H], c2[l], a0);
+            t[g] = __dsub_rn(t[g], (a0 + a1) + (a2 + a3));
         }
         __syncthreads();
     }
@@ -315,14 +423,17 @@ __global__ void fscale_kernel(double *__restrict__ F, int64_t n, const double *_
 // Outputs: Ub (columns = left vectors), sb (descending), Vb (columns = right vectors),
 // all row-major work x work.  Then residuals / convergence / restart bookkeeping (:225-234).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ Ub, double *__restrict__ sb,
                    double *__restrict__ Vb, double *__restrict__ Gws /* 2*work*work scratch */,
                    double *__restrict__ scal, int *__restrict__ ctrl, double *__restrict__ R, int nu, double tol,
-                   int it, int keep_prev) {
+                   int it, int keep_prev, int q_in_smem) {
     // G (col-major, work x work) starts as B and converges to U.diag(s); Q accumulates V.
-    double *G = Gws;
-    double *Q = Gws + (size_t)work * work;
+    // Both live in shared memory when they fit (the sweeps are latency-bound chains of tiny
+    // column operations); for the largest work dimensions Q stays in the global scratch.
+    extern __shared__ double svd_sm[];
+    double *G = svd_sm;
+    double *Q = q_in_smem ? svd_sm + (size_t)work * work : Gws + (size_t)work * work;
     __shared__ double nrm[IR_MAXWORK];
     __shared__ int order[IR_MAXWORK];
     __shared__ int rot_sm;
@@ -335,30 +446,45 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
     }
     __syncthreads();
     const int mp = (m + 1) & ~1;                        // round-robin needs an even player count
+    // one HALF-warp per column pair, so that a whole round (mp/2 <= 64 pairs) is one pass of the
+    // 1024-thread CTA: the sweeps are a chain of ~mp dependent rounds, each a few hundred cycles of
+    // shuffle/divide/sqrt latency, and the kernel's time is that chain times the number of sweeps
+    const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15, nhw = blockDim.x >> 4;
     for (int sweep = 0; sweep < 60; ++sweep) {
         if (threadIdx.x == 0) rot_sm = 0;
         __syncthreads();
         for (int round = 0; round < mp - 1; ++round) {
-            for (int pr = warp; pr < mp / 2; pr += nwarp) {
+            for (int pr0 = 0; pr0 < mp / 2; pr0 += nhw) {
+                const int pr = pr0 + hw;
                 // circle method: player mp-1 fixed, the others rotate
-                int a = (pr == 0) ? mp - 1 : (round + pr) % (mp - 1);
-                int b = (round + mp - 1 - pr) % (mp - 1);
-                int p = min(a, b), q = max(a, b);
-                if (q >= m) continue;
-                double *gp = G + (size_t)p * m, *gq = G + (size_t)q * m;
+                const int a = (pr == 0) ? mp - 1 : (round + pr) % (mp - 1);
+                const int b = (round + mp - 1 - pr) % (mp - 1);
+                const int p = min(a, b), q = max(a, b);
+                const bool valid = pr < mp / 2 && q < m;
+                double *gp = G + (size_t)(valid ? p : 0) * m, *gq = G + (size_t)(valid ? q : 0) * m;
                 double al = 0.0, be = 0.0, ga = 0.0;
-                for (int r = lane; r < m; r += 32) {
-                    const double x = gp[r], y = gq[r];
-                    al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+                if (valid) {
+                    for (int r = hl; r < m; r += 16) {
+                        const double x = gp[r], y = gq[r];
+                        al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+                    }
                 }
-                al = ab_warp_sum_f64(al); be = ab_warp_sum_f64(be); ga = ab_warp_sum_f64(ga);
-                if (fabs(ga) > 1e-15 * sqrt(al * be) && fabs(ga) > 1e-300) {
-                    if (lane == 0) rot_sm = 1;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) {                // stays inside the half-warp
+                    al += ab_shfl_xor_f64(al, o);
+                    be += ab_shfl_xor_f64(be, o);
+                    ga += ab_shfl_xor_f64(ga, o);
+                }
+                // rotate down to rounding level, but call the sweep "dirty" only above 1e-14: pairs
+                // hovering at 1e-15..1e-16 (pure rounding noise) would otherwise keep the loop alive
+                // for all 60 sweeps without changing any singular vector beyond 1e-14
+                if (valid && fabs(ga) > 1e-15 * sqrt(al * be) && fabs(ga) > 1e-300) {
+                    if (hl == 0 && fabs(ga) > 1e-14 * sqrt(al * be)) rot_sm = 1;
                     const double zeta = (be - al) / (2.0 * ga);
                     const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
                     const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
                     double *qp = Q + (size_t)p * m, *qq = Q + (size_t)q * m;
-                    for (int r = lane; r < m; r += 32) {
+                    for (int r = hl; r < m; r += 16) {
                         const double x = gp[r], y = gq[r];
                         gp[r] = cs * x - sn * y; gq[r] = sn * x + cs * y;
                         const double u = qp[r], v = qq[r];
@@ -456,7 +582,18 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
     double *ms = smr + (size_t)work * RZ_THREADS;       // [work][RZ_COLS]
     const int64_t row = (int64_t)blockIdx.x * RZ_THREADS + threadIdx.x;
     const bool live = row < n;
-    for (int l = 0; l < work; ++l) xs[(size_t)l * RZ_THREADS + threadIdx.x] = live ? X[(int64_t)l * ld + row] : 0.0;
+    {
+        // eight loads in flight per thread (a plain load->store loop keeps one)
+        int l = 0;
+        for (; l + 8 <= work; l += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = live ? X[(int64_t)(l + u) * ld + row] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xs[(size_t)(l + u) * RZ_THREADS + threadIdx.x] = t[u];
+        }
+        for (; l < work; ++l) xs[(size_t)l * RZ_THREADS + threadIdx.x] = live ? X[(int64_t)l * ld + row] : 0.0;
+    }
     for (int c0 = 0; c0 < ncols; c0 += RZ_COLS) {
         __syncthreads();
         for (int e = threadIdx.x; e < work * RZ_COLS; e += RZ_THREADS) {
@@ -518,8 +655,8 @@ static int irlb_work_dim(int nval, int64_t n_total) {
 }
 
 static int av_warps_for(int H) {
-    int w = (int)((200 * 1024) / ((size_t)H * 8));
-    if (w > 8) w = 8;
+    int w = (int)((216 * 1024) / ((size_t)H * 8));
+    if (w > 12) w = 12;
     return w;
 }
 
@@ -543,7 +680,7 @@ static size_t irlb_layout(int64_t n, int H, int nval, int64_t n_total_hint, int 
     w.scal = a.take<double>(SC_COUNT);
     w.coef = a.take<double>(IR_MAXWORK);
     w.wraw = a.take<double>(H);
-    w.dot_grid = (n + DOT_TILE - 1) / DOT_TILE;
+    w.dot_grid = std::min<int64_t>((n + DOT_THREADS - 1) / DOT_THREADS, (int64_t)sm_count * 4);
     if (w.dot_grid < 1) w.dot_grid = 1;
     w.dot_partial = a.take<double>((size_t)w.dot_grid * IR_MAXWORK);
     w.nrm_partial = a.take<double>((size_t)(w.dot_grid > 1024 ? w.dot_grid : 1024));
@@ -579,6 +716,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     const int64_t n = n_local, ld = n_local > 0 ? n_local : 1;
     int *cnt = ctx->d_counter;
 
+    ab_prof_begin(ctx, AB_PROF_IRLB_TOTAL, st);
     AB_CUDA(cudaMemsetAsync(w.V, 0, (size_t)ld * work * 8, st));
     AB_CUDA(cudaMemsetAsync(w.V2, 0, (size_t)ld * work * 8, st));
     AB_CUDA(cudaMemsetAsync(w.W, 0, (size_t)H * work * 8, st));
@@ -591,6 +729,9 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     AB_CUDA(cudaFuncSetAttribute(av_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
     const size_t ws_smem = ((size_t)H + IR_MAXWORK + 40) * 8;
     AB_CUDA(cudaFuncSetAttribute(wstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem));
+    const int q_in_smem = (size_t)2 * work * work * 8 <= (size_t)200 * 1024 ? 1 : 0;
+    const size_t svd_smem = (size_t)(q_in_smem ? 2 : 1) * work * work * 8;
+    AB_CUDA(cudaFuncSetAttribute(svd_restart_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
     const size_t rz_smem_v = ((size_t)work * RZ_THREADS + (size_t)work * RZ_COLS) * 8;
     AB_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rz_smem_v));
 
@@ -603,11 +744,13 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     int64_t nmult = 0, sum_panel = 0;
 
     auto av = [&](const double *src, const double *sumsq, double *vdst) -> int {
-        av_kernel<<<w.av_grid, 256, av_smem, st>>>(rowptr_h, col_h, val_h, n, H, src, sumsq, vdst, w.av_warps,
+        ab_prof_begin(ctx, AB_PROF_IRLB_AV, st);
+        av_kernel<<<w.av_grid, 384, av_smem, st>>>(rowptr_h, col_h, val_h, n, H, src, sumsq, vdst, w.av_warps,
                                                     w.av_partial);
         AB_LAUNCH_CHECK(ctx);
         av_reduce_kernel<<<(H + 127) / 128, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw);
         AB_LAUNCH_CHECK(ctx);
+        ab_prof_end(ctx, AB_PROF_IRLB_AV, st);
         if (ab_allreduce_f64(ctx, w.wraw, H, st)) return 1;
         nmult++;
         return 0;
@@ -628,39 +771,51 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         int j = it > 0 ? keep : 0;
         // W[:,j] = A.V[:,j]  (irlb.py:165), orthogonalised against W[:, :j] on restarts (:173-175)
         if (av(w.V + (int64_t)j * ld, nullptr, nullptr)) return 1;
+        ab_prof_begin(ctx, AB_PROF_IRLB_SMALL, st);
         wstep_kernel<<<1, 1024, ws_smem, st>>>(w.wraw, w.W, H, j, it > 0 ? j : 0, 0, w.scal, w.B, work, -1);
         AB_LAUNCH_CHECK(ctx);
+        ab_prof_end(ctx, AB_PROF_IRLB_SMALL, st);
         while (j < work) {
+            ab_prof_begin(ctx, AB_PROF_IRLB_ATW, st);
             atw_kernel<<<g_rows, 256, 0, st>>>(rowptr_h, col_h, val_h, n, w.W + (size_t)j * H, w.V + (int64_t)j * ld,
                                                 w.scal, w.F);
             AB_LAUNCH_CHECK(ctx);
+            ab_prof_end(ctx, AB_PROF_IRLB_ATW, st);
             nmult++;
+            ab_prof_begin(ctx, AB_PROF_IRLB_PANEL, st);
             panel_dot_kernel<<<g_dot, DOT_THREADS, 0, st>>>(w.V, ld, n, j + 1, w.F, w.dot_partial, w.coef, cnt + 1);
             AB_LAUNCH_CHECK(ctx);
             if (ab_allreduce_f64(ctx, w.coef, j + 1, st)) return 1;
             panel_update_kernel<<<g_dot, DOT_THREADS, 0, st>>>(w.V, ld, n, j + 1, w.coef, w.F, w.nrm_partial,
                                                                 w.scal + SC_FN2, cnt + 2);
             AB_LAUNCH_CHECK(ctx);
+            ab_prof_end(ctx, AB_PROF_IRLB_PANEL, st);
             if (ab_allreduce_f64(ctx, w.scal + SC_FN2, 1, st)) return 1;
             sum_panel += j + 1;
             if (j < work - 1) {
                 // V[:,j+1] = F/fn ; W[:,j+1] = A.V[:,j+1] - fn W[:,j], CGS, normalise (irlb.py:195-219)
                 if (av(w.F, w.scal + SC_FN2, w.V + (int64_t)(j + 1) * ld)) return 1;
+                ab_prof_begin(ctx, AB_PROF_IRLB_SMALL, st);
                 wstep_kernel<<<1, 1024, ws_smem, st>>>(w.wraw, w.W, H, j + 1, j + 1, 1, w.scal, w.B, work, j);
                 AB_LAUNCH_CHECK(ctx);
+                ab_prof_end(ctx, AB_PROF_IRLB_SMALL, st);
             } else {
                 fscale_kernel<<<g_vec, 256, 0, st>>>(w.F, n, w.scal, w.B, work, j);
                 AB_LAUNCH_CHECK(ctx);
             }
             ++j;
         }
-        svd_restart_kernel<<<1, 512, 0, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it, keep);
+        ab_prof_begin(ctx, AB_PROF_IRLB_SVD, st);
+        svd_restart_kernel<<<1, 1024, svd_smem, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it,
+                                                     keep, q_in_smem);
         AB_LAUNCH_CHECK(ctx);
+        ab_prof_end(ctx, AB_PROF_IRLB_SVD, st);
         AB_CUDA(cudaMemcpyAsync(h_ctrl, w.ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, st));
         AB_CUDA(cudaStreamSynchronize(st));
         if (h_ctrl[CT_DONE]) { converged = true; break; }
         keep = h_ctrl[CT_KEEP];
         // Ritz vectors (irlb.py:238-246)
+        ab_prof_begin(ctx, AB_PROF_IRLB_RITZ, st);
         ritz_kernel<<<g_rz, RZ_THREADS, rz_smem_v, st>>>(w.V, ld, n, work, w.Vb, keep, w.V2, ld, 0, nullptr, nullptr);
         AB_LAUNCH_CHECK(ctx);
         copy_vec_kernel<<<g_vec, 256, 0, st>>>(w.F, w.V2 + (int64_t)keep * ld, n);
@@ -669,6 +824,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         AB_LAUNCH_CHECK(ctx);
         reset_b_kernel<<<8, 256, 0, st>>>(w.B, work, w.sb, w.R, keep);
         AB_LAUNCH_CHECK(ctx);
+        ab_prof_end(ctx, AB_PROF_IRLB_RITZ, st);
         std::swap(w.V, w.V2);
         std::swap(w.W, w.W2);
         ++it;
@@ -681,6 +837,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         AB_LAUNCH_CHECK(ctx);
     }
     if (s_out) AB_CUDA(cudaMemcpyAsync(s_out, w.sb, (size_t)nval * 8, cudaMemcpyDeviceToDevice, st));
+    ab_prof_end(ctx, AB_PROF_IRLB_TOTAL, st);
     AB_CUDA(cudaStreamSynchronize(st));
     if (h_info) {
         h_info[0] = it;

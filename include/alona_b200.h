@@ -161,7 +161,7 @@ int64_t ab_launch_count(ab_ctx *ctx);
 /* ---- measurement: CUDA-event pairs recorded on the launching stream around the named kernels ----
  * level 0 = off (default), 1 = one pair per stage-level kernel (norm_moments, hvg_extract, knn_prep,
  * knn_main, knn_rerank, snn_build, snn_count, snn_fill, irlb_total), 2 = additionally every IRLBA launch
- * (irlb_av, irlb_atw, irlb_panel, irlb_small).  ab_prof_read synchronises the slot's events, returns the
+ * (irlb_av, irlb_atw, irlb_panel, irlb_small, irlb_ritz, irlb_svd).  ab_prof_read synchronises the slot's events, returns the
  * summed device time in ms and the number of pairs since the last read, and clears the slot.
  * (bench.py's roofline fields come from here; the reference has no counterpart.) */
 #define AB_PROF_SLOTS 16
