@@ -73,9 +73,11 @@ extern "C" int ab_norm_moments(ab_ctx *ctx, const int64_t *rowptr, const int32_t
     int64_t blocks = (n_local + NORM_WARPS - 1) / NORM_WARPS;
     int64_t cap = (int64_t)ctx->sm_count * 8 * 4;         // 8 CTAs/SM resident, 4 waves
     if (blocks > cap) blocks = cap;
+    ab_prof_begin(ctx, AB_PROF_NORM, (cudaStream_t)stream);
     norm_moments_kernel<<<(unsigned)blocks, NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rowptr, col, val, n_local, n_genes, scale, libsize, gsum, gsumsq);
     AB_LAUNCH_CHECK(ctx);
+    ab_prof_end(ctx, AB_PROF_NORM, (cudaStream_t)stream);
     return 0;
 }
 
@@ -141,8 +143,10 @@ extern "C" int ab_hvg_extract_count(ab_ctx *ctx, const int64_t *rowptr, const in
         int64_t blocks = (n_local + NORM_WARPS - 1) / NORM_WARPS;
         int64_t cap = (int64_t)ctx->sm_count * 8 * 4;
         if (blocks > cap) blocks = cap;
+        ab_prof_begin(ctx, AB_PROF_HVG_EXTRACT, st);
         hvg_count_kernel<<<(unsigned)blocks, NORM_WARPS * 32, 0, st>>>(rowptr, col, n_local, gene2hvg, rowptr_h);
         AB_LAUNCH_CHECK(ctx);
+        ab_prof_end(ctx, AB_PROF_HVG_EXTRACT, st);
     }
     if (ab_exclusive_scan_i64(ctx, rowptr_h, rowptr_h, n_local, ws, ws_bytes, st)) return 1;
     if (h_nnz) {
@@ -161,8 +165,10 @@ extern "C" int ab_hvg_extract_fill(ab_ctx *ctx, const int64_t *rowptr, const int
     int64_t blocks = (n_local + NORM_WARPS - 1) / NORM_WARPS;
     int64_t cap = (int64_t)ctx->sm_count * 8 * 4;
     if (blocks > cap) blocks = cap;
+    ab_prof_begin(ctx, AB_PROF_HVG_EXTRACT, (cudaStream_t)stream);
     hvg_fill_kernel<<<(unsigned)blocks, NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rowptr, col, val, libsize, n_local, gene2hvg, scale, rowptr_h, col_h, val_h);
     AB_LAUNCH_CHECK(ctx);
+    ab_prof_end(ctx, AB_PROF_HVG_EXTRACT, (cudaStream_t)stream);
     return 0;
 }

@@ -694,6 +694,7 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     AB_CUDA(cudaMemsetAsync(w.counters, 0, 16 * sizeof(int), st));
     AB_CUDA(cudaMemsetAsync(w.walk_stats, 0, 2 * sizeof(unsigned long long), st));
     const unsigned eb = (unsigned)((total + 255) / 256);
+    ab_prof_begin(ctx, AB_PROF_SNN_BUILD, st);
     snn_degree_kernel<<<eb, 256, 0, st>>>(knn_all, total, n_total, w.deg, w.counters + 3);
     AB_LAUNCH_CHECK(ctx);
     if (ab_exclusive_scan_i64(ctx, w.deg, w.deg, n_total, w.scan_ws, w.scan_bytes, st)) return 1;
@@ -707,6 +708,8 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     AB_LAUNCH_CHECK(ctx);
     snn_sort_long_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(w.deg, w.rlist, w.long_ids, w.counters + 0, w.tmp);
     AB_LAUNCH_CHECK(ctx);
+    ab_prof_end(ctx, AB_PROF_SNN_BUILD, st);
+    ab_prof_begin(ctx, AB_PROF_SNN_COUNT, st);
     if (n_rows > 0) {
         snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
             knn_all, k, row_begin, n_rows, w.deg, w.cls_rows, w.counters + 4, snn_walk_cap(SNN_MID_SLOTS),
@@ -720,6 +723,7 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
             return 1;
     }
     if (ab_exclusive_scan_i64(ctx, w.rowcount, rowptr, n_rows, w.scan_ws, w.scan_bytes, st)) return 1;
+    ab_prof_end(ctx, AB_PROF_SNN_COUNT, st);
     int h_cnt[8];
     unsigned long long h_walk[2] = {0, 0};
     AB_CUDA(cudaMemcpyAsync(h_cnt, w.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -748,6 +752,9 @@ extern "C" int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total,
     size_t need = snn_layout(n_total, k, n_rows, ws, ws_bytes, &w);
     AB_REQUIRE(need != 0, "ab_snn_fill: workspace too small");
     if (n_rows == 0) return 0;
-    return snn_launch_rows<true>(ctx, w, knn_all, n_total, k, row_begin, n_rows, v_min, rowptr, src, dst, overlap,
-                                 (cudaStream_t)stream);
+    ab_prof_begin(ctx, AB_PROF_SNN_FILL, (cudaStream_t)stream);
+    const int rc = snn_launch_rows<true>(ctx, w, knn_all, n_total, k, row_begin, n_rows, v_min, rowptr, src, dst, overlap,
+                                         (cudaStream_t)stream);
+    ab_prof_end(ctx, AB_PROF_SNN_FILL, (cudaStream_t)stream);
+    return rc;
 }

@@ -205,6 +205,8 @@ def main():
     for _ in range(args.warmup):
         out = one_step()
     barrier()
+    eng.prof_set_level(1)                       # one CUDA-event pair per stage-level kernel (no per-launch events)
+    eng.prof_read()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -220,6 +222,7 @@ def main():
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
+    kernel_ms = {k: v[0] / v[1] for k, v in eng.prof_read().items()}     # mean device ms per launch, timed region
     clocks = sampler.stop() if rank == 0 else None
     stage_ms = {k: v / args.steps for k, v in timer.result().items()}
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -284,7 +287,16 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except Exception:
         pass
-    roof = roofline(args, wl, world, stage_ms, info, peaks)
+    roof = roofline(wl, world, kernel_ms, peaks)
+    # per-kernel table from one extra, untimed pass with an event pair around every launch
+    eng.prof_set_level(2)
+    eng.prof_read()
+    o2 = one_step()
+    torch.cuda.synchronize()
+    fine = eng.prof_read()
+    eng.prof_set_level(0)
+    stages_roof = stage_rooflines(wl, world, fine, info, o2, peaks)
+    del o2
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -300,29 +312,66 @@ def main():
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f64 (normalise/HVG/IRLBA/re-rank), tf32x3 fp32-accumulate (distance GEMM), int32 (SNN)',
+            'dtype': 'f64 (normalise/HVG/IRLBA/re-rank), fp16x3 with fp32 accumulate (distance GEMM candidates), int32 (SNN)',
             'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': launches // max(1, args.steps),
-            'stage_ms': stage_ms, 'info': info, 'roofline': roof, 'cpu_baseline': cpu, 'e2e': e2e}
+            'stage_ms': stage_ms, 'kernel_ms': kernel_ms, 'info': info, 'roofline': roof,
+            'roofline_stages': stages_roof, 'cpu_baseline': cpu, 'e2e': e2e}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def roofline(args, wl, world, stage_ms, info, peaks):
-    """Dominant kernel = the kNN distance pass.  Algorithmic work: 2*N_q*N*d flops (true d)."""
+def roofline(wl, world, kernel_ms, peaks):
+    """Dominant kernel = knn_tc_kernel (the FP16x3 distance GEMM + top-m epilogue).
+    Algorithmic work per launch: 2 * N_q * N * d flops (true d); duration = the CUDA-event
+    pair the library records around the launch on its stream, averaged over the timed steps."""
     n, d = wl['cells'], wl['pca_n']
     nq = n / world
-    knn_ms = stage_ms.get('knn')
-    if not knn_ms:
+    ms = kernel_ms.get('knn_main')
+    if not ms:
         return None
     flops = 2.0 * nq * n * d
-    achieved = flops / (knn_ms / 1e3) / 1e12
-    bf16 = peaks.get('bf16_tflops_sustained') or 1400.0
-    peak = bf16 / 2.0
-    return {'bound': 'tensor', 'kernel': 'knn distance pass (stage time incl. re-rank)', 'achieved': achieved,
-            'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
-            'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 = half the bf16 rate)'
-                           if peaks else 'fallback 1.4 PFLOP/s bf16 sustained / 2'}
+    achieved = flops / (ms / 1e3) / 1e12
+    peak = peaks.get('bf16_tflops_sustained') or 1400.0
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'knn_main_traffic.json')))
+        if t.get('n_total') == n and t.get('n_query') == int(nq):
+            traffic = t['dram_bytes']
+    except Exception:
+        pass
+    return {'bound': 'tensor', 'kernel': 'knn_tc_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': achieved / peak, 'traffic': traffic, 'ms_per_launch': ms, 'flops_per_launch': flops,
+            'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step; FP16 and '
+                            'bf16 share the tensor rate); 3 FP16 products per useful flop + K padding 153->160 cap '
+                            'this fraction at 0.3125') if peaks else 'fallback 1.4 PFLOP/s sustained'}
+
+
+def stage_rooflines(wl, world, fine, info, out, peaks):
+    """HBM-bound kernels: achieved GB/s = algorithmic bytes / device ms of the event slot."""
+    hbm = peaks.get('hbm_gbs') or 6650.0
+    n_loc = wl['cells'] / world
+    G, H, k = wl['genes'], wl['hvg_n'], wl['k']
+    nnz, nnz_h = info['nnz'], info['nnz_hvg']
+    nmult, sum_panel = info['nmult'], info['sum_panel']
+    rows = []
+
+    def add(name, slot, nbytes):
+        if slot in fine and fine[slot][0] > 0:
+            ms = fine[slot][0]
+            rows.append({'kernel': name, 'bound': 'hbm', 'ms_total': ms, 'launches': fine[slot][1],
+                         'bytes': nbytes, 'achieved': nbytes / (ms / 1e3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                         'frac': nbytes / (ms / 1e3) / 1e9 / hbm})
+    add('norm_moments_kernel', 'norm_moments', nnz * 8 + (n_loc + 1) * 8 + n_loc * 8 + 2 * G * 8)
+    add('hvg_count+hvg_fill', 'hvg_extract', nnz * 8 + nnz * 4 + n_loc * 8 + nnz_h * 12)
+    add('atw_kernel (A^T w)', 'irlb_atw', (nmult / 2) * (nnz_h * 12 + n_loc * 24))
+    add('av_kernel (A v)', 'irlb_av', (nmult / 2) * (nnz_h * 12 + n_loc * 24))
+    add('panel_dot+panel_update', 'irlb_panel', 8 * n_loc * (2 * sum_panel + 3 * (nmult / 2)))
+    walk = out['snn'].get('sum_walk', 0)
+    e = int(out['snn']['src'].numel())
+    add('snn count kernels', 'snn_count', 4 * wl['cells'] * k + 4 * walk)
+    add('snn fill kernels', 'snn_fill', 4 * wl['cells'] * k + 8 * walk + e * 8)
+    return rows
 
 
 if __name__ == '__main__':
