@@ -29,11 +29,17 @@ def start_vector(n_total, seed):
 class StageTimer:
     """CUDA-event timer per stage (events on the current stream)."""
 
-    def __init__(self, enabled=True):
+    def __init__(self, enabled=True, verbose=False):
         self.enabled = enabled
+        self.verbose = verbose
         self.marks = []
 
     def mark(self, name):
+        if self.enabled and self.verbose:
+            import sys
+            torch.cuda.synchronize()
+            sys.stderr.write('[frontend] reached %s\n' % name)
+            sys.stderr.flush()
         if self.enabled:
             e = torch.cuda.Event(enable_timing=True)
             e.record()

@@ -37,6 +37,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cells', type=int, default=0, help='override the workload cell count (debug)')
+    ap.add_argument('--verbose', action='store_true', help='progress markers on stderr (debug)')
     return ap.parse_args()
 
 
@@ -170,6 +171,16 @@ def main():
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 
+    def note(msg):
+        if args.verbose:
+            sys.stderr.write('[bench rank %d %.1fs] %s\n' % (rank, time.perf_counter() - t_start, msg))
+            sys.stderr.flush()
+    t_start = time.perf_counter()
+    if args.verbose:
+        import faulthandler
+        import signal
+        faulthandler.register(signal.SIGUSR1, all_threads=True)
+        faulthandler.dump_traceback_later(int(os.environ.get('AB_BENCH_DUMP_AFTER', '90')), exit=True)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -180,8 +191,10 @@ def main():
     from alona_b200.engine import get_engine
     from alona_b200.pipeline import frontend, StageTimer, shard_bounds, start_vector
     from alona_b200.synth import make_profiles
+    note('process group up')
     eng = get_engine()
     dev = eng.device
+    note('engine + NCCL communicator up')
 
     # ---- synthetic input, generated on the device, shard by shard ---------------------------
     bounds = shard_bounds(wl['cells'], world)
@@ -189,6 +202,7 @@ def main():
     prof = torch.from_numpy(make_profiles(wl['genes'])).to(dev)
     A = eng.synth_counts(prof, lo, hi - lo, wl['lbar'], n_total=wl['cells'])
     torch.cuda.synchronize()
+    note('synthetic shard generated: %d nnz' % A.nnz)
     nnz_local = A.nnz
     v0 = start_vector(wl['cells'], args.seed)
 
@@ -202,9 +216,11 @@ def main():
         return frontend(eng, A, wl['hvg_n'], wl['pca_n'], wl['k'], 0.067, args.seed, knn_mode=args.knn_mode, v0=v0,
                         timer=timer)
 
-    for _ in range(args.warmup):
-        out = one_step()
+    for i in range(args.warmup):
+        out = one_step(StageTimer(True, verbose=True) if args.verbose else None)
+        note('warm-up step %d done' % i)
     barrier()
+    note('barrier after warm-up passed')
     eng.prof_set_level(1)                       # one CUDA-event pair per stage-level kernel (no per-launch events)
     eng.prof_read()
     sampler = ClockSampler(local_rank)
@@ -219,7 +235,9 @@ def main():
     for _ in range(args.steps):
         out = one_step(timer)
     ev1.record()
+    note('timed steps enqueued')
     barrier()
+    note('timed region closed')
     total_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
     kernel_ms = {k: v[0] / v[1] for k, v in eng.prof_read().items()}     # mean device ms per launch, timed region
@@ -236,6 +254,18 @@ def main():
             'nnz': nnz_local, 'nnz_hvg': nnz_h, 'edges': edges_local,
             'knn_stats': out['knn_stats'].cpu().numpy().tolist(), 'snn_big_rows': out['snn']['big_rows'],
             'snn_max_walk': out['snn']['max_walk'], 'hvg_stats': out['hvg_stats'].cpu().numpy().tolist()}
+
+    # ---- per-kernel table: one extra, untimed pass (ALL ranks: it contains the collectives) with an
+    # event pair around every launch -----------------------------------------------------------
+    eng.prof_set_level(2)
+    eng.prof_read()
+    o2 = one_step()
+    torch.cuda.synchronize()
+    fine = eng.prof_read()
+    eng.prof_set_level(0)
+    fine_snn = {'sum_walk': o2['snn'].get('sum_walk', 0), 'edges': int(o2['snn']['src'].numel())}
+    del o2
+    note('fine-grained profiling pass done')
 
     # ---- end to end through the public API with HOST buffers -------------------------------
     e2e = None
@@ -288,15 +318,7 @@ def main():
     except Exception:
         pass
     roof = roofline(wl, world, kernel_ms, peaks)
-    # per-kernel table from one extra, untimed pass with an event pair around every launch
-    eng.prof_set_level(2)
-    eng.prof_read()
-    o2 = one_step()
-    torch.cuda.synchronize()
-    fine = eng.prof_read()
-    eng.prof_set_level(0)
-    stages_roof = stage_rooflines(wl, world, fine, info, o2, peaks)
-    del o2
+    stages_roof = stage_rooflines(wl, world, fine, info, fine_snn, peaks)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -367,8 +389,8 @@ def stage_rooflines(wl, world, fine, info, out, peaks):
     add('atw_kernel (A^T w)', 'irlb_atw', (nmult / 2) * (nnz_h * 12 + n_loc * 24))
     add('av_kernel (A v)', 'irlb_av', (nmult / 2) * (nnz_h * 12 + n_loc * 24))
     add('panel_dot+panel_update', 'irlb_panel', 8 * n_loc * (2 * sum_panel + 3 * (nmult / 2)))
-    walk = out['snn'].get('sum_walk', 0)
-    e = int(out['snn']['src'].numel())
+    walk = out['sum_walk']
+    e = out['edges']
     add('snn count kernels', 'snn_count', 4 * wl['cells'] * k + 4 * walk)
     add('snn fill kernels', 'snn_fill', 4 * wl['cells'] * k + 8 * walk + e * 8)
     return rows
