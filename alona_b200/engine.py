@@ -117,18 +117,14 @@ class Engine:
         """All-gather of row blocks with per-rank row counts `counts` (list); returns [sum(counts), ...]."""
         if self.world == 1:
             return local
+        from .pipeline import pack_rows, unpack_rows
         mx = max(counts)
-        rest = tuple(local.shape[1:])
-        pad = self.zeros((mx,) + rest, local.dtype)
-        pad[:local.shape[0]] = local
-        out = self.empty((self.world * mx,) + rest, local.dtype)
+        pad = pack_rows(local, mx)
+        out = self.empty((self.world * mx,) + tuple(local.shape[1:]), local.dtype)
         nbytes = pad.numel() * pad.element_size()
         _lib.check(self.lib.ab_allgather_bytes(self.ctx, _ptr(pad), _ptr(out), nbytes, self.stream()),
                    'ab_allgather_bytes')
-        if all(c == mx for c in counts):
-            return out
-        parts = [out[r * mx: r * mx + counts[r]] for r in range(self.world)]
-        return torch.cat(parts, dim=0)
+        return unpack_rows(out, counts)
 
     # -- uploads ----------------------------------------------------------------------
     def upload_csr(self, csr, row_begin=0, n_total=None, non_blocking=False):

@@ -20,6 +20,26 @@ def shard_bounds(n_total, world):
     return [(n_total * r) // world for r in range(world + 1)]
 
 
+def pack_rows(local, n_max):
+    """Pads a rank's row block to n_max rows (zeros) so that an equal-sized all-gather can carry
+    ragged shards.  Works on any torch tensor (device or host)."""
+    if local.shape[0] == n_max:
+        return local.contiguous()
+    pad = local.new_zeros((n_max,) + tuple(local.shape[1:]))
+    pad[:local.shape[0]] = local
+    return pad
+
+
+def unpack_rows(gathered, counts):
+    """Inverse of pack_rows on the gathered [world * max(counts), ...] tensor: drops the padding and
+    returns the rows in rank order (= global row order, shards are contiguous row ranges)."""
+    n_max = max(counts)
+    if all(c == n_max for c in counts):
+        return gathered
+    import torch as _torch
+    return _torch.cat([gathered[r * n_max: r * n_max + c] for r, c in enumerate(counts)], dim=0)
+
+
 def start_vector(n_total, seed):
     """The reference's start vector (alona/irlbpy/irlb.py:151-152)."""
     np.random.seed(seed)
