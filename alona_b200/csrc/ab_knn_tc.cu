@@ -344,6 +344,10 @@ __device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long 
 __device__ __forceinline__ void sts_b64(uint32_t addr, unsigned long long v) {
     asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
+// 64-bit shared store of (lo, hi) without assembling a 64-bit register pair first
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t lo, uint32_t hi) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi) : "memory");
+}
 __device__ __forceinline__ unsigned long long lds_b64(uint32_t addr) {
     unsigned long long v;
     asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
@@ -369,7 +373,11 @@ __device__ __noinline__ float warp_prune_t(unsigned lanes, unsigned long long *c
         unsigned long long x[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) x[e] = list[e * 32 + lane];
-        unsigned long long b = lane < cntL ? lds_b64(colL + (uint32_t)lane * (TC_EPI_THREADS * 8)) : TC_KEY_MAX;
+        unsigned long long b = TC_KEY_MAX;
+        if (lane < cntL) {                                   // buffer entries are raw (score bits, point id) pairs
+            const unsigned long long raw = lds_b64(colL + (uint32_t)lane * (TC_EPI_THREADS * 8));
+            b = cand_key(__uint_as_float((uint32_t)(raw >> 32)), (int)(uint32_t)raw);
+        }
         b = warp_sort_desc(b, lane);
         // bitonic split against the (virtual) upper half [MAX.. , b descending]: only the top 32 slots matter
         x[E - 1] = x[E - 1] < b ? x[E - 1] : b;
@@ -446,7 +454,7 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, boo
             for (int jj = 0; jj < 8; ++jj) {
                 const float sc = __uint_as_float(r[8 * g + jj]);
                 if (sc < tau) {
-                    sts_b64(bufaddr + (uint32_t)cnt * (TC_EPI_THREADS * 8), cand_key(sc, cbase + 8 * g + jj));
+                    sts_v2(bufaddr + (uint32_t)cnt * (TC_EPI_THREADS * 8), (uint32_t)(cbase + 8 * g + jj), r[8 * g + jj]);
                     ++cnt;
                 }
             }
@@ -632,18 +640,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             tc_fence_after();
             const int64_t col0 = t * x_per_tile + (P.mt == 1 ? half * TC_TILE : 0);
             const uint32_t taddr = taddr0 + (uint32_t)buf * 256;
-            uint32_t ra[32], rb[32];
+            uint32_t ra[32];
 #pragma unroll 1
-            for (int c2 = 0; c2 < ((P.dbg & 4) ? 0 : ((P.dbg & 8) ? 1 : TC_TILE / 64)); ++c2) {
-                // two units per wait: no tcgen05.ld is in flight while the (call-heavy) rare path runs
-                tc_ld32(taddr + (2 * c2) * 32, ra);
-                tc_ld32(taddr + (2 * c2 + 1) * 32, rb);
+            for (int cc = 0; cc < ((P.dbg & 4) ? 0 : TC_TILE / 32); ++cc) {
+                // one unit per load/wait: a single instantiation of the scan keeps the hot loop small enough for
+                // the instruction cache (two inlined copies cost 19 % of the cycles in no-instruction stalls);
+                // the other epilogue warp of the scheduler covers the tcgen05.ld latency
+                tc_ld32(taddr + cc * 32, ra);
                 tc_wait_ld();
                 tc_touch32(ra);
-                tc_touch32(rb);
                 if (P.dbg & 1) continue;
-                epi_unit(ra, (int)col0 + (2 * c2) * 32, live, P, list_id, q, cnt, tau, bufaddr, lane);
-                epi_unit(rb, (int)col0 + (2 * c2 + 1) * 32, live, P, list_id, q, cnt, tau, bufaddr, lane);
+                epi_unit(ra, (int)col0 + cc * 32, live, P, list_id, q, cnt, tau, bufaddr, lane);
             }
             tc_fence_before();
             __syncwarp();
