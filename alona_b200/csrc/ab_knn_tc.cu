@@ -49,7 +49,7 @@ int ab_knn_exact_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, con
 static constexpr int TC_TILE = 128;          // UMMA M and N
 static constexpr int TC_KCH = 32;            // halves per K chunk = one 64-byte swizzle row
 static constexpr int TC_SLAB = TC_TILE * 64; // bytes of one 128-row x 64-byte operand slab (8 KB)
-static constexpr int TC_MAX_STAGES = 12;
+static constexpr int TC_MAX_STAGES = 16;
 static constexpr int TC_MAX_CHUNKS = 10;     // 3d+3 <= 320  ->  d <= 105
 static constexpr double TC_KAPPA = 1.52587890625e-05;   // 2^-16
 
@@ -316,12 +316,13 @@ struct TcParams {
     int64_t nq;            // number of queries
     int chunks;            // K chunks of 32 halves
     int ksteps;            // UMMA K steps (16 halves) that carry data: ceil((3d+3)/16)
-    int stages;            // B ring depth
-    int group;             // chunks handled per barrier round (<= stages, <= 30)
+    int stages;            // B ring depth, in slots of `group` chunks
+    int group;             // K chunks per ring slot = per bulk copy and per barrier round
     int mt;                // 2: two query tiles x one 128-point B tile; 1: one query tile x 256-point B tile
     int m;                 // candidates kept per list
     unsigned long long *cand;   // [lists][nq][m] sorted keys, lists = 3 - mt
     const unsigned char *bop;   // tiled, pre-swizzled B operand (knn_b_pos)
+    unsigned long long *bufg;   // [grid][TC_BUF][256] append buffers
     int dbg;               // experiments only (AB_KNN_DBG): 1 = epilogue skips the score scan, 2 = no MMA issue
 };
 
@@ -361,21 +362,21 @@ __device__ __forceinline__ unsigned long long lds_b64(uint32_t addr) {
 // Bitonic split + merge entirely in registers/shuffles.  Warp-uniform call.
 template <int E>
 __device__ __noinline__ float warp_prune_t(unsigned lanes, unsigned long long *cand_list0, long long q_lane, int cnt,
-                                           uint32_t bufaddr, int lane) {
+                                           const unsigned long long *bufp, int lane) {
     float my_tau = 0.f;
     while (lanes) {
         const int L = __ffs(lanes) - 1;
         lanes &= lanes - 1;
         const int cntL = __shfl_sync(AB_FULL, cnt, L);
         const long long qL = __shfl_sync(AB_FULL, q_lane, L);
-        const uint32_t colL = __shfl_sync(AB_FULL, bufaddr, L);
+        const unsigned long long *colL = (const unsigned long long *)__shfl_sync(AB_FULL, (unsigned long long)bufp, L);
         unsigned long long *list = cand_list0 + (size_t)qL * (32 * E);
         unsigned long long x[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) x[e] = list[e * 32 + lane];
         unsigned long long b = TC_KEY_MAX;
         if (lane < cntL) {                                   // buffer entries are raw (score bits, point id) pairs
-            const unsigned long long raw = lds_b64(colL + (uint32_t)lane * (TC_EPI_THREADS * 8));
+            const unsigned long long raw = __ldcg(colL + (size_t)lane * TC_EPI_THREADS);
             b = cand_key(__uint_as_float((uint32_t)(raw >> 32)), (int)(uint32_t)raw);
         }
         b = warp_sort_desc(b, lane);
@@ -415,14 +416,14 @@ __device__ __noinline__ float warp_prune_t(unsigned lanes, unsigned long long *c
 
 // prunes the lanes in `lanes` (warp-uniform mask), updating their (cnt, tau)
 __device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, int list_id, long long q_lane, int &cnt,
-                                           float &tau, uint32_t bufaddr, int lane) {
+                                           float &tau, unsigned long long *bufp, int lane) {
     unsigned long long *cg = P.cand + (size_t)list_id * P.nq * P.m;
     float t;
     switch (P.m) {
-        case 32: t = warp_prune_t<1>(lanes, cg, q_lane, cnt, bufaddr, lane); break;
-        case 64: t = warp_prune_t<2>(lanes, cg, q_lane, cnt, bufaddr, lane); break;
-        case 128: t = warp_prune_t<4>(lanes, cg, q_lane, cnt, bufaddr, lane); break;
-        default: t = warp_prune_t<8>(lanes, cg, q_lane, cnt, bufaddr, lane); break;
+        case 32: t = warp_prune_t<1>(lanes, cg, q_lane, cnt, bufp, lane); break;
+        case 64: t = warp_prune_t<2>(lanes, cg, q_lane, cnt, bufp, lane); break;
+        case 128: t = warp_prune_t<4>(lanes, cg, q_lane, cnt, bufp, lane); break;
+        default: t = warp_prune_t<8>(lanes, cg, q_lane, cnt, bufp, lane); break;
     }
     if ((lanes >> lane) & 1u) { tau = t; cnt = 0; }
 }
@@ -433,7 +434,7 @@ __device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, in
 // group is guaranteed beforehand; lanes short of room are pruned first, which also tightens
 // their threshold).  Padding columns carry a huge score (see knn_prep_kernel) and never pass.
 __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, bool live, const TcParams &P, int list_id,
-                                         long long q, int &cnt, float &tau, uint32_t bufaddr, int lane) {
+                                         long long q, int &cnt, float &tau, unsigned long long *bufp, int lane) {
     float gmin[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -448,13 +449,15 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, boo
     for (int g = 0; g < 4; ++g) {
         if (!__any_sync(AB_FULL, live && gmin[g] < tau)) continue;
         const unsigned tight = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
-        if (tight) warp_prune(tight, P, list_id, q, cnt, tau, bufaddr, lane);
+        if (tight) warp_prune(tight, P, list_id, q, cnt, tau, bufp, lane);
         if (live && gmin[g] < tau) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
                 const float sc = __uint_as_float(r[8 * g + jj]);
                 if (sc < tau) {
-                    sts_v2(bufaddr + (uint32_t)cnt * (TC_EPI_THREADS * 8), (uint32_t)(cbase + 8 * g + jj), r[8 * g + jj]);
+                    // append buffers live in global memory (L2): appends are rare fire-and-forget stores, and the
+                    // shared memory they would take is worth more as operand ring
+                    bufp[(size_t)cnt * TC_EPI_THREADS] = ((unsigned long long)r[8 * g + jj] << 32) | (uint32_t)(cbase + 8 * g + jj);
                     ++cnt;
                 }
             }
@@ -466,14 +469,13 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, boo
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // layout: [A chunks][B stages][append buffers][barriers]
+    // layout: [A chunks][B ring: stages x group chunks][barriers]
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_chunk_bytes = P.mt * TC_SLAB;             // 128*mt query rows x 64 B
     const int b_stage_bytes = (3 - P.mt) * TC_SLAB;       // 128*(3-mt) database rows x 64 B
     unsigned char *sA = smem;
     unsigned char *sB = sA + (size_t)P.chunks * a_chunk_bytes;
-    unsigned long long *sBuf = reinterpret_cast<unsigned long long *>(sB + (size_t)P.stages * b_stage_bytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sBuf + (size_t)TC_BUF * TC_EPI_THREADS);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + (size_t)P.stages * P.group * b_stage_bytes);
     uint64_t *full = bars;                          // [stages]
     uint64_t *empty = bars + TC_MAX_STAGES;         // [stages]
     uint64_t *a_full = bars + 2 * TC_MAX_STAGES;
@@ -523,31 +525,28 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             for (int64_t t = 0; t < n_tiles; ++t) {
                 // slabs of this tile: one (mt = 2) or two (mt = 1) blocks of `chunks` x 8 KB
                 const unsigned char *slab0 = P.bop + (size_t)t * (3 - P.mt) * P.chunks * TC_SLAB;
+                // one ring slot = `group` consecutive K chunks of the tile = ONE contiguous bulk copy and ONE
+                // barrier round (measured: the per-copy / per-barrier issue overhead of 8 KB stages, not bytes
+                // or MMAs, set the floor of this kernel)
                 for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
                     const int gsz = min(P.group, P.chunks - c0);
-                    // lane l waits for the slot of chunk c0+l: the waits of a group overlap
-                    if (lane < gsz) {
-                        int sl = stage + lane;
-                        uint32_t ph = phase;
-                        if (sl >= P.stages) { sl -= P.stages; ph ^= 1; }
-                        mbar_wait(empty + sl, ph ^ 1);
-                    }
-                    __syncwarp();
+                    mbar_wait(empty + stage, phase ^ 1);
                     if (elect_one()) {
-                        for (int l = 0; l < gsz; ++l) {
-                            int sl = stage + l;
-                            if (sl >= P.stages) sl -= P.stages;
-                            const int c = c0 + l;
-                            mbar_expect_tx(full + sl, (uint32_t)b_stage_bytes);
-                            unsigned char *dst = sB + (size_t)sl * b_stage_bytes;
-                            bulk_load(dst, slab0 + (size_t)c * TC_SLAB, TC_SLAB, full + sl);
-                            if (P.mt == 1)
-                                bulk_load(dst + TC_SLAB, slab0 + (size_t)(P.chunks + c) * TC_SLAB, TC_SLAB, full + sl);
+                        const uint32_t bytes = (uint32_t)gsz * TC_SLAB;
+                        unsigned char *dst = sB + (size_t)stage * P.group * b_stage_bytes;
+                        if (P.dbg & 32) {                           // experiment: 1 KB per slot
+                            mbar_expect_tx(full + stage, 1024u);
+                            bulk_load(dst, slab0 + (size_t)c0 * TC_SLAB, 1024u, full + stage);
+                        } else {
+                            mbar_expect_tx(full + stage, bytes * (uint32_t)(3 - P.mt));
+                            bulk_load(dst, slab0 + (size_t)c0 * TC_SLAB, bytes, full + stage);
+                            if (P.mt == 1)                          // second 128-point slab of the 256-point tile
+                                bulk_load(dst + (size_t)P.group * TC_SLAB, slab0 + (size_t)(P.chunks + c0) * TC_SLAB, bytes,
+                                          full + stage);
                         }
                     }
                     __syncwarp();
-                    stage += gsz;
-                    if (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -560,9 +559,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         uint32_t phase = 0, aphase = 0;
         // descriptors: only the 14-bit start-address field changes; every offset used here is a multiple of 16
         const uint64_t a_desc0 = umma_desc_sw64(smem_u32(sA)), b_desc0 = umma_desc_sw64(smem_u32(sB));
-        const uint32_t a_step = (uint32_t)a_chunk_bytes >> 4, b_step = (uint32_t)b_stage_bytes >> 4;
-        const uint32_t a_half = P.mt == 2 ? (TC_SLAB >> 4) : 0;       // second query tile
-        const uint32_t b_half = P.mt == 1 ? (TC_SLAB >> 4) : 0;       // second half of a 256-point B tile
+        const uint32_t a_step = (uint32_t)a_chunk_bytes >> 4;
+        const uint32_t slot_step = (uint32_t)(P.group * b_stage_bytes) >> 4;      // ring slot
+        const uint32_t a_half = P.mt == 2 ? (TC_SLAB >> 4) : 0;                   // second query tile
+        const uint32_t b_half = P.mt == 1 ? ((uint32_t)(P.group * TC_SLAB) >> 4) : 0;   // second slab of a 256-point tile
         for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
             mbar_wait(a_full, aphase);
             aphase ^= 1;
@@ -571,37 +571,30 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
                 for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
                     const int gsz = min(P.group, P.chunks - c0);
-                    // lane l waits for chunk c0+l, lane 31 for the accumulator buffer: the waits overlap
-                    // (a serial try_wait per 8 KB stage costs more than the 256 tensor cycles the stage feeds)
-                    if (lane < gsz) {
-                        int sl = stage + lane;
-                        uint32_t ph = phase;
-                        if (sl >= P.stages) { sl -= P.stages; ph ^= 1; }
-                        mbar_wait(full + sl, ph);
-                    } else if (lane == 31 && c0 == 0) {
-                        mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
-                    }
+                    // lane 0 waits for the operands, lane 31 for the accumulator buffer: the waits overlap
+                    if (lane == 0) mbar_wait(full + stage, phase);
+                    else if (lane == 31 && c0 == 0) mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
                     __syncwarp();
                     tc_fence_after();
                     if (elect_one()) {
+                        const uint64_t b_slot = b_desc0 + (uint64_t)((uint32_t)stage * slot_step);
                         for (int l = 0; l < gsz; ++l) {
-                            int sl = stage + l;
-                            if (sl >= P.stages) sl -= P.stages;
                             const int c = c0 + l;
                             const uint64_t a_c = a_desc0 + (uint64_t)((uint32_t)c * a_step);
-                            const uint64_t b_s = b_desc0 + (uint64_t)((uint32_t)sl * b_step);
+                            const uint64_t b_s = b_slot + (uint64_t)((uint32_t)l * (TC_SLAB >> 4));
                             const bool two = P.ksteps - 2 * c >= 2 && !(P.dbg & 2);
-                            tc_mma_f16(tmem_d, a_c, b_s, idesc, (uint32_t)(c != 0));
-                            if (two) tc_mma_f16(tmem_d, a_c + 2, b_s + 2, idesc, 1u);
-                            tc_mma_f16(tmem_d + TC_TILE, a_c + a_half, b_s + b_half, idesc, (uint32_t)(c != 0));
-                            if (two) tc_mma_f16(tmem_d + TC_TILE, a_c + a_half + 2, b_s + b_half + 2, idesc, 1u);
-                            tc_commit(empty + sl);              // smem slot free once these MMAs retire
+                            if (!(P.dbg & 16)) {
+                                tc_mma_f16(tmem_d, a_c, b_s, idesc, (uint32_t)(c != 0));
+                                if (two) tc_mma_f16(tmem_d, a_c + 2, b_s + 2, idesc, 1u);
+                                tc_mma_f16(tmem_d + TC_TILE, a_c + a_half, b_s + b_half, idesc, (uint32_t)(c != 0));
+                                if (two) tc_mma_f16(tmem_d + TC_TILE, a_c + a_half + 2, b_s + b_half + 2, idesc, 1u);
+                            }
                         }
+                        tc_commit(empty + stage);                   // ring slot free once these MMAs retire
                         if (c0 + gsz == P.chunks) tc_commit(t_full + buf);   // accumulators ready for the epilogue
                     }
                     __syncwarp();
-                    stage += gsz;
-                    if (stage >= P.stages) { stage -= P.stages; phase ^= 1; }
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
             if (elect_one()) tc_commit(a_empty);                // A tiles may be overwritten
@@ -618,7 +611,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         const int row = lane_base + lane;
         const int etid = ew * 32 + lane;
         const int list_id = P.mt == 1 ? half : 0;
-        const uint32_t bufaddr = smem_u32(sBuf + etid);         // entry e at bufaddr + e * TC_EPI_THREADS * 8
+        unsigned long long *bufp = P.bufg + (size_t)blockIdx.x * TC_BUF * TC_EPI_THREADS + etid;   // entry e at bufp[e * 256]
         const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)half * TC_TILE;
         int64_t cur_block = -1;
         long long q = 0;
@@ -629,7 +622,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             const int64_t blk = it / n_tiles, t = it - blk * n_tiles;
             const int buf = (int)(it & 1);
             if (blk != cur_block) {
-                if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufaddr, lane);
+                if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufp, lane);
                 cur_block = blk;
                 q = (blockIdx.x + blk * gridDim.x) * q_per_block + (P.mt == 2 ? half * TC_TILE : 0) + row;
                 live = q < P.nq;
@@ -650,7 +643,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 tc_wait_ld();
                 tc_touch32(ra);
                 if (P.dbg & 1) continue;
-                epi_unit(ra, (int)col0 + cc * 32, live, P, list_id, q, cnt, tau, bufaddr, lane);
+                epi_unit(ra, (int)col0 + cc * 32, live, P, list_id, q, cnt, tau, bufp, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -658,9 +651,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             // prune AFTER handing the accumulator back: the merge (two L2 round trips + a bitonic network)
             // then overlaps the MMAs of the next tiles instead of sitting on the MMA->epilogue handoff
             const unsigned due = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
-            if (due) warp_prune(due, P, list_id, q, cnt, tau, bufaddr, lane);
+            if (due) warp_prune(due, P, list_id, q, cnt, tau, bufp, lane);
         }
-        if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufaddr, lane);
+        if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufp, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -782,6 +775,7 @@ struct TcWs {
     unsigned long long *cand;
     int64_t *fb_list;
     unsigned int *scal;      // [0] rmax bits, [1] relerr bits
+    unsigned long long *bufg; // append buffers of the main kernel: [<=256 CTAs][TC_BUF][256]
     void *exact_ws;
     size_t exact_bytes;
 };
@@ -798,6 +792,7 @@ static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t by
     w.cand = a.take<unsigned long long>((size_t)2 * nq * m);
     w.fb_list = a.take<int64_t>((size_t)2 * nq);
     w.scal = a.take<unsigned int>(4);
+    w.bufg = a.take<unsigned long long>((size_t)256 * TC_BUF * TC_EPI_THREADS);
     // the exact scan only ever sees the uncertified minority; reserve room for 1/8 of the queries
     w.exact_bytes = ab_knn_exact_ws_bytes(std::max<int64_t>(1024, nq / 8), k, 64);
     w.exact_ws = a.take<char>(w.exact_bytes);
@@ -863,17 +858,22 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     if (make_map(&map_a, w.aop, n_total, kt, TC_TILE * mt)) return 1;
     const size_t a_bytes = (size_t)chunks * mt * TC_SLAB;
     const size_t b_stage = (size_t)(3 - mt) * TC_SLAB;
-    const size_t bar_bytes = 256;
-    const size_t epi_bytes = (size_t)TC_BUF * TC_EPI_THREADS * 8;
-    AB_REQUIRE((size_t)ctx->smem_optin > 1024 + a_bytes + bar_bytes + epi_bytes + 2 * b_stage,
-               "ab_knn: not enough shared memory for d=%d k=%d", d, k);
-    int stages = (int)(((size_t)ctx->smem_optin - 1024 - a_bytes - bar_bytes - epi_bytes) / b_stage);
-    stages = std::min(stages, TC_MAX_STAGES);
-    const size_t smem = 1024 + a_bytes + (size_t)stages * b_stage + epi_bytes + bar_bytes;
+    const size_t bar_bytes = 512;
+    const size_t avail = (size_t)ctx->smem_optin - 1024 - a_bytes - bar_bytes;
+    // ring slot = `group` K chunks (one bulk copy, one barrier round): the largest group that still leaves
+    // three slots in flight
+    int group = 0, stages = 0;
+    for (int parts = 1; parts <= chunks; ++parts) {
+        const int g = (chunks + parts - 1) / parts;
+        const int r = (int)(avail / ((size_t)g * b_stage));
+        if (r >= 3 || g == 1) { group = g; stages = std::min(r, TC_MAX_STAGES); break; }
+    }
+    AB_REQUIRE(stages >= 2, "ab_knn: not enough shared memory for d=%d k=%d", d, k);
+    const size_t smem = 1024 + a_bytes + (size_t)stages * group * b_stage + bar_bytes;
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcParams P;
     P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (3 * d + 3 + 15) / 16;
-    P.stages = stages; P.group = std::min(chunks, std::max(1, stages / 2)); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
+    P.stages = stages; P.group = group; P.bufg = w.bufg; P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
     P.dbg = getenv("AB_KNN_DBG") ? atoi(getenv("AB_KNN_DBG")) : 0;
     const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
     const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
