@@ -530,7 +530,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 // or MMAs, set the floor of this kernel)
                 for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
                     const int gsz = min(P.group, P.chunks - c0);
+                    const bool ptrace = (P.dbg & 64) && blockIdx.x == 0 && qb == blockIdx.x && t >= 200 && t < 264 && lane == 0;
+                    if (ptrace) P.bufg[1024 + (t - 200) * 2] = (unsigned long long)clock64();
                     mbar_wait(empty + stage, phase ^ 1);
+                    if (ptrace) P.bufg[1024 + (t - 200) * 2 + 1] = (unsigned long long)clock64();
                     if (elect_one()) {
                         const uint32_t bytes = (uint32_t)gsz * TC_SLAB;
                         unsigned char *dst = sB + (size_t)stage * P.group * b_stage_bytes;
@@ -552,6 +555,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         }
     } else if (warp == 1) {
         // ================= MMA issuer (warp-uniform control flow, one elected lane issues) =================
+        // (Two issuer warps alternating tiles were tried: the barrier waits of one then overlap the MMAs of the
+        // other, but two in-order consumers of one ring can alias mbarrier phases, and the full kernel is
+        // epilogue-bound anyway; see profiles/r1_knn_notes.md.)
         // instruction descriptor: D=F32, A=B=F16, K-major both, N=128, M=128
         const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_TILE >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
         int stage = 0;
@@ -571,9 +577,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
                 for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
                     const int gsz = min(P.group, P.chunks - c0);
-                    // lane 0 waits for the operands, lane 31 for the accumulator buffer: the waits overlap
-                    if (lane == 0) mbar_wait(full + stage, phase);
-                    else if (lane == 31 && c0 == 0) mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
+                    // lane 0 waits for the operands, lane 31 for the accumulator buffer
+                    const bool trace = (P.dbg & 64) && blockIdx.x == 0 && it >= 200 && it < 264;
+                    long long tr0 = 0, tr1 = 0;
+                    if (trace) tr0 = clock64();
+                    if (lane == 0) { mbar_wait(full + stage, phase); if (trace) tr1 = clock64(); }
+                    else if (lane == 31 && c0 == 0) { mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1)); if (trace) tr1 = clock64(); }
                     __syncwarp();
                     tc_fence_after();
                     if (elect_one()) {
@@ -594,6 +603,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                         if (c0 + gsz == P.chunks) tc_commit(t_full + buf);   // accumulators ready for the epilogue
                     }
                     __syncwarp();
+                    if (trace && (lane == 0 || lane == 31)) {       // experiment: per-tile timeline of the issuer
+                        unsigned long long *o = P.bufg + ((it - 200) * 2 + (lane == 31)) * 4;
+                        o[0] = (unsigned long long)tr0; o[1] = (unsigned long long)tr1;
+                        o[3] = (unsigned long long)clock64();
+                    }
                     if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -629,7 +643,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 tau = INFINITY;
                 cnt = 0;
             }
-            mbar_wait(t_full + buf, (uint32_t)((it >> 1) & 1));
+            const bool etrace = (P.dbg & 64) && blockIdx.x == 0 && it >= 200 && it < 264 && ew == 0 && lane == 0;
+            if (etrace) P.bufg[2048 + (it - 200) * 3] = (unsigned long long)clock64();
+            mbar_wait(t_full + buf, (uint32_t)((it >> 1) & 1));     // (one poller per warp + __syncwarp measured slower)
+            if (etrace) P.bufg[2048 + (it - 200) * 3 + 1] = (unsigned long long)clock64();
             tc_fence_after();
             const int64_t col0 = t * x_per_tile + (P.mt == 1 ? half * TC_TILE : 0);
             const uint32_t taddr = taddr0 + (uint32_t)buf * 256;
@@ -648,6 +665,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty + buf);
+            if (etrace) P.bufg[2048 + (it - 200) * 3 + 2] = (unsigned long long)clock64();
             // prune AFTER handing the accumulator back: the merge (two L2 round trips + a bitonic network)
             // then overlaps the MMAs of the next tiles instead of sitting on the MMA->epilogue handoff
             const unsigned due = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
@@ -881,6 +899,20 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, P);
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_MAIN, st);
+    if (P.dbg & 64) {                                               // experiment: print the three roles' timelines
+        static unsigned long long h[4096];
+        AB_CUDA(cudaStreamSynchronize(st));
+        AB_CUDA(cudaMemcpy(h, w.bufg, sizeof(h), cudaMemcpyDeviceToHost));
+        const unsigned long long t0 = h[8 * 20];
+        for (int i = 20; i < 28; ++i) {
+            const unsigned long long *a = h + i * 8, *b = a + 4, *pp = h + 1024 + i * 2, *e = h + 2048 + i * 3;
+            fprintf(stderr, "[knn trace] tile %3d  mma: start %6lld full_ready %6lld tempty_ready %6lld issue_end %6lld | producer: start %6lld "
+                            "empty_ready %6lld | epilogue: start %6lld tfull_ready %6lld arrived %6lld\n",
+                    i, (long long)(a[0] - t0), (long long)(a[1] - t0), (long long)(b[1] - t0), (long long)(a[3] - t0),
+                    (long long)(pp[0] - t0), (long long)(pp[1] - t0), (long long)(e[0] - t0), (long long)(e[1] - t0),
+                    (long long)(e[2] - t0));
+        }
+    }
     // ---- exact re-rank + certificate ----
     ab_prof_begin(ctx, AB_PROF_KNN_RERANK, st);
     const int mp = lists * m;
