@@ -570,60 +570,111 @@ __global__ void reset_b_kernel(double *__restrict__ B, int work, const double *_
 // X column-major (ld), M row-major work x work (use columns 0..ncols-1).
 // out column-major (ldo) or, if rowmajor_out, row-major [n x ncols] scaled by colscale[c].
 // ---------------------------------------------------------------------------------------
-static constexpr int RZ_THREADS = 128;
-static constexpr int RZ_COLS = 16;
+// FP64 on the CUDA cores of this part runs at ~8 FMA/clk/SM (measured: 4.4 TFLOP/s for a register-tiled
+// DFMA kernel), so the one GEMM-shaped step of IRLBA (n x work times work x ncols, 6e9 FMA per restart at C3)
+// goes to the FP64 tensor path: mma.sync.m8n8k4.f64 (DMMA).  A warp owns RG*8 rows and all output columns;
+// M is staged in shared memory (zero padded to multiples of 4 x 8), X is read straight from global memory
+// in the A-fragment layout (lane -> row lane/4, k lane%4: four 64-byte segments per load).
+static constexpr int RZ_WARPS = 8;
 
-__global__ void __launch_bounds__(RZ_THREADS)
+__device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// m16n8k8: rows {lane/4, lane/4+8}, k {lane%4, lane%4+4}; one instruction = four m8n8k4 (the Ampere shape, which
+// newer parts execute at a reduced rate)
+__device__ __forceinline__ void dmma16x8x8(double &c0, double &c1, double &c2, double &c3, double a0, double a1, double a2,
+                                           double a3, double b0, double b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3)
+                 : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+}
+
+template <int NCBT, int RG>
+__global__ void __launch_bounds__(RZ_WARPS * 32)
 ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const double *__restrict__ M, int ncols,
             double *__restrict__ out, int64_t ldo, int rowmajor_out, const double *__restrict__ colscale,
             double *__restrict__ out2 /* optional second row-major output without scaling */) {
-    extern __shared__ double smr[];
-    double *xs = smr;                                   // [work][RZ_THREADS]
-    double *ms = smr + (size_t)work * RZ_THREADS;       // [work][RZ_COLS]
-    const int64_t row = (int64_t)blockIdx.x * RZ_THREADS + threadIdx.x;
-    const bool live = row < n;
-    {
-        // eight loads in flight per thread (a plain load->store loop keeps one)
-        int l = 0;
-        for (; l + 8 <= work; l += 8) {
-            double t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = live ? X[(int64_t)(l + u) * ld + row] : 0.0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) xs[(size_t)(l + u) * RZ_THREADS + threadIdx.x] = t[u];
-        }
-        for (; l < work; ++l) xs[(size_t)l * RZ_THREADS + threadIdx.x] = live ? X[(int64_t)l * ld + row] : 0.0;
+    extern __shared__ double smr[];                       // ms[kpad][NCBT*8]
+    constexpr int MC = NCBT * 8;
+    const int kpad = (work + 7) & ~7;                     // zero rows up to a multiple of 8 (two k-steps per iteration)
+    for (int e = threadIdx.x; e < kpad * MC; e += blockDim.x) {
+        const int l = e / MC, c = e - l * MC;
+        smr[e] = (l < work && c < ncols) ? M[l * work + c] : 0.0;
     }
-    for (int c0 = 0; c0 < ncols; c0 += RZ_COLS) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < work * RZ_COLS; e += RZ_THREADS) {
-            const int l = e / RZ_COLS, c = e % RZ_COLS;
-            ms[e] = (c0 + c < ncols) ? M[l * work + c0 + c] : 0.0;
-        }
-        __syncthreads();
-        double acc[RZ_COLS];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncb = (ncols + 7) >> 3;
+    const int ar = lane >> 2, ak = lane & 3;              // A fragment: row ar, k ak;  B fragment: k ak, col ar
+    const int64_t row0 = ((int64_t)blockIdx.x * RZ_WARPS + warp) * (8 * RG);
+    if (row0 >= n) return;
+    double acc[RG][NCBT][2];
 #pragma unroll
-        for (int c = 0; c < RZ_COLS; ++c) acc[c] = 0.0;
-        for (int l = 0; l < work; ++l) {
-            const double x = xs[(size_t)l * RZ_THREADS + threadIdx.x];
-            const double2 *mrow = reinterpret_cast<const double2 *>(ms + (size_t)l * RZ_COLS);
+    for (int g = 0; g < RG; ++g)
 #pragma unroll
-            for (int c = 0; c < RZ_COLS / 2; ++c) {
-                const double2 mm = mrow[c];
-                acc[2 * c] = fma(x, mm.x, acc[2 * c]);
-                acc[2 * c + 1] = fma(x, mm.y, acc[2 * c + 1]);
+        for (int j = 0; j < NCBT; ++j) { acc[g][j][0] = 0.0; acc[g][j][1] = 0.0; }
+    const double *xr[RG];
+    bool ok[RG];
+#pragma unroll
+    for (int g = 0; g < RG; ++g) {
+        const int64_t r = row0 + 8 * g + ar;
+        ok[g] = r < n;
+        xr[g] = X + (ok[g] ? r : 0);
+    }
+    for (int k0 = 0; k0 < kpad; k0 += 8) {                // two k-steps per iteration: four loads in flight
+        double a[2][RG];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int g = 0; g < RG; ++g) {
+                const int l = k0 + 4 * h + ak;
+                a[h][g] = (ok[g] && l < work) ? xr[g][(int64_t)l * ld] : 0.0;
+            }
+        if (RG == 2) {
+            const double *mrow0 = smr + (size_t)(k0 + ak) * MC + ar;
+            const double *mrow1 = mrow0 + (size_t)4 * MC;            // rows >= kpad read as zero: smr is padded to 8
+#pragma unroll
+            for (int j = 0; j < NCBT; ++j) {
+                if (j < ncb)
+                    dmma16x8x8(acc[0][j][0], acc[0][j][1], acc[RG - 1][j][0], acc[RG - 1][j][1], a[0][0], a[0][RG - 1], a[1][0],
+                               a[1][RG - 1], mrow0[8 * j], mrow1[8 * j]);
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (k0 + 4 * h >= kpad) break;
+                const double *mrow = smr + (size_t)(k0 + 4 * h + ak) * MC + ar;
+#pragma unroll
+                for (int j = 0; j < NCBT; ++j) {
+                    if (j < ncb) {
+                        const double b = mrow[8 * j];
+#pragma unroll
+                        for (int g = 0; g < RG; ++g) dmma8x8x4(acc[g][j][0], acc[g][j][1], a[h][g], b);
+                    }
+                }
             }
         }
-        if (live) {
+    }
+    // C fragment: row lane/4, columns (lane%4)*2 + {0,1} of each 8-column block
 #pragma unroll
-            for (int c = 0; c < RZ_COLS; ++c) {
-                if (c0 + c < ncols) {
+    for (int g = 0; g < RG; ++g) {
+        const int64_t r = row0 + 8 * g + ar;
+        if (r >= n) continue;
+#pragma unroll
+        for (int j = 0; j < NCBT; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = 8 * j + 2 * ak + e;
+                if (j < ncb && col < ncols) {
+                    const double v = acc[g][j][e];
                     if (rowmajor_out) {
-                        const double sc = colscale ? colscale[c0 + c] : 1.0;
-                        out[row * (int64_t)ncols + c0 + c] = __dmul_rn(acc[c], sc);
-                        if (out2) out2[row * (int64_t)ncols + c0 + c] = acc[c];
+                        const double sc = colscale ? colscale[col] : 1.0;
+                        out[r * (int64_t)ncols + col] = __dmul_rn(v, sc);
+                        if (out2) out2[r * (int64_t)ncols + col] = v;
                     } else {
-                        out[(int64_t)(c0 + c) * ldo + row] = acc[c];
+                        out[(int64_t)col * ldo + r] = v;
                     }
                 }
             }
@@ -732,14 +783,27 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     const int q_in_smem = (size_t)2 * work * work * 8 <= (size_t)200 * 1024 ? 1 : 0;
     const size_t svd_smem = (size_t)(q_in_smem ? 2 : 1) * work * work * 8;
     AB_CUDA(cudaFuncSetAttribute(svd_restart_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
-    const size_t rz_smem_v = ((size_t)work * RZ_THREADS + (size_t)work * RZ_COLS) * 8;
-    AB_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rz_smem_v));
-
+    // ritz: <= 64 output columns -> 16 rows per warp, up to 128 -> 8 rows per warp; smem = kpad x (64|128) doubles
+    const size_t rz_kpad = (size_t)((work + 7) & ~7);
+    AB_CUDA(cudaFuncSetAttribute(ritz_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rz_kpad * 64 * 8)));
+    AB_CUDA(cudaFuncSetAttribute(ritz_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rz_kpad * 128 * 8)));
+    auto ritz = [&](const double *X, int64_t ldx, int64_t rows, const double *M, int ncols, double *out, int64_t ldo,
+                    int rowmajor, const double *colscale, double *out2) -> int {
+        if (ncols <= 64) {
+            const unsigned g = (unsigned)std::max<int64_t>(1, (rows + RZ_WARPS * 16 - 1) / (RZ_WARPS * 16));
+            ritz_kernel<8, 2><<<g, RZ_WARPS * 32, rz_kpad * 64 * 8, st>>>(X, ldx, rows, work, M, ncols, out, ldo, rowmajor,
+                                                                          colscale, out2);
+        } else {
+            const unsigned g = (unsigned)std::max<int64_t>(1, (rows + RZ_WARPS * 8 - 1) / (RZ_WARPS * 8));
+            ritz_kernel<16, 1><<<g, RZ_WARPS * 32, rz_kpad * 128 * 8, st>>>(X, ldx, rows, work, M, ncols, out, ldo, rowmajor,
+                                                                            colscale, out2);
+        }
+        AB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
     const unsigned g_rows = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 32));
     const unsigned g_vec = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
     const unsigned g_dot = (unsigned)w.dot_grid;
-    const unsigned g_rz = (unsigned)std::max<int64_t>(1, (n + RZ_THREADS - 1) / RZ_THREADS);
-    const unsigned g_rzw = (unsigned)((H + RZ_THREADS - 1) / RZ_THREADS);
 
     int64_t nmult = 0, sum_panel = 0;
 
@@ -816,12 +880,10 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         keep = h_ctrl[CT_KEEP];
         // Ritz vectors (irlb.py:238-246)
         ab_prof_begin(ctx, AB_PROF_IRLB_RITZ, st);
-        ritz_kernel<<<g_rz, RZ_THREADS, rz_smem_v, st>>>(w.V, ld, n, work, w.Vb, keep, w.V2, ld, 0, nullptr, nullptr);
-        AB_LAUNCH_CHECK(ctx);
+        if (ritz(w.V, ld, n, w.Vb, keep, w.V2, ld, 0, nullptr, nullptr)) return 1;
         copy_vec_kernel<<<g_vec, 256, 0, st>>>(w.F, w.V2 + (int64_t)keep * ld, n);
         AB_LAUNCH_CHECK(ctx);
-        ritz_kernel<<<g_rzw, RZ_THREADS, rz_smem_v, st>>>(w.W, H, H, work, w.Ub, keep, w.W2, H, 0, nullptr, nullptr);
-        AB_LAUNCH_CHECK(ctx);
+        if (ritz(w.W, H, H, w.Ub, keep, w.W2, H, 0, nullptr, nullptr)) return 1;
         reset_b_kernel<<<8, 256, 0, st>>>(w.B, work, w.sb, w.R, keep);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_RITZ, st);
@@ -830,11 +892,9 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         ++it;
     }
     // outputs (irlb.py:249-257; clustering.py:111)
-    ritz_kernel<<<g_rz, RZ_THREADS, rz_smem_v, st>>>(w.V, ld, n, work, w.Vb, nval, scores_local, 0, 1, w.sb, v_local);
-    AB_LAUNCH_CHECK(ctx);
+    if (ritz(w.V, ld, n, w.Vb, nval, scores_local, 0, 1, w.sb, v_local)) return 1;
     if (u_out) {
-        ritz_kernel<<<g_rzw, RZ_THREADS, rz_smem_v, st>>>(w.W, H, H, work, w.Ub, nval, u_out, 0, 1, nullptr, nullptr);
-        AB_LAUNCH_CHECK(ctx);
+        if (ritz(w.W, H, H, w.Ub, nval, u_out, 0, 1, nullptr, nullptr)) return 1;
     }
     if (s_out) AB_CUDA(cudaMemcpyAsync(s_out, w.sb, (size_t)nval * 8, cudaMemcpyDeviceToDevice, st));
     ab_prof_end(ctx, AB_PROF_IRLB_TOTAL, st);
