@@ -137,8 +137,9 @@ snn_sort_long_kernel(const int64_t *__restrict__ rptr, int32_t *__restrict__ rli
 // per-row walk length and classification
 //   class 0: walk <= SNN_WALK_LIMIT          one warp per row, 2048-slot table per warp
 //   class 1: walk <= 0.7 * SNN_MID_SLOTS     one CTA (256 threads) per row, 4096-slot table
-//   class 2: walk <= 0.7 * large slots       one CTA (512 threads) per row, 16384 (k<=32) / 8192 slots
-//   class 3: anything longer                 one CTA per row, dense arrays in global scratch
+//   class 2: walk <= 0.7 * 8192              one CTA (512 threads) per row, 8192-slot table (3 CTAs/SM for k<=32)
+//   class 3: walk <= 0.7 * 16384 (k<=32)     one CTA (512 threads) per row, 16384-slot table
+//   class 4: anything longer                 one CTA per row, dense arrays in global scratch
 // High-dimensional kNN graphs have hubs (in-degrees in the thousands), so classes 1-2 are the
 // common case at scale, not the exception.
 // ---------------------------------------------------------------------------------------
@@ -149,8 +150,8 @@ static inline int snn_large_slots(int k) { return k <= 32 ? 16384 : 8192; }
 static inline int snn_walk_cap(int slots) { return slots / 10 * 7; }
 
 __global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_t n_rows,
-                                const int64_t *__restrict__ rptr, int32_t *__restrict__ cls_rows /*[4][n_rows]*/,
-                                int *__restrict__ n_cls /*[4]*/, int lim1, int lim2,
+                                const int64_t *__restrict__ rptr, int32_t *__restrict__ cls_rows /*[5][n_rows]*/,
+                                int *__restrict__ n_cls /*[5]*/, int lim1, int lim2, int lim3,
                                 unsigned long long *__restrict__ max_walk, unsigned long long *__restrict__ sum_walk,
                                 int *__restrict__ n_dup) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,7 +163,7 @@ __global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t 
             walk += rptr[j + 1] - rptr[j];
         }
         if (row[0] != row_begin + r) atomicAdd(n_dup, 1);
-        const int cls = walk <= SNN_WALK_LIMIT ? 0 : (walk <= lim1 ? 1 : (walk <= lim2 ? 2 : 3));
+        const int cls = walk <= SNN_WALK_LIMIT ? 0 : (walk <= lim1 ? 1 : (walk <= lim2 ? 2 : (walk <= lim3 ? 3 : 4)));
         cls_rows[(int64_t)cls * n_rows + atomicAdd(n_cls + cls, 1)] = (int32_t)r;
     }
     // block-level max / sum before touching the global atomics
@@ -598,7 +599,7 @@ struct SnnWs {
     int32_t *rlist;      // n_total*k
     int32_t *tmp;        // n_total*k
     int32_t *long_ids;   // n_total
-    int32_t *cls_rows;   // 4*n_rows
+    int32_t *cls_rows;   // 5*n_rows
     int *dense;          // SNN_BIG_CTAS*2*n_total
     int *counters;       // 16 ints: [0] n_long, [2] n_dup, [3] bad, [4..7] rows per class
     unsigned long long *walk_stats;   // [0] max walk, [1] sum of walks
@@ -615,7 +616,7 @@ static size_t snn_layout(int64_t n_total, int32_t k, int64_t n_rows, void *ws, s
     w.rlist = a.take<int32_t>((size_t)n_total * k);
     w.tmp = a.take<int32_t>((size_t)n_total * k);
     w.long_ids = a.take<int32_t>(n_total);
-    w.cls_rows = a.take<int32_t>((size_t)4 * (n_rows > 0 ? n_rows : 1));
+    w.cls_rows = a.take<int32_t>((size_t)5 * (n_rows > 0 ? n_rows : 1));
     w.dense = a.take<int>((size_t)SNN_BIG_CTAS * 2 * n_total);
     w.counters = a.take<int>(16);
     w.walk_stats = a.take<unsigned long long>(2);
@@ -640,7 +641,7 @@ static int snn_launch_rows(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, 
                            uint8_t *overlap, cudaStream_t st) {
     int64_t *rowcount = FILL ? nullptr : w.rowcount;
     const int32_t *rows0 = w.cls_rows, *rows1 = w.cls_rows + n_rows, *rows2 = w.cls_rows + 2 * n_rows,
-                  *rows3 = w.cls_rows + 3 * n_rows;
+                  *rows3 = w.cls_rows + 3 * n_rows, *rows4 = w.cls_rows + 4 * n_rows;
     const int *ncls = w.counters + 4;
     {
         const size_t smem = snn_small_smem();
@@ -663,14 +664,15 @@ static int snn_launch_rows(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, 
     } while (0)
     if (k <= 32) {
         AB_SNN_CTA(SNN_MID_SLOTS, 1, SNN_MID_THREADS, rows1, ncls + 1, 6);
-        AB_SNN_CTA(16384, 1, SNN_LARGE_THREADS, rows2, ncls + 2, 1);
+        AB_SNN_CTA(8192, 1, SNN_LARGE_THREADS, rows2, ncls + 2, 3);
+        AB_SNN_CTA(16384, 1, SNN_LARGE_THREADS, rows3, ncls + 3, 1);
     } else {
         AB_SNN_CTA(SNN_MID_SLOTS, 4, SNN_MID_THREADS, rows1, ncls + 1, 2);
-        AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows2, ncls + 2, 1);
+        AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows2, ncls + 2, 1);     // (class 3 stays empty: lim3 == lim2)
     }
 #undef AB_SNN_CTA
     snn_big_kernel<FILL><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
-        knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, rows3, ncls + 3, w.dense, rowcount, rowptr, src, dst,
+        knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, rows4, ncls + 4, w.dense, rowcount, rowptr, src, dst,
         overlap);
     AB_LAUNCH_CHECK(ctx);
     return 0;
@@ -713,7 +715,7 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     if (n_rows > 0) {
         snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
             knn_all, k, row_begin, n_rows, w.deg, w.cls_rows, w.counters + 4, snn_walk_cap(SNN_MID_SLOTS),
-            snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2);
+            snn_walk_cap(8192), snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2);
         AB_LAUNCH_CHECK(ctx);
         snn_init_dense_kernel<<<(unsigned)(((int64_t)SNN_BIG_CTAS * 2 * n_total + 255) / 256), 256, 0, st>>>(
             w.dense, n_total, SNN_BIG_CTAS);
@@ -724,9 +726,9 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     }
     if (ab_exclusive_scan_i64(ctx, w.rowcount, rowptr, n_rows, w.scan_ws, w.scan_bytes, st)) return 1;
     ab_prof_end(ctx, AB_PROF_SNN_COUNT, st);
-    int h_cnt[8];
+    int h_cnt[12];
     unsigned long long h_walk[2] = {0, 0};
-    AB_CUDA(cudaMemcpyAsync(h_cnt, w.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    AB_CUDA(cudaMemcpyAsync(h_cnt, w.counters, 12 * sizeof(int), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaMemcpyAsync(h_walk, w.walk_stats, sizeof(h_walk), cudaMemcpyDeviceToHost, st));
     if (h_edges) AB_CUDA(cudaMemcpyAsync(h_edges, rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaStreamSynchronize(st));
@@ -734,10 +736,11 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
         // host array: {rows beyond the one-warp path (classes 1-3), longest 2-hop walk, rows whose first
         // neighbour is not the cell itself (duplicate points; alona/clustering.py:204 assumes it is),
         // rows on the dense global path (class 3), sum of all walk lengths (the gather traffic / 4 B)}
-        stats[0] = (int64_t)h_cnt[5] + h_cnt[6] + h_cnt[7];
+        stats[0] = (int64_t)h_cnt[5] + h_cnt[6] + h_cnt[7] + h_cnt[8];
         stats[1] = (int64_t)h_walk[0];
         stats[2] = h_cnt[2];
-        stats[3] = h_cnt[7];
+        stats[3] = h_cnt[8];
+        stats[5] = h_cnt[5]; stats[6] = h_cnt[6]; stats[7] = h_cnt[7];     // rows per CTA class
         stats[4] = (int64_t)h_walk[1];
     }
     return 0;

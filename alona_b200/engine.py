@@ -231,7 +231,8 @@ class Engine:
                    'ab_snn_fill')
         return {'rowptr': rowptr, 'src': src, 'dst': dst, 'overlap': ov,
                 'big_rows': int(stats[0]), 'max_walk': int(stats[1]), 'dup_rows': int(stats[2]),
-                'dense_rows': int(stats[3]), 'sum_walk': int(stats[4])}
+                'dense_rows': int(stats[3]), 'sum_walk': int(stats[4]),
+                'class_rows': [int(stats[5]), int(stats[6]), int(stats[7])]}
 
     # -- synthetic data ---------------------------------------------------------------
     def synth_counts(self, prof, cell_begin, n_local, lbar, n_total=None, depth_sigma=0.35, r_disp=5.0,

@@ -130,7 +130,7 @@ int ab_knn(ab_ctx *ctx, const double *emb_all, int64_t n_total, int32_t d, int64
  * count: rowptr [nrows+1] int64 (exclusive scan), returns edges in *h_edges (synchronises);
  * stats (HOST int64[8], may be NULL) = {rows beyond the one-warp path, longest 2-hop walk, rows whose
  * first neighbour is not the cell itself (duplicate points), rows on the dense global path,
- * sum of all 2-hop walk lengths (x4 B = the gather traffic), 0, 0, 0};
+ * sum of all 2-hop walk lengths (x4 B = the gather traffic), rows in the 4096- / 8192- / 16384-slot CTA classes};
  * fill: src/dst int32 [E], overlap uint8 [E] (may be NULL). */
 size_t ab_snn_ws_bytes(int64_t n_total, int32_t k, int64_t n_rows);
 int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k,
