@@ -217,9 +217,66 @@ __global__ void scale_by_invnorm_kernel(const double *__restrict__ src, double *
 // and plain load/FMA/store is race-free and order-deterministic; __syncwarp separates rows.
 // Row metadata (row end, x) travels in registers, 32 rows per refill, read by shuffle.
 // ---------------------------------------------------------------------------------------
-static constexpr int AV_U = 8;
+static constexpr int AV_U = 12;
 
-__global__ void __launch_bounds__(384)
+struct AvRowState {           // row metadata of one warp: 32 rows per refill, read by shuffle
+    int64_t blk;              // first row of the register block
+    int rp_l;                 // lane l: end offset (relative to the warp's first nonzero) of row blk + l
+    double x_l;               // lane l: x of row blk + l
+    int ri;                   // current row = blk + ri
+    int rend;                 // end offset of the current row
+    double xrow;              // x of the current row
+};
+
+__device__ __forceinline__ void av_load_block(AvRowState &r, const int64_t *__restrict__ rowptr, int64_t p0, int64_t r1,
+                                              const double *__restrict__ src, double scale, double *__restrict__ vdst,
+                                              int lane) {
+    const int64_t row = r.blk + lane;
+    const bool ok = row < r1;
+    r.rp_l = ok ? (int)(rowptr[row + 1] - p0) : INT_MAX;         // sentinel: never reached
+    r.x_l = ok ? __dmul_rn(scale, src[row]) : 0.0;
+    if (ok && vdst) vdst[row] = r.x_l;
+}
+
+// consumes one batch of AV_U steps of 32 nonzeros.  FULL: every step of the batch is complete (no bounds checks).
+template <bool FULL>
+__device__ __forceinline__ void av_consume(AvRowState &r, double *acc, const int (&cg)[AV_U], const double (&vv)[AV_U],
+                                           int base, int len, const int64_t *__restrict__ rowptr, int64_t p0, int64_t r1,
+                                           const double *__restrict__ src, double scale, double *__restrict__ vdst, int lane) {
+#pragma unroll
+    for (int u = 0; u < AV_U; ++u) {
+        const int s0 = base + 32 * u;
+        if (!FULL && s0 >= len) break;
+        const int s1 = FULL ? s0 + 32 : min(s0 + 32, len);
+        const int p = s0 + lane;
+        if (r.rend >= s1) {
+            // the whole step lies inside the current row: no ordering needed against the previous steps of this
+            // row (distinct genes), the load/FMA/store chains of consecutive steps overlap freely
+            if (FULL || p < s1) acc[cg[u]] = fma(vv[u], r.xrow, acc[cg[u]]);
+        } else {
+            int cur = s0;
+            while (cur < s1) {
+                if (r.rend <= cur) {
+                    __syncwarp();                            // row switch: order the two rows' updates
+                    do {                                     // advance to the row that owns `cur` (skips empty rows)
+                        if (++r.ri == 32) {
+                            r.blk += 32;
+                            av_load_block(r, rowptr, p0, r1, src, scale, vdst, lane);
+                            r.ri = 0;
+                        }
+                        r.rend = __shfl_sync(AB_FULL, r.rp_l, r.ri);
+                        r.xrow = ab_shfl_f64(r.x_l, r.ri);
+                    } while (r.rend <= cur);
+                }
+                const int seg = min(r.rend, s1);
+                if (p >= cur && p < seg) acc[cg[u]] = fma(vv[u], r.xrow, acc[cg[u]]);
+                cur = seg;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(384, 1)
 av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
           int64_t n, int H, const double *__restrict__ src, const double *__restrict__ sumsq,
           double *__restrict__ vdst, int nwarps_cta, double *__restrict__ partial /*[grid][H]*/) {
@@ -239,21 +296,14 @@ av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, c
             const int len = (int)(rowptr[r1] - p0);              // a warp's share is far below 2^31 nonzeros
             const int32_t *colw = col + p0;
             const double *valw = val + p0;
-            // row metadata block: lane l holds the end offset (relative to p0) and x of row blk + l
-            int64_t blk = r0;
-            int rp_l;
-            double x_l;
-            {
-                const int64_t r = blk + lane;
-                const bool ok = r < r1;
-                rp_l = ok ? (int)(rowptr[r + 1] - p0) : INT_MAX;
-                x_l = ok ? __dmul_rn(scale, src[r]) : 0.0;
-                if (ok && vdst) vdst[r] = x_l;
-            }
-            int ri = 0;                                          // current row = blk + ri
-            int rend = __shfl_sync(AB_FULL, rp_l, 0);
-            double xrow = ab_shfl_f64(x_l, 0);
+            AvRowState r;
+            r.blk = r0;
+            av_load_block(r, rowptr, p0, r1, src, scale, vdst, lane);
+            r.ri = 0;
+            r.rend = __shfl_sync(AB_FULL, r.rp_l, 0);
+            r.xrow = ab_shfl_f64(r.x_l, 0);
             // two register batches: the loads of batch b+1 are in flight while batch b is consumed
+            constexpr int B = 32 * AV_U;
             int cg[2][AV_U];
             double vv[2][AV_U];
 #pragma unroll
@@ -263,59 +313,35 @@ av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, c
                 cg[0][u] = ok ? __ldg(colw + p) : 0;
                 vv[0][u] = ok ? __ldg(valw + p) : 0.0;
             }
-            for (int base2 = 0; base2 < len; base2 += 64 * AV_U) {
+            for (int base2 = 0; base2 < len; base2 += 2 * B) {
 #pragma unroll
                 for (int bb = 0; bb < 2; ++bb) {
-                    const int base = base2 + bb * 32 * AV_U;
+                    const int base = base2 + bb * B;
+                    const int nb = base + B;                     // batch fetched now, consumed next
+                    if (nb + B <= len) {
 #pragma unroll
-                    for (int u = 0; u < AV_U; ++u) {
-                        const int p = base + 32 * AV_U + 32 * u + lane;
-                        const bool ok = p < len;
-                        cg[bb ^ 1][u] = ok ? __ldg(colw + p) : 0;
-                        vv[bb ^ 1][u] = ok ? __ldg(valw + p) : 0.0;
-                    }
+                        for (int u = 0; u < AV_U; ++u) {
+                            cg[bb ^ 1][u] = __ldg(colw + nb + 32 * u + lane);
+                            vv[bb ^ 1][u] = __ldg(valw + nb + 32 * u + lane);
+                        }
+                    } else {
 #pragma unroll
-                    for (int u = 0; u < AV_U; ++u) {
-                        const int s0 = base + 32 * u;
-                        if (s0 >= len) break;
-                        const int s1 = min(s0 + 32, len);
-                        const int p = s0 + lane;
-                        if (rend >= s1) {
-                            // the whole step lies inside the current row: no ordering needed against the
-                            // previous steps of this row (distinct genes), the chains overlap freely
-                            if (p < s1) acc[cg[bb][u]] = fma(vv[bb][u], xrow, acc[cg[bb][u]]);
-                        } else {
-                            int cur = s0;
-                            while (cur < s1) {
-                                if (rend <= cur) {
-                                    __syncwarp();                // row switch: order the two rows' updates
-                                    do {                         // advance to the row that owns `cur` (skips empty rows)
-                                        if (++ri == 32) {
-                                            blk += 32;
-                                            const int64_t r = blk + lane;
-                                            const bool ok = r < r1;
-                                            rp_l = ok ? (int)(rowptr[r + 1] - p0) : INT_MAX;
-                                            x_l = ok ? __dmul_rn(scale, src[r]) : 0.0;
-                                            if (ok && vdst) vdst[r] = x_l;
-                                            ri = 0;
-                                        }
-                                        rend = __shfl_sync(AB_FULL, rp_l, ri);
-                                        xrow = ab_shfl_f64(x_l, ri);
-                                    } while (rend <= cur);
-                                }
-                                const int seg = min(rend, s1);
-                                if (p >= cur && p < seg) acc[cg[bb][u]] = fma(vv[bb][u], xrow, acc[cg[bb][u]]);
-                                cur = seg;
-                            }
+                        for (int u = 0; u < AV_U; ++u) {
+                            const int p = nb + 32 * u + lane;
+                            const bool ok = p < len;
+                            cg[bb ^ 1][u] = ok ? __ldg(colw + p) : 0;
+                            vv[bb ^ 1][u] = ok ? __ldg(valw + p) : 0.0;
                         }
                     }
+                    if (base + B <= len) av_consume<true>(r, acc, cg[bb], vv[bb], base, len, rowptr, p0, r1, src, scale, vdst, lane);
+                    else av_consume<false>(r, acc, cg[bb], vv[bb], base, len, rowptr, p0, r1, src, scale, vdst, lane);
                 }
             }
             // rows after the last nonzero (empty tail rows) still need their x stored
             if (vdst) {
-                for (int64_t b2 = blk + 32; b2 < r1; b2 += 32) {
-                    const int64_t r = b2 + lane;
-                    if (r < r1) vdst[r] = __dmul_rn(scale, src[r]);
+                for (int64_t b2 = r.blk + 32; b2 < r1; b2 += 32) {
+                    const int64_t row = b2 + lane;
+                    if (row < r1) vdst[row] = __dmul_rn(scale, src[row]);
                 }
             }
         }
