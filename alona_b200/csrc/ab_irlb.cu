@@ -454,30 +454,39 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
                    double *__restrict__ Vb, double *__restrict__ Gws /* 2*work*work scratch */,
                    double *__restrict__ scal, int *__restrict__ ctrl, double *__restrict__ R, int nu, double tol,
                    int it, int keep_prev, int q_in_smem) {
-    // G (col-major, work x work) starts as B and converges to U.diag(s); Q accumulates V.
-    // Both live in shared memory when they fit (the sweeps are latency-bound chains of tiny
-    // column operations); for the largest work dimensions Q stays in the global scratch.
+    // G (col-major, work x work) starts as B and converges to U.diag(s) under right rotations.  The right
+    // vectors are NOT accumulated through the rotations (that doubles the FP64 work of a kernel that is
+    // bound by one SM's FP64 pipe): V = B^T U diag(1/s) is formed once at the end.  A copy of B sits next
+    // to G in shared memory when it fits (q_in_smem), else it is read from global memory.
     extern __shared__ double svd_sm[];
     double *G = svd_sm;
-    double *Q = q_in_smem ? svd_sm + (size_t)work * work : Gws + (size_t)work * work;
+    double *Bs = q_in_smem ? svd_sm + (size_t)work * work : Gws + (size_t)work * work;   // row-major copy of B
     __shared__ double nrm[IR_MAXWORK];
+    __shared__ double cn[IR_MAXWORK];                   // running squared column norms
     __shared__ int order[IR_MAXWORK];
     __shared__ int rot_sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int m = work;
     for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
         const int r = e % m, c = e / m;
-        G[(size_t)c * m + r] = B[r * m + c];
-        Q[(size_t)c * m + r] = (r == c) ? 1.0 : 0.0;
+        const double v = B[r * m + c];
+        G[(size_t)c * m + r] = v;
+        Bs[r * m + c] = v;
     }
     __syncthreads();
     const int mp = (m + 1) & ~1;                        // round-robin needs an even player count
     // one HALF-warp per column pair, so that a whole round (mp/2 <= 64 pairs) is one pass of the
-    // 1024-thread CTA: the sweeps are a chain of ~mp dependent rounds, each a few hundred cycles of
-    // shuffle/divide/sqrt latency, and the kernel's time is that chain times the number of sweeps
+    // 1024-thread CTA
     const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15, nhw = blockDim.x >> 4;
     for (int sweep = 0; sweep < 60; ++sweep) {
         if (threadIdx.x == 0) rot_sm = 0;
+        // refresh the running norms once per sweep (they are updated incrementally inside it)
+        for (int c = warp; c < m; c += nwarp) {
+            double acc = 0.0;
+            for (int r = lane; r < m; r += 32) acc = fma(G[(size_t)c * m + r], G[(size_t)c * m + r], acc);
+            acc = ab_warp_sum_f64(acc);
+            if (lane == 0) cn[c] = acc;
+        }
         __syncthreads();
         for (int round = 0; round < mp - 1; ++round) {
             for (int pr0 = 0; pr0 < mp / 2; pr0 += nhw) {
@@ -488,34 +497,27 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
                 const int p = min(a, b), q = max(a, b);
                 const bool valid = pr < mp / 2 && q < m;
                 double *gp = G + (size_t)(valid ? p : 0) * m, *gq = G + (size_t)(valid ? q : 0) * m;
-                double al = 0.0, be = 0.0, ga = 0.0;
-                if (valid) {
-                    for (int r = hl; r < m; r += 16) {
-                        const double x = gp[r], y = gq[r];
-                        al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
-                    }
-                }
+                double ga = 0.0;
+                if (valid)
+                    for (int r = hl; r < m; r += 16) ga = fma(gp[r], gq[r], ga);
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) {                // stays inside the half-warp
-                    al += ab_shfl_xor_f64(al, o);
-                    be += ab_shfl_xor_f64(be, o);
-                    ga += ab_shfl_xor_f64(ga, o);
-                }
+                for (int o = 8; o > 0; o >>= 1) ga += ab_shfl_xor_f64(ga, o);    // stays inside the half-warp
+                const double al = valid ? cn[p] : 1.0, be = valid ? cn[q] : 1.0;
                 // rotate down to rounding level, but call the sweep "dirty" only above 1e-14: pairs
                 // hovering at 1e-15..1e-16 (pure rounding noise) would otherwise keep the loop alive
                 // for all 60 sweeps without changing any singular vector beyond 1e-14
-                if (valid && fabs(ga) > 1e-15 * sqrt(al * be) && fabs(ga) > 1e-300) {
-                    if (hl == 0 && fabs(ga) > 1e-14 * sqrt(al * be)) rot_sm = 1;
-                    const double zeta = (be - al) / (2.0 * ga);
-                    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
-                    double *qp = Q + (size_t)p * m, *qq = Q + (size_t)q * m;
+                const double g2 = ga * ga, ab2 = al * be;
+                if (valid && g2 > 1e-30 * ab2 && fabs(ga) > 1e-300) {
+                    if (hl == 0 && g2 > 1e-28 * ab2) rot_sm = 1;
+                    // tan(theta) of the rotation that zeroes the pair's inner product
+                    const double dd = be - al;
+                    const double tt = (2.0 * ga) / (dd + (dd >= 0.0 ? 1.0 : -1.0) * sqrt(fma(dd, dd, 4.0 * g2)));
+                    const double cs = rsqrt(fma(tt, tt, 1.0)), sn = cs * tt;
                     for (int r = hl; r < m; r += 16) {
                         const double x = gp[r], y = gq[r];
                         gp[r] = cs * x - sn * y; gq[r] = sn * x + cs * y;
-                        const double u = qp[r], v = qq[r];
-                        qp[r] = cs * u - sn * v; qq[r] = sn * u + cs * v;
                     }
+                    if (hl == 0) { cn[p] = al - tt * ga; cn[q] = be + tt * ga; }
                 }
             }
             __syncthreads();
@@ -543,7 +545,11 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
         const int c = order[i];
         const double sv = nrm[c];
         Ub[r * m + i] = sv > 0.0 ? G[(size_t)c * m + r] / sv : 0.0;
-        Vb[r * m + i] = Q[(size_t)c * m + r];
+        // right vector i = B^T u_i / s_i = B^T G[:, c] / s_i^2
+        double acc = 0.0;
+        const double *gc = G + (size_t)c * m;
+        for (int l = 0; l < m; ++l) acc = fma(Bs[l * m + r], gc[l], acc);
+        Vb[r * m + i] = sv > 0.0 ? acc / (sv * sv) : 0.0;
     }
     for (int i = threadIdx.x; i < m; i += blockDim.x) sb[i] = nrm[order[i]];
     __syncthreads();
