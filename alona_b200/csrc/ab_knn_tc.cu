@@ -323,6 +323,7 @@ struct TcParams {
     unsigned long long *cand;   // [lists][nq][m] sorted keys, lists = 3 - mt
     const unsigned char *bop;   // tiled, pre-swizzled B operand (knn_b_pos)
     unsigned long long *bufg;   // [grid][TC_BUF][256] append buffers
+    int *cursor;                // tile CTA 0 is currently loading: the other CTAs start their sweeps there
     int dbg;               // experiments only (AB_KNN_DBG): 1 = epilogue skips the score scan, 2 = no MMA issue
 };
 
@@ -483,6 +484,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
     uint64_t *t_full = a_full + 2;                  // [2]
     uint64_t *t_empty = a_full + 4;                 // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 6);
+    volatile int *sweep_start = reinterpret_cast<volatile int *>(a_full + 7);     // [8], by local query-block index
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_per_block = TC_TILE * P.mt;
@@ -522,7 +524,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             }
             __syncwarp();
             aphase ^= 1;
-            for (int64_t t = 0; t < n_tiles; ++t) {
+            // Every sweep covers all tiles, so where it starts is free: CTA 0 publishes the tile it is loading
+            // and the other CTAs start their sweeps there.  CTAs drift apart (a few per cent per sweep); without
+            // this they end up streaming different parts of an operand array that is larger than L2 (measured:
+            // 370 GB of DRAM reads at C3 for 14 GB of ideal traffic), with it the pack stays inside an L2 window.
+            int s0 = blockIdx.x == 0 ? 0 : *reinterpret_cast<volatile int *>(P.cursor);
+            if (s0 < 0 || s0 >= n_tiles) s0 = 0;
+            s0 = __shfl_sync(AB_FULL, s0, 0);
+            if (lane == 0) { sweep_start[((qb - blockIdx.x) / gridDim.x) & 7] = s0; __threadfence_block(); }
+            __syncwarp();
+            for (int64_t ti = 0; ti < n_tiles; ++ti) {
+                int64_t t = s0 + ti;
+                if (t >= n_tiles) t -= n_tiles;
+                if (blockIdx.x == 0 && lane == 0 && (ti & 7) == 0) *reinterpret_cast<volatile int *>(P.cursor) = (int)t;
                 // slabs of this tile: one (mt = 2) or two (mt = 1) blocks of `chunks` x 8 KB
                 const unsigned char *slab0 = P.bop + (size_t)t * (3 - P.mt) * P.chunks * TC_SLAB;
                 // one ring slot = `group` consecutive K chunks of the tile = ONE contiguous bulk copy and ONE
@@ -530,10 +544,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 // or MMAs, set the floor of this kernel)
                 for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
                     const int gsz = min(P.group, P.chunks - c0);
-                    const bool ptrace = (P.dbg & 64) && blockIdx.x == 0 && qb == blockIdx.x && t >= 200 && t < 264 && lane == 0;
-                    if (ptrace) P.bufg[1024 + (t - 200) * 2] = (unsigned long long)clock64();
+                    const bool ptrace = (P.dbg & 64) && blockIdx.x == 0 && qb == blockIdx.x && ti >= 200 && ti < 264 && lane == 0;
+                    if (ptrace) P.bufg[1024 + (ti - 200) * 2] = (unsigned long long)clock64();
                     mbar_wait(empty + stage, phase ^ 1);
-                    if (ptrace) P.bufg[1024 + (t - 200) * 2 + 1] = (unsigned long long)clock64();
+                    if (ptrace) P.bufg[1024 + (ti - 200) * 2 + 1] = (unsigned long long)clock64();
                     if (elect_one()) {
                         const uint32_t bytes = (uint32_t)gsz * TC_SLAB;
                         unsigned char *dst = sB + (size_t)stage * P.group * b_stage_bytes;
@@ -628,13 +642,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         unsigned long long *bufp = P.bufg + (size_t)blockIdx.x * TC_BUF * TC_EPI_THREADS + etid;   // entry e at bufp[e * 256]
         const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)half * TC_TILE;
         int64_t cur_block = -1;
+        int sweep0 = 0;
         long long q = 0;
         bool live = false;
         float tau = INFINITY;
         int cnt = 0;
         for (int64_t it = 0; it < my_tiles; ++it) {
-            const int64_t blk = it / n_tiles, t = it - blk * n_tiles;
+            const int64_t blk = it / n_tiles, ti = it - blk * n_tiles;
             const int buf = (int)(it & 1);
+            const bool new_block = blk != cur_block;
             if (blk != cur_block) {
                 if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufp, lane);
                 cur_block = blk;
@@ -648,6 +664,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             mbar_wait(t_full + buf, (uint32_t)((it >> 1) & 1));     // (one poller per warp + __syncwarp measured slower)
             if (etrace) P.bufg[2048 + (it - 200) * 3 + 1] = (unsigned long long)clock64();
             tc_fence_after();
+            if (new_block) sweep0 = sweep_start[blk & 7];           // published by the producer before this block's first load
+            int64_t t = sweep0 + ti;
+            if (t >= n_tiles) t -= n_tiles;
             const int64_t col0 = t * x_per_tile + (P.mt == 1 ? half * TC_TILE : 0);
             const uint32_t taddr = taddr0 + (uint32_t)buf * 256;
             uint32_t ra[32];
@@ -891,7 +910,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcParams P;
     P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (3 * d + 3 + 15) / 16;
-    P.stages = stages; P.group = group; P.bufg = w.bufg; P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
+    P.stages = stages; P.group = group; P.bufg = w.bufg; P.cursor = (int *)(w.scal + 2); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
     P.dbg = getenv("AB_KNN_DBG") ? atoi(getenv("AB_KNN_DBG")) : 0;
     const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
     const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
