@@ -318,6 +318,8 @@ struct TcParams {
     int ksteps;            // UMMA K steps (16 halves) that carry data: ceil((3d+3)/16)
     int stages;            // B ring depth, in slots of `group` chunks
     int group;             // K chunks per ring slot = per bulk copy and per barrier round
+    int merged;            // 1: one slot per tile and the epilogue releases its accumulator buffer straight onto the
+                           //    `full` barrier of the tile that will reuse it (one wait per tile for the issuer)
     int mt;                // 2: two query tiles x one 128-point B tile; 1: one query tile x 256-point B tile
     int m;                 // candidates kept per list
     unsigned long long *cand;   // [lists][nq][m] sorted keys, lists = 3 - mt
@@ -495,7 +497,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
     const int64_t my_tiles = my_blocks * n_tiles;   // global tile counter `it` runs over [0, my_tiles)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, P.merged ? 1 + TC_EPI_WARPS : 1); mbar_init(empty + s, 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(t_full + b, 1); mbar_init(t_empty + b, TC_EPI_WARPS); }
@@ -595,8 +597,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                     const bool trace = (P.dbg & 64) && blockIdx.x == 0 && it >= 200 && it < 264;
                     long long tr0 = 0, tr1 = 0;
                     if (trace) tr0 = clock64();
+                    // merged protocol: ONE barrier per tile (operands landed AND accumulator buffer released); an
+                    // mbarrier wait costs 180-300 cycles even when already complete, with the tensor pipe idle
                     if (lane == 0) { mbar_wait(full + stage, phase); if (trace) tr1 = clock64(); }
-                    else if (lane == 31 && c0 == 0) { mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1)); if (trace) tr1 = clock64(); }
+                    else if (lane == 31 && c0 == 0 && !P.merged) { mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1)); if (trace) tr1 = clock64(); }
                     __syncwarp();
                     tc_fence_after();
                     if (elect_one()) {
@@ -641,6 +645,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         const int list_id = P.mt == 1 ? half : 0;
         unsigned long long *bufp = P.bufg + (size_t)blockIdx.x * TC_BUF * TC_EPI_THREADS + etid;   // entry e at bufp[e * 256]
         const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)half * TC_TILE;
+        if (P.merged && lane == 0) {                            // tiles 0 and 1 find their accumulator buffers free
+            mbar_arrive(full + 0);
+            mbar_arrive(full + (1 % P.stages));
+        }
         int64_t cur_block = -1;
         int sweep0 = 0;
         long long q = 0;
@@ -683,7 +691,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty + buf);
+            if (lane == 0) mbar_arrive(P.merged ? full + (int)((it + 2) % P.stages) : t_empty + buf);
             if (etrace) P.bufg[2048 + (it - 200) * 3 + 2] = (unsigned long long)clock64();
             // prune AFTER handing the accumulator back: the merge (two L2 round trips + a bitonic network)
             // then overlaps the MMAs of the next tiles instead of sitting on the MMA->epilogue handoff
@@ -910,7 +918,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcParams P;
     P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (3 * d + 3 + 15) / 16;
-    P.stages = stages; P.group = group; P.bufg = w.bufg; P.cursor = (int *)(w.scal + 2); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
+    P.stages = stages; P.group = group; P.merged = (group == chunks && stages >= 3 && !getenv("AB_KNN_UNMERGED")) ? 1 : 0; P.bufg = w.bufg; P.cursor = (int *)(w.scal + 2); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
     P.dbg = getenv("AB_KNN_DBG") ? atoi(getenv("AB_KNN_DBG")) : 0;
     const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
     const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
