@@ -447,26 +447,26 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, boo
         gmin[g] = fminf(v, __uint_as_float(r[8 * g + 7]));
     }
     const float mn = fminf(fmin3(gmin[0], gmin[1], gmin[2]), gmin[3]);
-    if (!__any_sync(AB_FULL, live && mn < tau)) return;
+    if (!__any_sync(AB_FULL, live && mn < tau) || (P.dbg & 256)) return;      // (256: experiment, common path only)
+    // Rare path.  A candidate is a GROUP of 8 consecutive points keyed by its smallest score: appending it is one
+    // compare and one store per group, with no search inside the 32 registers (measured: that search, executed by
+    // the whole warp for the ~1.7 lanes that hit, was everything the kernel cost above its MMA/copy floor).  The
+    // certificate is unchanged - every point outside the listed groups scores >= its group's minimum >= tau - and
+    // the re-rank expands the m listed groups to their 8*m points.
+    const unsigned tight = __ballot_sync(AB_FULL, cnt > TC_BUF - 4);
+    if (tight) warp_prune(tight, P, list_id, q, cnt, tau, bufp, lane);
+    if (live && mn < tau) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        if (!__any_sync(AB_FULL, live && gmin[g] < tau)) continue;
-        const unsigned tight = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
-        if (tight) warp_prune(tight, P, list_id, q, cnt, tau, bufp, lane);
-        if (live && gmin[g] < tau) {
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const float sc = __uint_as_float(r[8 * g + jj]);
-                if (sc < tau) {
-                    // append buffers live in global memory (L2): appends are rare fire-and-forget stores, and the
-                    // shared memory they would take is worth more as operand ring
-                    bufp[(size_t)cnt * TC_EPI_THREADS] = ((unsigned long long)r[8 * g + jj] << 32) | (uint32_t)(cbase + 8 * g + jj);
-                    ++cnt;
-                }
+        for (int g = 0; g < 4; ++g) {
+            if (gmin[g] < tau) {
+                // append buffers live in global memory (L2): appends are rare fire-and-forget stores, and the
+                // shared memory they would take is worth more as operand ring
+                bufp[(size_t)cnt * TC_EPI_THREADS] = ((unsigned long long)__float_as_uint(gmin[g]) << 32) | (uint32_t)(cbase + 8 * g);
+                ++cnt;
             }
         }
-        __syncwarp();
     }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(TC_NTHREADS, 1)
@@ -719,44 +719,86 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                   const unsigned int *__restrict__ rmax_bits, int32_t *__restrict__ idx, double *__restrict__ rdist,
                   int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mp = lists * m;                              // all lists of the query; power of two
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int mg = lists * m;                              // candidate groups of the query (all lists)
+    const int mp = mg * 8;                                 // candidate points; power of two
     double *sd = reinterpret_cast<double *>(sm_raw) + (size_t)warp * mp;
-    int *si = reinterpret_cast<int *>(sm_raw + (size_t)8 * mp * sizeof(double)) + (size_t)warp * mp;
+    int *si = reinterpret_cast<int *>(sm_raw + (size_t)nwarp * mp * sizeof(double)) + (size_t)warp * mp;
     const float R = __uint_as_float(*rmax_bits);
     const double sc = knn_scale_of(R);
     const double inv_sc2 = 1.0 / (sc * sc);                // scores are in scaled units
-    for (int64_t q = (int64_t)blockIdx.x * 8 + warp; q < nq; q += (int64_t)gridDim.x * 8) {
+    int *sel = reinterpret_cast<int *>(sm_raw + (size_t)nwarp * mp * (sizeof(double) + sizeof(int))) + (size_t)warp * mg;
+    for (int64_t q = (int64_t)blockIdx.x * nwarp + warp; q < nq; q += (int64_t)gridDim.x * nwarp) {
         const int64_t qid = q_begin + q;
         const double *qv = emb + qid * d;
         const double qnorm2 = qn[qid];
         const double scale = sqrt(qnorm2) + (double)R;
+        const double eps = TC_KAPPA * scale * scale;
+        // Only groups that can hold one of the k nearest are expanded.  With the lists sorted by key, the k-th
+        // smallest approximate group minimum a_k of any one list bounds D_k <= a_k + eps (k distinct groups, each
+        // contributing its minimum); a group whose approximate minimum exceeds a_k + 2 eps has every point
+        // strictly farther than D_k.
+        double thr = INFINITY;
+        if (lane < lists) {
+            const unsigned long long kk = cand[((size_t)lane * nq + q) * m + (k - 1 < m ? k - 1 : m - 1)];
+            if (kk != TC_KEY_MAX && k <= m) thr = (double)key_score(kk) * inv_sc2 + qnorm2 + 2.0 * eps;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) thr = fmin(thr, ab_shfl_xor_f64(thr, o));
+        int n_exp = 0;
+        for (int g0 = 0; g0 < mg; g0 += 32) {
+            const int gi = g0 + lane;
+            bool take = false;
+            if (gi < mg) {
+                const int g = gi / m, e = gi - g * m;
+                const unsigned long long key = cand[((size_t)g * nq + q) * m + e];
+                take = key != TC_KEY_MAX && ((double)key_score(key) * inv_sc2 + qnorm2 <= thr);
+            }
+            const unsigned bal = __ballot_sync(AB_FULL, take);
+            if (take) sel[n_exp + __popc(bal & ((1u << lane) - 1))] = gi;
+            n_exp += __popc(bal);
+        }
+        __syncwarp();
+        const int np = n_exp * 8;
+        int p2 = 32;
+        while (p2 < np || p2 < k + 1) p2 <<= 1;            // sort size: power of two covering the expanded points
+        if (p2 > mp) p2 = mp;
         double worst_rel = 0.0;
-        for (int c = lane; c < mp; c += 32) {
-            const int g = c / m, e = c - g * m;
-            const unsigned long long key = cand[((size_t)g * nq + q) * m + e];
+        for (int c = lane; c < p2; c += 32) {              // 8 consecutive lanes = the 8 points of one group
             double dist = INFINITY;
             int id = INT_MAX;
-            const int cnd = (int)(uint32_t)(key & 0xFFFFFFFFull);
-            if (key != TC_KEY_MAX && cnd < n_total) {             // (padding columns can enter only while a list is short)
-                const double *xv = emb + (int64_t)cnd * d;
-                double acc = 0.0;
-                for (int j = 0; j < d; ++j) {                 // the reference's arithmetic, no FMA
-                    const double df = __dsub_rn(qv[j], xv[j]);
-                    acc = __dadd_rn(acc, __dmul_rn(df, df));
+            unsigned long long key = TC_KEY_MAX;
+            if (c < np) {
+                const int gi = sel[c >> 3], sub = c & 7;
+                const int g = gi / m, e = gi - g * m;
+                key = cand[((size_t)g * nq + q) * m + e];
+                const long long cnd = (long long)(uint32_t)(key & 0xFFFFFFFFull) + sub;
+                if (cnd < n_total) {                          // (padding columns: ids past the end)
+                    const double *xv = emb + cnd * d;
+                    double acc = 0.0;
+                    for (int j = 0; j < d; ++j) {             // the reference's arithmetic, no FMA
+                        const double df = __dsub_rn(qv[j], xv[j]);
+                        acc = __dadd_rn(acc, __dmul_rn(df, df));
+                    }
+                    dist = acc;
+                    id = (int)cnd;
                 }
-                dist = acc;
-                id = cnd;
+            }
+            // the key's score approximates the SMALLEST distance of the group
+            double gmin = dist;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) gmin = fmin(gmin, ab_shfl_xor_f64(gmin, o));
+            if (key != TC_KEY_MAX && gmin < INFINITY) {
                 const double approx = (double)key_score(key) * inv_sc2 + qnorm2;
-                worst_rel = fmax(worst_rel, fabs(approx - acc) / (scale * scale));
+                worst_rel = fmax(worst_rel, fabs(approx - gmin) / (scale * scale));
             }
             sd[c] = dist;
             si[c] = id;
         }
         __syncwarp();
-        for (int size = 2; size <= mp; size <<= 1) {
+        for (int size = 2; size <= p2; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = lane; i < (mp >> 1); i += 32) {
+                for (int i = lane; i < (p2 >> 1); i += 32) {
                     const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
                     const int hi = lo | stride;
                     const bool up = ((lo & size) == 0);
@@ -774,18 +816,17 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         }
         if (lane == 0) {
             const double dk = sd[k - 1];
-            // a list that is not full holds every point it saw -> no outside point there
+            // a list that is not full holds every group it saw -> no outside point there
             double tau = INFINITY;
             for (int g = 0; g < lists; ++g) {
                 const unsigned long long last = cand[((size_t)g * nq + q) * m + (m - 1)];
                 if (last != TC_KEY_MAX) tau = fmin(tau, (double)key_score(last) * inv_sc2);
             }
-            const double eps = TC_KAPPA * scale * scale;
-            // every point outside the lists has  D >= tau + ||q||^2 - eps ; strict '>' also settles ties
+            // every point outside the listed groups has  D >= tau + ||q||^2 - eps ; strict '>' also settles ties
             const bool certified = (tau + qnorm2 - eps > dk);
             if (certified) {
                 atomicAdd(stats + 3, 1ull);
-                if (k < mp && sd[k] == dk) atomicAdd(stats + 0, 1ull);
+                if (k < p2 && sd[k] == dk) atomicAdd(stats + 0, 1ull);
                 if (si[0] != (int)qid || (k > 1 && sd[1] == 0.0)) atomicAdd(stats + 2, 1ull);
             } else {
                 const unsigned long long slot = atomicAdd(stats + 1, 1ull);
@@ -942,12 +983,14 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     }
     // ---- exact re-rank + certificate ----
     ab_prof_begin(ctx, AB_PROF_KNN_RERANK, st);
-    const int mp = lists * m;
-    const size_t rr_smem = (size_t)8 * mp * (sizeof(double) + sizeof(int));
+    const int mp = lists * m * 8;                                   // candidate points per query (m groups of 8 per list)
+    int rr_warps = 8;
+    while (rr_warps > 1 && (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) > (size_t)160 * 1024) rr_warps >>= 1;
+    const size_t rr_smem = (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) + (size_t)rr_warps * (mp / 8) * sizeof(int);
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
-    const unsigned g_rr = (unsigned)std::min<int64_t>((nq + 7) / 8, (int64_t)ctx->sm_count * 8);
-    knn_rerank_kernel<<<g_rr, 256, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
-                                                  idx, rdist, w.fb_list, stats, w.scal + 1);
+    const unsigned g_rr = (unsigned)std::min<int64_t>((nq + rr_warps - 1) / rr_warps, (int64_t)ctx->sm_count * 16);
+    knn_rerank_kernel<<<g_rr, rr_warps * 32, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
+                                                           idx, rdist, w.fb_list, stats, w.scal + 1);
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_RERANK, st);
     // ---- uncertified queries: exact scan ----
