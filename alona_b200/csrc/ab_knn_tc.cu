@@ -286,6 +286,7 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d,
 static constexpr int TC_EPI_WARPS = 8;                       // two halves of four warps
 static constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 static constexpr int TC_NTHREADS = 64 + TC_EPI_THREADS;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+static constexpr int TC_GRP = 8;                             // points per candidate group (4 or 8; 4: main +5 %, re-rank -50 %, same total)
 static constexpr int TC_BUF = 32;                            // per-thread append buffer (entries; one prune merges <= 32)
 static constexpr unsigned long long TC_KEY_MAX = 0xFFFFFFFFFFFFFFFFull;
 
@@ -438,30 +439,39 @@ __device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, in
 // their threshold).  Padding columns carry a huge score (see knn_prep_kernel) and never pass.
 __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, bool live, const TcParams &P, int list_id,
                                          long long q, int &cnt, float &tau, unsigned long long *bufp, int lane) {
-    float gmin[4];
+    constexpr int NG = 32 / TC_GRP;
+    float gmin[NG];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        float v = fmin3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
-        v = fmin3(v, __uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]));
-        v = fmin3(v, __uint_as_float(r[8 * g + 5]), __uint_as_float(r[8 * g + 6]));
-        gmin[g] = fminf(v, __uint_as_float(r[8 * g + 7]));
+    for (int g = 0; g < NG; ++g) {
+        if (TC_GRP == 8) {
+            float v = fmin3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+            v = fmin3(v, __uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]));
+            v = fmin3(v, __uint_as_float(r[8 * g + 5]), __uint_as_float(r[8 * g + 6]));
+            gmin[g] = fminf(v, __uint_as_float(r[8 * g + 7]));
+        } else {
+            gmin[g] = fminf(fmin3(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2])),
+                            __uint_as_float(r[4 * g + 3]));
+        }
     }
-    const float mn = fminf(fmin3(gmin[0], gmin[1], gmin[2]), gmin[3]);
+    float mn = gmin[0];
+#pragma unroll
+    for (int g = 1; g + 1 < NG; g += 2) mn = fmin3(mn, gmin[g], gmin[g + 1]);
+    mn = fminf(mn, gmin[NG - 1]);
     if (!__any_sync(AB_FULL, live && mn < tau) || (P.dbg & 256)) return;      // (256: experiment, common path only)
-    // Rare path.  A candidate is a GROUP of 8 consecutive points keyed by its smallest score: appending it is one
+    // Rare path.  A candidate is a GROUP of TC_GRP consecutive points keyed by its smallest score: appending it is one
     // compare and one store per group, with no search inside the 32 registers (measured: that search, executed by
     // the whole warp for the ~1.7 lanes that hit, was everything the kernel cost above its MMA/copy floor).  The
     // certificate is unchanged - every point outside the listed groups scores >= its group's minimum >= tau - and
-    // the re-rank expands the m listed groups to their 8*m points.
-    const unsigned tight = __ballot_sync(AB_FULL, cnt > TC_BUF - 4);
+    // the re-rank expands the listed groups to their points.
+    const unsigned tight = __ballot_sync(AB_FULL, cnt > TC_BUF - NG);
     if (tight) warp_prune(tight, P, list_id, q, cnt, tau, bufp, lane);
     if (live && mn < tau) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < NG; ++g) {
             if (gmin[g] < tau) {
                 // append buffers live in global memory (L2): appends are rare fire-and-forget stores, and the
                 // shared memory they would take is worth more as operand ring
-                bufp[(size_t)cnt * TC_EPI_THREADS] = ((unsigned long long)__float_as_uint(gmin[g]) << 32) | (uint32_t)(cbase + 8 * g);
+                bufp[(size_t)cnt * TC_EPI_THREADS] = ((unsigned long long)__float_as_uint(gmin[g]) << 32) | (uint32_t)(cbase + TC_GRP * g);
                 ++cnt;
             }
         }
@@ -721,7 +731,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int mg = lists * m;                              // candidate groups of the query (all lists)
-    const int mp = mg * 8;                                 // candidate points; power of two
+    const int mp = mg * TC_GRP;                            // candidate points; power of two
     double *sd = reinterpret_cast<double *>(sm_raw) + (size_t)warp * mp;
     int *si = reinterpret_cast<int *>(sm_raw + (size_t)nwarp * mp * sizeof(double)) + (size_t)warp * mp;
     const float R = __uint_as_float(*rmax_bits);
@@ -759,17 +769,17 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
             n_exp += __popc(bal);
         }
         __syncwarp();
-        const int np = n_exp * 8;
+        const int np = n_exp * TC_GRP;
         int p2 = 32;
         while (p2 < np || p2 < k + 1) p2 <<= 1;            // sort size: power of two covering the expanded points
         if (p2 > mp) p2 = mp;
         double worst_rel = 0.0;
-        for (int c = lane; c < p2; c += 32) {              // 8 consecutive lanes = the 8 points of one group
+        for (int c = lane; c < p2; c += 32) {              // TC_GRP consecutive lanes = the points of one group
             double dist = INFINITY;
             int id = INT_MAX;
             unsigned long long key = TC_KEY_MAX;
             if (c < np) {
-                const int gi = sel[c >> 3], sub = c & 7;
+                const int gi = sel[c / TC_GRP], sub = c & (TC_GRP - 1);
                 const int g = gi / m, e = gi - g * m;
                 key = cand[((size_t)g * nq + q) * m + e];
                 const long long cnd = (long long)(uint32_t)(key & 0xFFFFFFFFull) + sub;
@@ -787,7 +797,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
             // the key's score approximates the SMALLEST distance of the group
             double gmin = dist;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) gmin = fmin(gmin, ab_shfl_xor_f64(gmin, o));
+            for (int o = TC_GRP / 2; o > 0; o >>= 1) gmin = fmin(gmin, ab_shfl_xor_f64(gmin, o));
             if (key != TC_KEY_MAX && gmin < INFINITY) {
                 const double approx = (double)key_score(key) * inv_sc2 + qnorm2;
                 worst_rel = fmax(worst_rel, fabs(approx - gmin) / (scale * scale));
@@ -983,10 +993,10 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     }
     // ---- exact re-rank + certificate ----
     ab_prof_begin(ctx, AB_PROF_KNN_RERANK, st);
-    const int mp = lists * m * 8;                                   // candidate points per query (m groups of 8 per list)
+    const int mp = lists * m * TC_GRP;                              // candidate points per query (m groups per list)
     int rr_warps = 8;
     while (rr_warps > 1 && (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) > (size_t)160 * 1024) rr_warps >>= 1;
-    const size_t rr_smem = (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) + (size_t)rr_warps * (mp / 8) * sizeof(int);
+    const size_t rr_smem = (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) + (size_t)rr_warps * (mp / TC_GRP) * sizeof(int);
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     const unsigned g_rr = (unsigned)std::min<int64_t>((nq + rr_warps - 1) / rr_warps, (int64_t)ctx->sm_count * 16);
     knn_rerank_kernel<<<g_rr, rr_warps * 32, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
