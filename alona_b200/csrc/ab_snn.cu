@@ -27,6 +27,7 @@ static constexpr int SNN_MAXK = 128;
 static constexpr int SNN_BIG_CTAS = 32;
 static constexpr int SNN_BIG_THREADS = 256;
 static constexpr int SORT_CTA_MAX = 4096;
+static constexpr int SNN_STAGE_CAP = 64;          // staged edges per row (single-pass protocol); more -> second pass
 
 // ---------------------------------------------------------------------------------------
 // reverse graph
@@ -153,7 +154,7 @@ __global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t 
                                 const int64_t *__restrict__ rptr, int32_t *__restrict__ cls_rows /*[5][n_rows]*/,
                                 int *__restrict__ n_cls /*[5]*/, int lim1, int lim2, int lim3,
                                 unsigned long long *__restrict__ max_walk, unsigned long long *__restrict__ sum_walk,
-                                int *__restrict__ n_dup) {
+                                int *__restrict__ n_dup, uint8_t *__restrict__ row_cls) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     long long walk = 0;
     if (r < n_rows) {
@@ -165,6 +166,7 @@ __global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t 
         if (row[0] != row_begin + r) atomicAdd(n_dup, 1);
         const int cls = walk <= SNN_WALK_LIMIT ? 0 : (walk <= lim1 ? 1 : (walk <= lim2 ? 2 : (walk <= lim3 ? 3 : 4)));
         cls_rows[(int64_t)cls * n_rows + atomicAdd(n_cls + cls, 1)] = (int32_t)r;
+        row_cls[r] = (uint8_t)cls;
     }
     // block-level max / sum before touching the global atomics
     unsigned long long wmax = (unsigned long long)walk, wsum = (unsigned long long)walk;
@@ -254,7 +256,7 @@ snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, cons
                  const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
                  const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
                  const int64_t *__restrict__ rowptr_out, int32_t *__restrict__ src, int32_t *__restrict__ dst,
-                 uint8_t *__restrict__ overlap) {
+                 uint8_t *__restrict__ overlap, int cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpRowState &st = reinterpret_cast<WarpRowState *>(smem_raw)[warp];
@@ -293,7 +295,10 @@ snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, cons
             c = ab_warp_sum_i32(c);
             if (lane == 0) rowcount[r] = c;
         } else {
-            int64_t out = rowptr_out[r];
+            // cap > 0: "staging" mode of the single-pass protocol: the row's edges go to its own slot of `cap`
+            // entries (dst/overlap are the staging arrays, src is implied) and the row count is written as well
+            const int64_t obase = cap ? r * (int64_t)cap : rowptr_out[r];
+            int64_t out = obase;
             const int grow = (int)(row_begin + r);
             for (int p0 = ((walk - 1) / 32) * 32; p0 >= 0; p0 -= 32) {
                 const int p = p0 + lane;
@@ -310,12 +315,15 @@ snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, cons
                 const unsigned b = __ballot_sync(AB_FULL, keep);
                 if (keep) {
                     const int64_t o = out + __popc(b & ~((2u << lane) - 1));     // higher lanes first
-                    dst[o] = m;
-                    src[o] = grow;
-                    if (overlap) overlap[o] = (uint8_t)cnt;
+                    if (!cap || o - obase < cap) {
+                        dst[o] = m;
+                        if (!cap) src[o] = grow;
+                        if (overlap) overlap[o] = (uint8_t)cnt;
+                    }
                 }
                 out += __popc(b);
             }
+            if (cap && lane == 0) rowcount[r] = out - obase;
         }
         __syncwarp();
     }
@@ -341,7 +349,7 @@ snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const 
                const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
                const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
                const int64_t *__restrict__ rowptr_out, int32_t *__restrict__ src, int32_t *__restrict__ dst,
-               uint8_t *__restrict__ overlap) {
+               uint8_t *__restrict__ overlap, int cap) {
     static_assert(SLOTS / 10 * 7 / 32 + SNN_MAXK + 1 <= THREADS, "chunk table must fit one scan pass");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *keys = reinterpret_cast<int *>(smem_raw);
@@ -469,10 +477,11 @@ snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const 
                 }
                 __syncthreads();
                 if (cidx >= 0) choff[cidx] = red[warp] + inc - v;      // entries emitted before this chunk
+                if (cap && cidx == 0) rowcount[r] = red[warp] + inc;   // staging mode: the row's edge count
             }
             __syncthreads();
-            // ---- pass B: emit ----
-            const int64_t out = rowptr_out[r];
+            // ---- pass B: emit (cap > 0: into the row's staging slot of `cap` entries, see snn_small_kernel) ----
+            const int64_t out = cap ? r * (int64_t)cap : rowptr_out[r];
             const int grow = (int)(row_begin + r);
             for (int c = warp; c < C; c += NW) {
                 const unsigned b = ballots[c];
@@ -485,10 +494,13 @@ snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const 
                     int pc = 0;
 #pragma unroll
                     for (int w2 = 0; w2 < W; ++w2) pc += __popc(masks[(size_t)s * W + w2]);
-                    const int64_t o = out + choff[c] + __popc(b & ~((2u << lane) - 1));   // higher lanes first
-                    dst[o] = m;
-                    src[o] = grow;
-                    if (overlap) overlap[o] = (uint8_t)pc;
+                    const int rel = choff[c] + __popc(b & ~((2u << lane) - 1));            // higher lanes first
+                    if (!cap || rel < cap) {
+                        const int64_t o = out + rel;
+                        dst[o] = m;
+                        if (!cap) src[o] = grow;
+                        if (overlap) overlap[o] = (uint8_t)pc;
+                    }
                 }
             }
         }
@@ -590,6 +602,32 @@ __global__ void snn_init_dense_kernel(int *dense, int64_t n_total, int nctas) {
     if (i < per * nctas) dense[i] = ((i % per) < n_total) ? 0 : INT_MAX;
 }
 
+// staging -> final edge list: one warp per row; rows whose edges did not fit their staging slot are queued
+__global__ void __launch_bounds__(256)
+snn_compact_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ stage_dst,
+                   const uint8_t *__restrict__ stage_ov, int cap, int64_t n_rows, int64_t row_begin,
+                   const uint8_t *__restrict__ row_cls, int32_t *__restrict__ src, int32_t *__restrict__ dst,
+                   uint8_t *__restrict__ overlap, int32_t *__restrict__ ovf_rows, int *__restrict__ n_ovf) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    for (int64_t r = w; r < n_rows; r += nw) {
+        if (row_cls[r] == 4) continue;                       // dense-path rows are filled by snn_big_kernel<true>
+        const int64_t a = rowptr[r];
+        const int64_t cnt = rowptr[r + 1] - a;
+        if (cnt > cap) {
+            if (lane == 0) ovf_rows[atomicAdd(n_ovf, 1)] = (int32_t)r;
+            continue;
+        }
+        const int grow = (int)(row_begin + r);
+        for (int i = lane; i < (int)cnt; i += 32) {
+            dst[a + i] = stage_dst[r * cap + i];
+            src[a + i] = grow;
+            if (overlap) overlap[a + i] = stage_ov[r * cap + i];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -600,6 +638,10 @@ struct SnnWs {
     int32_t *tmp;        // n_total*k
     int32_t *long_ids;   // n_total
     int32_t *cls_rows;   // 5*n_rows
+    uint8_t *row_cls;    // n_rows: class of every row
+    int32_t *stage_dst;  // n_rows * SNN_STAGE_CAP: edges of each row, staged by the (single) walk pass
+    uint8_t *stage_ov;   // n_rows * SNN_STAGE_CAP
+    int32_t *ovf_rows;   // n_rows: rows whose edges did not fit their staging slot
     int *dense;          // SNN_BIG_CTAS*2*n_total
     int *counters;       // 16 ints: [0] n_long, [2] n_dup, [3] bad, [4..7] rows per class
     unsigned long long *walk_stats;   // [0] max walk, [1] sum of walks
@@ -617,6 +659,10 @@ static size_t snn_layout(int64_t n_total, int32_t k, int64_t n_rows, void *ws, s
     w.tmp = a.take<int32_t>((size_t)n_total * k);
     w.long_ids = a.take<int32_t>(n_total);
     w.cls_rows = a.take<int32_t>((size_t)5 * (n_rows > 0 ? n_rows : 1));
+    w.row_cls = a.take<uint8_t>((size_t)(n_rows > 0 ? n_rows : 1));
+    w.stage_dst = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1) * SNN_STAGE_CAP);
+    w.stage_ov = a.take<uint8_t>((size_t)(n_rows > 0 ? n_rows : 1) * SNN_STAGE_CAP);
+    w.ovf_rows = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1));
     w.dense = a.take<int>((size_t)SNN_BIG_CTAS * 2 * n_total);
     w.counters = a.take<int>(16);
     w.walk_stats = a.take<unsigned long long>(2);
@@ -634,32 +680,31 @@ extern "C" size_t ab_snn_ws_bytes(int64_t n_total, int32_t k, int64_t n_rows) {
 
 static size_t snn_small_smem() { return sizeof(WarpRowState) * SNN_WARPS + (size_t)SNN_WARPS * SNN_SLOTS * 2 * sizeof(int); }
 
-// launches the four per-class kernels (count or fill)
-template <bool FILL>
-static int snn_launch_rows(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, int64_t n_total, int k, int64_t row_begin,
-                           int64_t n_rows, int v_min, const int64_t *rowptr, int32_t *src, int32_t *dst,
-                           uint8_t *overlap, cudaStream_t st) {
-    int64_t *rowcount = FILL ? nullptr : w.rowcount;
+// launches the shared-memory-table kernels of classes 0-3 in FILL mode: cap > 0 stages every row's edges into its own
+// slot (dst/overlap = staging arrays, rowcount written), cap == 0 writes final positions given by rowptr
+static int snn_launch_tables(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, int k, int64_t row_begin, int64_t n_rows,
+                             int v_min, int64_t *rowcount, const int64_t *rowptr, int32_t *src, int32_t *dst,
+                             uint8_t *overlap, int cap, cudaStream_t st) {
     const int32_t *rows0 = w.cls_rows, *rows1 = w.cls_rows + n_rows, *rows2 = w.cls_rows + 2 * n_rows,
-                  *rows3 = w.cls_rows + 3 * n_rows, *rows4 = w.cls_rows + 4 * n_rows;
+                  *rows3 = w.cls_rows + 3 * n_rows;
     const int *ncls = w.counters + 4;
     {
         const size_t smem = snn_small_smem();
-        AB_CUDA(cudaFuncSetAttribute(snn_small_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AB_CUDA(cudaFuncSetAttribute(snn_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int64_t blocks = std::min<int64_t>((n_rows + SNN_WARPS - 1) / SNN_WARPS, (int64_t)ctx->sm_count * 4);
-        snn_small_kernel<FILL><<<(unsigned)blocks, SNN_WARPS * 32, smem, st>>>(
-            knn_all, k, row_begin, rows0, ncls + 0, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap);
+        snn_small_kernel<true><<<(unsigned)blocks, SNN_WARPS * 32, smem, st>>>(
+            knn_all, k, row_begin, rows0, ncls + 0, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap, cap);
         AB_LAUNCH_CHECK(ctx);
     }
-    const int64_t cap = std::max<int64_t>(1, n_rows);
+    const int64_t gcap = std::max<int64_t>(1, n_rows);
 #define AB_SNN_CTA(SLOTS, W, THREADS, ROWS, NPTR, PER_SM)                                                        \
     do {                                                                                                       \
         const size_t smem = snn_cta_smem<SLOTS, W, THREADS>();                                                 \
-        AB_CUDA(cudaFuncSetAttribute(snn_cta_kernel<SLOTS, W, THREADS, FILL>,                                  \
+        AB_CUDA(cudaFuncSetAttribute(snn_cta_kernel<SLOTS, W, THREADS, true>,                                  \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        const unsigned grid = (unsigned)std::min<int64_t>(cap, (int64_t)ctx->sm_count * (PER_SM));             \
-        snn_cta_kernel<SLOTS, W, THREADS, FILL><<<grid, THREADS, smem, st>>>(                                  \
-            knn_all, k, row_begin, ROWS, NPTR, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap);    \
+        const unsigned grid = (unsigned)std::min<int64_t>(gcap, (int64_t)ctx->sm_count * (PER_SM));            \
+        snn_cta_kernel<SLOTS, W, THREADS, true><<<grid, THREADS, smem, st>>>(                                  \
+            knn_all, k, row_begin, ROWS, NPTR, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap, cap); \
         AB_LAUNCH_CHECK(ctx);                                                                                  \
     } while (0)
     if (k <= 32) {
@@ -670,11 +715,21 @@ static int snn_launch_rows(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, 
         AB_SNN_CTA(SNN_MID_SLOTS, 4, SNN_MID_THREADS, rows1, ncls + 1, 2);
         AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows2, ncls + 2, 1);     // (class 3 stays empty: lim3 == lim2)
     }
+    return 0;
+}
+
+// second pass for the rows whose edges did not fit their staging slot: the largest table kernel takes any class-0..3 row
+static int snn_launch_overflow(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, int k, int64_t row_begin, int64_t n_rows,
+                               int v_min, const int64_t *rowptr, int32_t *src, int32_t *dst, uint8_t *overlap,
+                               cudaStream_t st) {
+    const int64_t gcap = std::max<int64_t>(1, n_rows);
+    const int32_t *rows = w.ovf_rows;
+    const int *nptr = w.counters + 10;
+    int64_t *rowcount = nullptr;
+    const int cap = 0;
+    if (k <= 32) AB_SNN_CTA(16384, 1, SNN_LARGE_THREADS, rows, nptr, 1);
+    else AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows, nptr, 1);
 #undef AB_SNN_CTA
-    snn_big_kernel<FILL><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
-        knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, rows4, ncls + 4, w.dense, rowcount, rowptr, src, dst,
-        overlap);
-    AB_LAUNCH_CHECK(ctx);
     return 0;
 }
 
@@ -715,14 +770,20 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     if (n_rows > 0) {
         snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
             knn_all, k, row_begin, n_rows, w.deg, w.cls_rows, w.counters + 4, snn_walk_cap(SNN_MID_SLOTS),
-            snn_walk_cap(8192), snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2);
+            snn_walk_cap(8192), snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2, w.row_cls);
         AB_LAUNCH_CHECK(ctx);
         snn_init_dense_kernel<<<(unsigned)(((int64_t)SNN_BIG_CTAS * 2 * n_total + 255) / 256), 256, 0, st>>>(
             w.dense, n_total, SNN_BIG_CTAS);
         AB_LAUNCH_CHECK(ctx);
-        if (snn_launch_rows<false>(ctx, w, knn_all, n_total, k, row_begin, n_rows, v_min, nullptr, nullptr, nullptr,
-                                   nullptr, st))
+        // ONE walk per row: the table kernels run in fill mode and stage each row's edges (emission order
+        // included) in a per-row slot; ab_snn_fill then only compacts the slots into the final list
+        if (snn_launch_tables(ctx, w, knn_all, k, row_begin, n_rows, v_min, w.rowcount, nullptr, nullptr, w.stage_dst,
+                              w.stage_ov, SNN_STAGE_CAP, st))
             return 1;
+        snn_big_kernel<false><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
+            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.cls_rows + 4 * n_rows, w.counters + 8, w.dense,
+            w.rowcount, nullptr, nullptr, nullptr, nullptr);
+        AB_LAUNCH_CHECK(ctx);
     }
     if (ab_exclusive_scan_i64(ctx, w.rowcount, rowptr, n_rows, w.scan_ws, w.scan_bytes, st)) return 1;
     ab_prof_end(ctx, AB_PROF_SNN_COUNT, st);
@@ -755,9 +816,21 @@ extern "C" int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total,
     size_t need = snn_layout(n_total, k, n_rows, ws, ws_bytes, &w);
     AB_REQUIRE(need != 0, "ab_snn_fill: workspace too small");
     if (n_rows == 0) return 0;
-    ab_prof_begin(ctx, AB_PROF_SNN_FILL, (cudaStream_t)stream);
-    const int rc = snn_launch_rows<true>(ctx, w, knn_all, n_total, k, row_begin, n_rows, v_min, rowptr, src, dst, overlap,
-                                         (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    ab_prof_begin(ctx, AB_PROF_SNN_FILL, st);
+    int rc = 0;
+    AB_CUDA(cudaMemsetAsync(w.counters + 10, 0, sizeof(int), st));
+    snn_compact_kernel<<<(unsigned)std::min<int64_t>((n_rows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, st>>>(
+        rowptr, w.stage_dst, w.stage_ov, SNN_STAGE_CAP, n_rows, row_begin, w.row_cls, src, dst, overlap, w.ovf_rows,
+        w.counters + 10);
+    AB_LAUNCH_CHECK(ctx);
+    rc = snn_launch_overflow(ctx, w, knn_all, k, row_begin, n_rows, v_min, rowptr, src, dst, overlap, st);
+    if (!rc) {
+        snn_big_kernel<true><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
+            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.cls_rows + 4 * n_rows, w.counters + 8, w.dense, nullptr,
+            rowptr, src, dst, overlap);
+        AB_LAUNCH_CHECK(ctx);
+    }
     ab_prof_end(ctx, AB_PROF_SNN_FILL, (cudaStream_t)stream);
     return rc;
 }
