@@ -391,8 +391,8 @@ def stage_rooflines(wl, world, fine, info, out, peaks):
     add('panel_dot+panel_update', 'irlb_panel', 8 * n_loc * (2 * sum_panel + 3 * (nmult / 2)))
     walk = out['sum_walk']
     e = out['edges']
-    add('snn count kernels', 'snn_count', 4 * wl['cells'] * k + 4 * walk)
-    add('snn fill kernels', 'snn_fill', 4 * wl['cells'] * k + 8 * walk + e * 8)
+    add('snn walk kernels (count + staged edges)', 'snn_count', 4 * wl['cells'] * k + 4 * walk + e * 5)
+    add('snn compaction (fill)', 'snn_fill', e * 5 + e * 9)
     return rows
 
 
