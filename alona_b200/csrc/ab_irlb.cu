@@ -16,6 +16,7 @@
 // order, so a run is bitwise reproducible for a given (n_local, world).
 #include "ab_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <float.h>
 #include <limits.h>
 #include <algorithm>
@@ -510,6 +511,8 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
                 if (valid && g2 > 1e-30 * ab2 && fabs(ga) > 1e-300) {
                     if (hl == 0 && g2 > 1e-28 * ab2) rot_sm = 1;
                     // tan(theta) of the rotation that zeroes the pair's inner product
+                    // (FP32-seeded Newton variants of this scalar math were measured: same kernel time - the round
+                    // is a latency chain of dot / shuffle-reduce / this / rotate / __syncthreads, ~2700 cycles)
                     const double dd = be - al;
                     const double tt = (2.0 * ga) / (dd + (dd >= 0.0 ? 1.0 : -1.0) * sqrt(fma(dd, dd, 4.0 * g2)));
                     const double cs = rsqrt(fma(tt, tt, 1.0)), sn = cs * tt;
@@ -524,6 +527,7 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
         }
         const int any = rot_sm;
         __syncthreads();
+        if (threadIdx.x == 0) ctrl[CT_ROT] = sweep + 1;     // diagnostics: Jacobi sweeps of this call
         if (!any) break;
     }
     // singular values = column norms; sort descending by counting rank (ties by index)
@@ -908,6 +912,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         ab_prof_end(ctx, AB_PROF_IRLB_SVD, st);
         AB_CUDA(cudaMemcpyAsync(h_ctrl, w.ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, st));
         AB_CUDA(cudaStreamSynchronize(st));
+        if (getenv("AB_IRLB_DEBUG")) fprintf(stderr, "[irlb] restart %d: jacobi sweeps %d, converged %d, keep %d\n", it, h_ctrl[CT_ROT], h_ctrl[CT_CONV], h_ctrl[CT_KEEP]);
         if (h_ctrl[CT_DONE]) { converged = true; break; }
         keep = h_ctrl[CT_KEEP];
         // Ritz vectors (irlb.py:238-246)
