@@ -52,6 +52,9 @@ SIGNATURES = {
                                     c_void_p, c_size, c_void_p]),
     'ab_snn_fill': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i64, c_i32, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_size, c_void_p]),
+    'ab_edges_csv_ws_bytes': (c_size, [c_i64]),
+    'ab_edges_csv_count': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, p_i64, c_void_p, c_size, c_void_p]),
+    'ab_edges_csv_fill': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
     'ab_synth_ws_bytes': (c_size, [c_i64]),
     'ab_synth_nb_count': (ctypes.c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i64, c_f64, c_f64, c_f64, c_u64,
                                          c_void_p, p_i64, c_void_p, c_size, c_void_p]),

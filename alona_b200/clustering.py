@@ -153,7 +153,8 @@ class AlonaClustering(AlonaCell):
                         'on the duplicate (clustering.py:204) - reported, not emulated.' % res['dup_rows'])
         df = pd.DataFrame({'source_node': src.cpu().numpy(), 'target_node': dst.cpu().numpy()})
         if snn_path:
-            self._write(lambda fn: df.to_csv(fn, header=None, index=None), None, snn_path)
+            # same bytes as df.to_csv(fn, header=None, index=None) (clustering.py:237-238), formatted on the device
+            self._write(lambda fn: eng.write_edges_csv(src.contiguous(), dst.contiguous(), fn), None, snn_path)
         self.snn_graph = df
         log_debug('Done computing SNN.')
 

@@ -234,6 +234,30 @@ class Engine:
                 'dense_rows': int(stats[3]), 'sum_walk': int(stats[4]),
                 'class_rows': [int(stats[5]), int(stats[6]), int(stats[7])]}
 
+    # -- hand-off ---------------------------------------------------------------------
+    def edges_csv_bytes(self, src, dst):
+        """The edge list as the bytes alona writes to snn_graph.csv (clustering.py:237-238), formatted on the
+        device; returns a pinned host uint8 tensor."""
+        n = int(src.numel())
+        assert src.dtype == torch.int32 and dst.dtype == torch.int32 and int(dst.numel()) == n
+        ws = self.workspace(self.lib.ab_edges_csv_ws_bytes(n))
+        off = self.empty((n + 1,), torch.int64)
+        nbytes = ctypes.c_int64(0)
+        _lib.check(self.lib.ab_edges_csv_count(self.ctx, _ptr(src), _ptr(dst), n, _ptr(off), ctypes.byref(nbytes), _ptr(ws),
+                                               ws.numel(), self.stream()), 'ab_edges_csv_count')
+        out = self.empty((nbytes.value,), torch.uint8)
+        _lib.check(self.lib.ab_edges_csv_fill(self.ctx, _ptr(src), _ptr(dst), n, _ptr(off), _ptr(out), self.stream()),
+                   'ab_edges_csv_fill')
+        host = torch.empty((nbytes.value,), dtype=torch.uint8, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host
+
+    def write_edges_csv(self, src, dst, path):
+        buf = self.edges_csv_bytes(src, dst)
+        with open(path, 'wb') as fh:
+            fh.write(memoryview(buf.numpy()))
+
     # -- synthetic data ---------------------------------------------------------------
     def synth_counts(self, prof, cell_begin, n_local, lbar, n_total=None, depth_sigma=0.35, r_disp=5.0,
                      seed=20251019):

@@ -141,6 +141,17 @@ int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k,
                 int32_t *src, int32_t *dst, uint8_t *overlap, void *ws, size_t ws_bytes,
                 void *stream);
 
+/* ---- hand-off: the edge list as the bytes of csvs/snn_graph.csv --------------------------------
+ * replaces  df.to_csv(snn_path, header=None, index=None)  (alona/clustering.py:237-238): one
+ * "source,target\n" line per edge.  count: offsets[n_edges+1] (exclusive scan of the line lengths), total
+ * bytes in *h_bytes (synchronises);  fill: out[bytes] (device).  The caller copies `out` to the host and writes
+ * it with one write(). */
+size_t ab_edges_csv_ws_bytes(int64_t n_edges);
+int ab_edges_csv_count(ab_ctx *ctx, const int32_t *src, const int32_t *dst, int64_t n_edges, int64_t *offsets,
+                       int64_t *h_bytes, void *ws, size_t ws_bytes, void *stream);
+int ab_edges_csv_fill(ab_ctx *ctx, const int32_t *src, const int32_t *dst, int64_t n_edges, const int64_t *offsets,
+                      char *out, void *stream);
+
 /* ---- synthetic negative-binomial counts generated on the device (bench / tests only) ----
  * cluster model, Gamma-Poisson counts; data are a pure function of
  * (seed, cell id, gene id), hence identical for any sharding.  count: rowptr[n_local+1];

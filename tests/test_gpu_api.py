@@ -53,6 +53,11 @@ def test_alona_clustering_dropin(case, tmp_path):
         assert os.path.exists(wd + rel), rel
     back = pd.read_csv(wd + '/csvs/snn_graph.csv', header=None).values
     assert np.array_equal(back, o.snn_graph.values)
+    # the device-formatted file is byte-identical to what the reference writes (clustering.py:237-238)
+    import io
+    ref_bytes = io.StringIO()
+    o.snn_graph.to_csv(ref_bytes, header=None, index=None)
+    assert open(wd + '/csvs/snn_graph.csv', 'rb').read() == ref_bytes.getvalue().encode()
     hv = pd.read_csv(wd + '/csvs/highly_variable_genes.tsv', header=None, sep='\t')[0].values
     assert np.array_equal(hv, o.hvg)
     # cache rule: an existing snn_graph.csv is loaded, not recomputed (clustering.py:197-201)
@@ -88,3 +93,21 @@ def test_out_of_scope_options_exit_like_log_error():
         AlonaHighlyVariableGenes('scran', 10, None, None).find()
     with pytest.raises(SystemExit):
         AlonaHighlyVariableGenes('nonsense', 10, None, None).find()
+
+
+def test_edges_csv_bytes_match_pandas():
+    """ab_edges_csv_*: every digit count (1..10 digits), empty list, one edge."""
+    import io
+    import torch
+    from alona_b200.engine import get_engine
+    eng = get_engine()
+    rng = np.random.RandomState(1)
+    vals = np.concatenate([[0, 9, 10, 99, 100, 999999, 1000000, 2147483647],
+                           (10 ** rng.uniform(0, 9.3, 5000)).astype(np.int64)]).astype(np.int32)
+    for n in (0, 1, len(vals)):
+        src = vals[:n]
+        dst = vals[::-1][:n].copy()
+        buf = eng.edges_csv_bytes(torch.from_numpy(src).to(eng.device), torch.from_numpy(dst).to(eng.device))
+        ref = io.StringIO()
+        pd.DataFrame({'source_node': src, 'target_node': dst}).to_csv(ref, header=None, index=None)
+        assert bytes(buf.numpy().tobytes()) == ref.getvalue().encode()
