@@ -476,9 +476,11 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
     }
     __syncthreads();
     const int mp = (m + 1) & ~1;                        // round-robin needs an even player count
-    // one HALF-warp per column pair, so that a whole round (mp/2 <= 64 pairs) is one pass of the
-    // 1024-thread CTA
-    const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15, nhw = blockDim.x >> 4;
+    // eight lanes per column pair, so that a whole round (mp/2 <= 64 pairs) is one pass of the 512-thread
+    // CTA: a round costs every warp the same ~150 instructions whatever the number of pairs it hosts, and with
+    // 32 warps (half a warp per pair) instruction issue, not latency, set the round time
+    constexpr int LP = 8;                               // lanes per column pair (4 pairs per warp)
+    const int hw = threadIdx.x / LP, hl = threadIdx.x % LP, nhw = blockDim.x / LP;
     for (int sweep = 0; sweep < 60; ++sweep) {
         if (threadIdx.x == 0) rot_sm = 0;
         // refresh the running norms once per sweep (they are updated incrementally inside it)
@@ -500,9 +502,9 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
                 double *gp = G + (size_t)(valid ? p : 0) * m, *gq = G + (size_t)(valid ? q : 0) * m;
                 double ga = 0.0;
                 if (valid)
-                    for (int r = hl; r < m; r += 16) ga = fma(gp[r], gq[r], ga);
+                    for (int r = hl; r < m; r += LP) ga = fma(gp[r], gq[r], ga);
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) ga += ab_shfl_xor_f64(ga, o);    // stays inside the half-warp
+                for (int o = LP / 2; o > 0; o >>= 1) ga += ab_shfl_xor_f64(ga, o);    // stays inside the lane group
                 const double al = valid ? cn[p] : 1.0, be = valid ? cn[q] : 1.0;
                 // rotate down to rounding level, but call the sweep "dirty" only above 1e-14: pairs
                 // hovering at 1e-15..1e-16 (pure rounding noise) would otherwise keep the loop alive
@@ -516,7 +518,7 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
                     const double dd = be - al;
                     const double tt = (2.0 * ga) / (dd + (dd >= 0.0 ? 1.0 : -1.0) * sqrt(fma(dd, dd, 4.0 * g2)));
                     const double cs = rsqrt(fma(tt, tt, 1.0)), sn = cs * tt;
-                    for (int r = hl; r < m; r += 16) {
+                    for (int r = hl; r < m; r += LP) {
                         const double x = gp[r], y = gq[r];
                         gp[r] = cs * x - sn * y; gq[r] = sn * x + cs * y;
                     }
@@ -906,7 +908,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
             ++j;
         }
         ab_prof_begin(ctx, AB_PROF_IRLB_SVD, st);
-        svd_restart_kernel<<<1, 1024, svd_smem, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it,
+        svd_restart_kernel<<<1, 512, svd_smem, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it,
                                                      keep, q_in_smem);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_SVD, st);
