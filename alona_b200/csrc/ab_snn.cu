@@ -27,7 +27,10 @@ static constexpr int SNN_MAXK = 128;
 static constexpr int SNN_BIG_CTAS = 32;
 static constexpr int SNN_BIG_THREADS = 256;
 static constexpr int SORT_CTA_MAX = 4096;
-static constexpr int SNN_STAGE_CAP = 64;          // staged edges per row (single-pass protocol); more -> second pass
+// staged edges per row (single-pass protocol); rows with more take a second pass.  Edges per row grow with k
+// (C3, k = 20: 21 on average; a C5-shaped run, k = 30: 324), the slot is sized generously: it is only ever read up
+// to the row's count.
+static inline int snn_stage_cap(int k) { return std::min(1024, std::max(64, 16 * k)); }
 
 // ---------------------------------------------------------------------------------------
 // reverse graph
@@ -639,8 +642,8 @@ struct SnnWs {
     int32_t *long_ids;   // n_total
     int32_t *cls_rows;   // 5*n_rows
     uint8_t *row_cls;    // n_rows: class of every row
-    int32_t *stage_dst;  // n_rows * SNN_STAGE_CAP: edges of each row, staged by the (single) walk pass
-    uint8_t *stage_ov;   // n_rows * SNN_STAGE_CAP
+    int32_t *stage_dst;  // n_rows * snn_stage_cap(k): edges of each row, staged by the (single) walk pass
+    uint8_t *stage_ov;   // n_rows * snn_stage_cap(k)
     int32_t *ovf_rows;   // n_rows: rows whose edges did not fit their staging slot
     int *dense;          // SNN_BIG_CTAS*2*n_total
     int *counters;       // 16 ints: [0] n_long, [2] n_dup, [3] bad, [4..7] rows per class
@@ -660,8 +663,8 @@ static size_t snn_layout(int64_t n_total, int32_t k, int64_t n_rows, void *ws, s
     w.long_ids = a.take<int32_t>(n_total);
     w.cls_rows = a.take<int32_t>((size_t)5 * (n_rows > 0 ? n_rows : 1));
     w.row_cls = a.take<uint8_t>((size_t)(n_rows > 0 ? n_rows : 1));
-    w.stage_dst = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1) * SNN_STAGE_CAP);
-    w.stage_ov = a.take<uint8_t>((size_t)(n_rows > 0 ? n_rows : 1) * SNN_STAGE_CAP);
+    w.stage_dst = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1) * snn_stage_cap(k));
+    w.stage_ov = a.take<uint8_t>((size_t)(n_rows > 0 ? n_rows : 1) * snn_stage_cap(k));
     w.ovf_rows = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1));
     w.dense = a.take<int>((size_t)SNN_BIG_CTAS * 2 * n_total);
     w.counters = a.take<int>(16);
@@ -778,7 +781,7 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
         // ONE walk per row: the table kernels run in fill mode and stage each row's edges (emission order
         // included) in a per-row slot; ab_snn_fill then only compacts the slots into the final list
         if (snn_launch_tables(ctx, w, knn_all, k, row_begin, n_rows, v_min, w.rowcount, nullptr, nullptr, w.stage_dst,
-                              w.stage_ov, SNN_STAGE_CAP, st))
+                              w.stage_ov, snn_stage_cap(k), st))
             return 1;
         snn_big_kernel<false><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
             knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.cls_rows + 4 * n_rows, w.counters + 8, w.dense,
@@ -821,7 +824,7 @@ extern "C" int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total,
     int rc = 0;
     AB_CUDA(cudaMemsetAsync(w.counters + 10, 0, sizeof(int), st));
     snn_compact_kernel<<<(unsigned)std::min<int64_t>((n_rows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, st>>>(
-        rowptr, w.stage_dst, w.stage_ov, SNN_STAGE_CAP, n_rows, row_begin, w.row_cls, src, dst, overlap, w.ovf_rows,
+        rowptr, w.stage_dst, w.stage_ov, snn_stage_cap(k), n_rows, row_begin, w.row_cls, src, dst, overlap, w.ovf_rows,
         w.counters + 10);
     AB_LAUNCH_CHECK(ctx);
     rc = snn_launch_overflow(ctx, w, knn_all, k, row_begin, n_rows, v_min, rowptr, src, dst, overlap, st);
