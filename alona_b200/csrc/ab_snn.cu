@@ -24,7 +24,7 @@ static constexpr int SNN_WARPS = 8;
 static constexpr int SNN_SLOTS = 2048;            // per warp, power of two
 static constexpr int SNN_WALK_LIMIT = 1400;       // rows with a longer walk go to the big path
 static constexpr int SNN_MAXK = 128;
-static constexpr int SNN_BIG_CTAS = 32;
+static constexpr int SNN_BIG_CTAS = 148;         // one per SM (each owns 2*n_total ints of global scratch)
 static constexpr int SNN_BIG_THREADS = 256;
 static constexpr int SORT_CTA_MAX = 4096;
 // staged edges per row (single-pass protocol); rows with more take a second pass.  Edges per row grow with k
