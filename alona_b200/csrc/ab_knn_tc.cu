@@ -1020,9 +1020,12 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_REQUIRE(stages >= 2, "ab_knn: not enough shared memory for d=%d k=%d", d, k);
     const size_t smem = 1024 + a_bytes + (size_t)stages * group * b_stage + bar_bytes;
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TcParams P;
+    TcParams P{};
     P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (3 * d + 3 + 15) / 16;
-    P.stages = stages; P.group = group; P.merged = (group == chunks && stages >= 3 && getenv("AB_KNN_MERGED")) ? 1 : 0;   // measured: floor -10 %, full kernel +9 % -> off P.bufg = w.bufg; P.cursor = (int *)(w.scal + 2); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
+    P.stages = stages; P.group = group; P.bufg = w.bufg;
+    // one barrier round per tile instead of two: measured floor -10 %, full kernel +9 % -> experiment knob only
+    P.merged = (group == chunks && stages >= 3 && getenv("AB_KNN_MERGED")) ? 1 : 0;
+    P.cursor = (int *)(w.scal + 2); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
     P.dbg = getenv("AB_KNN_DBG") ? atoi(getenv("AB_KNN_DBG")) : 0;
     const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
     const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
