@@ -11,7 +11,8 @@ hdr, units = rows[0], rows[1]
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_sector_hit_rate.pct', 'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum',
         'sm__inst_executed_pipe_lsu.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'sm__cycles_elapsed.avg', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
@@ -19,9 +20,11 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 for r in rows[2:]:
     print('== kernel:', r[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else '')
     for k in KEYS:
-        if k in hdr:
-            i = hdr.index(k)
-            print('  %-75s %s %s' % (k, r[i], units[i]))
+        # some metrics carry a section prefix (TPC.TriageCompute.): exact name first, then a non-empty suffix match
+        hit = [i for i, name in enumerate(hdr) if name == k and r[i] != ''] or \
+              [i for i, name in enumerate(hdr) if name.endswith('.' + k) and r[i] != '']
+        if hit:
+            print('  %-75s %s %s' % (k, r[hit[0]], units[hit[0]]))
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 lines = src.splitlines()
 # the source page repeats a 2-line header per kernel
