@@ -70,6 +70,98 @@ atw_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Compact A_H for the row-dot products.  The values of one cell row are x(c) = log2(c/S*1e4+1)
+// for the handful of distinct counts c the row holds, so a row is stored as its table of
+// distinct values plus one 32-bit word per nonzero: gene (low 16 bits) | table slot (high 16).
+// 4 bytes per nonzero instead of 12; a row's table (typically 10-30 doubles) is read once from
+// HBM and then lives in L1.  The values are the very doubles of val_h, taken in the same order,
+// so A^T.w is bit-identical to the plain kernel.
+// Built once per ab_irlb call (warp per row; linear search of the row's table in shared memory,
+// new values de-duplicated inside each 32-nonzero step with match.any).
+// ---------------------------------------------------------------------------------------
+static constexpr int CB_WARPS = 8;
+static constexpr int CB_CAP = 256;              // distinct values per row the compact form supports
+
+__global__ void __launch_bounds__(CB_WARPS * 32)
+ah_compact_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
+                  int64_t n, uint32_t *__restrict__ ent, double *__restrict__ tabv, uint32_t *__restrict__ taboff,
+                  unsigned int *__restrict__ cursor /*[0] next table slot, [1] overflow flag*/) {
+    __shared__ unsigned long long tab_sm[CB_WARPS][CB_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *tab = tab_sm[warp];
+    const int64_t wid = (int64_t)blockIdx.x * CB_WARPS + warp;
+    const int64_t nw = (int64_t)gridDim.x * CB_WARPS;
+    for (int64_t row = wid; row < n; row += nw) {
+        const int64_t a = rowptr[row], b = rowptr[row + 1];
+        int t = 0;                                                      // table entries so far (warp-uniform)
+        for (int64_t base = a; base < b; base += 32) {
+            const int64_t p = base + lane;
+            const bool live = p < b;
+            const unsigned long long bits = live ? (unsigned long long)__double_as_longlong(__ldg(val + p)) : 0ull;
+            const int c = live ? __ldg(col + p) : 0;
+            int slot = -1;
+            const int tt = min(t, CB_CAP);
+            for (int i = 0; i < tt; ++i)
+                if (tab[i] == bits) slot = i;
+            const bool miss = live && slot < 0;
+            const unsigned need = __ballot_sync(AB_FULL, miss);
+            if (need) {
+                int leader = lane;
+                if (miss) leader = __ffs(__match_any_sync(need, bits)) - 1;
+                const bool lead = miss && leader == lane;
+                const unsigned leads = __ballot_sync(AB_FULL, lead);
+                const int mine = t + __popc(leads & ((1u << lane) - 1));
+                if (lead && mine < CB_CAP) tab[mine] = bits;
+                const int got = __shfl_sync(AB_FULL, mine, leader);
+                if (miss) slot = got;
+                t += __popc(leads);
+                __syncwarp();
+            }
+            if (live) ent[p] = (uint32_t)c | ((uint32_t)slot << 16);
+        }
+        unsigned int off = 0;
+        if (t > CB_CAP) {
+            if (lane == 0) cursor[1] = 1u;                              // the caller falls back to the plain kernels
+            t = CB_CAP;
+        }
+        if (lane == 0) off = atomicAdd(cursor, (unsigned int)t);
+        off = __shfl_sync(AB_FULL, off, 0);
+        if (lane == 0) taboff[row] = off;
+        for (int i = lane; i < t; i += 32) tabv[(size_t)off + i] = __longlong_as_double((long long)tab[i]);
+        __syncwarp();
+    }
+}
+
+// The A^T.w kernel on it: w (H doubles) is staged in shared memory once per CTA; the row's table is read through
+// L1.  With 4 bytes per nonzero the kernel is no longer HBM-bound but bound by the L1/shared data pipe (random
+// 8-byte reads of w: ~8 wavefronts per 32 nonzeros).  Measured dead ends: table slots from registers by shuffle
+// (the shuffles ride the same pipe: 139 ms against 105), software-pipelined rows with 8 steps of look-ahead at
+// half the occupancy (128 ms).
+__global__ void __launch_bounds__(256)
+atw_compact_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ ent, const double *__restrict__ tabv,
+                   const uint32_t *__restrict__ taboff, int64_t n, int H, const double *__restrict__ w,
+                   const double *__restrict__ vj, const double *__restrict__ scal, double *__restrict__ F) {
+    extern __shared__ double w_sm[];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) w_sm[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    const double s = scal[SC_S];
+    for (int64_t row = wid; row < n; row += nw) {
+        const int64_t a = rowptr[row], b = rowptr[row + 1];
+        const double *__restrict__ tb = tabv + taboff[row];
+        double acc = 0.0;
+        for (int64_t p = a + lane; p < b; p += 32) {
+            const uint32_t e = __ldcs(ent + p);
+            acc = fma(__ldg(tb + (e >> 16)), w_sm[e & 0xFFFFu], acc);
+        }
+        acc = ab_warp_sum_f64(acc);
+        if (lane == 0) F[row] = __dsub_rn(acc, __dmul_rn(s, vj[row]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // c[l] = sum_i V[i,l] F[i]  for l < ncols     (irlb.py:74 dotY, contraction over cells)
 // Thread <-> cell row inside a 256-row tile, CTAs stride over the tiles; PD_CB columns are
 // accumulated in registers per pass, so every thread has PD_CB independent coalesced loads in
@@ -239,7 +331,41 @@ __device__ __forceinline__ void av_load_block(AvRowState &r, const int64_t *__re
     if (ok && vdst) vdst[row] = r.x_l;
 }
 
+// one step of 32 nonzeros starting at stream offset s0
+template <bool FULL>
+__device__ __forceinline__ void av_step(AvRowState &r, double *acc, int cgu, double vvu, int s0, int len,
+                                        const int64_t *__restrict__ rowptr, int64_t p0, int64_t r1,
+                                        const double *__restrict__ src, double scale, double *__restrict__ vdst, int lane) {
+    const int s1 = FULL ? s0 + 32 : min(s0 + 32, len);
+    const int p = s0 + lane;
+    if (r.rend >= s1) {
+        // the whole step lies inside the current row
+        if (FULL || p < s1) acc[cgu] = fma(vvu, r.xrow, acc[cgu]);
+    } else {
+        int cur = s0;
+        while (cur < s1) {
+            if (r.rend <= cur) {
+                __syncwarp();                            // row switch: order the two rows' updates
+                do {                                     // advance to the row that owns `cur` (skips empty rows)
+                    if (++r.ri == 32) {
+                        r.blk += 32;
+                        av_load_block(r, rowptr, p0, r1, src, scale, vdst, lane);
+                        r.ri = 0;
+                    }
+                    r.rend = __shfl_sync(AB_FULL, r.rp_l, r.ri);
+                    r.xrow = ab_shfl_f64(r.x_l, r.ri);
+                } while (r.rend <= cur);
+            }
+            const int seg = min(r.rend, s1);
+            if (p >= cur && p < seg) acc[cgu] = fma(vvu, r.xrow, acc[cgu]);
+            cur = seg;
+        }
+    }
+}
+
 // consumes one batch of AV_U steps of 32 nonzeros.  FULL: every step of the batch is complete (no bounds checks).
+// (Issuing two in-row steps interleaved - their 64 genes are distinct - was measured slower: the kernel is
+// sensitive to its own code size, 17 % of its stalls are instruction fetch.)
 template <bool FULL>
 __device__ __forceinline__ void av_consume(AvRowState &r, double *acc, const int (&cg)[AV_U], const double (&vv)[AV_U],
                                            int base, int len, const int64_t *__restrict__ rowptr, int64_t p0, int64_t r1,
@@ -248,32 +374,7 @@ __device__ __forceinline__ void av_consume(AvRowState &r, double *acc, const int
     for (int u = 0; u < AV_U; ++u) {
         const int s0 = base + 32 * u;
         if (!FULL && s0 >= len) break;
-        const int s1 = FULL ? s0 + 32 : min(s0 + 32, len);
-        const int p = s0 + lane;
-        if (r.rend >= s1) {
-            // the whole step lies inside the current row: no ordering needed against the previous steps of this
-            // row (distinct genes), the load/FMA/store chains of consecutive steps overlap freely
-            if (FULL || p < s1) acc[cg[u]] = fma(vv[u], r.xrow, acc[cg[u]]);
-        } else {
-            int cur = s0;
-            while (cur < s1) {
-                if (r.rend <= cur) {
-                    __syncwarp();                            // row switch: order the two rows' updates
-                    do {                                     // advance to the row that owns `cur` (skips empty rows)
-                        if (++r.ri == 32) {
-                            r.blk += 32;
-                            av_load_block(r, rowptr, p0, r1, src, scale, vdst, lane);
-                            r.ri = 0;
-                        }
-                        r.rend = __shfl_sync(AB_FULL, r.rp_l, r.ri);
-                        r.xrow = ab_shfl_f64(r.x_l, r.ri);
-                    } while (r.rend <= cur);
-                }
-                const int seg = min(r.rend, s1);
-                if (p >= cur && p < seg) acc[cg[u]] = fma(vv[u], r.xrow, acc[cg[u]]);
-                cur = seg;
-            }
-        }
+        av_step<FULL>(r, acc, cg[u], vv[u], s0, len, rowptr, p0, r1, src, scale, vdst, lane);
     }
 }
 
@@ -786,6 +887,32 @@ extern "C" size_t ab_irlb_ws_bytes(int64_t n_local, int32_t n_hvg, int32_t nval)
     return irlb_layout(n_local, n_hvg, nval, (int64_t)1 << 40, 256, nullptr, 0, nullptr) + 256;
 }
 
+// compact A_H (see ah_compact_kernel): entries, worst-case value tables (every value distinct), table offsets
+struct IrlbCompact {
+    uint32_t *ent, *taboff;
+    double *tabv;
+    unsigned int *cursor;
+};
+static size_t irlb_compact_layout(int64_t n, int64_t nnz, void *base, size_t bytes, IrlbCompact *out) {
+    ab_arena a(base ? base : (void *)256, base ? bytes : (size_t)-1 / 2);
+    IrlbCompact c;
+    c.tabv = a.take<double>((size_t)std::max<int64_t>(nnz, 1) + 32);      // +32: a lane-wide table read never leaves the buffer
+    c.ent = a.take<uint32_t>((size_t)std::max<int64_t>(nnz, 1));
+    c.taboff = a.take<uint32_t>((size_t)std::max<int64_t>(n, 1));
+    c.cursor = a.take<unsigned int>(4);
+    if (out) *out = c;
+    return a.ok ? a.off : 0;
+}
+static bool irlb_compact_eligible(int64_t n, int H, int64_t nnz) {
+    return n > 0 && H <= 65536 && nnz > 0 && nnz < ((int64_t)1 << 32);
+}
+
+extern "C" size_t ab_irlb_ws_bytes_compact(int64_t n_local, int32_t n_hvg, int32_t nval, int64_t nnz_local) {
+    const size_t base = ab_irlb_ws_bytes(n_local, n_hvg, nval);
+    if (!irlb_compact_eligible(n_local, n_hvg, nnz_local)) return base;
+    return base + irlb_compact_layout(n_local, nnz_local, nullptr, 0, nullptr) + 256;
+}
+
 extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_h, const double *val_h,
                        int64_t n_local, int64_t n_total, int32_t n_hvg, int32_t nval, double tol, int32_t maxit,
                        const double *v0_local, double *scores_local, double *v_local, double *s_out, double *u_out,
@@ -813,6 +940,33 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     AB_CUDA(cudaMemsetAsync(w.B, 0, (size_t)work * work * 8, st));
     AB_CUDA(cudaMemsetAsync(w.scal, 0, SC_COUNT * 8, st));
     AB_CUDA(cudaMemsetAsync(w.ctrl, 0, CT_COUNT * 4, st));
+
+    // compact row-dot operand when the caller's workspace has room for it (ab_irlb_ws_bytes_compact)
+    bool compact = false;
+    IrlbCompact cp{};
+    if (n > 0 && (size_t)H * 8 <= (size_t)48 * 1024 && !getenv("AB_IRLB_PLAIN")) {
+        int64_t nnz = 0;
+        AB_CUDA(cudaMemcpyAsync(&nnz, rowptr_h + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        AB_CUDA(cudaStreamSynchronize(st));
+        const size_t tail_off = (need + 255) / 256 * 256;
+        if (irlb_compact_eligible(n, H, nnz) && ws_bytes > tail_off) {
+            const size_t got = irlb_compact_layout(n, nnz, (char *)ws + tail_off, ws_bytes - tail_off, &cp);
+            if (got != 0) {
+                ab_prof_begin(ctx, AB_PROF_IRLB_ATW, st);
+                AB_CUDA(cudaMemsetAsync(cp.cursor, 0, 4 * sizeof(unsigned int), st));
+                const unsigned g_cb = (unsigned)std::max<int64_t>(
+                    1, std::min<int64_t>((n + CB_WARPS - 1) / CB_WARPS, (int64_t)ctx->sm_count * 32));
+                ah_compact_kernel<<<g_cb, CB_WARPS * 32, 0, st>>>(rowptr_h, col_h, val_h, n, cp.ent, cp.tabv, cp.taboff,
+                                                                  cp.cursor);
+                AB_LAUNCH_CHECK(ctx);
+                ab_prof_end(ctx, AB_PROF_IRLB_ATW, st);
+                unsigned int h_cur[2] = {0, 0};
+                AB_CUDA(cudaMemcpyAsync(h_cur, cp.cursor, sizeof(h_cur), cudaMemcpyDeviceToHost, st));
+                AB_CUDA(cudaStreamSynchronize(st));
+                compact = h_cur[1] == 0;                             // a row with > CB_CAP distinct values: plain kernels
+            }
+        }
+    }
 
     const size_t av_smem = (size_t)w.av_warps * H * 8;
     AB_CUDA(cudaFuncSetAttribute(av_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
@@ -843,12 +997,16 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     const unsigned g_vec = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
     const unsigned g_dot = (unsigned)w.dot_grid;
 
+    // compact A^T.w: 8 resident CTAs per SM, each with its own copy of w in shared memory
+    const unsigned g_atw = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8));
+    AB_CUDA(cudaFuncSetAttribute(atw_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)H * 8)));
     int64_t nmult = 0, sum_panel = 0;
 
     auto av = [&](const double *src, const double *sumsq, double *vdst) -> int {
         ab_prof_begin(ctx, AB_PROF_IRLB_AV, st);
-        av_kernel<<<w.av_grid, 384, av_smem, st>>>(rowptr_h, col_h, val_h, n, H, src, sumsq, vdst, w.av_warps,
-                                                    w.av_partial);
+        // (A.x keeps the plain operand: its 12 warps per SM leave ~30 KB of L1, a table look-up per nonzero at consume
+        // time misses it, and the compact variant measured 344 ms against 195)
+        av_kernel<<<w.av_grid, 384, av_smem, st>>>(rowptr_h, col_h, val_h, n, H, src, sumsq, vdst, w.av_warps, w.av_partial);
         AB_LAUNCH_CHECK(ctx);
         av_reduce_kernel<<<(H + 127) / 128, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw);
         AB_LAUNCH_CHECK(ctx);
@@ -879,8 +1037,12 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         ab_prof_end(ctx, AB_PROF_IRLB_SMALL, st);
         while (j < work) {
             ab_prof_begin(ctx, AB_PROF_IRLB_ATW, st);
-            atw_kernel<<<g_rows, 256, 0, st>>>(rowptr_h, col_h, val_h, n, w.W + (size_t)j * H, w.V + (int64_t)j * ld,
-                                                w.scal, w.F);
+            if (compact)
+                atw_compact_kernel<<<g_atw, 256, (size_t)H * 8, st>>>(rowptr_h, cp.ent, cp.tabv, cp.taboff, n, H,
+                                                                       w.W + (size_t)j * H, w.V + (int64_t)j * ld, w.scal, w.F);
+            else
+                atw_kernel<<<g_rows, 256, 0, st>>>(rowptr_h, col_h, val_h, n, w.W + (size_t)j * H, w.V + (int64_t)j * ld,
+                                                    w.scal, w.F);
             AB_LAUNCH_CHECK(ctx);
             ab_prof_end(ctx, AB_PROF_IRLB_ATW, st);
             nmult++;
@@ -942,7 +1104,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         h_info[0] = it;
         h_info[1] = nmult;
         h_info[2] = sum_panel;
-        h_info[3] = converged ? 0 : 1;
+        h_info[3] = (converged ? 0 : 1) | (compact ? 2 : 0);
     }
     return 0;
 }

@@ -321,12 +321,16 @@ struct TcParams {
     int group;             // K chunks per ring slot = per bulk copy and per barrier round
     int merged;            // 1: one slot per tile and the epilogue releases its accumulator buffer straight onto the
                            //    `full` barrier of the tile that will reuse it (one wait per tile for the issuer)
+    int split;             // 1: the two 128-column halves of an accumulator buffer are committed and released
+                           //    separately (needs one ring slot per tile): the epilogue of half 0 starts while the
+                           //    MMAs of half 1 run, and a half is reusable as soon as ITS four warps are done
     int mt;                // 2: two query tiles x one 128-point B tile; 1: one query tile x 256-point B tile
     int m;                 // candidates kept per list
     unsigned long long *cand;   // [lists][nq][m] sorted keys, lists = 3 - mt
     const unsigned char *bop;   // tiled, pre-swizzled B operand (knn_b_pos)
     unsigned long long *bufg;   // [grid][TC_BUF][256] append buffers
     int *cursor;                // tile CTA 0 is currently loading: the other CTAs start their sweeps there
+    const float *tau0;          // optional per-query starting threshold (scaled score units); NULL = +inf
     int dbg;               // experiments only (AB_KNN_DBG): 1 = epilogue skips the score scan, 2 = no MMA issue
 };
 
@@ -429,7 +433,7 @@ __device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, in
         case 128: t = warp_prune_t<4>(lanes, cg, q_lane, cnt, bufp, lane); break;
         default: t = warp_prune_t<8>(lanes, cg, q_lane, cnt, bufp, lane); break;
     }
-    if ((lanes >> lane) & 1u) { tau = t; cnt = 0; }
+    if ((lanes >> lane) & 1u) { tau = fminf(tau, t); cnt = 0; }       // (a list that is not full yet returns +inf)
 }
 
 // one unit = 32 consecutive scores of this thread's query row.  Common path: a min-tree and one
@@ -497,6 +501,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
     uint64_t *t_empty = a_full + 4;                 // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 6);
     volatile int *sweep_start = reinterpret_cast<volatile int *>(a_full + 7);     // [8], by local query-block index
+    uint64_t *h_full = a_full + 12;                 // [2 buffers][2 halves]   (split protocol)
+    uint64_t *h_empty = a_full + 16;                // [2 buffers][2 halves]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_per_block = TC_TILE * P.mt;
@@ -511,6 +517,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(t_full + b, 1); mbar_init(t_empty + b, TC_EPI_WARPS); }
+        for (int b = 0; b < 4; ++b) { mbar_init(h_full + b, 1); mbar_init(h_empty + b, TC_EPI_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -595,7 +602,46 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         const uint32_t slot_step = (uint32_t)(P.group * b_stage_bytes) >> 4;      // ring slot
         const uint32_t a_half = P.mt == 2 ? (TC_SLAB >> 4) : 0;                   // second query tile
         const uint32_t b_half = P.mt == 1 ? ((uint32_t)(P.group * TC_SLAB) >> 4) : 0;   // second slab of a 256-point tile
-        if (P.merged) {
+        if (P.split) {
+            // One ring slot per tile; all K steps of half 0 (query tile 0, or the first 128 points of a wide tile),
+            // commit, then all K steps of half 1, commit.  Each half has its own ready/released barrier pair.
+            for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+                mbar_wait(a_full, aphase);
+                aphase ^= 1;
+                for (int64_t t = 0; t < n_tiles; ++t, ++it) {
+                    const int buf = (int)(it & 1);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
+                    const uint32_t eph = (uint32_t)(((it >> 1) & 1) ^ 1);
+                    if (lane == 0) mbar_wait(full + stage, phase);
+                    else if (lane == 31) mbar_wait(h_empty + buf * 2, eph);
+                    __syncwarp();
+                    tc_fence_after();
+                    const uint64_t b_slot = b_desc0 + (uint64_t)((uint32_t)stage * slot_step);
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1) { mbar_wait(h_empty + buf * 2 + 1, eph); tc_fence_after(); }
+                        if (elect_one()) {
+                            const uint32_t d_h = tmem_d + (uint32_t)h * TC_TILE;
+                            const uint64_t a_h = a_desc0 + (uint64_t)((uint32_t)h * a_half);
+                            const uint64_t b_h = b_slot + (uint64_t)((uint32_t)h * b_half);
+                            for (int l = 0; l < P.chunks; ++l) {
+                                const uint64_t a_c = a_h + (uint64_t)((uint32_t)l * a_step);
+                                const uint64_t b_s = b_h + (uint64_t)((uint32_t)l * (TC_SLAB >> 4));
+                                const bool two = P.ksteps - 2 * l >= 2;
+                                tc_mma_f16(d_h, a_c, b_s, idesc, (uint32_t)(l != 0));
+                                if (two) tc_mma_f16(d_h, a_c + 2, b_s + 2, idesc, 1u);
+                            }
+                            if (h == 1) tc_commit(empty + stage);   // ring slot free once every MMA of the tile retires
+                            tc_commit(h_full + buf * 2 + h);        // this half's accumulators ready for its four warps
+                        }
+                        __syncwarp();
+                    }
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+                if (elect_one()) tc_commit(a_empty);            // A tiles may be overwritten
+                __syncwarp();
+                ++nblocks_done;
+            }
+        } else if (P.merged) {
             // One ring slot and one barrier per tile.  The wait for tile it+1 is taken BEFORE the last K chunk of
             // tile it is issued: it then overlaps the MMAs still queued in the tensor pipe instead of leaving the
             // pipe idle between tiles (measured: 1490 cycles of issue per tile, then 180-300 for the wait).
@@ -727,12 +773,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 cur_block = blk;
                 q = (blockIdx.x + blk * gridDim.x) * q_per_block + (P.mt == 2 ? half * TC_TILE : 0) + row;
                 live = q < P.nq;
-                tau = INFINITY;
+                tau = (P.tau0 && live) ? __ldg(P.tau0 + q) : INFINITY;
                 cnt = 0;
             }
             const bool etrace = (P.dbg & 64) && blockIdx.x == 0 && it >= 200 && it < 264 && ew == 0 && lane == 0;
             if (etrace) P.bufg[2048 + (it - 200) * 3] = (unsigned long long)clock64();
-            mbar_wait(t_full + buf, (uint32_t)((it >> 1) & 1));     // (one poller per warp + __syncwarp measured slower)
+            mbar_wait(P.split ? h_full + buf * 2 + half : t_full + buf, (uint32_t)((it >> 1) & 1));   // (one poller per warp + __syncwarp measured slower)
             if (etrace) P.bufg[2048 + (it - 200) * 3 + 1] = (unsigned long long)clock64();
             tc_fence_after();
             if (new_block) sweep0 = sweep_start[blk & 7];           // published by the producer before this block's first load
@@ -754,7 +800,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(P.merged ? full + (int)((it + 2) % P.stages) : t_empty + buf);
+            if (lane == 0) mbar_arrive(P.split ? h_empty + buf * 2 + half : P.merged ? full + (int)((it + 2) % P.stages) : t_empty + buf);
             if (etrace) P.bufg[2048 + (it - 200) * 3 + 2] = (unsigned long long)clock64();
             // prune AFTER handing the accumulator back: the merge (two L2 round trips + a bitonic network)
             // then overlaps the MMAs of the next tiles instead of sitting on the MMA->epilogue handoff
@@ -780,7 +826,8 @@ __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k, int m,
                   int lists, const unsigned long long *__restrict__ cand, const double *__restrict__ qn,
                   const unsigned int *__restrict__ rmax_bits, int32_t *__restrict__ idx, double *__restrict__ rdist,
-                  int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits) {
+                  int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits,
+                  const float *__restrict__ tau0) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int mg = lists * m;                              // candidate groups of the query (all lists)
@@ -880,7 +927,8 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         if (lane == 0) {
             const double dk = sd[k - 1];
             // a list that is not full holds every group it saw -> no outside point there
-            double tau = INFINITY;
+            // (with a starting threshold, groups at or above it were never listed)
+            double tau = tau0 ? (double)tau0[q] * inv_sc2 : INFINITY;
             for (int g = 0; g < lists; ++g) {
                 const unsigned long long last = cand[((size_t)g * nq + q) * m + (m - 1)];
                 if (last != TC_KEY_MAX) tau = fmin(tau, (double)key_score(last) * inv_sc2);
@@ -902,6 +950,15 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         if (lane == 0) atomicMax(relerr_bits, __float_as_uint((float)worst_rel));
         __syncwarp();
     }
+}
+
+// experiment (AB_KNN_DBG & 512): the final threshold of a finished run, nudged up, as the starting threshold of a
+// second run - the best case any threshold-seeding scheme could reach
+__global__ void knn_final_tau_kernel(const unsigned long long *__restrict__ cand, int64_t nq, int m, float *__restrict__ tau0) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float t = key_score(cand[(size_t)q * m + (m - 1)]);
+    tau0[q] = t + 1e-3f * fabsf(t) + 1e-6f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1025,6 +1082,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     P.stages = stages; P.group = group; P.bufg = w.bufg;
     // one barrier round per tile instead of two: measured floor -10 %, full kernel +9 % -> experiment knob only
     P.merged = (group == chunks && stages >= 3 && getenv("AB_KNN_MERGED")) ? 1 : 0;
+    P.split = (group == chunks && !P.merged && !getenv("AB_KNN_NOSPLIT")) ? 1 : 0;
     P.cursor = (int *)(w.scal + 2); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
     P.dbg = getenv("AB_KNN_DBG") ? atoi(getenv("AB_KNN_DBG")) : 0;
     const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
@@ -1033,6 +1091,24 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, P);
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_MAIN, st);
+    if ((P.dbg & 512) && lists == 1) {
+        float *t0 = reinterpret_cast<float *>(w.fb_list);          // scratch until the re-rank
+        knn_final_tau_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(w.cand, nq, m, t0);
+        AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)nq * m * sizeof(unsigned long long), st));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        P.tau0 = t0;
+        cudaEventRecord(e0, st);
+        knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, P);
+        cudaEventRecord(e1, st);
+        AB_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "[knn dbg] second run seeded with the first run's final thresholds: %.3f ms\n", ms);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        // the re-rank below sees the second run's lists; fb_list is overwritten there, so certify without tau0
+        P.tau0 = nullptr;
+    }
     if (P.dbg & 64) {                                               // experiment: print the three roles' timelines
         static unsigned long long h[4096];
         AB_CUDA(cudaStreamSynchronize(st));
@@ -1056,7 +1132,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     const unsigned g_rr = (unsigned)std::min<int64_t>((nq + rr_warps - 1) / rr_warps, (int64_t)ctx->sm_count * 16);
     knn_rerank_kernel<<<g_rr, rr_warps * 32, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
-                                                           idx, rdist, w.fb_list, stats, w.scal + 1);
+                                                           idx, rdist, w.fb_list, stats, w.scal + 1, P.tau0);
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_RERANK, st);
     // ---- uncertified queries: exact scan ----

@@ -182,7 +182,7 @@ class Engine:
     # -- K4-K8 ------------------------------------------------------------------------
     def irlb(self, AH, nval, tol=1e-4, maxit=1000, v0_local=None, want_v=True, want_u=True):
         n, H = AH.n_local, AH.n_genes
-        ws = self.workspace(self.lib.ab_irlb_ws_bytes(n, H, nval))
+        ws = self.workspace(self.lib.ab_irlb_ws_bytes_compact(n, H, nval, int(AH.val.numel())))
         scores = self.empty((n, nval), torch.float64)
         v = self.empty((n, nval), torch.float64) if want_v else None
         s = self.empty((nval,), torch.float64)
@@ -192,7 +192,7 @@ class Engine:
                                     float(tol), int(maxit), _ptr(v0_local), _ptr(scores), _ptr(v), _ptr(s), _ptr(u),
                                     info, _ptr(ws), ws.numel(), self.stream()), 'ab_irlb')
         return {'scores': scores, 'V': v, 's': s, 'U': u, 'steps': int(info[0]), 'nmult': int(info[1]),
-                'sum_panel': int(info[2]), 'not_converged': int(info[3])}
+                'sum_panel': int(info[2]), 'not_converged': int(info[3]) & 1, 'compact': bool(int(info[3]) & 2)}
 
     # -- K9 ---------------------------------------------------------------------------
     def knn(self, emb_all, k, q_begin=0, q_end=None, mode=0):

@@ -95,9 +95,15 @@ int ab_hvg_extract_fill(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, 
  * np.random.seed(seed); randn(N), irlb.py:151-152; normalised here).
  * Outputs: scores_local [n_local x nval] row-major = V.diag(s) (clustering.py:111),
  * v_local [n_local x nval] row-major (may be NULL), s[nval], u[H x nval] row-major (may be
- * NULL); h_info[4] (host int64) = {steps, nmult, sum of CGS panel widths, status flags}.
- * Synchronises the stream (one small D2H per restart decides convergence). */
+ * NULL); h_info[4] (host int64) = {steps, nmult, sum of CGS panel widths, status flags:
+ * bit 0 = not converged within maxit, bit 1 = the compact row operand was used}.
+ * Synchronises the stream (one small D2H per restart decides convergence).
+ * Workspace: ab_irlb_ws_bytes is the minimum; with ab_irlb_ws_bytes_compact (which also needs
+ * the shard's nonzero count) ab_irlb re-encodes A_H once as 4-byte (gene | value-slot) words
+ * plus per-row tables of the distinct values and runs the A^T.w products from that (same
+ * doubles, same order, identical bits; a third of the HBM traffic). */
 size_t ab_irlb_ws_bytes(int64_t n_local, int32_t n_hvg, int32_t nval);
+size_t ab_irlb_ws_bytes_compact(int64_t n_local, int32_t n_hvg, int32_t nval, int64_t nnz_local);
 int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_h, const double *val_h,
             int64_t n_local, int64_t n_total, int32_t n_hvg, int32_t nval, double tol,
             int32_t maxit, const double *v0_local, double *scores_local, double *v_local,

@@ -119,6 +119,38 @@ def test_irlb_follows_reference_trajectory(eng, case):
     assert np.allclose(v * s, res['scores'].cpu().numpy(), rtol=1e-14, atol=0)
 
 
+def test_irlb_compact_operand_is_bit_identical_to_plain(eng, monkeypatch):
+    """The 4-byte (gene | value-slot) re-encoding of A_H feeds the same doubles in the same order."""
+    g = load_golden('pipe_small')
+    AH = _golden_AH(eng, g)
+    v0 = torch.from_numpy(g['v0']).to(eng.device)
+    a = eng.irlb(AH, int(g['pca_n']), tol=1e-4, maxit=1000, v0_local=v0)
+    assert a['compact']
+    monkeypatch.setenv('AB_IRLB_PLAIN', '1')
+    b = eng.irlb(AH, int(g['pca_n']), tol=1e-4, maxit=1000, v0_local=v0)
+    assert not b['compact']
+    assert (a['steps'], a['nmult']) == (b['steps'], b['nmult'])
+    assert torch.equal(a['scores'], b['scores']) and torch.equal(a['U'], b['U'])
+
+
+def test_irlb_compact_falls_back_on_rows_with_many_distinct_values(eng):
+    """More than 256 distinct values in one row: the plain kernels run, results unchanged in meaning."""
+    from alona_b200.engine import DeviceCSR
+    rng = np.random.RandomState(0)
+    n, H = 300, 400
+    dense = rng.rand(n, H) * (rng.rand(n, H) < 0.9)                   # ~360 distinct doubles per row
+    import scipy.sparse as sp
+    m = sp.csr_matrix(dense)
+    AH = DeviceCSR(torch.from_numpy(m.indptr.astype(np.int64)).to(eng.device),
+                   torch.from_numpy(m.indices.astype(np.int32)).to(eng.device),
+                   torch.from_numpy(m.data).to(eng.device), H, 0, n)
+    v0 = torch.from_numpy(rng.randn(n)).to(eng.device)
+    res = eng.irlb(AH, 5, tol=1e-4, maxit=1000, v0_local=v0)
+    assert not res['compact'] and res['not_converged'] == 0
+    s_ref = np.linalg.svd(dense, compute_uv=False)[:5]
+    assert np.max(np.abs(res["s"].cpu().numpy() - s_ref) / s_ref) < 1e-4
+
+
 def test_lanczos_api_matches_reference_signature(eng):
     from alona_b200 import irlbpy
     g = load_golden('pipe_small')
