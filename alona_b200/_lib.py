@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, 'libalona_b200.so')
+# ALONA_B200_LIB: load another build of the same library (A/B timing of kernel variants on one box)
+_LIB_PATH = os.environ.get('ALONA_B200_LIB') or os.path.join(_HERE, 'libalona_b200.so')
 
 _lib = None
 _lock = threading.Lock()
