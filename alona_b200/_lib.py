@@ -42,6 +42,13 @@ SIGNATURES = {
                                             c_void_p, c_size, c_void_p]),
     'ab_hvg_extract_fill': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                            c_f64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ab_qc_metrics': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    'ab_filter_ws_bytes': (c_size, [c_i64]),
+    'ab_filter_count': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, p_i64, p_i64,
+                                       c_void_p, c_size, c_void_p]),
+    'ab_filter_fill': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_size, c_void_p]),
     'ab_irlb_ws_bytes': (c_size, [c_i64, c_i32, c_i32]),
     'ab_irlb_ws_bytes_compact': (c_size, [c_i64, c_i32, c_i32, c_i64]),
     'ab_irlb': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_i32,

@@ -15,7 +15,7 @@ import scipy.sparse as sp
 import torch
 
 from .engine import get_engine, DeviceCSR
-from .log import log_debug, log_error
+from .log import log_debug, log_error, log_info
 
 
 class CountMatrix:
@@ -37,6 +37,62 @@ class CountMatrix:
                 log_error('Non-count values detected in data matrix while data type is set to "raw".')
             vals = vals.astype(np.int64)
         return cls(sp.csr_matrix(vals.T), np.asarray(df.index), np.asarray(df.columns))
+
+
+class DeviceCounts:
+    """`self.data` of the drop-in once a filter has touched it: the raw counts as a device-resident cell-major
+    CSR plus the gene / cell labels the reference keeps on the DataFrame axes.  `.shape` is (genes, cells) like
+    the reference's frame; `.to_dataframe()` rebuilds that frame for small inputs."""
+
+    def __init__(self, engine, csr, genes, cells):
+        self.engine = engine
+        self.csr = csr                  # DeviceCSR, rows = cells
+        self.index = pd.Index(genes)
+        self.columns = pd.Index(cells)
+
+    @classmethod
+    def from_any(cls, data):
+        if isinstance(data, DeviceCounts):
+            return data
+        if isinstance(data, pd.DataFrame):
+            cm = CountMatrix.from_dataframe(data)
+        elif isinstance(data, CountMatrix):
+            cm = data
+        elif sp.issparse(data):
+            cm = CountMatrix(sp.csr_matrix(data.T))
+        else:
+            log_error('unsupported count container %s' % type(data))
+        eng = get_engine()
+        if eng.world > 1:
+            raise RuntimeError('the QC filters compact one device-resident matrix; run them on one rank '
+                               '(re-sharding the filtered rows across ranks is not implemented yet)')
+        return cls(eng, eng.upload_csr(cm.csr), cm.genes, cm.cells)
+
+    @property
+    def shape(self):
+        return (self.csr.n_genes, self.csr.n_local)
+
+    def to_dataframe(self, max_bytes=8 << 30):
+        g, n = self.shape
+        if g * n * 8 > max_bytes:
+            raise MemoryError('dense count frame would need %.1f GB' % (g * n * 8 / 2 ** 30))
+        c = self.csr
+        m = sp.csr_matrix((c.val.cpu().numpy().astype(np.int64), c.col.cpu().numpy(), c.rowptr.cpu().numpy()),
+                          shape=(n, g))
+        return pd.DataFrame(m.T.toarray(), index=self.index, columns=self.columns)
+
+    def subset(self, keep_cells=None, keep_genes=None):
+        """Rows (cells) and columns (genes) selected by boolean masks, compacted on the device."""
+        g, n = self.shape
+        gene_map = None
+        genes = self.index
+        if keep_genes is not None:
+            keep_genes = np.asarray(keep_genes, dtype=bool)
+            gene_map = np.where(keep_genes, np.cumsum(keep_genes) - 1, -1).astype(np.int32)
+            genes = self.index[keep_genes]
+        cells = self.columns if keep_cells is None else self.columns[np.asarray(keep_cells, dtype=bool)]
+        out, _ = self.engine.filter_csr(self.csr, keep_cells, gene_map, n_genes_out=len(genes))
+        return DeviceCounts(self.engine, out, genes, cells)
 
 
 class NormalizedMatrix:
@@ -91,6 +147,79 @@ class AlonaCell:
     def get_wd(self):
         return self.params['output_directory']
 
+    # ---- N3: upstream filters ----------------------------------------------------------
+    def qc_metrics(self, rRNA_genes=()):
+        """Per-cell QC metrics of find_low_quality_cells (alona/cell.py:306-312) as a DataFrame indexed by cell:
+        reads_per_cell, no_genes_det, perc_rRNA, perc_mt (the MinCovDet outlier model that consumes them, :313-329,
+        is outside the accelerated path)."""
+        self.data = DeviceCounts.from_any(self.data)
+        d = self.data
+        is_mt = d.index.astype(str).str.contains('^mt-', regex=True, case=False)          # cell.py:309
+        is_r = d.index.isin(list(rRNA_genes))                                              # cell.py:308
+        flags = is_mt.astype(np.uint8) | (is_r.astype(np.uint8) << 1)
+        q = d.engine.qc_metrics(d.csr, flags)
+        reads = q['reads_per_cell'].cpu().numpy()
+        sets = q['set_reads'].cpu().numpy()
+        with np.errstate(invalid='ignore', divide='ignore'):
+            return pd.DataFrame({'reads_per_cell': reads, 'no_genes_det': q['genes_det'].cpu().numpy(),
+                                 'perc_rRNA': sets[1] / reads * 100, 'perc_mt': sets[0] / reads * 100},
+                                index=d.columns)
+
+    def remove_empty(self):
+        """Removes empty cells and genes - with the reference's own comparisons (alona/cell.py:64-81): the zero
+        count of a cell is compared with the number of CELLS and that of a gene with the number of GENES (the
+        totals are swapped in the reference, :72/:77; the drop-in reproduces what it does)."""
+        self.data = DeviceCounts.from_any(self.data)
+        d = self.data
+        total_genes, total_cells = d.shape
+        q = d.engine.qc_metrics(d.csr)
+        cells = total_genes - q['genes_det'].cpu().numpy().astype(np.int64)       # zero entries per cell
+        genes = total_cells - q['gene_cells'].cpu().numpy()                       # zero entries per gene
+        keep_cells = keep_genes = None
+        if np.sum(cells == total_cells) > 0:
+            log_info('%s empty cells will be removed' % np.sum(cells == total_cells))
+            keep_cells = np.logical_not(cells == total_cells)
+        if np.sum(genes == total_genes) > 0:
+            log_info('%s empty genes will be removed' % np.sum(genes == total_genes))
+            keep_genes = np.logical_not(genes == total_genes)
+        if keep_cells is not None or keep_genes is not None:
+            self.data = d.subset(keep_cells, keep_genes)
+        log_info('Current dimensions: %s' % str(self.data.shape))
+
+    def remove_mito(self):
+        """Remove mitochondrial genes (alona/cell.py:83-94)."""
+        if self.params['remove_mito'] == 'yes':
+            self.data = DeviceCounts.from_any(self.data)
+            mt_count = self.data.index.astype(str).str.contains('^mt-', regex=True, case=False)
+            if np.sum(mt_count) > 0:
+                log_info('detected and removed %s mitochondrial gene(s)' % np.sum(mt_count))
+                self.data = self.data.subset(None, np.logical_not(mt_count))
+
+    def simple_filters(self):
+        """Removes cells with too few reads (`--minreads`) and underexpressed genes (`--minexpgenes`, a fraction
+        of the cells if it has a fractional part, else a number of cells) - alona/cell.py:141-173."""
+        self.data = DeviceCounts.from_any(self.data)
+        if self.params['dataformat'] == 'raw':
+            min_reads = self.params['minreads']
+            d = self.data
+            cell_counts = d.engine.qc_metrics(d.csr)['reads_per_cell'].cpu().numpy()
+            log_info('Keeping %s out of %s cells' % (np.sum(cell_counts > min_reads), len(cell_counts)))
+            self.data = d.subset(cell_counts > min_reads, None)
+            if self.data.shape[1] < 100:
+                log_error(msg='After removing cells with < %s reads, less than 100 cells remain. Please adjust '
+                              'filtering stringency with --minreads' % min_reads)
+        if self.params['minexpgenes'] > 0:
+            log_debug('Filtering genes based on --minexpgenes')
+            thres = float(self.params['minexpgenes'])
+            d = self.data
+            counts = d.engine.qc_metrics(d.csr)['gene_cells'].cpu().numpy()
+            if thres.is_integer():
+                genes_expressed = counts
+            else:
+                genes_expressed = counts / d.shape[1]                             # sum(x > 0)/len(x), cell.py:168
+            log_info('Removing %s genes.' % '{0:,g}'.format(np.sum(genes_expressed <= thres)))
+            self.data = d.subset(None, genes_expressed > thres)
+
     def normalize(self, data, fn_out='', input_type='raw', mrnafull=False):
         """Normalizes gene expression values (alona/cell.py:224-255).
 
@@ -107,6 +236,15 @@ class AlonaCell:
             if remove_low_quality and self.low_quality_cells is not None and len(self.low_quality_cells):
                 data = data.drop(self.low_quality_cells, axis=1, errors='ignore')     # cell.py:232-239
             cm = CountMatrix.from_dataframe(data)
+        elif isinstance(data, DeviceCounts):
+            if remove_low_quality and self.low_quality_cells is not None and len(self.low_quality_cells):
+                data = data.subset(~np.isin(np.asarray(data.columns), np.asarray(self.low_quality_cells)), None)
+            eng = data.engine
+            if int((data.csr.rowptr[1:] == data.csr.rowptr[:-1]).sum().item()):
+                log_error('normalize(): cells without any count must be removed first (alona/cell.py:64-81).')
+            libsize, gsum, gsumsq = eng.norm_moments(data.csr)
+            log_debug('Finished normalize()')
+            return NormalizedMatrix(eng, data.csr, libsize, gsum, gsumsq, np.asarray(data.index), np.asarray(data.columns))
         elif isinstance(data, CountMatrix):
             cm = data
             if remove_low_quality and self.low_quality_cells is not None and len(self.low_quality_cells):

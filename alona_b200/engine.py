@@ -137,6 +137,47 @@ class Engine:
                          torch.from_numpy(data).to(self.device, non_blocking=non_blocking),
                          csr.shape[1], row_begin, n_total)
 
+    # -- N3: QC metrics and filters (alona/cell.py:64-81, 141-173, 306-312) -----------------
+    def qc_metrics(self, A, gene_flags=None, allreduce=True):
+        """One pass over the counts: reads per cell, genes detected per cell, reads on up to two gene
+        sets per cell, and per gene the number of cells expressing it (summed over ranks)."""
+        n, G = A.n_local, A.n_genes
+        reads = self.empty((n,), torch.int64)
+        det = self.empty((n,), torch.int32)
+        flags = None
+        sets = None
+        if gene_flags is not None:
+            flags = torch.as_tensor(np.ascontiguousarray(gene_flags, dtype=np.uint8)).to(self.device)
+            sets = self.empty((2, n), torch.int64)
+        gene_cells = self.zeros((G,), torch.int64)
+        _lib.check(self.lib.ab_qc_metrics(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), n, G, _ptr(flags),
+                                          _ptr(reads), _ptr(det), _ptr(sets), _ptr(gene_cells), self.stream()),
+                   'ab_qc_metrics')
+        if allreduce and self.world > 1:
+            self.allreduce_i64(gene_cells)
+        return {'reads_per_cell': reads, 'genes_det': det, 'set_reads': sets, 'gene_cells': gene_cells}
+
+    def filter_csr(self, A, keep_row=None, gene_map=None, n_genes_out=None):
+        """Compacts the shard: rows with keep_row != 0, genes with gene_map >= 0 (renumbered by gene_map).
+        Returns (DeviceCSR with row_begin = 0 / n_total = kept rows of THIS shard, source row of every kept row)."""
+        n = A.n_local
+        kr = None if keep_row is None else torch.as_tensor(np.ascontiguousarray(keep_row, dtype=np.uint8)).to(self.device)
+        gm = None if gene_map is None else torch.as_tensor(np.ascontiguousarray(gene_map, dtype=np.int32)).to(self.device)
+        ws = self.workspace(self.lib.ab_filter_ws_bytes(n))
+        rows, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(self.lib.ab_filter_count(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), n, _ptr(kr), _ptr(gm),
+                                            ctypes.byref(rows), ctypes.byref(nnz), _ptr(ws), ws.numel(), self.stream()),
+                   'ab_filter_count')
+        rowptr = self.empty((rows.value + 1,), torch.int64)
+        col = self.empty((nnz.value,), torch.int32)
+        val = self.empty((nnz.value,), torch.int32)
+        src = self.empty((rows.value,), torch.int64)
+        _lib.check(self.lib.ab_filter_fill(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), n, _ptr(kr), _ptr(gm),
+                                           _ptr(rowptr), _ptr(col), _ptr(val), _ptr(src), _ptr(ws), ws.numel(),
+                                           self.stream()), 'ab_filter_fill')
+        G = int(n_genes_out) if n_genes_out is not None else (A.n_genes if gene_map is None else int(np.max(gene_map)) + 1)
+        return DeviceCSR(rowptr, col, val, G, 0, rows.value), src
+
     # -- K1 ---------------------------------------------------------------------------
     def norm_moments(self, A, gsum=None, gsumsq=None, allreduce=True):
         lib = self.empty((A.n_local,), torch.int64)

@@ -87,6 +87,33 @@ int ab_hvg_extract_fill(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, 
                         double scale, const int64_t *rowptr_h, int32_t *col_h, double *val_h,
                         void *stream);
 
+/* ---- N3 (next row of the scope table): QC metrics and filters on the count CSR -----------
+ * replaces the dense-DataFrame passes of AlonaCell.remove_empty (alona/cell.py:64-81),
+ * AlonaCell.simple_filters (alona/cell.py:141-173) and the per-cell QC metrics of
+ * AlonaCell.find_low_quality_cells (alona/cell.py:306-312: reads per cell, genes detected,
+ * reads on a gene set).  ab_qc_metrics: one pass; gene_flags (may be NULL) holds per gene
+ * bit 0 / bit 1 = member of gene set 0 / 1 (e.g. '^mt-' genes, rRNA genes); outputs
+ * reads_per_cell int64[n_local], genes_det int32[n_local] (entries > 0), set_reads
+ * int64[2][n_local] (may be NULL), gene_cells int64[G] = number of cells with a count > 0,
+ * ACCUMULATED into the caller-zeroed array (sum over shards with ab_allreduce_i64).
+ * The keep/drop rules are evaluated by the caller with the reference's comparisons;
+ * ab_filter_count / ab_filter_fill compact the CSR: keep_row uint8[n_local] (NULL = all),
+ * gene_map int32[G] = new gene id or -1 (NULL = identity); explicit zeros are dropped.
+ * count -> h_rows, h_nnz (host) -> caller allocates rowptr_out[h_rows+1], col_out/val_out[h_nnz],
+ * optional row_src int64[h_rows] (source row of each kept row) -> fill, same workspace. */
+int ab_qc_metrics(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                  int64_t n_local, int32_t n_genes, const uint8_t *gene_flags,
+                  int64_t *reads_per_cell, int32_t *genes_det, int64_t *set_reads,
+                  int64_t *gene_cells, void *stream);
+size_t ab_filter_ws_bytes(int64_t n_local);
+int ab_filter_count(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                    int64_t n_local, const uint8_t *keep_row, const int32_t *gene_map,
+                    int64_t *h_rows, int64_t *h_nnz, void *ws, size_t ws_bytes, void *stream);
+int ab_filter_fill(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                   int64_t n_local, const uint8_t *keep_row, const int32_t *gene_map,
+                   int64_t *rowptr_out, int32_t *col_out, int32_t *val_out, int64_t *row_src,
+                   void *ws, size_t ws_bytes, void *stream);
+
 /* ---- K4-K8: truncated SVD by augmented implicitly-restarted Lanczos bidiagonalisation ---
  * replaces alona.irlbpy.lanczos (alona/irlbpy/irlb.py:95-258) as called by
  * AlonaClustering.PCA (alona/clustering.py:108-111): A = A_H^T (H x N), no centring/scaling.

@@ -75,6 +75,45 @@ def make_knn_case(name, n, d, k, seed, dup=0, quantise=None):
     print(name, emb.shape, 'k', k, 'edges', edges.shape[0])
 
 
+def make_qc_case(name, n, g, lbar, seed, minreads, thresholds=(0.05, 4.0)):
+    """N3 fixtures: remove_empty / remove_mito / simple_filters of the live reference (alona/cell.py:64-94,
+    141-173) and the per-cell QC expressions of cell.py:306-312 evaluated with pandas on the same frame."""
+    m, _ = synth_np.nb_counts(n, g, lbar=lbar, n_clusters=4, seed=seed, drop_empty=False)
+    m = m.tolil()
+    m[5, :] = 0
+    m[:, 7] = 0
+    m[:, 9] = 0
+    m = m.tocsr()
+    m.eliminate_zeros()
+    genes = np.array(['g%d' % i for i in range(g)], dtype=object)
+    genes[::17] = np.array(['mt-x%d' % i for i in range(len(genes[::17]))], dtype=object)     # '^mt-' genes (cell.py:88)
+    genes[3::29] = np.array(['MT-y%d' % i for i in range(len(genes[3::29]))], dtype=object)   # case=False
+    cells = np.array(['c%d' % i for i in range(n)], dtype=object)
+    df = pd.DataFrame(m.T.toarray().astype(np.int64), index=genes, columns=cells)
+    gpos = {x: i for i, x in enumerate(genes)}
+    cpos = {x: i for i, x in enumerate(cells)}
+    rec = dict(indptr=m.indptr.astype(np.int64), indices=m.indices.astype(np.int32), data=m.data.astype(np.int32),
+               shape=np.array(m.shape, dtype=np.int64), genes=genes.astype(str), minreads=minreads,
+               thresholds=np.array(thresholds, dtype=np.float64))
+    # cell.py:306-312 (the MinCovDet step that consumes them is outside the scope)
+    reads_per_cell = df.sum(axis=0)
+    rec['reads_per_cell'] = reads_per_cell.values.astype(np.int64)
+    rec['no_genes_det'] = np.sum(df > 0, axis=0).values.astype(np.int64)
+    data_mt = df[df.index.str.contains('^mt-', regex=True, case=False)]
+    with np.errstate(invalid='ignore', divide='ignore'):
+        rec['perc_mt'] = (data_mt.sum(axis=0) / reads_per_cell * 100).values
+    for remove_mito in ('no', 'yes'):
+        for ti, thr in enumerate(thresholds):
+            out = ref_shim.run_reference_filters(df, minreads, thr, remove_mito=remove_mito)
+            for step, frame in out.items():
+                key = '%s_mito%s_t%d' % (step, remove_mito, ti)
+                rec[key + '_genes'] = np.array([gpos[x] for x in frame.index], dtype=np.int32)
+                rec[key + '_cells'] = np.array([cpos[x] for x in frame.columns], dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **rec)
+    print(name, m.shape, 'nnz', m.nnz, 'kept', rec['after_simple_filters_mitono_t0_cells'].size, 'cells',
+          rec['after_simple_filters_mitono_t0_genes'].size, 'genes')
+
+
 def main():
     if not ref_shim.available():
         sys.exit('reference tree not present; fixtures can only be minted in the dev container')
@@ -87,6 +126,8 @@ def main():
     make_knn_case('knn_mix_1500x100_k30', 1500, 100, 30, seed=9)
     make_knn_case('knn_mix_1000x50_k100', 1000, 50, 100, seed=4)
     make_knn_case('knn_dup_800x50_k10', 800, 50, 10, seed=6, dup=5)
+    make_qc_case('qc_square_400', 400, 400, 8.0, 3, 3)
+    make_qc_case('qc_rect_700x300', 700, 300, 10.0, 5, 4)
 
 
 if __name__ == '__main__':

@@ -115,6 +115,27 @@ def run_reference(counts_df, hvg_n, pca_n, nn_k, prune_snn=0.067, seed=42, workd
     return out
 
 
+def run_reference_filters(counts_df, minreads, minexpgenes, remove_mito='no'):
+    """remove_empty -> remove_mito -> simple_filters of the reference (alona/cell.py:64-94, 141-173) on a
+    genes x cells int64 DataFrame; returns the surviving frame after each step."""
+    import warnings
+    C, _ = load()
+    o = C.AlonaClustering()
+    o.params = {'dataformat': 'raw', 'minreads': minreads, 'minexpgenes': float(minexpgenes),
+                'remove_mito': remove_mito, 'loglevel': 'regular'}
+    o.data = counts_df.copy()
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        o.remove_empty()
+        out['after_remove_empty'] = o.data.copy()
+        o.remove_mito()
+        out['after_remove_mito'] = o.data.copy()
+        o.simple_filters()
+        out['after_simple_filters'] = o.data.copy()
+    return out
+
+
 def reference_knn(emb, k):
     """alona/clustering.py:179-188 on a given embedding (1-based indices)."""
     C, _ = load()

@@ -27,6 +27,57 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 # ----------------------------------------------------------------------------------------
+# N3: QC metrics and filters on CSR  (alona/cell.py:64-81, 141-173, 306-312)
+# ----------------------------------------------------------------------------------------
+def qc_metrics(csr, gene_sets=()):
+    """reads per cell = data.sum(axis=0) (cell.py:306), genes detected = sum(data > 0, axis=0) (:307),
+    reads on each gene set (numerators of :310-312), per gene the number of cells with a count > 0
+    (simple_filters' `sum(x > 0)`, :161)."""
+    pos = csr.data > 0
+    rows = np.repeat(np.arange(csr.shape[0]), np.diff(csr.indptr))
+    reads = np.bincount(rows, weights=np.where(pos, csr.data, 0), minlength=csr.shape[0]).astype(np.int64)
+    det = np.bincount(rows[pos], minlength=csr.shape[0]).astype(np.int64)
+    gene_cells = np.bincount(csr.indices[pos], minlength=csr.shape[1]).astype(np.int64)
+    sets = []
+    for mask in gene_sets:
+        m = np.asarray(mask, dtype=bool)[csr.indices] & pos
+        sets.append(np.bincount(rows[m], weights=csr.data[m], minlength=csr.shape[0]).astype(np.int64))
+    return reads, det, gene_cells, sets
+
+
+def remove_empty_masks(csr):
+    """cell.py:64-81, AS WRITTEN: `cells` = zero entries per cell is compared with the number of CELLS
+    (`cells == total_cells`, :72) and `genes` = zero entries per gene with the number of GENES (:77) - the two
+    totals are swapped relative to the intent, so an all-zero cell is only removed when G == N.  The genes are
+    tested on the frame AFTER the cell removal (the frame is re-sliced first, the masks were computed before).
+    The drop-in reproduces the reference's behaviour, not its intent."""
+    n, g = csr.shape
+    _, det, gene_cells, _ = qc_metrics(csr)
+    keep_cells = (g - det) != n
+    keep_genes = (n - gene_cells) != g
+    return keep_cells, keep_genes
+
+
+def simple_filter_masks(csr, minreads, minexpgenes):
+    """cell.py:141-173 (raw counts): keep cells with reads > minreads; THEN, on the remaining cells, keep genes
+    expressed in more than `minexpgenes` cells (integral value) or in more than that fraction of the cells.
+    The comparisons are evaluated exactly like the reference's (Python ints / numpy float division)."""
+    reads, _, _, _ = qc_metrics(csr)
+    keep_cells = reads > minreads
+    sub = csr[keep_cells]
+    _, _, gene_cells, _ = qc_metrics(sub)
+    thres = float(minexpgenes)
+    if thres > 0:
+        if thres.is_integer():
+            keep_genes = gene_cells > thres
+        else:
+            keep_genes = gene_cells / sub.shape[0] > thres
+    else:
+        keep_genes = np.ones(csr.shape[1], dtype=bool)
+    return keep_cells, keep_genes
+
+
+# ----------------------------------------------------------------------------------------
 # normalise + per-gene moments on CSR  (alona/cell.py:241-243, alona/hvg.py:148,157)
 # ----------------------------------------------------------------------------------------
 def libsize(csr):

@@ -4,7 +4,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES
+from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES, QC_CASES
 from oracle import alona_port as P, restate as R
 
 
@@ -103,3 +103,49 @@ def test_prune_threshold_matches_python_expression():
         for p in (0.0, 0.067, 1 / 15, 0.2, 0.5, 1.0):
             v = R.prune_threshold(k, p)
             assert all((u / (k + (k - u)) > p) == (u >= v) for u in range(0, k + 1))
+
+
+# ---- N3: QC metrics and filters (alona/cell.py:64-94, 141-173, 306-312) -------------------------------------
+def qc_chain_oracle(m, genes, minreads, thr, remove_mito):
+    """remove_empty -> remove_mito -> simple_filters with the restated masks; returns kept (genes, cells) per step."""
+    gi, ci = np.arange(m.shape[1]), np.arange(m.shape[0])
+    out = {}
+    kc, kg = R.remove_empty_masks(m)
+    m, gi, ci = m[kc][:, kg], gi[kg], ci[kc]
+    out['after_remove_empty'] = (gi, ci)
+    if remove_mito == 'yes':
+        mt = pd.Index(genes[gi]).str.contains('^mt-', regex=True, case=False)
+        m, gi = m[:, ~mt], gi[~mt]
+    out['after_remove_mito'] = (gi, ci)
+    kc, kg = R.simple_filter_masks(m, minreads, thr)
+    out['after_simple_filters'] = (gi[kg], ci[kc])
+    return out
+
+
+@pytest.mark.parametrize('case', QC_CASES)
+def test_restated_qc_filters_match_reference(case):
+    g = load_golden(case)
+    m = golden_csr(g)
+    genes = g['genes']
+    for remove_mito in ('no', 'yes'):
+        for ti, thr in enumerate(g['thresholds']):
+            got = qc_chain_oracle(m, genes, int(g['minreads']), float(thr), remove_mito)
+            for step, (gi, ci) in got.items():
+                key = '%s_mito%s_t%d' % (step, remove_mito, ti)
+                assert np.array_equal(gi, g[key + '_genes']), key
+                assert np.array_equal(ci, g[key + '_cells']), key
+
+
+@pytest.mark.parametrize('case', QC_CASES)
+def test_restated_qc_metrics_match_reference_expressions(case):
+    g = load_golden(case)
+    m = golden_csr(g)
+    mt = pd.Index(g['genes']).str.contains('^mt-', regex=True, case=False)
+    reads, det, gene_cells, sets = R.qc_metrics(m, [mt])
+    assert np.array_equal(reads, g['reads_per_cell'])
+    assert np.array_equal(det, g['no_genes_det'])
+    with np.errstate(invalid='ignore', divide='ignore'):
+        perc = sets[0] / reads * 100
+    assert np.array_equal(np.isnan(perc), np.isnan(g['perc_mt']))
+    assert np.array_equal(perc[~np.isnan(perc)], g['perc_mt'][~np.isnan(perc)])
+    assert np.array_equal(gene_cells, np.asarray((m > 0).sum(axis=0)).ravel())
