@@ -49,6 +49,12 @@ SIGNATURES = {
                                        c_void_p, c_size, c_void_p]),
     'ab_filter_fill': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_size, c_void_p]),
+    'ab_cluster_moments': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_f64, c_void_p,
+                                          c_i32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'ab_cluster_median_ws_bytes': (c_size, [c_i32, c_i32, c_i64]),
+    'ab_cluster_median_count': (ctypes.c_int, [c_void_p, c_void_p, p_i64, c_i32, c_i32, p_i64, c_void_p, c_size, c_void_p]),
+    'ab_cluster_median_fill': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_f64, c_void_p,
+                                              c_i32, c_void_p, p_i64, c_i64, c_void_p, c_void_p, c_size, c_void_p]),
     'ab_irlb_ws_bytes': (c_size, [c_i64, c_i32, c_i32]),
     'ab_irlb_ws_bytes_compact': (c_size, [c_i64, c_i32, c_i32, c_i64]),
     'ab_irlb': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_i32,

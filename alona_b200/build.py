@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libalona_b200.so')
 SOURCES = ['ab_api.cu', 'ab_norm.cu', 'ab_hvg.cu', 'ab_irlb.cu', 'ab_knn.cu', 'ab_knn_exact.cu',
-           'ab_knn_tc.cu', 'ab_snn.cu', 'ab_synth.cu', 'ab_io.cu', 'ab_qc.cu']
+           'ab_knn_tc.cu', 'ab_snn.cu', 'ab_synth.cu', 'ab_io.cu', 'ab_qc.cu', 'ab_cluster.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--fmad=true', '-Xptxas', '-v']
 

@@ -8,6 +8,8 @@ OUTPUT = {
     'FILENAME_HVG': '/csvs/highly_variable_genes.tsv',
     'FILENAME_SNN_GRAPH': '/csvs/snn_graph.csv',
     'FILENAME_CLUSTERS_LEIDEN': '/csvs/clusters_leiden.csv',
+    'FILENAME_MEDIAN_EXP': '/csvs/median_exp.tsv',
+    'FILENAME_MEAN_EXP': '/csvs/mean_exp.tsv',
     'FILENAME_SETTINGS': '/settings.txt',
     'FILENAME_KNN_map': '/KNN.joblib',
 }

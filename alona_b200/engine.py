@@ -178,6 +178,48 @@ class Engine:
         G = int(n_genes_out) if n_genes_out is not None else (A.n_genes if gene_map is None else int(np.max(gene_map)) + 1)
         return DeviceCSR(rowptr, col, val, G, 0, rows.value), src
 
+    # -- N2: per-cluster summaries (alona/celltypes.py:42-68, find_markers.py:75-111) ---------
+    def cluster_moments(self, A, libsize, cluster, n_clusters, want_sumsq=True, allreduce=True):
+        """[C][G] tables: sum of normalised values, sum of squares, number of nonzeros per (cluster, gene)."""
+        cl = torch.as_tensor(np.ascontiguousarray(cluster, dtype=np.int32)).to(self.device)
+        C, G = int(n_clusters), A.n_genes
+        sm = self.zeros((C, G), torch.float64)
+        sq = self.zeros((C, G), torch.float64) if want_sumsq else None
+        nz = self.zeros((C, G), torch.int64)
+        _lib.check(self.lib.ab_cluster_moments(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), _ptr(libsize), A.n_local,
+                                               G, SCALE, _ptr(cl), C, _ptr(sm), _ptr(sq), _ptr(nz), self.stream()),
+                   'ab_cluster_moments')
+        if allreduce and self.world > 1:
+            self.allreduce_f64(sm)
+            if sq is not None:
+                self.allreduce_f64(sq)
+            self.allreduce_i64(nz)
+        return {'sum': sm, 'sumsq': sq, 'nnz': nz, 'cluster_dev': cl}
+
+    def cluster_median(self, A, libsize, cluster, n_clusters, nnz=None, max_batch=1 << 29):
+        """[C][G] medians of the normalised values per (cluster, gene); single shard."""
+        if self.world > 1:
+            raise RuntimeError('cluster_median needs every cell of a cluster on one device')
+        cluster = np.ascontiguousarray(cluster, dtype=np.int32)
+        C, G = int(n_clusters), A.n_genes
+        cl = torch.from_numpy(cluster).to(self.device)
+        if nnz is None:
+            nnz = self.cluster_moments(A, libsize, cluster, C, want_sumsq=False)['nnz']
+        sizes = np.bincount(cluster[cluster >= 0], minlength=C)[:C].astype(np.int64)
+        h_sizes = (ctypes.c_int64 * C)(*sizes.tolist())
+        per = (ctypes.c_int64 * C)()
+        ws = self.workspace(self.lib.ab_cluster_median_ws_bytes(G, C, 0))
+        _lib.check(self.lib.ab_cluster_median_count(self.ctx, _ptr(nnz), h_sizes, G, C, per, _ptr(ws), ws.numel(),
+                                                    self.stream()), 'ab_cluster_median_count')
+        per = np.array(list(per), dtype=np.int64)
+        batch = int(max(per.max() if C else 0, min(int(per.sum()), int(max_batch))))
+        ws = self.workspace(self.lib.ab_cluster_median_ws_bytes(G, C, batch))
+        med = self.empty((C, G), torch.float64)
+        _lib.check(self.lib.ab_cluster_median_fill(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), _ptr(libsize),
+                                                   A.n_local, G, SCALE, _ptr(cl), C, _ptr(nnz), h_sizes, batch, _ptr(med),
+                                                   _ptr(ws), ws.numel(), self.stream()), 'ab_cluster_median_fill')
+        return med, {'gathered': int(per.sum()), 'batch': batch}
+
     # -- K1 ---------------------------------------------------------------------------
     def norm_moments(self, A, gsum=None, gsumsq=None, allreduce=True):
         lib = self.empty((A.n_local,), torch.int64)

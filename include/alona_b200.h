@@ -114,6 +114,33 @@ int ab_filter_fill(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const
                    int64_t *rowptr_out, int32_t *col_out, int32_t *val_out, int64_t *row_src,
                    void *ws, size_t ws_bytes, void *stream);
 
+/* ---- N2 (next row of the scope table): per-cluster summaries of the normalised expression ---
+ * replaces the dense passes of AlonaCellTypePred.mean_exp / median_exp (alona/celltypes.py:42-68:
+ * data_norm.groupby(cluster, axis=1).aggregate(np.mean | np.median)) and supplies the sufficient
+ * statistics of the one-way model of find_markers (alona/find_markers.py:75-111: coefficients =
+ * cluster means, residual variance from sum x^2) without ever building the genes x cells frame.
+ * cluster: int32[n_local], cluster id of each cell or -1 (cell ignored).  Tables are [C][G] row-major.
+ * ab_cluster_moments ACCUMULATES sum x, sum x^2 (may be NULL) and the number of nonzeros into
+ * caller-zeroed tables (sum over shards with ab_allreduce_f64 / _i64).
+ * Medians (single shard): ab_cluster_median_count -> host int64[C] = values each cluster has to
+ * gather (only (cluster, gene) pairs whose median can be nonzero); the caller picks a batch capacity
+ * >= the largest entry (< 2^31), sizes the workspace with ab_cluster_median_ws_bytes and calls
+ * ab_cluster_median_fill, which gathers, sorts (cub::DeviceSegmentedSort) and reads off the middle
+ * order statistics, np.median convention (mean of the two middle values; NaN for an empty cluster). */
+int ab_cluster_moments(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                       const int64_t *libsize, int64_t n_local, int32_t n_genes, double scale,
+                       const int32_t *cluster, int32_t n_clusters, double *sum, double *sumsq,
+                       int64_t *nnz, void *stream);
+size_t ab_cluster_median_ws_bytes(int32_t n_genes, int32_t n_clusters, int64_t batch_values);
+int ab_cluster_median_count(ab_ctx *ctx, const int64_t *nnz, const int64_t *h_cluster_size,
+                            int32_t n_genes, int32_t n_clusters, int64_t *h_values_per_cluster,
+                            void *ws, size_t ws_bytes, void *stream);
+int ab_cluster_median_fill(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                           const int64_t *libsize, int64_t n_local, int32_t n_genes, double scale,
+                           const int32_t *cluster, int32_t n_clusters, const int64_t *nnz,
+                           const int64_t *h_cluster_size, int64_t batch_values, double *median,
+                           void *ws, size_t ws_bytes, void *stream);
+
 /* ---- K4-K8: truncated SVD by augmented implicitly-restarted Lanczos bidiagonalisation ---
  * replaces alona.irlbpy.lanczos (alona/irlbpy/irlb.py:95-258) as called by
  * AlonaClustering.PCA (alona/clustering.py:108-111): A = A_H^T (H x N), no centring/scaling.

@@ -114,6 +114,28 @@ def make_qc_case(name, n, g, lbar, seed, minreads, thresholds=(0.05, 4.0)):
           rec['after_simple_filters_mitono_t0_genes'].size, 'genes')
 
 
+def make_cluster_exp_case(name, n, g, lbar, ncl, seed):
+    """N2 fixtures: the reference's own normalize() output (alona/cell.py:241-243) reduced per cluster with the
+    numpy functions mean_exp / median_exp hand to groupby (alona/celltypes.py:49,61; `groupby(axis=1)` itself is
+    gone from the installed pandas), and the residual variance of find_markers.py:96-97 with coef = cluster means."""
+    m, labels = synth_np.nb_counts(n, g, lbar=lbar, n_clusters=ncl, seed=seed)
+    labels = np.asarray(labels)[:m.shape[0]].astype(np.int64)
+    labels[:3] = ncl                                    # a tiny extra cluster (odd size)
+    df = _counts_df(m)
+    ref = ref_shim.run_reference(df, hvg_n=10, pca_n=2, nn_k=2, stages=('normalize',))
+    dn = ref['data_norm']                               # genes x cells float64 DataFrame
+    ids = np.unique(labels)
+    mean = np.stack([np.mean(dn.values[:, labels == c], axis=1) for c in ids])
+    med = np.stack([np.median(dn.values[:, labels == c], axis=1) for c in ids])
+    fitted = mean[np.searchsorted(ids, labels)].T       # dm_full.dot(coef), genes x cells
+    sigma2 = ((dn.values - fitted) ** 2).sum(axis=1) / (dn.shape[1] - len(ids))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'),
+                        indptr=m.indptr.astype(np.int64), indices=m.indices.astype(np.int32),
+                        data=m.data.astype(np.int32), shape=np.array(m.shape, dtype=np.int64),
+                        labels=labels, cluster_ids=ids, mean=mean, median=med, sigma2=sigma2)
+    print(name, m.shape, 'clusters', len(ids), 'nonzero medians', int((med > 0).sum()), 'of', med.size)
+
+
 def main():
     if not ref_shim.available():
         sys.exit('reference tree not present; fixtures can only be minted in the dev container')
@@ -127,6 +149,8 @@ def main():
     make_knn_case('knn_mix_1000x50_k100', 1000, 50, 100, seed=4)
     make_knn_case('knn_dup_800x50_k10', 800, 50, 10, seed=6, dup=5)
     make_qc_case('qc_square_400', 400, 400, 8.0, 3, 3)
+    make_cluster_exp_case('clexp_700x900', 700, 900, 700.0, 5, 13)
+    make_cluster_exp_case('clexp_401x500', 401, 500, 150.0, 3, 17)
     make_qc_case('qc_rect_700x300', 700, 300, 10.0, 5, 4)
 
 

@@ -78,6 +78,31 @@ def simple_filter_masks(csr, minreads, minexpgenes):
 
 
 # ----------------------------------------------------------------------------------------
+# N2: per-cluster mean / median of the normalised expression  (alona/celltypes.py:42-68)
+# ----------------------------------------------------------------------------------------
+def cluster_mean_median(csr, cluster, n_clusters, lib=None):
+    """data_norm.groupby(cluster, axis=1).aggregate(np.mean | np.median) restated on the dense normalised matrix
+    of a SMALL input: per cluster, np.mean / np.median over its cells, gene by gene (an empty cluster gives NaN).
+    (`groupby(axis=1)` no longer exists in the pandas this image ships, 3.0.2, so the reference's own call cannot
+    be executed here; this is the same per-group numpy reduction it applied.)  Returns [C][G] arrays and the
+    per-cluster residual sum of squares of find_markers' one-way model (find_markers.py:96-97)."""
+    x = np.zeros(csr.shape)
+    rows = np.repeat(np.arange(csr.shape[0]), np.diff(csr.indptr))
+    x[rows, csr.indices] = normalized_values(csr, lib)
+    cluster = np.asarray(cluster)
+    mean = np.full((n_clusters, csr.shape[1]), np.nan)
+    med = np.full((n_clusters, csr.shape[1]), np.nan)
+    rss = np.zeros(csr.shape[1])
+    for c in range(n_clusters):
+        sel = cluster == c
+        if sel.any():
+            mean[c] = np.mean(x[sel], axis=0)
+            med[c] = np.median(x[sel], axis=0)
+            rss += ((x[sel] - mean[c]) ** 2).sum(axis=0)
+    return mean, med, rss
+
+
+# ----------------------------------------------------------------------------------------
 # normalise + per-gene moments on CSR  (alona/cell.py:241-243, alona/hvg.py:148,157)
 # ----------------------------------------------------------------------------------------
 def libsize(csr):

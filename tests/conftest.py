@@ -27,6 +27,7 @@ def golden_csr(g):
 
 PIPE_CASES = ['pipe_small', 'pipe_medium', 'pipe_k20']
 QC_CASES = ['qc_square_400', 'qc_rect_700x300']
+CLEXP_CASES = ['clexp_700x900', 'clexp_401x500']
 KNN_CASES = ['knn_mix_3000x50_k20', 'knn_mix_2000x50_k10', 'knn_mix_1500x100_k30',
              'knn_mix_1000x50_k100']
 

@@ -4,7 +4,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES, QC_CASES
+from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES, QC_CASES, CLEXP_CASES
 from oracle import alona_port as P, restate as R
 
 
@@ -149,3 +149,16 @@ def test_restated_qc_metrics_match_reference_expressions(case):
     assert np.array_equal(np.isnan(perc), np.isnan(g['perc_mt']))
     assert np.array_equal(perc[~np.isnan(perc)], g['perc_mt'][~np.isnan(perc)])
     assert np.array_equal(gene_cells, np.asarray((m > 0).sum(axis=0)).ravel())
+
+
+# ---- N2: per-cluster mean / median (alona/celltypes.py:42-68) and the model statistics of find_markers --------
+@pytest.mark.parametrize('case', CLEXP_CASES)
+def test_restated_cluster_mean_median(case):
+    g = load_golden(case)
+    m = golden_csr(g)
+    dense_id = np.searchsorted(g['cluster_ids'], g['labels'])
+    mean, med, rss = R.cluster_mean_median(m, dense_id, len(g['cluster_ids']))
+    assert np.allclose(mean, g['mean'], rtol=1e-13, atol=1e-15)
+    assert np.allclose(med, g['median'], rtol=1e-13, atol=0)
+    assert np.array_equal(med == 0, g['median'] == 0)
+    assert np.allclose(rss / (m.shape[0] - len(g['cluster_ids'])), g['sigma2'], rtol=1e-11, atol=1e-15)
