@@ -52,6 +52,13 @@ static constexpr int TC_SLAB = TC_TILE * 64; // bytes of one 128-row x 64-byte o
 static constexpr int TC_MAX_STAGES = 16;
 static constexpr int TC_MAX_CHUNKS = 10;     // 3d+3 <= 320  ->  d <= 105
 static constexpr double TC_KAPPA = 1.52587890625e-05;   // 2^-16
+// FP16 products kept per coordinate pair (AB_KNN_NPROD experiment): dropping q_lo.x_hi leaves an error of at most
+// 2.|q_lo.x| <= 2^-11.|q|.R <= 2^-13.(|q|+R)^2 (FP16 rounds a coordinate to 2^-12 relative); dropping x_lo as well
+// doubles it.  The certificate and the exact fall-back keep the result exact either way; only the number of
+// uncertified queries can grow.
+__host__ __device__ inline double tc_kappa(int np) {
+    return np >= 3 ? TC_KAPPA : np == 2 ? TC_KAPPA + 1.220703125e-04 : TC_KAPPA + 2.44140625e-04;
+}
 
 // ---------------------------------------------------------------------------------------
 // PTX helpers
@@ -235,7 +242,7 @@ __host__ __device__ __forceinline__ size_t knn_b_pos(int64_t i, int j, int chunk
 // B has n_pad >= n rows (a whole number of tiles): padding rows are all zero except a norm of
 // 60000, larger than any real score (<= (2*64)^2), so padded columns never pass a threshold.
 __global__ void __launch_bounds__(256)
-knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d, int kt, const double *__restrict__ mean,
+knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d, int kt, int np, const double *__restrict__ mean,
                 const unsigned int *__restrict__ rmax_bits, __half *__restrict__ aop, __half *__restrict__ bop,
                 double *__restrict__ qn) {
     const int lane = threadIdx.x & 31;
@@ -247,7 +254,8 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d,
     for (int64_t i = w; i < n; i += nw) {
         __half *a = aop + i * kt;
         double n2 = 0.0;
-        for (int j = 3 * d + lane; j < kt; j += 32) {            // clear the tail (norm slots are rewritten below)
+        const int nd = np * d;                                   // first norm column
+        for (int j = nd + lane; j < kt; j += 32) {               // clear the tail (norm slots are rewritten below)
             a[j] = zero; bop[knn_b_pos(i, j, chunks)] = zero;
         }
         for (int j = lane; j < d; j += 32) {
@@ -255,10 +263,11 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d,
             const __half hi = __float2half_rn(x);
             const __half lo = __float2half_rn(x - __half2float(hi));
             const __half mhi = __float2half_rn(-2.f * __half2float(hi)), mlo = __float2half_rn(-2.f * __half2float(lo));
-            a[j] = hi; a[d + j] = hi; a[2 * d + j] = lo;
+            // np = 3: q_hi.x_hi + q_hi.x_lo + q_lo.x_hi;  np = 2: q_hi.(x_hi + x_lo);  np = 1: q_hi.x_hi
+            a[j] = hi;
             bop[knn_b_pos(i, j, chunks)] = mhi;
-            bop[knn_b_pos(i, d + j, chunks)] = mlo;
-            bop[knn_b_pos(i, 2 * d + j, chunks)] = mhi;
+            if (np >= 2) { a[d + j] = hi; bop[knn_b_pos(i, d + j, chunks)] = mlo; }
+            if (np >= 3) { a[2 * d + j] = lo; bop[knn_b_pos(i, 2 * d + j, chunks)] = mhi; }
             n2 += (double)x * (double)x;
         }
         n2 = ab_warp_sum_f64(n2);
@@ -268,15 +277,15 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d,
             const double r1 = n2 - (double)__half2float(n0);
             const __half n1 = __double2half(r1);
             const __half n2h = __double2half(r1 - (double)__half2float(n1));
-            bop[knn_b_pos(i, 3 * d, chunks)] = n0;
-            bop[knn_b_pos(i, 3 * d + 1, chunks)] = n1;
-            bop[knn_b_pos(i, 3 * d + 2, chunks)] = n2h;
-            a[3 * d] = one; a[3 * d + 1] = one; a[3 * d + 2] = one;
+            bop[knn_b_pos(i, nd, chunks)] = n0;
+            bop[knn_b_pos(i, nd + 1, chunks)] = n1;
+            bop[knn_b_pos(i, nd + 2, chunks)] = n2h;
+            a[nd] = one; a[nd + 1] = one; a[nd + 2] = one;
             qn[i] = n2 / (sc * sc);
         }
     }
     for (int64_t i = n + w; i < n_pad; i += nw) {
-        for (int j = lane; j < kt; j += 32) bop[knn_b_pos(i, j, chunks)] = (j == 3 * d) ? __float2half_rn(60000.f) : zero;
+        for (int j = lane; j < kt; j += 32) bop[knn_b_pos(i, j, chunks)] = (j == np * d) ? __float2half_rn(60000.f) : zero;
     }
 }
 
@@ -827,7 +836,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                   int lists, const unsigned long long *__restrict__ cand, const double *__restrict__ qn,
                   const unsigned int *__restrict__ rmax_bits, int32_t *__restrict__ idx, double *__restrict__ rdist,
                   int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits,
-                  const float *__restrict__ tau0) {
+                  const float *__restrict__ tau0, double kappa) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int mg = lists * m;                              // candidate groups of the query (all lists)
@@ -843,7 +852,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         const double *qv = emb + qid * d;
         const double qnorm2 = qn[qid];
         const double scale = sqrt(qnorm2) + (double)R;
-        const double eps = TC_KAPPA * scale * scale;
+        const double eps = kappa * scale * scale;
         // Only groups that can hold one of the k nearest are expanded.  With the lists sorted by key, the k-th
         // smallest approximate group minimum a_k of any one list bounds D_k <= a_k + eps (k distinct groups, each
         // contributing its minimum); a group whose approximate minimum exceeds a_k + 2 eps has every point
@@ -971,9 +980,9 @@ static int tc_candidates(int k) {
     return std::min(m, 256);
 }
 static int64_t tc_pad(int64_t n) { return (n + 255) / 256 * 256; }
-static int tc_kt(int d) { return (3 * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
+static int tc_kt(int d, int np = 3) { return (np * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
 // two resident query tiles when their A operand (256 rows x kt halves) leaves room for the B ring
-static int tc_mt(int d) { return tc_kt(d) * 2 * 256 <= 96 * 1024 ? 2 : 1; }
+static int tc_mt(int d, int np = 3) { return tc_kt(d, np) * 2 * 256 <= 96 * 1024 ? 2 : 1; }
 
 struct TcWs {
     double *mean, *partial, *qn;
@@ -1035,7 +1044,8 @@ static int make_map(CUtensorMap *map, __half *base, int64_t rows, int kt, int bo
 
 int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k,
                   int32_t *idx, double *rdist, unsigned long long *stats, void *ws, size_t ws_bytes, cudaStream_t st) {
-    const int kt = tc_kt(d), chunks = kt / TC_KCH, m = tc_candidates(k);
+    const int np = getenv("AB_KNN_NPROD") ? std::max(1, std::min(3, atoi(getenv("AB_KNN_NPROD")))) : 3;
+    const int kt = tc_kt(d, np), chunks = kt / TC_KCH, m = tc_candidates(k);
     if (chunks > TC_MAX_CHUNKS || n_total < m || n_total >= ((int64_t)1 << 31) - 512) {
         // outside the tensor path's envelope (very wide embeddings, tiny inputs): exact scan
         return ab_knn_exact_run(ctx, emb, n_total, d, nullptr, q_begin, nq, k, ab_knn_exact_pick_splits(ctx, nq), nullptr,
@@ -1044,7 +1054,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     TcWs w;
     AB_REQUIRE(tc_layout(n_total, d, nq, k, ws, ws_bytes, &w) != 0, "ab_knn: workspace too small");
     AB_CUDA(cudaMemsetAsync(w.scal, 0, 4 * sizeof(unsigned int), st));
-    const int mt = tc_mt(d), lists = 3 - mt;
+    const int mt = tc_mt(d, np), lists = 3 - mt;
     // ---- prep ----
     ab_prof_begin(ctx, AB_PROF_KNN_PREP, st);
     const int parts = (int)std::min<int64_t>(1024, std::max<int64_t>(1, n_total / 64));
@@ -1055,7 +1065,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     const unsigned g_prep = (unsigned)std::min<int64_t>((n_total + 7) / 8, (int64_t)ctx->sm_count * 16);
     knn_rmax_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, w.mean, w.scal);
     AB_LAUNCH_CHECK(ctx);
-    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, tc_pad(n_total), d, kt, w.mean, w.scal, w.aop, w.bop, w.qn);
+    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, tc_pad(n_total), d, kt, np, w.mean, w.scal, w.aop, w.bop, w.qn);
     AB_LAUNCH_CHECK(ctx);
     AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)lists * nq * m * sizeof(unsigned long long), st));
     ab_prof_end(ctx, AB_PROF_KNN_PREP, st);
@@ -1078,7 +1088,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     const size_t smem = 1024 + a_bytes + (size_t)stages * group * b_stage + bar_bytes;
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcParams P{};
-    P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (3 * d + 3 + 15) / 16;
+    P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (np * d + 3 + 15) / 16;
     P.stages = stages; P.group = group; P.bufg = w.bufg;
     // one barrier round per tile instead of two: measured floor -10 %, full kernel +9 % -> experiment knob only
     P.merged = (group == chunks && stages >= 3 && getenv("AB_KNN_MERGED")) ? 1 : 0;
@@ -1132,7 +1142,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     const unsigned g_rr = (unsigned)std::min<int64_t>((nq + rr_warps - 1) / rr_warps, (int64_t)ctx->sm_count * 16);
     knn_rerank_kernel<<<g_rr, rr_warps * 32, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
-                                                           idx, rdist, w.fb_list, stats, w.scal + 1, P.tau0);
+                                                           idx, rdist, w.fb_list, stats, w.scal + 1, P.tau0, tc_kappa(np));
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_RERANK, st);
     // ---- uncertified queries: exact scan ----
