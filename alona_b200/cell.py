@@ -63,23 +63,38 @@ class DeviceCounts:
         else:
             log_error('unsupported count container %s' % type(data))
         eng = get_engine()
-        if eng.world > 1:
-            raise RuntimeError('the QC filters compact one device-resident matrix; run them on one rank '
-                               '(re-sharding the filtered rows across ranks is not implemented yet)')
-        return cls(eng, eng.upload_csr(cm.csr), cm.genes, cm.cells)
+        n = cm.csr.shape[0]
+        lo, hi = (n * eng.rank) // eng.world, (n * (eng.rank + 1)) // eng.world       # = pipeline.shard_bounds
+        return cls(eng, eng.upload_csr(cm.csr[lo:hi], row_begin=lo, n_total=n), cm.genes, cm.cells)
 
     @property
     def shape(self):
-        return (self.csr.n_genes, self.csr.n_local)
+        return (self.csr.n_genes, self.csr.n_total)
+
+    @property
+    def local_columns(self):
+        """Labels of the cells this rank holds (all of them on one GPU)."""
+        return self.columns[self.csr.row_begin:self.csr.row_begin + self.csr.n_local]
 
     def to_dataframe(self, max_bytes=8 << 30):
         g, n = self.shape
         if g * n * 8 > max_bytes:
             raise MemoryError('dense count frame would need %.1f GB' % (g * n * 8 / 2 ** 30))
+        if self.engine.world > 1:
+            raise RuntimeError('to_dataframe() is a single-GPU convenience')
         c = self.csr
         m = sp.csr_matrix((c.val.cpu().numpy().astype(np.int64), c.col.cpu().numpy(), c.rowptr.cpu().numpy()),
                           shape=(n, g))
         return pd.DataFrame(m.T.toarray(), index=self.index, columns=self.columns)
+
+    def gsum(self, x):
+        """Sum of a per-rank host integer over the ranks (decisions that lead to collectives must agree)."""
+        if self.engine.world == 1:
+            return int(x)
+        import torch.distributed as dist
+        parts = [None] * self.engine.world
+        dist.all_gather_object(parts, int(x))
+        return int(sum(parts))
 
     def subset(self, keep_cells=None, keep_genes=None):
         """Rows (cells) and columns (genes) selected by boolean masks, compacted on the device."""
@@ -90,9 +105,20 @@ class DeviceCounts:
             keep_genes = np.asarray(keep_genes, dtype=bool)
             gene_map = np.where(keep_genes, np.cumsum(keep_genes) - 1, -1).astype(np.int32)
             genes = self.index[keep_genes]
-        cells = self.columns if keep_cells is None else self.columns[np.asarray(keep_cells, dtype=bool)]
-        out, _ = self.engine.filter_csr(self.csr, keep_cells, gene_map, n_genes_out=len(genes))
-        return DeviceCounts(self.engine, out, genes, cells)
+        eng = self.engine
+        out, _ = eng.filter_csr(self.csr, keep_cells, gene_map, n_genes_out=len(genes))
+        if eng.world == 1:
+            cells = self.columns if keep_cells is None else self.columns[np.asarray(keep_cells, dtype=bool)]
+            return DeviceCounts(eng, out, genes, cells)
+        # keep_cells is this rank's mask: the global mask decides the labels, the kept rows are re-balanced
+        import torch.distributed as dist
+        from .pipeline import reshard_csr
+        local = np.ones(self.csr.n_local, dtype=bool) if keep_cells is None else np.asarray(keep_cells, dtype=bool)
+        masks = [None] * eng.world
+        dist.all_gather_object(masks, local)
+        cells = self.columns[np.concatenate(masks)]
+        rowptr, col, val, row_begin, n_total = reshard_csr(out.rowptr, out.col, out.val, eng.rank, eng.world)
+        return DeviceCounts(eng, DeviceCSR(rowptr, col, val, len(genes), row_begin, n_total), genes, cells)
 
 
 class NormalizedMatrix:
@@ -163,7 +189,7 @@ class AlonaCell:
         with np.errstate(invalid='ignore', divide='ignore'):
             return pd.DataFrame({'reads_per_cell': reads, 'no_genes_det': q['genes_det'].cpu().numpy(),
                                  'perc_rRNA': sets[1] / reads * 100, 'perc_mt': sets[0] / reads * 100},
-                                index=d.columns)
+                                index=d.local_columns)       # this rank's cells
 
     def remove_empty(self):
         """Removes empty cells and genes - with the reference's own comparisons (alona/cell.py:64-81): the zero
@@ -176,8 +202,9 @@ class AlonaCell:
         cells = total_genes - q['genes_det'].cpu().numpy().astype(np.int64)       # zero entries per cell
         genes = total_cells - q['gene_cells'].cpu().numpy()                       # zero entries per gene
         keep_cells = keep_genes = None
-        if np.sum(cells == total_cells) > 0:
-            log_info('%s empty cells will be removed' % np.sum(cells == total_cells))
+        n_empty = d.gsum(np.sum(cells == total_cells))
+        if n_empty > 0:
+            log_info('%s empty cells will be removed' % n_empty)
             keep_cells = np.logical_not(cells == total_cells)
         if np.sum(genes == total_genes) > 0:
             log_info('%s empty genes will be removed' % np.sum(genes == total_genes))
@@ -203,7 +230,7 @@ class AlonaCell:
             min_reads = self.params['minreads']
             d = self.data
             cell_counts = d.engine.qc_metrics(d.csr)['reads_per_cell'].cpu().numpy()
-            log_info('Keeping %s out of %s cells' % (np.sum(cell_counts > min_reads), len(cell_counts)))
+            log_info('Keeping %s out of %s cells' % (d.gsum(np.sum(cell_counts > min_reads)), d.shape[1]))
             self.data = d.subset(cell_counts > min_reads, None)
             if self.data.shape[1] < 100:
                 log_error(msg='After removing cells with < %s reads, less than 100 cells remain. Please adjust '
@@ -238,7 +265,7 @@ class AlonaCell:
             cm = CountMatrix.from_dataframe(data)
         elif isinstance(data, DeviceCounts):
             if remove_low_quality and self.low_quality_cells is not None and len(self.low_quality_cells):
-                data = data.subset(~np.isin(np.asarray(data.columns), np.asarray(self.low_quality_cells)), None)
+                data = data.subset(~np.isin(np.asarray(data.local_columns), np.asarray(self.low_quality_cells)), None)
             eng = data.engine
             if int((data.csr.rowptr[1:] == data.csr.rowptr[:-1]).sum().item()):
                 log_error('normalize(): cells without any count must be removed first (alona/cell.py:64-81).')

@@ -40,6 +40,59 @@ def unpack_rows(gathered, counts):
     return _torch.cat([gathered[r * n_max: r * n_max + c] for r, c in enumerate(counts)], dim=0)
 
 
+def reshard_plan(counts, world):
+    """Row exchange that turns ragged contiguous shards (rank r holds `counts[r]` consecutive rows of the global
+    order) into the balanced shards of shard_bounds(): plan[r][t] = (first local row, number of rows) rank r sends
+    to rank t.  Pure host logic (tested over gloo)."""
+    total = int(sum(counts))
+    bounds = shard_bounds(total, world)
+    first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    plan = []
+    for r in range(world):
+        row = []
+        for t in range(world):
+            lo = max(int(first[r]), bounds[t])
+            hi = min(int(first[r + 1]), bounds[t + 1])
+            row.append((lo - int(first[r]), hi - lo) if hi > lo else (0, 0))
+        plan.append(row)
+    return plan, bounds
+
+
+def reshard_csr(rowptr, col, val, rank, world):
+    """After a filter every rank holds a ragged number of rows; downstream stages expect shard_bounds().  Moves
+    whole rows between ranks with torch.distributed all-to-all (plumbing, no arithmetic): row lengths, column ids and
+    counts travel as three variable-split exchanges; rows arrive in source-rank order = global order.
+    Works on device (NCCL) or host (gloo) tensors.  Returns (rowptr, col, val, row_begin, n_total)."""
+    import torch.distributed as dist
+    n_local = int(rowptr.numel() - 1)
+    counts = [None] * world
+    dist.all_gather_object(counts, n_local)
+    plan, bounds = reshard_plan(counts, world)
+    mine = plan[rank]
+    rp = rowptr.cpu()
+    send_rows = [c for (_, c) in mine]
+    send_nnz = [int(rp[s + c] - rp[s]) if c else 0 for (s, c) in mine]
+    recv_rows = [plan[r][rank][1] for r in range(world)]
+    sizes = [None] * world
+    dist.all_gather_object(sizes, send_nnz)
+    recv_nnz = [sizes[r][rank] for r in range(world)]
+    # what this rank sends is one contiguous run of rows (targets are consecutive ranges of the global order)
+    sent = [(s, c) for (s, c) in mine if c]
+    s0 = sent[0][0] if sent else 0
+    s1 = sent[-1][0] + sent[-1][1] if sent else 0
+    lens = (rowptr[1:] - rowptr[:-1])[s0:s1].contiguous()
+    a, b = int(rp[s0]), int(rp[s1])
+    out_lens = lens.new_empty((sum(recv_rows),))
+    out_col = col.new_empty((sum(recv_nnz),))
+    out_val = val.new_empty((sum(recv_nnz),))
+    dist.all_to_all_single(out_lens, lens, recv_rows, send_rows)
+    dist.all_to_all_single(out_col, col[a:b].contiguous(), recv_nnz, send_nnz)
+    dist.all_to_all_single(out_val, val[a:b].contiguous(), recv_nnz, send_nnz)
+    new_rowptr = rowptr.new_zeros((out_lens.numel() + 1,))
+    new_rowptr[1:] = torch.cumsum(out_lens, 0)
+    return new_rowptr, out_col, out_val, bounds[rank], bounds[world]
+
+
 def start_vector(n_total, seed):
     """The reference's start vector (alona/irlbpy/irlb.py:151-152)."""
     np.random.seed(seed)

@@ -127,3 +127,51 @@ def test_pack_unpack_roundtrip():
     g = torch.cat([pack_rows(p, 3) for p in parts])
     assert torch.equal(unpack_rows(g, [3, 2]), torch.cat(parts))
     assert pack_rows(parts[0], 3).data_ptr() == parts[0].data_ptr()          # no copy when already full
+
+
+def _reshard_worker(rank, world, port):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sp
+        from alona_b200.pipeline import reshard_csr, shard_bounds
+        rng = np.random.RandomState(0)
+        full = sp.random(97, 40, density=0.2, random_state=rng, format='csr')
+        full.data = rng.randint(1, 9, size=full.nnz).astype(np.int32)
+        full.sort_indices()
+        # ragged shards, as a filter leaves them: rank 0 holds 11 rows, rank 1 holds 80, rank 2 holds 6
+        cuts = [0, 11, 91, 97]
+        mine = full[cuts[rank]:cuts[rank + 1]]
+        rowptr, col, val, row_begin, n_total = reshard_csr(torch.from_numpy(mine.indptr.astype(np.int64)),
+                                                           torch.from_numpy(mine.indices.astype(np.int32)),
+                                                           torch.from_numpy(mine.data.astype(np.int32)), rank, world)
+        b = shard_bounds(97, world)
+        want = full[b[rank]:b[rank + 1]]
+        assert (row_begin, n_total) == (b[rank], 97)
+        assert np.array_equal(rowptr.numpy(), want.indptr)
+        assert np.array_equal(col.numpy(), want.indices)
+        assert np.array_equal(val.numpy(), want.data)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reshard_after_filter_over_gloo():
+    """N3 on N > 1: ragged shards left by the filters are re-balanced to shard_bounds() by whole-row exchange."""
+    mp.spawn(_reshard_worker, args=(3, _free_port()), nprocs=3, join=True)
+
+
+def test_reshard_plan_covers_every_row_once():
+    from alona_b200.pipeline import reshard_plan
+    for counts in ([5, 0, 7], [0, 0, 9], [1, 1, 1, 1], [100, 3], [0, 0]):
+        world = len(counts)
+        plan, bounds = reshard_plan(counts, world)
+        for r in range(world):
+            sent = sorted((s, c) for (s, c) in plan[r] if c)
+            assert sum(c for _, c in sent) == counts[r]
+            pos = sent[0][0] if sent else 0
+            for s, c in sent:
+                assert s == pos
+                pos += c
+        for t in range(world):
+            assert sum(plan[r][t][1] for r in range(world)) == bounds[t + 1] - bounds[t]
