@@ -979,8 +979,17 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     const size_t rz_kpad = (size_t)((work + 7) & ~7);
     AB_CUDA(cudaFuncSetAttribute(ritz_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rz_kpad * 64 * 8)));
     AB_CUDA(cudaFuncSetAttribute(ritz_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rz_kpad * 128 * 8)));
+    bool use_cublas = getenv("AB_IRLB_OWN_RITZ") == nullptr;
     auto ritz = [&](const double *X, int64_t ldx, int64_t rows, const double *M, int ncols, double *out, int64_t ldo,
                     int rowmajor, const double *colscale, double *out2) -> int {
+        // the restart's plain column-major products go to the library GEMM; the fused output form (row-major, column
+        // scaling, second output) and boxes without cuBLAS use the kernel below
+        if (!rowmajor && use_cublas && rows > 0) {
+            const int rc = ab_dgemm_colmajor_rowb(ctx, rows, ncols, work, X, ldx, M, work, out, ldo, st);
+            if (rc == 0) return 0;
+            if (rc == 1) return 1;
+            use_cublas = false;
+        }
         if (ncols <= 64) {
             const unsigned g = (unsigned)std::max<int64_t>(1, (rows + RZ_WARPS * 16 - 1) / (RZ_WARPS * 16));
             ritz_kernel<8, 2><<<g, RZ_WARPS * 32, rz_kpad * 64 * 8, st>>>(X, ldx, rows, work, M, ncols, out, ldo, rowmajor,
