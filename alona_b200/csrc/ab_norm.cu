@@ -50,15 +50,24 @@ norm_moments_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restric
         const double lib = (double)S;
         // lane l holds x for count l+1
         const double tab = ab_norm_value((double)(lane + 1), lib, scale);
-        for (int64_t p = a + lane; p < ((b - a + 31) / 32) * 32 + a; p += 32) {
-            const bool live = p < b;
-            int c = 0, g = 0;
-            if (live) { c = __ldg(val + p); g = __ldg(col + p); }
-            double x = ab_shfl_f64(tab, (c - 1) & 31);
-            if (live) {
-                if (c > 32) x = ab_norm_value((double)c, lib, scale);
-                atomicAdd(gsum + g, x);
-                atomicAdd(gsumsq + g, __dmul_rn(x, x));
+        for (int64_t p0 = a + lane; p0 - lane < b; p0 += 128) {
+            int cc[4], gg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                                 // four steps in flight before the reductions
+                const int64_t p = p0 + 32 * u;
+                cc[u] = p < b ? __ldcs(val + p) : 0;
+                gg[u] = p < b ? __ldcs(col + p) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (p0 - lane + 32 * u >= b) break;                       // warp-uniform
+                const int c = cc[u], g = gg[u];
+                double x = ab_shfl_f64(tab, (c - 1) & 31);
+                if (g >= 0) {
+                    if (c > 32) x = ab_norm_value((double)c, lib, scale);
+                    atomicAdd(gsum + g, x);
+                    atomicAdd(gsumsq + g, __dmul_rn(x, x));
+                }
             }
         }
     }
@@ -93,7 +102,14 @@ hvg_count_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__
     for (int64_t row = warp_global; row < n_local; row += nwarps) {
         const int64_t a = rowptr[row], b = rowptr[row + 1];
         int cnt = 0;
-        for (int64_t p = a + lane; p < b; p += 32) cnt += __ldg(gene2hvg + __ldg(col + p)) >= 0;
+        // four steps of 32 column ids in flight before the look-ups (a pure stream: bytes in flight set the speed)
+        for (int64_t p0 = a + lane; p0 < b; p0 += 128) {
+            int g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g[u] = p0 + 32 * u < b ? __ldcs(col + p0 + 32 * u) : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cnt += g[u] >= 0 && __ldg(gene2hvg + g[u]) >= 0;
+        }
         cnt = ab_warp_sum_i32(cnt);
         if (lane == 0) rowcount[row] = cnt;
     }
@@ -112,21 +128,31 @@ hvg_fill_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ 
         const double lib = (double)libsize[row];
         const double tab = ab_norm_value((double)(lane + 1), lib, scale);
         int64_t out = rowptr_h[row];
-        for (int64_t base = a; base < b; base += 32) {
-            const int64_t p = base + lane;
-            const bool live = p < b;
-            int c = 0, h = -1;
-            if (live) { c = __ldg(val + p); h = __ldg(gene2hvg + __ldg(col + p)); }
-            double x = ab_shfl_f64(tab, (c - 1) & 31);
-            const bool keep = live && h >= 0;
-            const unsigned m = __ballot_sync(AB_FULL, keep);
-            if (keep) {
-                if (c > 32) x = ab_norm_value((double)c, lib, scale);
-                const int64_t q = out + __popc(m & ((1u << lane) - 1));
-                col_h[q] = h;
-                val_h[q] = x;
+        for (int64_t base4 = a; base4 < b; base4 += 128) {
+            // four steps loaded before any is compacted
+            int cc[4], gg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = base4 + 32 * u + lane;
+                cc[u] = p < b ? __ldcs(val + p) : 0;
+                gg[u] = p < b ? __ldcs(col + p) : -1;
             }
-            out += __popc(m);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (base4 + 32 * u >= b) break;                               // warp-uniform
+                const int c = cc[u];
+                const int h = gg[u] >= 0 ? __ldg(gene2hvg + gg[u]) : -1;
+                double x = ab_shfl_f64(tab, (c - 1) & 31);
+                const bool keep = h >= 0;
+                const unsigned m = __ballot_sync(AB_FULL, keep);
+                if (keep) {
+                    if (c > 32) x = ab_norm_value((double)c, lib, scale);
+                    const int64_t q = out + __popc(m & ((1u << lane) - 1));
+                    col_h[q] = h;
+                    val_h[q] = x;
+                }
+                out += __popc(m);
+            }
         }
     }
 }
