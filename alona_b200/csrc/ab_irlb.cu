@@ -310,7 +310,8 @@ __global__ void scale_by_invnorm_kernel(const double *__restrict__ src, double *
 // and plain load/FMA/store is race-free and order-deterministic; __syncwarp separates rows.
 // Row metadata (row end, x) travels in registers, 32 rows per refill, read by shuffle.
 // ---------------------------------------------------------------------------------------
-static constexpr int AV_U = 12;
+static constexpr int AV_U = 8;       // steps per register batch (measured at C3: 4 -> 210 ms, 6 -> 187, 8 -> 179, 12 -> 196, 16 -> 193:
+                                     // fewer bytes in flight below 8, instruction-cache misses of the unrolled consume loop above)
 
 struct AvRowState {           // row metadata of one warp: 32 rows per refill, read by shuffle
     int64_t blk;              // first row of the register block
