@@ -322,14 +322,29 @@ struct AvRowState {           // row metadata of one warp: 32 rows per refill, r
     double xrow;              // x of the current row
 };
 
+// Refill of the 32-row metadata block: runs once per 32 rows but is reached from every unrolled step, so it is kept
+// out of line (values in, values out - no state by reference) to keep the consume loop inside the instruction cache.
+struct AvBlk {
+    double x;
+    int rp;
+};
+__device__ __noinline__ AvBlk av_fetch_block(const int64_t *__restrict__ rowptr, int64_t blk, int64_t p0, int64_t r1,
+                                             const double *__restrict__ src, double scale, double *__restrict__ vdst,
+                                             int lane) {
+    const int64_t row = blk + lane;
+    const bool ok = row < r1;
+    AvBlk b;
+    b.rp = ok ? (int)(rowptr[row + 1] - p0) : INT_MAX;           // sentinel: never reached
+    b.x = ok ? __dmul_rn(scale, src[row]) : 0.0;
+    if (ok && vdst) vdst[row] = b.x;
+    return b;
+}
 __device__ __forceinline__ void av_load_block(AvRowState &r, const int64_t *__restrict__ rowptr, int64_t p0, int64_t r1,
                                               const double *__restrict__ src, double scale, double *__restrict__ vdst,
                                               int lane) {
-    const int64_t row = r.blk + lane;
-    const bool ok = row < r1;
-    r.rp_l = ok ? (int)(rowptr[row + 1] - p0) : INT_MAX;         // sentinel: never reached
-    r.x_l = ok ? __dmul_rn(scale, src[row]) : 0.0;
-    if (ok && vdst) vdst[row] = r.x_l;
+    const AvBlk b = av_fetch_block(rowptr, r.blk, p0, r1, src, scale, vdst, lane);
+    r.rp_l = b.rp;
+    r.x_l = b.x;
 }
 
 // one step of 32 nonzeros starting at stream offset s0
