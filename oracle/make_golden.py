@@ -60,6 +60,50 @@ def make_pipeline_case(name, spec):
           ref['lanczos']['nmult'], 'edges', ref['snn_graph'].shape[0])
 
 
+# BASELINE.json configs[0] (C1: 2,700 x 32,738, hvg 1000, 40 PCs, k 10) and C1-shaped variants that drive the
+# IRLBA work dimensions the bench shapes run (m_b = nval + 20: 60 / 70 / 95 / 120).  One input
+# matrix (stored once, compactly) + one output file per variant.
+C1_INPUT = dict(cells=2700, genes=32738, lbar=1061.0, clusters=30, data_seed=20251019)
+C1_VARIANTS = {
+    # name: (hvg_n, pca_n, k, prune, seed)
+    'c1_full': (1000, 40, 10, 0.067, 42),            # BASELINE.json configs[0]; m_b = 60
+    'c1_h2000_d50_k20': (2000, 50, 20, 0.067, 42),   # C2/C3 parameters; m_b = 70
+    'c1_h2000_d75_k20': (2000, 75, 20, 0.067, 42),   # m_b = 95
+    'c1_h3000_d100_k30': (3000, 100, 30, 0.067, 42),  # C5 parameters; m_b = 120
+}
+
+
+def make_c1_cases():
+    spec = C1_INPUT
+    m, _ = synth_np.nb_counts(spec['cells'], spec['genes'], lbar=spec['lbar'], n_clusters=spec['clusters'],
+                              seed=spec['data_seed'])
+    assert m.shape[1] < 65536 and m.data.max() < 65536
+    np.savez_compressed(os.path.join(OUT, 'c1_input.npz'), indptr=m.indptr.astype(np.int64),
+                        indices=m.indices.astype(np.uint16), data=m.data.astype(np.uint16),
+                        shape=np.array(m.shape, dtype=np.int64))
+    print('c1_input', m.shape, 'nnz', m.nnz, 'genes detected per cell', m.nnz / m.shape[0])
+    df = _counts_df(m)
+    gene_pos = {gname: i for i, gname in enumerate(df.index)}
+    for name, (hvg_n, pca_n, k, prune, seed) in C1_VARIANTS.items():
+        ref = ref_shim.run_reference(df, hvg_n=hvg_n, pca_n=pca_n, nn_k=k, prune_snn=prune, seed=seed)
+        dn = ref['data_norm']
+        hvg_ranked = np.array([gene_pos[x] for x in ref['hvg']], dtype=np.int32)
+        _, counts = alona_port.snn(ref['nn_idx'], k, prune, return_counts=True)
+        np.random.seed(seed)
+        v0 = np.random.randn(m.shape[0])
+        np.savez_compressed(
+            os.path.join(OUT, name + '.npz'), input='c1_input',
+            hvg_n=hvg_n, pca_n=pca_n, k=k, prune=prune, seed=seed,
+            libsize=np.asarray(df.sum(axis=0).values, dtype=np.int64),
+            gene_mean=dn.mean(axis=1).values, gene_var=dn.var(axis=1).values, hvg_ranked=hvg_ranked,
+            pca_components=ref['pca_components'], s=ref['lanczos']['s'],
+            steps=ref['lanczos']['steps'], nmult=ref['lanczos']['nmult'], v0=v0,
+            nn_idx=ref['nn_idx'].astype(np.int32), snn_graph=ref['snn_graph'].astype(np.int32),
+            snn_overlap=counts.astype(np.int16))
+        print(name, 'steps', ref['lanczos']['steps'], 'nmult', ref['lanczos']['nmult'], 'edges',
+              ref['snn_graph'].shape[0])
+
+
 def make_knn_case(name, n, d, k, seed, dup=0, quantise=None):
     emb = synth_np.gaussian_mixture_embedding(n, d=d, seed=seed)
     if quantise:
@@ -141,6 +185,9 @@ def main():
         sys.exit('reference tree not present; fixtures can only be minted in the dev container')
     os.makedirs(OUT, exist_ok=True)
     warnings.simplefilter('ignore')
+    if '--c1' in sys.argv:                      # only the C1 family (minutes of the live reference)
+        make_c1_cases()
+        return
     for name, spec in PIPELINE_CASES.items():
         make_pipeline_case(name, spec)
     make_knn_case('knn_mix_3000x50_k20', 3000, 50, 20, seed=2)
@@ -152,6 +199,7 @@ def main():
     make_cluster_exp_case('clexp_700x900', 700, 900, 700.0, 5, 13)
     make_cluster_exp_case('clexp_401x500', 401, 500, 150.0, 3, 17)
     make_qc_case('qc_rect_700x300', 700, 300, 10.0, 5, 4)
+    make_c1_cases()
 
 
 if __name__ == '__main__':

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES
+from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES, C1_CASES
 from oracle import restate as R
 
 pytestmark = pytest.mark.gpu
@@ -32,7 +32,7 @@ def _ulp_diff(a, b):
     return np.abs(ia - ib)
 
 
-@pytest.mark.parametrize('case', PIPE_CASES)
+@pytest.mark.parametrize('case', PIPE_CASES + C1_CASES)
 def test_k1_normalise_moments(eng, case):
     g = load_golden(case)
     m = golden_csr(g)
@@ -46,7 +46,7 @@ def test_k1_normalise_moments(eng, case):
     assert np.max(np.abs(gsum.cpu().numpy() / n - g['gene_mean']) / g['gene_mean']) < MOMENT_RTOL
 
 
-@pytest.mark.parametrize('case', PIPE_CASES)
+@pytest.mark.parametrize('case', PIPE_CASES + C1_CASES)
 def test_k2_hvg_set_exact(eng, case):
     g = load_golden(case)
     m = golden_csr(g)
@@ -73,7 +73,7 @@ def test_k2_hvg_set_exact(eng, case):
     assert np.array_equal(g2h[cols], np.arange(cols.size))
 
 
-@pytest.mark.parametrize('case', PIPE_CASES)
+@pytest.mark.parametrize('case', PIPE_CASES + C1_CASES)
 def test_k3_hvg_extract(eng, case):
     g = load_golden(case)
     m = golden_csr(g)
@@ -99,7 +99,7 @@ def _golden_AH(eng, g):
     return eng.hvg_extract(A, lib, torch.from_numpy(g2h).to(eng.device), cols.size)
 
 
-@pytest.mark.parametrize('case', PIPE_CASES)
+@pytest.mark.parametrize('case', PIPE_CASES + C1_CASES)
 def test_irlb_follows_reference_trajectory(eng, case):
     g = load_golden(case)
     AH = _golden_AH(eng, g)
@@ -112,8 +112,9 @@ def test_irlb_follows_reference_trajectory(eng, case):
     assert np.max(np.abs(s - g['s']) / g['s']) < 1e-11
     err = R.column_rel_err(g['pca_components'], res['scores'].cpu().numpy())
     assert err.max() < PCA_RTOL, err
-    erru = R.column_rel_err(g['U'], res['U'].cpu().numpy())
-    assert erru.max() < 1e-8, erru
+    if 'U' in g.files:                                        # (the C1 family does not store the left vectors)
+        erru = R.column_rel_err(g['U'], res['U'].cpu().numpy())
+        assert erru.max() < 1e-8, erru
     # V.diag(s) == scores
     v = res['V'].cpu().numpy()
     assert np.allclose(v * s, res['scores'].cpu().numpy(), rtol=1e-14, atol=0)
@@ -182,7 +183,7 @@ def _check_knn(eng, emb, k, golden_nn, mode):
 
 
 @pytest.mark.parametrize('mode', [0, 1])
-@pytest.mark.parametrize('case', PIPE_CASES)
+@pytest.mark.parametrize('case', PIPE_CASES + C1_CASES)
 def test_knn_on_reference_pca(eng, case, mode):
     g = load_golden(case)
     _check_knn(eng, g['pca_components'], int(g['k']), g['nn_idx'], mode)
@@ -213,7 +214,7 @@ def test_knn_sharded_queries_equal_full(eng):
     assert torch.equal(full, torch.cat(parts))
 
 
-@pytest.mark.parametrize('case', PIPE_CASES + KNN_CASES)
+@pytest.mark.parametrize('case', PIPE_CASES + KNN_CASES + C1_CASES)
 def test_snn_edge_list_identical(eng, case):
     g = load_golden(case)
     k = int(g['k'])
@@ -279,22 +280,67 @@ def test_snn_hub_rows_cover_every_walk_class(eng, n, k, plan, prune):
     assert np.array_equal(np.concatenate([a['dst'].cpu().numpy(), b['dst'].cpu().numpy()]), ref_e[:, 1])
 
 
-@pytest.mark.parametrize('case', PIPE_CASES)
+def check_free_running_against_reference(out, g):
+    """Free-running pipeline output against a reference-minted fixture, with NO escape:
+    (1) the run's own chain is exact: its kNN table equals the brute-force checker on ITS embedding and its edge
+        list equals the restated SNN of ITS kNN table, order and overlaps included;
+    (2) against the reference: HVG set, steps/nmult, scores <= 1e-9; kNN rows may differ from the reference's only
+        where the reference's own candidate distances are closer than the embedding difference (near-tie rows,
+        counted and returned); with no such row the edge list must be identical, order included; otherwise every
+        edge between two unaffected cells must carry the reference's overlap count."""
+    k = int(g['k'])
+    prune = float(g['prune'])
+    assert set(out['hvg_ranked'].cpu().numpy().tolist()) == set(g['hvg_ranked'].tolist())
+    assert out['irlb']['steps'] == int(g['steps']) and out['irlb']['nmult'] == int(g['nmult'])
+    emb = out['emb_all'].cpu().numpy()
+    err = R.column_rel_err(g['pca_components'], emb)
+    assert err.max() < PCA_RTOL, err.max()
+    knn0 = out['knn_all'].cpu().numpy()
+    bi, bd = R.knn_bruteforce(emb, k + 1)
+    assert np.array_equal(knn0, bi[:, :k])
+    edges = np.stack([out['snn']['src'].cpu().numpy(), out['snn']['dst'].cpu().numpy()], 1)
+    ov = out['snn']['overlap'].cpu().numpy().astype(np.int16)
+    e_own, c_own = R.snn_restated(knn0.astype(np.int64), k, prune)
+    assert np.array_equal(edges, e_own) and np.array_equal(ov, c_own)
+    nn = knn0.astype(np.int64) + 1
+    diff_rows = np.where(~np.all(nn == g['nn_idx'], axis=1))[0]
+    # a differing row must be a near tie in the REFERENCE embedding: the symmetric difference of the two
+    # neighbour sets lies within a relative distance band of 1e-8 around the k-th neighbour
+    ref_emb = g['pca_components']
+    for r in diff_rows:
+        a, b = set(nn[r].tolist()), set(g['nn_idx'][r].tolist())
+        d = ((ref_emb - ref_emb[r]) ** 2).sum(axis=1)
+        dk = np.sort(d)[k - 1]
+        for j in (a ^ b) or (a | b):
+            if a == b:                                        # same set, different order: the swapped pair is tied
+                continue
+            assert abs(d[j - 1] - dk) <= 1e-8 * dk, (r, j, d[j - 1], dk)
+        if a == b:
+            pos = np.where(nn[r] != g['nn_idx'][r])[0]
+            dd = d[nn[r][pos] - 1]
+            assert np.ptp(dd) <= 1e-8 * dk, (r, dd)
+    if diff_rows.size == 0:
+        assert np.array_equal(edges, g['snn_graph'])                         # order included
+        assert np.array_equal(ov, g['snn_overlap'])
+    else:
+        bad = np.zeros(nn.shape[0], dtype=bool)
+        bad[diff_rows] = True
+        ge = g['snn_graph']
+
+        def clean(e, c):
+            keep = ~bad[e[:, 0]] & ~bad[e[:, 1]]
+            return set(zip(e[keep, 0].tolist(), e[keep, 1].tolist(), c[keep].tolist()))
+        assert clean(edges, ov) == clean(ge, g['snn_overlap'])
+    return diff_rows
+
+
+@pytest.mark.parametrize('case', PIPE_CASES + C1_CASES)
 def test_frontend_end_to_end(eng, case):
-    """Free-running pipeline: counts in, SNN edge list out; identical to the reference's."""
+    """Free-running pipeline: counts in, SNN edge list out, against the reference's; no skipped assertion."""
     from alona_b200.pipeline import frontend
     g = load_golden(case)
     A = eng.upload_csr(golden_csr(g))
     out = frontend(eng, A, int(g['hvg_n']), int(g['pca_n']), int(g['k']), float(g['prune']), int(g['seed']),
                    want_overlap=True)
-    assert set(out['hvg_ranked'].cpu().numpy().tolist()) == set(g['hvg_ranked'].tolist())
-    assert out['irlb']['steps'] == int(g['steps']) and out['irlb']['nmult'] == int(g['nmult'])
-    nn = out['knn_all'].cpu().numpy().astype(np.int64) + 1
-    # the free-running embedding differs from the reference's by ~1e-12 relative, so neighbour rows
-    # may differ only where two candidate distances are closer than that; require >= 99.9 % identical
-    same = np.all(nn == g['nn_idx'], axis=1)
-    assert same.mean() >= 0.999, same.mean()
-    if same.all():
-        edges = np.stack([out['snn']['src'].cpu().numpy(), out['snn']['dst'].cpu().numpy()], 1)
-        assert np.array_equal(edges, g['snn_graph'])
-        assert np.array_equal(out['snn']['overlap'].cpu().numpy().astype(np.int16), g['snn_overlap'])
+    diff_rows = check_free_running_against_reference(out, g)
+    assert diff_rows.size <= max(1, A.n_local // 1000), diff_rows

@@ -4,7 +4,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES, QC_CASES, CLEXP_CASES
+from conftest import load_golden, golden_csr, PIPE_CASES, KNN_CASES, QC_CASES, CLEXP_CASES, C1_CASES
 from oracle import alona_port as P, restate as R
 
 
@@ -29,7 +29,12 @@ def test_port_pipeline_matches_reference_bitwise(case):
     assert np.array_equal(out['snn_graph'], g['snn_graph'])
 
 
-@pytest.mark.parametrize('case', PIPE_CASES)
+def test_port_pipeline_matches_reference_bitwise_at_c1():
+    """BASELINE.json configs[0] in full (2,700 cells, hvg 1000, 40 PCs => work dimension 60, k 10)."""
+    test_port_pipeline_matches_reference_bitwise('c1_full')
+
+
+@pytest.mark.parametrize('case', PIPE_CASES + C1_CASES)
 def test_restated_normalise_moments_hvg(case):
     g = load_golden(case)
     m = golden_csr(g)
@@ -47,8 +52,8 @@ def test_restated_normalise_moments_hvg(case):
         assert set(idx.tolist()) == set(g['hvg_ranked'].tolist())
 
 
-@pytest.mark.parametrize('case', PIPE_CASES)
-@pytest.mark.parametrize('nshards', [1, 2, 8])
+@pytest.mark.parametrize('case,nshards', [(c, n) for c in PIPE_CASES for n in (1, 2, 8)] +
+                         [(c, n) for c in C1_CASES for n in (1, 8)])
 def test_restated_sharded_irlb_follows_reference_trajectory(case, nshards):
     g = load_golden(case)
     m = golden_csr(g)
@@ -60,7 +65,7 @@ def test_restated_sharded_irlb_follows_reference_trajectory(case, nshards):
     assert np.max(np.abs(l['s'] - g['s']) / g['s']) < 1e-12
 
 
-@pytest.mark.parametrize('case', PIPE_CASES)
+@pytest.mark.parametrize('case', PIPE_CASES + C1_CASES)
 def test_bruteforce_knn_and_restated_snn_on_pipeline(case):
     g = load_golden(case)
     k = int(g['k'])
