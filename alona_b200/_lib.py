@@ -33,8 +33,13 @@ SIGNATURES = {
     'ab_allreduce_f64': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     'ab_allreduce_i64': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     'ab_allgather_bytes': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    'ab_peer_handle_bytes': (c_size, []),
+    'ab_peer_alloc': (ctypes.c_int, [c_void_p, c_void_p]),
+    'ab_peer_open': (ctypes.c_int, [c_void_p, c_void_p]),
+    'ab_peer_enabled': (ctypes.c_int, [c_void_p]),
     'ab_norm_moments': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_f64,
-                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p]),
+    'ab_moments_finalize': (ctypes.c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p]),
     'ab_hvg_seurat': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ab_hvg_extract_ws_bytes': (c_size, [c_i64]),

@@ -14,6 +14,7 @@ import pandas as pd
 import scipy.sparse as sp
 import torch
 
+from .alonabase import AlonaBase
 from .engine import get_engine, DeviceCSR
 from .log import log_debug, log_error, log_info
 
@@ -23,6 +24,12 @@ class CountMatrix:
 
     def __init__(self, csr, genes=None, cells=None):
         csr = sp.csr_matrix(csr)
+        if csr.nnz and csr.data.min() < 0:
+            log_error('Negative values detected in the count matrix.')
+        # canonical CSR: the kernels take "one strictly positive entry per (cell, gene), columns ascending" for
+        # granted (an explicitly stored zero would otherwise pass the empty-cell checks)
+        csr.sum_duplicates()
+        csr.eliminate_zeros()
         csr.sort_indices()
         self.csr = csr
         self.genes = np.asarray(genes if genes is not None else np.arange(csr.shape[1]))
@@ -160,7 +167,7 @@ class NormalizedMatrix:
         return pd.DataFrame(dense, index=self.index, columns=self.columns)
 
 
-class AlonaCell:
+class AlonaCell(AlonaBase):
     """Cell data class (only the normalisation stage is in scope; alona/cell.py:30)."""
 
     def __init__(self):
@@ -168,10 +175,7 @@ class AlonaCell:
         self.data_norm = None
         self.data_ERCC = None
         self.low_quality_cells = None
-        self.params = getattr(self, 'params', None)
-
-    def get_wd(self):
-        return self.params['output_directory']
+        super().__init__()
 
     # ---- N3: upstream filters ----------------------------------------------------------
     def qc_metrics(self, rRNA_genes=()):

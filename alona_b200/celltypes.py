@@ -47,8 +47,7 @@ class AlonaCellTypePred(AlonaClustering):
         ret = ret.iloc[:, ret.columns.isin(self.clusters_targets)]
         if isinstance(self.anno, pd.DataFrame):
             ret = pd.concat([self.anno['desc'], ret], axis=1)
-        if self.params.get('output_directory'):
-            ret.to_csv(self.get_wd() + fn, header=True, sep='\t')
+        self._write(lambda path: ret.to_csv(path, header=True, sep='\t'), fn)       # rank 0 only
         return ret
 
     def median_exp(self, data_norm):

@@ -23,7 +23,7 @@ from .cell import AlonaCell
 from .constants import OUTPUT
 from .engine import get_engine
 from .hvg import AlonaHighlyVariableGenes
-from .log import log_debug, log_error, log_warning
+from .log import log_debug, log_error, log_info, log_warning
 from .pipeline import prune_threshold, shard_bounds
 
 
@@ -162,27 +162,75 @@ class AlonaClustering(AlonaCell):
     def cluster(self):
         """kNN -> SNN -> Leiden (alona/clustering.py:295-311, de-novo branch)."""
         if isinstance(self.preclust, pd.DataFrame):
-            log_error('--custom_clustering is outside the scope of alona_b200.')
+            # clustering.py:297-305: a pre-made clustering replaces kNN/SNN/Leiden; the cells must already be in
+            # the order of the clustering file (the device-resident data_norm is not re-indexed)
+            t = self.preclust.cell.isin(self.data_norm.columns)
+            self.preclust = self.preclust.loc[t, :]
+            if self.data_norm.shape[1] != self.preclust.shape[0]:
+                log_error('Number of cells mismatch (data_norm and preclust)')
+            if not np.array_equal(np.asarray(self.preclust['cell']), np.asarray(self.data_norm.columns)):
+                log_error('--custom_clustering must list the cells in the order of the data matrix.')
+            self.leiden_cl = list(self.preclust['cluster'])
+            self.leiden_prep()
+            return
         k = self.params['nn_k']
         self.knn(k, filename=(self.get_wd() + OUTPUT['FILENAME_KNN_map']) if self._has_wd() else '')
         self.snn(k, self.params['prune_snn'])
         self.leiden()
 
+    def snn_edge_array(self):
+        """The SNN edge list as ONE contiguous [E, 2] integer array (what igraph's Graph(edges=...) consumes
+        directly): the hand-off to the unchanged Leiden step without the per-edge Python tuples of
+        alona/clustering.py:277-280 (tens of millions of edges at the 1.3M-cell configuration)."""
+        return np.ascontiguousarray(self.snn_graph.values)
+
+    def leiden_prep(self):
+        """ Post-clustering stuff (alona/clustering.py:242-260): clusters file, cluster sizes, clusters_targets. """
+        idx = self.data_norm.columns
+        self._write(lambda fn: pd.DataFrame(self.leiden_cl, index=idx).to_csv(fn, header=False, index=True),
+                    OUTPUT['FILENAME_CLUSTERS_LEIDEN'])
+        cl, counts = np.unique(self.leiden_cl, return_counts=True)
+        ignore_clusters = self.params['ignore_small_clusters']
+        self.n_clusters = np.sum(counts > ignore_clusters)
+        n = len(set(self.leiden_cl))
+        log_info('there are %s cell clusters (n=%s are OK)' % (n, self.n_clusters))
+        self.clusters_targets = cl[counts > ignore_clusters]
+        log_debug(('cluster', 'cells'))
+        for item in zip(cl, counts):
+            log_debug(item)
+        if not getattr(self, 'cluster_colors', None):
+            # plot colours (the reference draws them with utils.uniqueColors; plots are outside the scope)
+            import colorsys
+            m = max(1, len(self.clusters_targets))
+            self.cluster_colors = ['#%02x%02x%02x' % tuple(int(255 * c) for c in colorsys.hsv_to_rgb(i / m, 0.75, 0.9))
+                                   for i in range(len(self.clusters_targets))]
+
     def leiden(self):
-        """Hands the SNN edge list to the unchanged leidenalg step (alona/clustering.py:262-293)."""
+        """Cluster the SNN graph using the Leiden algorithm: the unchanged leidenalg step of the reference
+        (alona/clustering.py:262-293), fed from the edge ARRAY instead of a list of tuples."""
+        log_debug('Running leiden clustering...')
         try:
             import igraph as ig
             import leidenalg
         except ImportError:
             log_warning('leidenalg/igraph are not installed; the SNN edge list is the hand-off point.')
             return
-        nn = set(self.snn_graph[self.snn_graph.columns[0]])
+        res = self.params['leiden_res']
+        seed = self.params['seed']
+        edges = self.snn_edge_array()
+        nn = np.unique(edges[:, 0]).size                              # len(set(source_node)), clustering.py:274
         g = ig.Graph()
-        g.add_vertices(len(nn))
-        g.add_edges(list(map(tuple, self.snn_graph.values.tolist())))
-        cl = leidenalg.find_partition(g, leidenalg.RBERVertexPartition, n_iterations=10,
-                                      resolution_parameter=self.params['leiden_res'], seed=self.params['seed'])
+        g.add_vertices(nn)
+        g.vs['name'] = list(range(1, nn + 1))
+        g.add_edges(edges)
+        if self.params == 'ModularityVertexPartition':               # (sic, clustering.py:281: never true)
+            part = leidenalg.ModularityVertexPartition
+        else:
+            part = leidenalg.RBERVertexPartition
+        cl = leidenalg.find_partition(g, part, n_iterations=10, resolution_parameter=res, seed=seed)
         self.leiden_cl = cl.membership
+        self.leiden_prep()
+        log_debug('Leiden has finished.')
 
     def analysis(self):
         """The hot-path part of AlonaCell.analysis (alona/cell.py:418-435) incl. its cache rule."""

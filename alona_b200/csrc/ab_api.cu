@@ -1,5 +1,6 @@
 // Context, error reporting, NCCL plumbing (dlopen) and the device scan utility.
 #include "ab_common.cuh"
+#include "ab_peer.cuh"
 
 #include <dlfcn.h>
 #include <limits.h>
@@ -122,54 +123,40 @@ extern "C" int ab_allgather_bytes(ab_ctx *ctx, const void *send, void *recv, int
 // context
 // ---------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------
-// cuBLAS through dlopen: one plain library GEMM (the FP64 Ritz-vector product of the IRLBA restart, measured at
-// 19-21 TFLOP/s for the 1.3M x 70 x 52 shape against 5.8 for the hand-written DMMA kernel, whose A-fragment loads
-// touch the column-major panel in 64-byte pieces).  No link-time dependency; without cuBLAS the own kernel runs.
+// peer-exchange buffers (ab_peer.cuh): allocation, IPC handles, mapping of the other ranks' buffers
 // ---------------------------------------------------------------------------------------
-struct ab_cublas_api {
-    void *handle;
-    int (*Create)(void **);
-    int (*Destroy)(void *);
-    int (*SetStream)(void *, cudaStream_t);
-    int (*Dgemm)(void *, int, int, int, int, int, const double *, const double *, int, const double *, int, const double *,
-                 double *, int);
-};
-static ab_cublas_api *ab_cublas_load() {
-    static ab_cublas_api api;
-    static int state = 0;
-    if (state) return state > 0 ? &api : nullptr;
-    const char *names[] = {"libcublas.so.12", "libcublas.so"};
-    void *h = nullptr;
-    for (const char *nm : names) {
-        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-        if (h) break;
+extern "C" size_t ab_peer_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int ab_peer_alloc(ab_ctx *ctx, void *h_handle) {
+    AB_REQUIRE(ctx && h_handle, "ab_peer_alloc: null argument");
+    AB_REQUIRE(ctx->world <= AB_PEER_MAX, "ab_peer_alloc: world %d exceeds %d", ctx->world, AB_PEER_MAX);
+    AB_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->peer_local) {
+        AB_CUDA(cudaMalloc(&ctx->peer_local, AB_PEER_BYTES));
+        AB_CUDA(cudaMemset(ctx->peer_local, 0, AB_PEER_BYTES));
+        AB_CUDA(cudaDeviceSynchronize());
     }
-    if (!h) { state = -1; return nullptr; }
-    api.handle = h;
-    *(void **)(&api.Create) = dlsym(h, "cublasCreate_v2");
-    *(void **)(&api.Destroy) = dlsym(h, "cublasDestroy_v2");
-    *(void **)(&api.SetStream) = dlsym(h, "cublasSetStream_v2");
-    *(void **)(&api.Dgemm) = dlsym(h, "cublasDgemm_v2");
-    state = (api.Create && api.Destroy && api.SetStream && api.Dgemm) ? 1 : -1;
-    return state > 0 ? &api : nullptr;
+    cudaIpcMemHandle_t h;
+    AB_CUDA(cudaIpcGetMemHandle(&h, ctx->peer_local));
+    memcpy(h_handle, &h, sizeof(h));
+    return 0;
 }
 
-int ab_dgemm_colmajor_rowb(ab_ctx *ctx, int64_t m, int n, int k, const double *A, int64_t lda, const double *B, int ldb,
-                           double *C, int64_t ldc, cudaStream_t st) {
-    if (ctx->cublas_state < 0 || m > INT_MAX || lda > INT_MAX || ldc > INT_MAX) return 2;
-    ab_cublas_api *api = ab_cublas_load();
-    if (!api) { ctx->cublas_state = -1; return 2; }
-    if (ctx->cublas_state == 0) {
-        if (api->Create(&ctx->cublas) != 0 || !ctx->cublas) { ctx->cublas_state = -1; return 2; }
-        ctx->cublas_state = 1;
+extern "C" int ab_peer_open(ab_ctx *ctx, const void *h_handles) {
+    AB_REQUIRE(ctx && h_handles, "ab_peer_open: null argument");
+    AB_REQUIRE(ctx->peer_local, "ab_peer_open: call ab_peer_alloc first");
+    AB_CUDA(cudaSetDevice(ctx->device));
+    for (int q = 0; q < ctx->world; ++q) {
+        if (q == ctx->rank) { ctx->peer_buf[q] = ctx->peer_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)h_handles + (size_t)q * sizeof(h), sizeof(h));
+        AB_CUDA(cudaIpcOpenMemHandle(&ctx->peer_buf[q], h, cudaIpcMemLazyEnablePeerAccess));
     }
-    if (api->SetStream(ctx->cublas, st) != 0) return ab_fail("cublasSetStream failed");
-    const double one = 1.0, zero = 0.0;
-    // column-major: C = A . op(B) with op = T on the row-major B viewed as a column-major [n x k] matrix
-    const int rc = api->Dgemm(ctx->cublas, /*N*/ 0, /*T*/ 1, (int)m, n, k, &one, A, (int)lda, B, ldb, &zero, C, (int)ldc);
-    if (rc != 0) return ab_fail("cublasDgemm failed with status %d", rc);
-    return 0;                                       // (a library kernel: not counted in ab_launch_count)
+    ctx->peer_ready = true;
+    return 0;
 }
+
+extern "C" int ab_peer_enabled(ab_ctx *ctx) { return ctx && ctx->peer_ready ? 1 : 0; }
 
 extern "C" int ab_ctx_create(ab_ctx **out, int device, int rank, int world) {
     AB_REQUIRE(out, "ab_ctx_create: null out");
@@ -200,7 +187,9 @@ extern "C" int ab_ctx_create(ab_ctx **out, int device, int rank, int world) {
 extern "C" int ab_ctx_destroy(ab_ctx *ctx) {
     if (!ctx) return 0;
     if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
-    if (ctx->cublas) { ab_cublas_api *api = ab_cublas_load(); if (api) api->Destroy(ctx->cublas); }
+    for (int q = 0; q < ctx->world && q < AB_PEER_MAX; ++q)
+        if (ctx->peer_ready && q != ctx->rank && ctx->peer_buf[q]) cudaIpcCloseMemHandle(ctx->peer_buf[q]);
+    if (ctx->peer_local) cudaFree(ctx->peer_local);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (int i = 0; i < AB_PROF_SLOTS; ++i) {
         for (cudaEvent_t e : ctx->prof[i].begin) cudaEventDestroy(e);

@@ -44,8 +44,10 @@ struct ab_ctx {
     int64_t launches = 0;
     ab_nccl_api *nccl = nullptr;
     void *comm = nullptr;          // ncclComm_t
-    void *cublas = nullptr;        // cublasHandle_t, created on first use (plain FP64 GEMM of the IRLBA restart)
-    int cublas_state = 0;          // 0 = not tried, 1 = ready, -1 = unavailable
+    void *peer_local = nullptr;    // this rank's peer-exchange buffer (ab_peer.cuh), cudaMalloc'ed
+    void *peer_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // all ranks' buffers, mapped
+    bool peer_ready = false;       // ab_peer_open succeeded on every rank
+    uint32_t peer_seq[4] = {0, 0, 0, 0};   // per-channel instance counters (identical on all ranks)
     int *d_counter = nullptr;      // device scratch: "last block done" tickets (64 ints, kept 0)
     int prof_level = 0;
     ab_prof_slot prof[AB_PROF_SLOTS];
@@ -154,10 +156,5 @@ __device__ __forceinline__ double ab_norm_value(double c, double lib, double sca
 // ---------------------------------------------------------------------------------------
 size_t ab_scan_ws_bytes(int64_t n);
 // out may alias in.  out has n+1 entries, out[n] = total.
-// C[m x n] (column-major, ldc) = A[m x k] (column-major, lda) . B^T, B given ROW-major [k x n] with row stride ldb,
-// through the cuBLAS this process already carries (dlopen, like NCCL).  Returns 0 on success, 2 if cuBLAS cannot be
-// loaded (callers then use their own kernel), 1 on a cuBLAS error.
-int ab_dgemm_colmajor_rowb(ab_ctx *ctx, int64_t m, int n, int k, const double *A, int64_t lda, const double *B, int ldb,
-                           double *C, int64_t ldc, cudaStream_t st);
 int ab_exclusive_scan_i64(ab_ctx *ctx, const int64_t *in, int64_t *out, int64_t n, void *ws,
                           size_t ws_bytes, cudaStream_t stream);

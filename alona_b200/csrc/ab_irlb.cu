@@ -15,6 +15,8 @@
 // Everything is FP64 (HBM-bound; FP64 costs bandwidth only).  All reductions use a fixed
 // order, so a run is bitwise reproducible for a given (n_local, world).
 #include "ab_common.cuh"
+#include "ab_async.cuh"
+#include "ab_peer.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <float.h>
@@ -36,9 +38,9 @@ __device__ __forceinline__ double invcheck(double x) {       // irlb.py:84-92
 }
 
 // "last block" ticket: returns true in exactly one block, after all others have published.
-__device__ __forceinline__ bool last_block_ticket(int *counter) {
+__device__ __forceinline__ bool last_block_ticket(int *counter, bool sys = false) {
     __shared__ int ticket_sm;
-    __threadfence();
+    if (sys) __threadfence_system(); else __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         int t = atomicAdd(counter, 1);
@@ -172,7 +174,8 @@ static constexpr int PD_CB = 16;
 
 __global__ void __launch_bounds__(DOT_THREADS)
 panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols, const double *__restrict__ F,
-                 double *__restrict__ partial /*[grid][IR_MAXWORK]*/, double *__restrict__ out, int *counter) {
+                 double *__restrict__ partial /*[grid][IR_MAXWORK]*/, double *__restrict__ out, int *counter,
+                 AbPeer peer, uint32_t seq_coef) {
     __shared__ double wsum[DOT_THREADS / 32][PD_CB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * DOT_THREADS;
@@ -214,7 +217,13 @@ panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols,
         for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) {
             double t = 0.0;
             for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + (int64_t)b * IR_MAXWORK + l);
-            out[l] = t;
+            if (peer.world > 1) ab_peer_push(peer, AB_CH_COEF, seq_coef, l, t);      // all-reduce, first half: push
+            else out[l] = t;
+        }
+        if (peer.world > 1) {
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) ab_peer_publish(peer, AB_CH_COEF, seq_coef);
         }
     }
 }
@@ -222,11 +231,17 @@ panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols,
 // F -= V[:, :ncols].c ;  fn2 = sum F^2      (irlb.py:79,191).  Thread <-> row, 8 loads in flight.
 __global__ void __launch_bounds__(DOT_THREADS)
 panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols, const double *__restrict__ c,
-                    double *__restrict__ F, double *__restrict__ partial, double *__restrict__ out_fn2, int *counter) {
+                    double *__restrict__ F, double *__restrict__ partial, double *__restrict__ out_fn2, int *counter,
+                    AbPeer peer, uint32_t seq_coef, uint32_t seq_fn2) {
     __shared__ double cs[IR_MAXWORK];
     __shared__ double red[DOT_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) cs[l] = c[l];
+    if (peer.world > 1) {
+        ab_peer_wait(peer, AB_CH_COEF, seq_coef);                                    // all-reduce, second half: sum
+        for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) cs[l] = ab_peer_sum(peer, AB_CH_COEF, seq_coef, l);
+    } else {
+        for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) cs[l] = c[l];
+    }
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * DOT_THREADS;
     double acc = 0.0;
@@ -259,9 +274,24 @@ panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int nco
         if (threadIdx.x == 0) {
             double tt = 0.0;
             for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
-            *out_fn2 = tt;
+            if (peer.world > 1) {
+                ab_peer_push(peer, AB_CH_SCAL, seq_fn2, 0, tt);
+                ab_peer_publish(peer, AB_CH_SCAL, seq_fn2);
+            } else {
+                *out_fn2 = tt;
+            }
         }
     }
+}
+
+// ||F||^2 summed over ranks: the consumer kernels (A.v or the final F scaling) finish the all-reduce themselves;
+// block 0 also leaves the total in scal[SC_FN2] for the kernels that follow on the stream.
+__device__ __forceinline__ double resolve_fn2(const AbPeer &peer, uint32_t seq_fn2, double *__restrict__ scal) {
+    if (peer.world == 1) return scal[SC_FN2];
+    ab_peer_wait(peer, AB_CH_SCAL, seq_fn2);
+    const double t = ab_peer_sum(peer, AB_CH_SCAL, seq_fn2, 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_FN2] = t;
+    return t;
 }
 
 // sum of squares of a vector (start vector normalisation, irlb.py:153)
@@ -396,11 +426,12 @@ __device__ __forceinline__ void av_consume(AvRowState &r, double *acc, const int
 
 __global__ void __launch_bounds__(384, 1)
 av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
-          int64_t n, int H, const double *__restrict__ src, const double *__restrict__ sumsq,
-          double *__restrict__ vdst, int nwarps_cta, double *__restrict__ partial /*[grid][H]*/) {
+          int64_t n, int H, const double *__restrict__ src, double *__restrict__ scal_fn2 /* scal, or NULL: scale 1 */,
+          double *__restrict__ vdst, int nwarps_cta, double *__restrict__ partial /*[grid][H]*/,
+          AbPeer peer, uint32_t seq_fn2) {
     extern __shared__ double acc_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double scale = sumsq ? invcheck(sqrt(*sumsq)) : 1.0;
+    const double scale = scal_fn2 ? invcheck(sqrt(resolve_fn2(peer, seq_fn2, scal_fn2))) : 1.0;
     for (int i = threadIdx.x; i < nwarps_cta * H; i += blockDim.x) acc_sm[i] = 0.0;
     __syncthreads();
     if (warp < nwarps_cta) {
@@ -472,91 +503,131 @@ av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, c
     }
 }
 
-__global__ void av_reduce_kernel(const double *__restrict__ partial, int nparts, int H, double *__restrict__ out) {
+// Sum of the per-CTA partial results of av_kernel in CTA order.  One GPU: the vector goes to `out`.  Sharded: it
+// is this rank's contribution to the all-reduce of A.v and goes straight into every rank's exchange slot over
+// NVLink; the last block raises the flags (the consumer, wstep_kernel, sums the slots in rank order).
+__global__ void __launch_bounds__(128)
+av_reduce_kernel(const double *__restrict__ partial, int nparts, int H, double *__restrict__ out, int *counter,
+                 AbPeer peer, uint32_t seq_vec) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= H) return;
-    double t = 0.0;
-    for (int b = 0; b < nparts; ++b) t += partial[(size_t)b * H + g];
-    out[g] = t;
+    if (g < H) {
+        double t = 0.0;
+        for (int b = 0; b < nparts; ++b) t += partial[(size_t)b * H + g];
+        if (peer.world > 1) ab_peer_push(peer, AB_CH_VEC, seq_vec, g, t);
+        else out[g] = t;
+    }
+    if (peer.world > 1 && last_block_ticket(counter, true)) {
+        if (threadIdx.x == 0) ab_peer_publish(peer, AB_CH_VEC, seq_vec);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
-// left-vector step (irlb.py:173-178 and :214-219), one CTA:
+// left-vector step (irlb.py:173-178 and :214-219):
 //   t = wraw - (sub_prev ? fn*W[:,jd-1] : 0);  t -= W[:, :ncols].(W[:, :ncols]^T t);
 //   s = ||t||;  W[:,jd] = invcheck(s)*t.   Also records B[jb,jb]=s_old, B[jb,jb+1]=fn (irlb.py:196-197).
+// One thread-block cluster of WS_CL CTAs (it was one CTA, 66 us per call, replicated on every rank): CTA c owns the
+// gene rows [H*c/WS_CL, H*(c+1)/WS_CL), keeps its slice of the panel W in shared memory (read once for both CGS
+// passes), and the two global sums (W^T t, ||t||^2) are exchanged through distributed shared memory: every CTA
+// stores its partial into all CTAs' inboxes, one cluster barrier, every CTA adds the WS_CL partials in CTA order.
+// The partition is fixed (WS_CL = 8 whatever the GPU count), so the result does not depend on the sharding.
+// Sharded runs: `wraw` is the sum over ranks of the exchange slots (the all-reduce of A.v finishes here).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-wstep_kernel(const double *__restrict__ wraw, double *__restrict__ W, int H, int jd, int ncols, int sub_prev,
-             double *__restrict__ scal, double *__restrict__ B, int work, int jb) {
-    extern __shared__ double sm[];
-    double *t = sm;                       // H
-    double *c2 = sm + H;                  // IR_MAXWORK
-    double *red = c2 + IR_MAXWORK;        // 33
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+static constexpr int WS_CL = 8;
+static constexpr int WS_THREADS = 512;
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+wstep_kernel(const double *__restrict__ wraw, double *__restrict__ W, int H, int64_t ldw, int jd, int ncols, int sub_prev,
+             double *__restrict__ scal, double *__restrict__ B, int work, int jb, int cache_w,
+             AbPeer peer, uint32_t seq_vec) {
+    extern __shared__ double ws_sm[];
+    __shared__ double inbox_c[WS_CL][IR_MAXWORK];        // partial W^T t of every CTA of the cluster
+    __shared__ double inbox_n[WS_CL];                    // partial ||t||^2
+    __shared__ double c2[IR_MAXWORK];
+    __shared__ double red[WS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = WS_THREADS / 32;
+    const uint32_t cr = ab_cluster_ctarank();
+    const int g0 = (int)(((int64_t)H * cr) / WS_CL), g1 = (int)(((int64_t)H * (cr + 1)) / WS_CL);
+    const int ns = g1 - g0;
+    const int nsp = (H + WS_CL - 1) / WS_CL + 1;         // slice capacity
+    double *t = ws_sm;                                   // [nsp]
+    double *Wc = ws_sm + nsp;                            // [ncols][ns] when cache_w
+    if (peer.world > 1) ab_peer_wait(peer, AB_CH_VEC, seq_vec);
     const double fn = sqrt(scal[SC_FN2]);
-    if (threadIdx.x == 0 && jb >= 0) {
+    if (cr == 0 && threadIdx.x == 0 && jb >= 0) {
         B[jb * work + jb] = scal[SC_S];
         if (jb + 1 < work) B[jb * work + jb + 1] = fn;
     }
-    for (int g = threadIdx.x; g < H; g += blockDim.x) {
-        double v = wraw[g];
-        if (sub_prev) v = __dsub_rn(v, __dmul_rn(fn, W[(size_t)(jd - 1) * H + g]));
+    for (int g = threadIdx.x; g < ns; g += WS_THREADS) {
+        double v = peer.world > 1 ? ab_peer_sum(peer, AB_CH_VEC, seq_vec, g0 + g) : wraw[g0 + g];
+        if (sub_prev) v = __dsub_rn(v, __dmul_rn(fn, W[(size_t)(jd - 1) * ldw + g0 + g]));
         t[g] = v;
     }
+    if (cache_w)
+        for (int l = warp; l < ncols; l += nwarp)
+            for (int g = lane; g < ns; g += 32) Wc[(size_t)l * ns + g] = W[(size_t)l * ldw + g0 + g];
     __syncthreads();
+    ab_cluster_sync();                                   // every CTA of the cluster is running: its inboxes may be written
     if (ncols > 0) {
-        // four independent partial sums per lane keep four loads of the (L2-resident) panel in flight
         for (int l = warp; l < ncols; l += nwarp) {
-            const double *wl = W + (size_t)l * H;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double *wl = cache_w ? Wc + (size_t)l * ns : W + (size_t)l * ldw + g0;
+            double a0 = 0.0, a1 = 0.0;
             int g = lane;
-            for (; g + 96 < H; g += 128) {
+            for (; g + 32 < ns; g += 64) {
                 a0 = fma(wl[g], t[g], a0);
                 a1 = fma(wl[g + 32], t[g + 32], a1);
-                a2 = fma(wl[g + 64], t[g + 64], a2);
-                a3 = fma(wl[g + 96], t[g + 96], a3);
             }
-            for (; g < H; g += 32) a0 = fma(wl[g], t[g], a0);
-            const double acc = ab_warp_sum_f64((a0 + a1) + (a2 + a3));
-            if (lane == 0) c2[l] = acc;
+            if (g < ns) a0 = fma(wl[g], t[g], a0);
+            const double acc = ab_warp_sum_f64(a0 + a1);
+            if (lane < WS_CL) ab_st_cluster_f64(ab_mapa(ab_smem_u32(&inbox_c[cr][l]), lane), acc);
+        }
+        ab_cluster_sync();
+        for (int l = threadIdx.x; l < ncols; l += WS_THREADS) {
+            double a = 0.0;
+#pragma unroll
+            for (int q = 0; q < WS_CL; ++q) a += inbox_c[q][l];
+            c2[l] = a;
         }
         __syncthreads();
-        for (int g = threadIdx.x; g < H; g += blockDim.x) {
-            const double *wg = W + g;
+        for (int g = threadIdx.x; g < ns; g += WS_THREADS) {
+            const double *wg = cache_w ? Wc + g : W + g0 + g;
+            const size_t st = cache_w ? (size_t)ns : (size_t)ldw;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int l = 0;
             for (; l + 3 < ncols; l += 4) {
-                a0 = fma(wg[(size_t)l * H], c2[l], a0);
-                a1 = fma(wg[(size_t)(l + 1) * H], c2[l + 1], a1);
-                a2 = fma(wg[(size_t)(l + 2) * H], c2[l + 2], a2);
-                a3 = fma(wg[(size_t)(l + 3) * H], c2[l + 3], a3);
+                a0 = fma(wg[(size_t)l * st], c2[l], a0);
+                a1 = fma(wg[(size_t)(l + 1) * st], c2[l + 1], a1);
+                a2 = fma(wg[(size_t)(l + 2) * st], c2[l + 2], a2);
+                a3 = fma(wg[(size_t)(l + 3) * st], c2[l + 3], a3);
             }
-            for (; l < ncols; ++l) a0 = fma(wg[(size_t)l * H], c2[l], a0);
+            for (; l < ncols; ++l) a0 = fma(wg[(size_t)l * st], c2[l], a0);
             t[g] = __dsub_rn(t[g], (a0 + a1) + (a2 + a3));
         }
         __syncthreads();
     }
     double acc = 0.0;
-    for (int g = threadIdx.x; g < H; g += blockDim.x) acc = fma(t[g], t[g], acc);
+    for (int g = threadIdx.x; g < ns; g += WS_THREADS) acc = fma(t[g], t[g], acc);
     acc = ab_warp_sum_f64(acc);
     if (lane == 0) red[warp] = acc;
     __syncthreads();
     if (warp == 0) {
         double v = lane < nwarp ? red[lane] : 0.0;
         v = ab_warp_sum_f64(v);
-        if (lane == 0) red[32] = v;
+        if (lane < WS_CL) ab_st_cluster_f64(ab_mapa(ab_smem_u32(&inbox_n[cr]), lane), v);
     }
-    __syncthreads();
-    const double s = sqrt(red[32]);
+    ab_cluster_sync();
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < WS_CL; ++q) tot += inbox_n[q];
+    const double s = sqrt(tot);
     const double sinv = invcheck(s);
-    for (int g = threadIdx.x; g < H; g += blockDim.x) W[(size_t)jd * H + g] = __dmul_rn(sinv, t[g]);
-    if (threadIdx.x == 0) scal[SC_S] = s;
+    for (int g = threadIdx.x; g < ns; g += WS_THREADS) W[(size_t)jd * ldw + g0 + g] = __dmul_rn(sinv, t[g]);
+    if (cr == 0 && threadIdx.x == 0) scal[SC_S] = s;
 }
 
 // last Lanczos step of a pass (j = work-1): F *= invcheck(fn); B[j,j] = s  (irlb.py:193,221)
-__global__ void fscale_kernel(double *__restrict__ F, int64_t n, const double *__restrict__ scal,
-                              double *__restrict__ B, int work, int jb) {
-    const double inv = invcheck(sqrt(scal[SC_FN2]));
+__global__ void fscale_kernel(double *__restrict__ F, int64_t n, double *__restrict__ scal,
+                              double *__restrict__ B, int work, int jb, AbPeer peer, uint32_t seq_fn2) {
+    const double inv = invcheck(sqrt(resolve_fn2(peer, seq_fn2, scal)));
     if (blockIdx.x == 0 && threadIdx.x == 0) B[jb * work + jb] = scal[SC_S];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         F[i] = __dmul_rn(inv, F[i]);
@@ -708,6 +779,204 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The same SVD on one thread-block cluster of SV_CL CTAs.  One-sided Jacobi is a chain of ~520 dependent rounds
+// (dot -> reduce -> divide / sqrt / rsqrt -> rotate -> barrier; ~2700 cycles each on one SM: 0.75 ms per restart,
+// replicated on every rank, 19 % of the 8-GPU step).  Here the ROWS of G are split across the cluster: CTA c keeps
+// rows [m*c/SV_CL, m*(c+1)/SV_CL) of every column in shared memory.  A round = partial inner products of the pairs
+// over the local rows -> every CTA sends its partials into all CTAs' inboxes with st.async (distributed shared
+// memory; each store completes 8 bytes of the RECEIVER's mbarrier, so a CTA only waits on its own barrier - no
+// cluster-wide barrier in the round) -> every CTA adds the SV_CL partials in CTA order, so all CTAs hold
+// bit-identical inner products, derive the same rotation and apply it to their own rows.  Running column norms, the
+// "dirty" flag and the pair schedule are replicated and stay identical.  Right vectors as before:
+// V = B^T U diag(1/s), formed from G written to global memory.
+// ---------------------------------------------------------------------------------------
+static constexpr int SV_CL = 8;
+static constexpr int SV_LP = 4;                          // lanes per column pair
+static constexpr int SV_THREADS = (IR_MAXWORK / 2) * SV_LP;      // 256: one pass covers every pair of a round
+static constexpr int SV_RS = IR_MAXWORK / SV_CL + 1;     // row-slice stride (17: odd -> conflict-free column walks)
+
+__global__ void __launch_bounds__(SV_THREADS, 1)
+svd_cluster_kernel(const double *__restrict__ B, int work, double *__restrict__ Ub, double *__restrict__ sb,
+                   double *__restrict__ Vb, double *__restrict__ Gws /* work*work scratch, G column-major */,
+                   double *__restrict__ scal, int *__restrict__ ctrl, double *__restrict__ R, int nu, double tol,
+                   int it, int keep_prev) {
+    __shared__ double Gs[IR_MAXWORK * SV_RS];            // Gs[c * SV_RS + (r - r0)]
+    __shared__ double inbox[2][SV_CL][IR_MAXWORK / 2];   // partial inner products, double-buffered by round parity
+    __shared__ double inbox_n[SV_CL][IR_MAXWORK];        // partial squared column norms
+    __shared__ double cn[IR_MAXWORK];
+    __shared__ double nrm[IR_MAXWORK];
+    __shared__ int order[IR_MAXWORK];
+    __shared__ int rot_sm, conv_sm;
+    __shared__ __align__(8) uint64_t rbar[2];            // "round r's partials have all landed", by round parity
+    const int m = work;
+    const uint32_t cr = ab_cluster_ctarank();
+    if (threadIdx.x == 0) {
+        ab_mbar_init(rbar + 0, 1);
+        ab_mbar_init(rbar + 1, 1);
+        ab_mbar_init_fence();
+    }
+    const int r0 = (m * (int)cr) / SV_CL, r1 = (m * ((int)cr + 1)) / SV_CL, nr = r1 - r0;
+    for (int e = threadIdx.x; e < m * nr; e += SV_THREADS) {
+        const int c = e / nr, r = e - c * nr;
+        Gs[c * SV_RS + r] = B[(r0 + r) * m + c];
+    }
+    __syncthreads();
+    ab_cluster_sync();                                   // all CTAs of the cluster run: inboxes may be written
+
+    // squared column norms, summed over the cluster (partials -> every CTA's inbox_n -> barrier -> CTA-order sum)
+    auto refresh_norms = [&]() {
+        for (int c = threadIdx.x; c < m; c += SV_THREADS) {
+            double acc = 0.0;
+            for (int r = 0; r < nr; ++r) acc = fma(Gs[c * SV_RS + r], Gs[c * SV_RS + r], acc);
+            const uint32_t a = ab_smem_u32(&inbox_n[cr][c]);
+#pragma unroll
+            for (int q = 0; q < SV_CL; ++q) ab_st_cluster_f64(ab_mapa(a, q), acc);
+        }
+        ab_cluster_sync();
+        for (int c = threadIdx.x; c < m; c += SV_THREADS) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < SV_CL; ++q) t += inbox_n[q][c];
+            cn[c] = t;
+        }
+        __syncthreads();
+        ab_cluster_sync();                               // inbox_n is free again before anyone refills it
+    };
+
+    const int mp = (m + 1) & ~1;
+    const int pr = threadIdx.x / SV_LP, hl = threadIdx.x % SV_LP;
+    uint32_t round_id = 0;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        if (threadIdx.x == 0) rot_sm = 0;
+        refresh_norms();
+        for (int round = 0; round < mp - 1; ++round, ++round_id) {
+            // circle method: player mp-1 fixed, the others rotate
+            const int a = (pr == 0) ? mp - 1 : (round + pr) % (mp - 1);
+            const int b = (round + mp - 1 - pr) % (mp - 1);
+            const int p = min(a, b), q = max(a, b);
+            const bool valid = pr < mp / 2 && q < m;
+            double *gp = Gs + (valid ? p : 0) * SV_RS, *gq = Gs + (valid ? q : 0) * SV_RS;
+            double ga = 0.0;
+            if (valid)
+                for (int r = hl; r < nr; r += SV_LP) ga = fma(gp[r], gq[r], ga);
+#pragma unroll
+            for (int o = SV_LP / 2; o > 0; o >>= 1) ga += ab_shfl_xor_f64(ga, o);
+            const int par = round_id & 1;
+            // a barrier is re-armed for round r+2 only after this CTA has consumed round r (two rounds ago), and a
+            // peer can only send round r+2 after it received this CTA's round r+1, sent after that consumption
+            if (threadIdx.x == 0) ab_mbar_expect_tx(rbar + par, (uint32_t)(SV_CL * (mp / 2) * 8));
+            if (pr < mp / 2) {
+                const uint32_t ad = ab_smem_u32(&inbox[par][cr][pr]), bd = ab_smem_u32(rbar + par);
+#pragma unroll
+                for (int qq = hl; qq < SV_CL; qq += SV_LP) ab_st_async_f64(ab_mapa(ad, qq), ga, ab_mapa(bd, qq));
+            }
+            ab_mbar_wait(rbar + par, (round_id >> 1) & 1);
+            // rotation parameters: one lane per pair runs the FP64 divide / sqrt / rsqrt chain (every lane of the
+            // pair doing it was most of a round on a part with ~8 FP64 operations per clock and SM), the others
+            // receive cos / sin by shuffle
+            double cs = 1.0, sn = 0.0;
+            if (valid && hl == 0) {
+                double gs = 0.0;
+#pragma unroll
+                for (int qq = 0; qq < SV_CL; ++qq) gs += inbox[par][qq][pr];
+                const double al = cn[p], be = cn[q];
+                const double g2 = gs * gs, ab2 = al * be;
+                // same thresholds as the one-CTA kernel: rotate down to rounding level, "dirty" only above 1e-14
+                if (g2 > 1e-30 * ab2 && fabs(gs) > 1e-300) {
+                    if (g2 > 1e-28 * ab2) rot_sm = 1;
+                    const double dd = be - al;
+                    const double tt = (2.0 * gs) / (dd + (dd >= 0.0 ? 1.0 : -1.0) * sqrt(fma(dd, dd, 4.0 * g2)));
+                    cs = rsqrt(fma(tt, tt, 1.0));
+                    sn = cs * tt;
+                    cn[p] = al - tt * gs;
+                    cn[q] = be + tt * gs;
+                }
+            }
+            cs = ab_shfl_f64(cs, (threadIdx.x & 31) & ~(SV_LP - 1));
+            sn = ab_shfl_f64(sn, (threadIdx.x & 31) & ~(SV_LP - 1));
+            if (valid && sn != 0.0) {
+                for (int r = hl; r < nr; r += SV_LP) {
+                    const double x = gp[r], y = gq[r];
+                    gp[r] = cs * x - sn * y; gq[r] = sn * x + cs * y;
+                }
+            }
+            __syncthreads();
+        }
+        const int any = rot_sm;
+        __syncthreads();
+        sweeps = sweep + 1;
+        if (!any) break;
+    }
+    if (cr == 0 && threadIdx.x == 0) ctrl[CT_ROT] = sweeps;
+    // singular values = column norms; sort descending by counting rank (ties by index)
+    refresh_norms();
+    for (int c = threadIdx.x; c < m; c += SV_THREADS) nrm[c] = sqrt(cn[c]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < m; c += SV_THREADS) {
+        int rank = 0;
+        for (int o = 0; o < m; ++o) rank += (nrm[o] > nrm[c]) || (nrm[o] == nrm[c] && o < c);
+        order[rank] = c;
+    }
+    __syncthreads();
+    // left vectors (own rows) and G to global memory for the right-vector products
+    for (int e = threadIdx.x; e < m * nr; e += SV_THREADS) {
+        const int i = e / nr, r = e - i * nr;
+        const int c = order[i];
+        const double sv = nrm[c];
+        const double g = Gs[c * SV_RS + r];
+        Ub[(r0 + r) * m + i] = sv > 0.0 ? g / sv : 0.0;
+        Gws[(size_t)c * m + r0 + r] = g;
+    }
+    if (cr == 0)
+        for (int i = threadIdx.x; i < m; i += SV_THREADS) sb[i] = nrm[order[i]];
+    __threadfence();
+    __syncthreads();
+    ab_cluster_sync();
+    // right vector i = B^T u_i / s_i = B^T G[:, c] / s_i^2 ; this CTA forms rows [r0, r1) of Vb
+    for (int e = threadIdx.x; e < m * nr; e += SV_THREADS) {
+        const int i = e % m, r = r0 + e / m;
+        const int c = order[i];
+        const double sv = nrm[c];
+        double acc = 0.0;
+        const double *gc = Gws + (size_t)c * m;
+        for (int l = 0; l < m; ++l) acc = fma(B[l * m + r], __ldcg(gc + l), acc);
+        Vb[r * m + i] = sv > 0.0 ? acc / (sv * sv) : 0.0;
+    }
+    // residuals and restart bookkeeping (irlb.py:225-234): the CTA that owns the last row of U
+    if (cr == SV_CL - 1) {
+        const double fn = sqrt(scal[SC_FN2]);
+        double smax = nrm[order[0]];
+        if (it > 0) smax = fmax(smax, scal[SC_SMAX]);
+        if (threadIdx.x == 0) conv_sm = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += SV_THREADS) {
+            const int c = order[i];
+            const double sv = nrm[c];
+            const double ulast = sv > 0.0 ? Gs[c * SV_RS + (m - 1 - r0)] / sv : 0.0;
+            const double res = __dmul_rn(fn, ulast);
+            R[i] = res;
+            if (i < nu && fabs(res) < tol * smax) atomicAdd(&conv_sm, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            scal[SC_SMAX] = smax;
+            const int conv = conv_sm;
+            ctrl[CT_CONV] = conv;
+            if (conv >= nu) {
+                ctrl[CT_DONE] = 1;
+                ctrl[CT_KEEP] = keep_prev;
+            } else {
+                int k = max(conv + nu, keep_prev);
+                k = min(k, m - 3);
+                ctrl[CT_DONE] = 0;
+                ctrl[CT_KEEP] = k;
+            }
+        }
+    }
+}
+
 // B = 0; B[l,l] = sb[l] (l<keep); B[l,keep] = R[l]   (irlb.py:240-244)
 __global__ void reset_b_kernel(double *__restrict__ B, int work, const double *__restrict__ sb,
                                const double *__restrict__ R, int keep) {
@@ -722,15 +991,29 @@ __global__ void reset_b_kernel(double *__restrict__ B, int work, const double *_
 
 // ---------------------------------------------------------------------------------------
 // Ritz update: out[:, c] = X[:, :work] . M[:, c]  for c < ncols     (irlb.py:238,246,249-250)
-// X column-major (ld), M row-major work x work (use columns 0..ncols-1).
-// out column-major (ldo) or, if rowmajor_out, row-major [n x ncols] scaled by colscale[c].
+// X column-major (ld even, >= n), M row-major work x work (columns 0..ncols-1 used).
+// out column-major (ldo even, >= n) or, if rowmajor_out, row-major [n x ncols] scaled by colscale[c].
+//
+// The one GEMM-shaped step of IRLBA (n x work times work x keep, FP64, 1.3 GB / 6e9 FMA per restart at C3).  The
+// products run on the FP64 tensor path (same 36 TFLOP/s peak as the FP64 CUDA cores on this part, measured with
+// benchmarks/micro_atomics.cu, but a quarter of the instructions)
+// (mma.sync.m8n8k4.f64, DMMA); what the first version got wrong was feeding the A fragments straight from the
+// column-major panel in global memory (four 64-byte pieces per load).  Here a producer warp streams the panel through
+// shared memory with 1-D bulk copies (one 1 KB column segment per copy, one copy per lane, completion on an
+// mbarrier, a ring of RZ_ST stages of RZ_KC columns each) and the eight consumer warps read conflict-free fragments:
+// the column stride of the staged tile is RZ_TR + 4 doubles, so the four k-rows of a fragment land 8 banks apart.
+// The result tile is staged in shared memory and leaves through bulk stores (1 KB contiguous per output column).
+// A warp owns 16 rows x 64 output columns (16 DMMA per k-step from 2 A + 8 B fragment loads).
 // ---------------------------------------------------------------------------------------
-// FP64 on the CUDA cores of this part runs at ~8 FMA/clk/SM (measured: 4.4 TFLOP/s for a register-tiled
-// DFMA kernel), so the one GEMM-shaped step of IRLBA (n x work times work x ncols, 6e9 FMA per restart at C3)
-// goes to the FP64 tensor path: mma.sync.m8n8k4.f64 (DMMA).  A warp owns RG*8 rows and all output columns;
-// M is staged in shared memory (zero padded to multiples of 4 x 8), X is read straight from global memory
-// in the A-fragment layout (lane -> row lane/4, k lane%4: four 64-byte segments per load).
-static constexpr int RZ_WARPS = 8;
+static constexpr int RZ_TR = 128;                // rows per tile
+static constexpr int RZ_NC = 64;                 // output columns per CTA (grid.y tiles wider products)
+static constexpr int RZ_KC = 24;                 // k-rows (panel columns) per pipeline stage
+static constexpr int RZ_ST = 3;                  // stages
+static constexpr int RZ_XS = RZ_TR + 4;          // staged-tile column stride (doubles): k-rows 8 banks apart
+static constexpr int RZ_MS = RZ_NC + 4;          // M row stride (doubles)
+static constexpr int RZ_CS = RZ_TR + 2;          // result-tile column stride (doubles): conflict-free fragment stores
+static constexpr int RZ_CONSUMERS = 8;           // consumer warps; warp RZ_CONSUMERS is the producer
+static constexpr int RZ_THREADS = (RZ_CONSUMERS + 1) * 32;
 
 __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -738,103 +1021,135 @@ __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-// m16n8k8: rows {lane/4, lane/4+8}, k {lane%4, lane%4+4}; one instruction = four m8n8k4 (the Ampere shape, which
-// newer parts execute at a reduced rate)
-__device__ __forceinline__ void dmma16x8x8(double &c0, double &c1, double &c2, double &c3, double a0, double a1, double a2,
-                                           double a3, double b0, double b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+d"(c0), "+d"(c1), "+d"(c2), "+d"(c3)
-                 : "d"(a0), "d"(a1), "d"(a2), "d"(a3), "d"(b0), "d"(b1));
+static size_t ritz_smem_bytes(int work) {
+    const int kpad = (work + 3) & ~3;
+    return ((size_t)kpad * RZ_MS + (size_t)RZ_ST * RZ_KC * RZ_XS + (size_t)RZ_NC * RZ_CS) * 8 + 2 * RZ_ST * 8 + 64;
 }
 
-template <int NCBT, int RG>
-__global__ void __launch_bounds__(RZ_WARPS * 32)
+__global__ void __launch_bounds__(RZ_THREADS, 1)
 ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const double *__restrict__ M, int ncols,
             double *__restrict__ out, int64_t ldo, int rowmajor_out, const double *__restrict__ colscale,
             double *__restrict__ out2 /* optional second row-major output without scaling */) {
-    extern __shared__ double smr[];                       // ms[kpad][NCBT*8]
-    constexpr int MC = NCBT * 8;
-    const int kpad = (work + 7) & ~7;                     // zero rows up to a multiple of 8 (two k-steps per iteration)
-    for (int e = threadIdx.x; e < kpad * MC; e += blockDim.x) {
-        const int l = e / MC, c = e - l * MC;
-        smr[e] = (l < work && c < ncols) ? M[l * work + c] : 0.0;
-    }
-    __syncthreads();
+    extern __shared__ __align__(128) unsigned char rz_raw[];
+    const int kpad = (work + 3) & ~3;
+    double *Ms = reinterpret_cast<double *>(rz_raw);                  // [kpad][RZ_MS]
+    double *Xs = Ms + (size_t)kpad * RZ_MS;                           // [RZ_ST][RZ_KC][RZ_XS]
+    double *Cs = Xs + (size_t)RZ_ST * RZ_KC * RZ_XS;                  // [RZ_NC][RZ_CS]
+    uint64_t *full = reinterpret_cast<uint64_t *>(Cs + (size_t)RZ_NC * RZ_CS);
+    uint64_t *empty = full + RZ_ST;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ncb = (ncols + 7) >> 3;
-    const int ar = lane >> 2, ak = lane & 3;              // A fragment: row ar, k ak;  B fragment: k ak, col ar
-    const int64_t row0 = ((int64_t)blockIdx.x * RZ_WARPS + warp) * (8 * RG);
-    if (row0 >= n) return;
-    double acc[RG][NCBT][2];
-#pragma unroll
-    for (int g = 0; g < RG; ++g)
-#pragma unroll
-        for (int j = 0; j < NCBT; ++j) { acc[g][j][0] = 0.0; acc[g][j][1] = 0.0; }
-    const double *xr[RG];
-    bool ok[RG];
-#pragma unroll
-    for (int g = 0; g < RG; ++g) {
-        const int64_t r = row0 + 8 * g + ar;
-        ok[g] = r < n;
-        xr[g] = X + (ok[g] ? r : 0);
+    const int c0 = blockIdx.y * RZ_NC;                                // first output column of this CTA
+    const int nc = min(RZ_NC, ncols - c0);
+    const int nchunks = (work + RZ_KC - 1) / RZ_KC;
+    const int64_t ntiles = (n + RZ_TR - 1) / RZ_TR;
+
+    for (int e = threadIdx.x; e < kpad * RZ_MS; e += blockDim.x) {
+        const int l = e / RZ_MS, c = e - l * RZ_MS;
+        Ms[e] = (l < work && c < nc) ? M[l * work + c0 + c] : 0.0;
     }
-    for (int k0 = 0; k0 < kpad; k0 += 8) {                // two k-steps per iteration: four loads in flight
-        double a[2][RG];
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int g = 0; g < RG; ++g) {
-                const int l = k0 + 4 * h + ak;
-                a[h][g] = (ok[g] && l < work) ? xr[g][(int64_t)l * ld] : 0.0;
+    for (int e = threadIdx.x; e < RZ_ST * RZ_KC * RZ_XS; e += blockDim.x) Xs[e] = 0.0;   // pad rows stay finite
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < RZ_ST; ++s2) { ab_mbar_init(full + s2, 1); ab_mbar_init(empty + s2, RZ_CONSUMERS); }
+        ab_mbar_init_fence();
+    }
+    ab_fence_proxy_async();
+    __syncthreads();
+
+    if (warp == RZ_CONSUMERS) {
+        // ---------------- producer warp: lane l issues the bulk copy of k-row l of every (tile, k-chunk) ------------
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const double *xt = X + tile * RZ_TR;
+            const uint32_t cb = (uint32_t)min((int64_t)RZ_TR, ld - tile * RZ_TR) * 8;     // last tile: clipped to ld
+            for (int ch = 0; ch < nchunks; ++ch, ++it) {
+                const int st = it % RZ_ST;
+                if (it >= RZ_ST) ab_mbar_wait(empty + st, ((it / RZ_ST) - 1) & 1);
+                const int k0 = ch * RZ_KC, nk = min(RZ_KC, work - k0);
+                if (lane == 0) ab_mbar_expect_tx(full + st, (uint32_t)nk * cb);
+                __syncwarp();
+                if (lane < nk)
+                    ab_bulk_g2s(Xs + ((size_t)st * RZ_KC + lane) * RZ_XS, xt + (int64_t)(k0 + lane) * ld, cb, full + st);
             }
-        if (RG == 2) {
-            const double *mrow0 = smr + (size_t)(k0 + ak) * MC + ar;
-            const double *mrow1 = mrow0 + (size_t)4 * MC;            // rows >= kpad read as zero: smr is padded to 8
+        }
+        return;
+    }
+
+    // ---------------- consumers: warp w owns rows [16w, 16w+16) of the tile and all RZ_NC columns -----------------
+    const int ar = lane >> 2, ak = lane & 3;              // A fragment: row ar, k ak;  B fragment: k ak, col ar
+    const int nb = (nc + 7) >> 3;                         // live 8-column blocks
+    uint32_t it = 0;
+    bool stored = false;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        double acc[2][8][2];
 #pragma unroll
-            for (int j = 0; j < NCBT; ++j) {
-                if (j < ncb)
-                    dmma16x8x8(acc[0][j][0], acc[0][j][1], acc[RG - 1][j][0], acc[RG - 1][j][1], a[0][0], a[0][RG - 1], a[1][0],
-                               a[1][RG - 1], mrow0[8 * j], mrow1[8 * j]);
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[g][j][0] = 0.0; acc[g][j][1] = 0.0; }
+        for (int ch = 0; ch < nchunks; ++ch, ++it) {
+            const int st = it % RZ_ST;
+            ab_mbar_wait(full + st, (it / RZ_ST) & 1);
+            const int k0 = ch * RZ_KC;
+            const int ksteps = (min(RZ_KC, work - k0) + 3) >> 2;
+            const double *xs = Xs + (size_t)st * RZ_KC * RZ_XS + (size_t)ak * RZ_XS + 16 * warp + ar;
+            const double *ms = Ms + (size_t)(k0 + ak) * RZ_MS + ar;
+#pragma unroll 2
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const double a0 = xs[(size_t)ks * 4 * RZ_XS], a1 = xs[(size_t)ks * 4 * RZ_XS + 8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < nb) {
+                        const double b = ms[(size_t)ks * 4 * RZ_MS + 8 * j];
+                        dmma8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
+                        dmma8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ab_mbar_arrive(empty + st);
+        }
+        // C fragment: row lane/4, columns (lane%4)*2 + {0,1} of each 8-column block
+        const int64_t row0 = tile * RZ_TR;
+        if (rowmajor_out) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int64_t r = row0 + 16 * warp + 8 * g + ar;
+                if (r >= n) continue;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int col = c0 + 8 * j + 2 * ak + e;
+                        if (j < nb && col < ncols) {
+                            const double v = acc[g][j][e];
+                            out[r * (int64_t)ncols + col] = __dmul_rn(v, colscale ? colscale[col] : 1.0);
+                            if (out2) out2[r * (int64_t)ncols + col] = v;
+                        }
+                    }
             }
         } else {
+            // the previous tile's bulk stores must have finished reading Cs
+            if (warp == 0 && stored) ab_bulk_wait_read0();
+            asm volatile("bar.sync 1, %0;" ::"n"(RZ_CONSUMERS * 32) : "memory");
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (k0 + 4 * h >= kpad) break;
-                const double *mrow = smr + (size_t)(k0 + 4 * h + ak) * MC + ar;
+            for (int g = 0; g < 2; ++g)
 #pragma unroll
-                for (int j = 0; j < NCBT; ++j) {
-                    if (j < ncb) {
-                        const double b = mrow[8 * j];
+                for (int j = 0; j < 8; ++j)
 #pragma unroll
-                        for (int g = 0; g < RG; ++g) dmma8x8x4(acc[g][j][0], acc[g][j][1], a[h][g], b);
-                    }
-                }
+                    for (int e = 0; e < 2; ++e)
+                        if (j < nb) Cs[(size_t)(8 * j + 2 * ak + e) * RZ_CS + 16 * warp + 8 * g + ar] = acc[g][j][e];
+            ab_fence_proxy_async();
+            asm volatile("bar.sync 1, %0;" ::"n"(RZ_CONSUMERS * 32) : "memory");
+            // one bulk store per output column, issued by the lanes of warp 0 (each tracks its own bulk group)
+            if (warp == 0) {
+                const uint32_t cb = (uint32_t)min((int64_t)RZ_TR, ldo - row0) * 8;
+                for (int c = lane; c < nc; c += 32)
+                    ab_bulk_s2g(out + (int64_t)(c0 + c) * ldo + row0, Cs + (size_t)c * RZ_CS, cb);
+                ab_bulk_commit();
+                stored = true;
             }
         }
     }
-    // C fragment: row lane/4, columns (lane%4)*2 + {0,1} of each 8-column block
-#pragma unroll
-    for (int g = 0; g < RG; ++g) {
-        const int64_t r = row0 + 8 * g + ar;
-        if (r >= n) continue;
-#pragma unroll
-        for (int j = 0; j < NCBT; ++j) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int col = 8 * j + 2 * ak + e;
-                if (j < ncb && col < ncols) {
-                    const double v = acc[g][j][e];
-                    if (rowmajor_out) {
-                        const double sc = colscale ? colscale[col] : 1.0;
-                        out[r * (int64_t)ncols + col] = __dmul_rn(v, sc);
-                        if (out2) out2[r * (int64_t)ncols + col] = v;
-                    } else {
-                        out[(int64_t)col * ldo + r] = v;
-                    }
-                }
-            }
-        }
-    }
+    if (warp == 0 && stored) ab_bulk_wait0();                 // global writes complete before the CTA retires
 }
 
 __global__ void copy_vec_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n) {
@@ -860,6 +1175,16 @@ static int irlb_work_dim(int nval, int64_t n_total) {
     return (int)w;
 }
 
+// leading dimension of the column-major panels: even (16-byte aligned columns for the bulk copies of ritz_kernel) and
+// with a column stride that is not close to a multiple of 4 KB (panel_dot / panel_update stream 8-16 columns at once:
+// a stride of 64 rows x 8 B cost them 11 % against the odd stride the first version happened to have)
+static int64_t irlb_ld(int64_t rows) {
+    int64_t ld = (std::max<int64_t>(rows, 2) + 1) & ~(int64_t)1;
+    const int64_t r = (ld * 8) & 4095;
+    if (r < 256 || r > 3840) ld += 64;
+    return ld;
+}
+
 static int av_warps_for(int H) {
     int w = (int)((216 * 1024) / ((size_t)H * 8));
     if (w > 12) w = 12;
@@ -871,11 +1196,13 @@ static size_t irlb_layout(int64_t n, int H, int nval, int64_t n_total_hint, int 
     const int work = irlb_work_dim(nval, n_total_hint);
     ab_arena a(ws ? ws : (void *)256, ws ? bytes : (size_t)-1 / 2);
     IrlbWs w;
-    const int64_t ld = n > 0 ? n : 1;
+    // (ritz_kernel clips its last row tile to ld, so its bulk copies never leave a column)
+    const int64_t ld = irlb_ld(n);
+    const int64_t ldw = irlb_ld(H);
     w.V = a.take<double>((size_t)ld * work);
     w.V2 = a.take<double>((size_t)ld * work);
-    w.W = a.take<double>((size_t)H * work);
-    w.W2 = a.take<double>((size_t)H * work);
+    w.W = a.take<double>((size_t)ldw * work);
+    w.W2 = a.take<double>((size_t)ldw * work);
     w.F = a.take<double>(ld);
     w.B = a.take<double>((size_t)work * work);
     w.Ub = a.take<double>((size_t)work * work);
@@ -945,14 +1272,26 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     AB_REQUIRE(need != 0, "ab_irlb: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int H = n_hvg;
-    const int64_t n = n_local, ld = n_local > 0 ? n_local : 1;
+    const int64_t n = n_local, ld = irlb_ld(n_local), ldw = irlb_ld(H);
     int *cnt = ctx->d_counter;
+    // small all-reduces: fused one-shot pushes over NVLink peer memory when the exchange buffers are mapped
+    // (ab_peer_open), ncclAllReduce between the kernels otherwise
+    AbPeer peer{};
+    peer.world = 1;
+    peer.rank = 0;
+    const bool fused = ctx->world > 1 && ctx->peer_ready && H <= AB_PEER_VEC && !getenv("AB_IRLB_NCCL");
+    if (fused) {
+        peer.world = ctx->world;
+        peer.rank = ctx->rank;
+        for (int q = 0; q < ctx->world; ++q) peer.buf[q] = (char *)ctx->peer_buf[q];
+    }
+    uint32_t *seq = ctx->peer_seq;
 
     ab_prof_begin(ctx, AB_PROF_IRLB_TOTAL, st);
     AB_CUDA(cudaMemsetAsync(w.V, 0, (size_t)ld * work * 8, st));
     AB_CUDA(cudaMemsetAsync(w.V2, 0, (size_t)ld * work * 8, st));
-    AB_CUDA(cudaMemsetAsync(w.W, 0, (size_t)H * work * 8, st));
-    AB_CUDA(cudaMemsetAsync(w.W2, 0, (size_t)H * work * 8, st));
+    AB_CUDA(cudaMemsetAsync(w.W, 0, (size_t)ldw * work * 8, st));
+    AB_CUDA(cudaMemsetAsync(w.W2, 0, (size_t)ldw * work * 8, st));
     AB_CUDA(cudaMemsetAsync(w.B, 0, (size_t)work * work * 8, st));
     AB_CUDA(cudaMemsetAsync(w.scal, 0, SC_COUNT * 8, st));
     AB_CUDA(cudaMemsetAsync(w.ctrl, 0, CT_COUNT * 4, st));
@@ -986,36 +1325,45 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
 
     const size_t av_smem = (size_t)w.av_warps * H * 8;
     AB_CUDA(cudaFuncSetAttribute(av_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
-    const size_t ws_smem = ((size_t)H + IR_MAXWORK + 40) * 8;
+    // wstep: one cluster of WS_CL CTAs; the W slice is cached in shared memory when it fits
+    const int ws_nsp = (H + WS_CL - 1) / WS_CL + 1;
+    const int cache_w = ((size_t)ws_nsp * (work + 1)) * 8 <= (size_t)200 * 1024 ? 1 : 0;
+    const size_t ws_smem = (size_t)ws_nsp * (cache_w ? work + 1 : 1) * 8;
     AB_CUDA(cudaFuncSetAttribute(wstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem));
     const int q_in_smem = (size_t)2 * work * work * 8 <= (size_t)200 * 1024 ? 1 : 0;
     const size_t svd_smem = (size_t)(q_in_smem ? 2 : 1) * work * work * 8;
     AB_CUDA(cudaFuncSetAttribute(svd_restart_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
-    // ritz: <= 64 output columns -> 16 rows per warp, up to 128 -> 8 rows per warp; smem = kpad x (64|128) doubles
-    const size_t rz_kpad = (size_t)((work + 7) & ~7);
-    AB_CUDA(cudaFuncSetAttribute(ritz_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rz_kpad * 64 * 8)));
-    AB_CUDA(cudaFuncSetAttribute(ritz_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rz_kpad * 128 * 8)));
-    bool use_cublas = getenv("AB_IRLB_OWN_RITZ") == nullptr;
+    const bool svd_one_cta = getenv("AB_IRLB_SVD1") != nullptr;       // A/B switch: the one-CTA Jacobi (round 1)
+    const size_t rz_smem = ritz_smem_bytes(work);
+    AB_REQUIRE(rz_smem <= ctx->smem_optin, "ab_irlb: work dimension %d needs %zu bytes of shared memory", work, rz_smem);
+    AB_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rz_smem));
     auto ritz = [&](const double *X, int64_t ldx, int64_t rows, const double *M, int ncols, double *out, int64_t ldo,
                     int rowmajor, const double *colscale, double *out2) -> int {
-        // the restart's plain column-major products go to the library GEMM; the fused output form (row-major, column
-        // scaling, second output) and boxes without cuBLAS use the kernel below
-        if (!rowmajor && use_cublas && rows > 0) {
-            const int rc = ab_dgemm_colmajor_rowb(ctx, rows, ncols, work, X, ldx, M, work, out, ldo, st);
-            if (rc == 0) return 0;
-            if (rc == 1) return 1;
-            use_cublas = false;
-        }
-        if (ncols <= 64) {
-            const unsigned g = (unsigned)std::max<int64_t>(1, (rows + RZ_WARPS * 16 - 1) / (RZ_WARPS * 16));
-            ritz_kernel<8, 2><<<g, RZ_WARPS * 32, rz_kpad * 64 * 8, st>>>(X, ldx, rows, work, M, ncols, out, ldo, rowmajor,
-                                                                          colscale, out2);
-        } else {
-            const unsigned g = (unsigned)std::max<int64_t>(1, (rows + RZ_WARPS * 8 - 1) / (RZ_WARPS * 8));
-            ritz_kernel<16, 1><<<g, RZ_WARPS * 32, rz_kpad * 128 * 8, st>>>(X, ldx, rows, work, M, ncols, out, ldo, rowmajor,
-                                                                            colscale, out2);
-        }
+        if (rows <= 0 || ncols <= 0) return 0;
+        const int64_t tiles = (rows + RZ_TR - 1) / RZ_TR;
+        const dim3 g((unsigned)std::min<int64_t>(tiles, ctx->sm_count), (unsigned)((ncols + RZ_NC - 1) / RZ_NC));
+        ritz_kernel<<<g, RZ_THREADS, rz_smem, st>>>(X, ldx, rows, work, M, ncols, out, ldo, rowmajor, colscale, out2);
         AB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    auto wstep = [&](int jd, int ncols, int sub_prev, int jb, uint32_t seq_vec) -> int {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(WS_CL);
+        cfg.blockDim = dim3(WS_THREADS);
+        cfg.dynamicSmemBytes = ws_smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = WS_CL;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        ab_prof_begin(ctx, AB_PROF_IRLB_SMALL, st);
+        AB_CUDA(cudaLaunchKernelEx(&cfg, wstep_kernel, (const double *)w.wraw, w.W, H, ldw, jd, ncols, sub_prev, w.scal, w.B,
+                                   work, jb, cache_w, peer, seq_vec));
+        AB_LAUNCH_CHECK(ctx);
+        ab_prof_end(ctx, AB_PROF_IRLB_SMALL, st);
         return 0;
     };
     const unsigned g_rows = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 32));
@@ -1027,16 +1375,21 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     AB_CUDA(cudaFuncSetAttribute(atw_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)H * 8)));
     int64_t nmult = 0, sum_panel = 0;
 
-    auto av = [&](const double *src, const double *sumsq, double *vdst) -> int {
+    // A.x, summed over the CTAs (and, sharded, pushed to every rank); returns the instance id the consumer waits for
+    uint32_t seq_fn2 = 0;                                    // instance of the last ||F||^2 exchange
+    auto av = [&](const double *src, bool scaled, double *vdst, uint32_t *seq_vec_out) -> int {
         ab_prof_begin(ctx, AB_PROF_IRLB_AV, st);
         // (A.x keeps the plain operand: its 12 warps per SM leave ~30 KB of L1, a table look-up per nonzero at consume
         // time misses it, and the compact variant measured 344 ms against 195)
-        av_kernel<<<w.av_grid, 384, av_smem, st>>>(rowptr_h, col_h, val_h, n, H, src, sumsq, vdst, w.av_warps, w.av_partial);
+        av_kernel<<<w.av_grid, 384, av_smem, st>>>(rowptr_h, col_h, val_h, n, H, src, scaled ? w.scal : nullptr, vdst,
+                                                   w.av_warps, w.av_partial, peer, seq_fn2);
         AB_LAUNCH_CHECK(ctx);
-        av_reduce_kernel<<<(H + 127) / 128, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw);
+        const uint32_t sv = fused ? ++seq[AB_CH_VEC] : 0;
+        av_reduce_kernel<<<(H + 127) / 128, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw, cnt + 3, peer, sv);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_AV, st);
-        if (ab_allreduce_f64(ctx, w.wraw, H, st)) return 1;
+        if (!fused && ab_allreduce_f64(ctx, w.wraw, H, st)) return 1;
+        *seq_vec_out = sv;
         nmult++;
         return 0;
     };
@@ -1054,49 +1407,62 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     bool converged = false;
     while (it < maxit) {
         int j = it > 0 ? keep : 0;
+        uint32_t sv = 0;
         // W[:,j] = A.V[:,j]  (irlb.py:165), orthogonalised against W[:, :j] on restarts (:173-175)
-        if (av(w.V + (int64_t)j * ld, nullptr, nullptr)) return 1;
-        ab_prof_begin(ctx, AB_PROF_IRLB_SMALL, st);
-        wstep_kernel<<<1, 1024, ws_smem, st>>>(w.wraw, w.W, H, j, it > 0 ? j : 0, 0, w.scal, w.B, work, -1);
-        AB_LAUNCH_CHECK(ctx);
-        ab_prof_end(ctx, AB_PROF_IRLB_SMALL, st);
+        if (av(w.V + (int64_t)j * ld, false, nullptr, &sv)) return 1;
+        if (wstep(j, it > 0 ? j : 0, 0, -1, sv)) return 1;
         while (j < work) {
             ab_prof_begin(ctx, AB_PROF_IRLB_ATW, st);
             if (compact)
                 atw_compact_kernel<<<g_atw, 256, (size_t)H * 8, st>>>(rowptr_h, cp.ent, cp.tabv, cp.taboff, n, H,
-                                                                       w.W + (size_t)j * H, w.V + (int64_t)j * ld, w.scal, w.F);
+                                                                       w.W + (size_t)j * ldw, w.V + (int64_t)j * ld, w.scal, w.F);
             else
-                atw_kernel<<<g_rows, 256, 0, st>>>(rowptr_h, col_h, val_h, n, w.W + (size_t)j * H, w.V + (int64_t)j * ld,
+                atw_kernel<<<g_rows, 256, 0, st>>>(rowptr_h, col_h, val_h, n, w.W + (size_t)j * ldw, w.V + (int64_t)j * ld,
                                                     w.scal, w.F);
             AB_LAUNCH_CHECK(ctx);
             ab_prof_end(ctx, AB_PROF_IRLB_ATW, st);
             nmult++;
             ab_prof_begin(ctx, AB_PROF_IRLB_PANEL, st);
-            panel_dot_kernel<<<g_dot, DOT_THREADS, 0, st>>>(w.V, ld, n, j + 1, w.F, w.dot_partial, w.coef, cnt + 1);
+            const uint32_t sc = fused ? ++seq[AB_CH_COEF] : 0;
+            panel_dot_kernel<<<g_dot, DOT_THREADS, 0, st>>>(w.V, ld, n, j + 1, w.F, w.dot_partial, w.coef, cnt + 1, peer, sc);
             AB_LAUNCH_CHECK(ctx);
-            if (ab_allreduce_f64(ctx, w.coef, j + 1, st)) return 1;
+            if (!fused && ab_allreduce_f64(ctx, w.coef, j + 1, st)) return 1;
+            seq_fn2 = fused ? ++seq[AB_CH_SCAL] : 0;
             panel_update_kernel<<<g_dot, DOT_THREADS, 0, st>>>(w.V, ld, n, j + 1, w.coef, w.F, w.nrm_partial,
-                                                                w.scal + SC_FN2, cnt + 2);
+                                                                w.scal + SC_FN2, cnt + 2, peer, sc, seq_fn2);
             AB_LAUNCH_CHECK(ctx);
             ab_prof_end(ctx, AB_PROF_IRLB_PANEL, st);
-            if (ab_allreduce_f64(ctx, w.scal + SC_FN2, 1, st)) return 1;
+            if (!fused && ab_allreduce_f64(ctx, w.scal + SC_FN2, 1, st)) return 1;
             sum_panel += j + 1;
             if (j < work - 1) {
                 // V[:,j+1] = F/fn ; W[:,j+1] = A.V[:,j+1] - fn W[:,j], CGS, normalise (irlb.py:195-219)
-                if (av(w.F, w.scal + SC_FN2, w.V + (int64_t)(j + 1) * ld)) return 1;
-                ab_prof_begin(ctx, AB_PROF_IRLB_SMALL, st);
-                wstep_kernel<<<1, 1024, ws_smem, st>>>(w.wraw, w.W, H, j + 1, j + 1, 1, w.scal, w.B, work, j);
-                AB_LAUNCH_CHECK(ctx);
-                ab_prof_end(ctx, AB_PROF_IRLB_SMALL, st);
+                if (av(w.F, true, w.V + (int64_t)(j + 1) * ld, &sv)) return 1;
+                if (wstep(j + 1, j + 1, 1, j, sv)) return 1;
             } else {
-                fscale_kernel<<<g_vec, 256, 0, st>>>(w.F, n, w.scal, w.B, work, j);
+                fscale_kernel<<<g_vec, 256, 0, st>>>(w.F, n, w.scal, w.B, work, j, peer, seq_fn2);
                 AB_LAUNCH_CHECK(ctx);
             }
             ++j;
         }
         ab_prof_begin(ctx, AB_PROF_IRLB_SVD, st);
-        svd_restart_kernel<<<1, 512, svd_smem, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it,
-                                                     keep, q_in_smem);
+        if (svd_one_cta) {
+            svd_restart_kernel<<<1, 512, svd_smem, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it,
+                                                         keep, q_in_smem);
+        } else {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(SV_CL);
+            cfg.blockDim = dim3(SV_THREADS);
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = SV_CL;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            AB_CUDA(cudaLaunchKernelEx(&cfg, svd_cluster_kernel, (const double *)w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal,
+                                       w.ctrl, w.R, (int)nval, tol, it, keep));
+        }
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_SVD, st);
         AB_CUDA(cudaMemcpyAsync(h_ctrl, w.ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, st));
@@ -1109,7 +1475,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         if (ritz(w.V, ld, n, w.Vb, keep, w.V2, ld, 0, nullptr, nullptr)) return 1;
         copy_vec_kernel<<<g_vec, 256, 0, st>>>(w.F, w.V2 + (int64_t)keep * ld, n);
         AB_LAUNCH_CHECK(ctx);
-        if (ritz(w.W, H, H, w.Ub, keep, w.W2, H, 0, nullptr, nullptr)) return 1;
+        if (ritz(w.W, ldw, H, w.Ub, keep, w.W2, ldw, 0, nullptr, nullptr)) return 1;
         reset_b_kernel<<<8, 256, 0, st>>>(w.B, work, w.sb, w.R, keep);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_RITZ, st);
@@ -1120,7 +1486,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     // outputs (irlb.py:249-257; clustering.py:111)
     if (ritz(w.V, ld, n, w.Vb, nval, scores_local, 0, 1, w.sb, v_local)) return 1;
     if (u_out) {
-        if (ritz(w.W, H, H, w.Ub, nval, u_out, 0, 1, nullptr, nullptr)) return 1;
+        if (ritz(w.W, ldw, H, w.Ub, nval, u_out, 0, 1, nullptr, nullptr)) return 1;
     }
     if (s_out) AB_CUDA(cudaMemcpyAsync(s_out, w.sb, (size_t)nval * 8, cudaMemcpyDeviceToDevice, st));
     ab_prof_end(ctx, AB_PROF_IRLB_TOTAL, st);
@@ -1129,7 +1495,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         h_info[0] = it;
         h_info[1] = nmult;
         h_info[2] = sum_panel;
-        h_info[3] = (converged ? 0 : 1) | (compact ? 2 : 0);
+        h_info[3] = (converged ? 0 : 1) | (compact ? 2 : 0) | (fused ? 4 : 0);
     }
     return 0;
 }

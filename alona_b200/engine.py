@@ -48,6 +48,7 @@ class Engine:
         _lib.check(self.lib.ab_ctx_create(ctypes.byref(h), self.device_index, self.rank, self.world), 'ab_ctx_create')
         self.ctx = h
         self._ws = None
+        self.peer = False
 
     def close(self):
         if self.ctx is not None:
@@ -106,6 +107,34 @@ class Engine:
         dist.broadcast_object_list(obj, src=0)
         idbuf = ctypes.create_string_buffer(obj[0], 128)
         _lib.check(self.lib.ab_ctx_init_nccl(self.ctx, path, idbuf), 'ab_ctx_init_nccl')
+        self.init_peer()
+
+    def init_peer(self):
+        """Maps every rank's peer-exchange buffer (cudaIpc handles travel over torch.distributed) so that ab_irlb
+        fuses its small all-reduces into its kernels as one-shot NVLink pushes.  All ranks agree on the outcome: if
+        any rank cannot map its peers (no NVLink/P2P between the devices), every rank stays on ncclAllReduce and says
+        so once on stderr."""
+        import sys
+        import torch.distributed as dist
+        if self.world == 1 or self.world > 8 or os.environ.get('AB_NO_PEER'):
+            return
+        nb = int(self.lib.ab_peer_handle_bytes())
+        mine = ctypes.create_string_buffer(nb)
+        ok = self.lib.ab_peer_alloc(self.ctx, mine) == 0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine.raw if ok else None)
+        ok = ok and all(h is not None for h in handles)
+        if ok:
+            allh = ctypes.create_string_buffer(b''.join(handles), nb * self.world)
+            ok = self.lib.ab_peer_open(self.ctx, allh) == 0
+        flags = [None] * self.world
+        dist.all_gather_object(flags, bool(ok))
+        self.peer = all(flags)
+        if not self.peer:
+            os.environ['AB_IRLB_NCCL'] = '1'
+            if self.rank == 0:
+                sys.stderr.write('alona_b200: peer exchange buffers unavailable (%s); IRLBA uses ncclAllReduce\n'
+                                 % _lib.last_error())
 
     def allreduce_f64(self, t):
         _lib.check(self.lib.ab_allreduce_f64(self.ctx, _ptr(t), t.numel(), self.stream()), 'ab_allreduce_f64')
@@ -127,8 +156,19 @@ class Engine:
         return unpack_rows(out, counts)
 
     # -- uploads ----------------------------------------------------------------------
-    def upload_csr(self, csr, row_begin=0, n_total=None, non_blocking=False):
-        """scipy/numpy CSR (cells x genes, ascending column ids) -> DeviceCSR."""
+    def upload_csr(self, csr, row_begin=0, n_total=None, non_blocking=False, canonical=True):
+        """scipy/numpy CSR (cells x genes, ascending column ids) -> DeviceCSR.  scipy matrices are brought to
+        canonical form first (duplicates summed, explicit zeros dropped, columns sorted); negative counts are
+        refused.  canonical=False uploads the arrays as they are (tests of the kernels' own guards)."""
+        import scipy.sparse as sp
+        if canonical and sp.issparse(csr):
+            if csr.nnz and csr.data.min() < 0:
+                raise ValueError('alona_b200: negative values in the count matrix')
+            if not csr.has_canonical_format or (csr.nnz and csr.data.min() == 0):
+                csr = sp.csr_matrix(csr, copy=True)
+                csr.sum_duplicates()
+                csr.eliminate_zeros()
+                csr.sort_indices()
         indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
         data = np.ascontiguousarray(csr.data, dtype=np.int32)
@@ -221,19 +261,29 @@ class Engine:
         return med, {'gathered': int(per.sum()), 'batch': batch}
 
     # -- K1 ---------------------------------------------------------------------------
-    def norm_moments(self, A, gsum=None, gsumsq=None, allreduce=True):
+    def norm_moments(self, A, acc=None, allreduce=True, finalize=True):
+        """Library sizes + per-gene sum x / sum x^2 of the normalised values.  `acc` ([G, 4] int64 fixed-point
+        accumulators, include/alona_b200.h) lets the caller chain row tiles; with finalize=False the raw accumulators
+        are returned instead of the FP64 sums."""
         lib = self.empty((A.n_local,), torch.int64)
-        if gsum is None:
-            gsum = self.zeros((A.n_genes,), torch.float64)
-            gsumsq = self.zeros((A.n_genes,), torch.float64)
+        if acc is None:
+            acc = self.zeros((A.n_genes, 4), torch.int64)
         _lib.check(self.lib.ab_norm_moments(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), A.n_local,
-                                            A.n_genes, SCALE, _ptr(lib), _ptr(gsum), _ptr(gsumsq), self.stream()),
-                   'ab_norm_moments')
+                                            A.n_genes, SCALE, _ptr(lib), _ptr(acc), self.stream()), 'ab_norm_moments')
+        if not finalize:
+            return lib, acc
         if allreduce and self.world > 1:
-            both = torch.cat([gsum, gsumsq])
-            self.allreduce_f64(both)
-            gsum, gsumsq = both[:A.n_genes].contiguous(), both[A.n_genes:].contiguous()
+            self.allreduce_i64(acc)
+        gsum, gsumsq = self.moments_finalize(acc)
         return lib, gsum, gsumsq
+
+    def moments_finalize(self, acc):
+        g = acc.shape[0]
+        gsum = self.empty((g,), torch.float64)
+        gsumsq = self.empty((g,), torch.float64)
+        _lib.check(self.lib.ab_moments_finalize(self.ctx, _ptr(acc), g, _ptr(gsum), _ptr(gsumsq), self.stream()),
+                   'ab_moments_finalize')
+        return gsum, gsumsq
 
     # -- K2 ---------------------------------------------------------------------------
     def hvg_seurat(self, gsum, gsumsq, n_total, hvg_n, nbins=20):
@@ -275,7 +325,8 @@ class Engine:
                                     float(tol), int(maxit), _ptr(v0_local), _ptr(scores), _ptr(v), _ptr(s), _ptr(u),
                                     info, _ptr(ws), ws.numel(), self.stream()), 'ab_irlb')
         return {'scores': scores, 'V': v, 's': s, 'U': u, 'steps': int(info[0]), 'nmult': int(info[1]),
-                'sum_panel': int(info[2]), 'not_converged': int(info[3]) & 1, 'compact': bool(int(info[3]) & 2)}
+                'sum_panel': int(info[2]), 'not_converged': int(info[3]) & 1, 'compact': bool(int(info[3]) & 2),
+                'fused_allreduce': bool(int(info[3]) & 4)}
 
     # -- K9 ---------------------------------------------------------------------------
     def knn(self, emb_all, k, q_begin=0, q_end=None, mode=0):

@@ -116,22 +116,53 @@ def cpu_threads():
 
 
 def sample_counts_host(wl, n_cells, seed_data=20251019):
-    """First n_cells cells of the workload's synthetic matrix: generated on the GPU when there is one
-    (identical to the GPU arm's data), else by the numpy twin of the generator."""
-    import scipy.sparse as sp
-    import torch
-    if torch.cuda.is_available():
-        from alona_b200.engine import Engine
-        from alona_b200.synth import make_profiles
-        eng = Engine()
-        prof = torch.from_numpy(make_profiles(wl['genes'])).to(eng.device)
-        A = eng.synth_counts(prof, 0, n_cells, wl['lbar'], n_total=wl['cells'], seed=seed_data)
-        m = sp.csr_matrix((A.val.cpu().numpy(), A.col.cpu().numpy(), A.rowptr.cpu().numpy()), shape=(n_cells, wl['genes']))
-        eng.close()
-        return m
+    """First n_cells cells of the workload's synthetic matrix, built on the HOST by the numpy twin of the device
+    generator (oracle/synth_np.device_twin_counts): the CPU arm loads no CUDA library of this repo."""
     from oracle import synth_np
-    m, _ = synth_np.nb_counts(n_cells, wl['genes'], lbar=wl['lbar'], seed=1, drop_empty=False)
-    return m
+    from alona_b200.synth import make_profiles
+    return synth_np.device_twin_counts(make_profiles(wl['genes']), 0, n_cells, wl['lbar'], seed=seed_data)
+
+
+def blas_threads(n):
+    """Pins the BLAS pool to n threads (torchrun exports OMP_NUM_THREADS=1) and returns the limiter to keep alive."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=int(n), user_api='blas')
+    except Exception:
+        return None
+
+
+def table_hashes(eng, out, lo, world):
+    """Order-sensitive 64-bit checksums of the kNN table and of the edge list, combinable across ranks (a wrapping
+    sum of per-entry mixes keyed on the GLOBAL position), plus the global edge count: identical lines at
+    N = 1/2/4/8 prove that the sharded runs produced the same graph.  Measurement only (torch integer ops)."""
+    import torch
+    import torch.distributed as dist
+    dev = eng.device
+    c1, c2, c3 = -7046029254386353131, -4417276706812531889, 1609587929392839161      # odd 64-bit constants
+
+    def mix(pos, val):
+        h = ((pos + 1) * c1) ^ ((val.to(torch.int64) + 1) * c2)
+        h = (h ^ (h >> 29)) * c3
+        return (h ^ (h >> 32)).sum()
+    knn = out['knn_idx']
+    k = knn.shape[1]
+    pos = (torch.arange(knn.shape[0], device=dev, dtype=torch.int64) + lo).unsqueeze(1) * k + \
+        torch.arange(k, device=dev, dtype=torch.int64).unsqueeze(0)
+    hk = mix(pos, knn)
+    ne = torch.tensor([out['snn']['src'].numel()], dtype=torch.int64, device=dev)
+    off = 0
+    if world > 1:
+        allc = [torch.zeros_like(ne) for _ in range(world)]
+        dist.all_gather(allc, ne)
+        off = int(sum(int(c.item()) for c in allc[:dist.get_rank()]))
+    epos = torch.arange(int(ne.item()), device=dev, dtype=torch.int64) + off
+    he = mix(2 * epos, out['snn']['src']) + mix(2 * epos + 1, out['snn']['dst'])
+    t = torch.stack([hk, he, ne[0]])
+    if world > 1:
+        dist.all_reduce(t)
+    v = t.cpu().numpy().astype(np.uint64)
+    return {'knn_hash': '%016x' % int(v[0]), 'edges_hash': '%016x' % int(v[1]), 'edges_total': int(t[2].item())}
 
 
 # ------------------------------------------------------------------------------------------
@@ -153,6 +184,8 @@ def main():
         if rank != 0:
             return
         n_s = min(CPU_SAMPLE_CELLS, wl['cells'])
+        ncores = os.cpu_count() or 1
+        limiter = blas_threads(ncores)                      # noqa: F841  (kept alive for the whole run)
         df = cpu_sample_frame(sample_counts_host(wl, n_s))
         times = []
         for i in range(args.warmup + args.steps):
@@ -161,13 +194,20 @@ def main():
                 times.append(dt)
         ms = 1e3 * float(np.mean(times))
         val = n_s / (ms / 1e3)
-        sample = 'first %d cells of the workload matrix (%d expressed genes), dense pandas path' % (n_s, df.shape[0])
+        if n_s == wl['cells']:
+            sample = 'the whole %d-cell matrix (%d expressed genes), dense pandas path of the reference' % (n_s, df.shape[0])
+        else:
+            sample = ('first %d cells of the workload matrix (%d expressed genes), dense pandas path of the reference; '
+                      'the full %d-cell matrix is infeasible on a CPU (dense float64 frames of %.0f GB, ~quadratic kNN)'
+                      % (n_s, df.shape[0], wl['cells'], wl['cells'] * wl['genes'] * 8 / 1e9))
+            config['workload'] += ' -- CPU ARM TIMED ON A SAMPLE: ' + sample
         print(json.dumps({
             'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': config,
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cpu_threads(), 'kind': 'port', 'sample': sample,
-                             'stage_s': tm},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': ncores, 'blas_threads': cpu_threads(), 'kind': 'port',
+                             'sample': sample, 'sample_cells': n_s, 'stage_s': tm,
+                             'single_threaded_stages': 'normalize, hvg (pandas), knn (BallTree, n_jobs default), snn'},
             'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
         return
 
@@ -250,8 +290,10 @@ def main():
     value = wl['cells'] / (ms_per_step / 1e3)
     edges_local = int(out['snn']['src'].numel())
     nnz_h = out['AH'].nnz
+    hashes = table_hashes(eng, out, lo, world)
     info = {'steps': out['irlb']['steps'], 'nmult': out['irlb']['nmult'], 'sum_panel': out['irlb']['sum_panel'],
-            'nnz': nnz_local, 'nnz_hvg': nnz_h, 'edges': edges_local,
+            'fused_allreduce': out['irlb'].get('fused_allreduce', False), **hashes,
+            'nnz': nnz_local, 'nnz_hvg': nnz_h, 'edges_local': edges_local,
             'knn_stats': out['knn_stats'].cpu().numpy().tolist(), 'snn_big_rows': out['snn']['big_rows'],
             'snn_max_walk': out['snn']['max_walk'], 'hvg_stats': out['hvg_stats'].cpu().numpy().tolist()}
 
@@ -336,7 +378,9 @@ def main():
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f64 (normalise/HVG/IRLBA/re-rank), fp16x3 with fp32 accumulate (distance GEMM candidates), int32 (SNN)',
             'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': launches // max(1, args.steps),
-            'stage_ms': stage_ms, 'kernel_ms': kernel_ms, 'info': info, 'roofline': roof,
+            'stage_ms': stage_ms, 'kernel_ms': kernel_ms,
+            'kernel_ms_fine_pass': {k: {'ms_total': v[0], 'launches': v[1]} for k, v in fine.items()},
+            'info': info, 'roofline': roof,
             'roofline_stages': stages_roof, 'cpu_baseline': cpu, 'e2e': e2e}
     print(json.dumps(line))
     if world > 1:

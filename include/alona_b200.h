@@ -51,17 +51,33 @@ int ab_allreduce_f64(ab_ctx *ctx, double *buf, int64_t count, void *stream);
 int ab_allreduce_i64(ab_ctx *ctx, int64_t *buf, int64_t count, void *stream);
 /* All-gather of equal-sized byte blocks (bytes_per_rank each) into recv (world*bytes). */
 int ab_allgather_bytes(ab_ctx *ctx, const void *send, void *recv, int64_t bytes_per_rank, void *stream);
+/* Multi-GPU, optional: peer-memory exchange buffers for the small all-reduces INSIDE ab_irlb (A.v result, CGS
+ * coefficients, ||F||^2: three per Lanczos step, latency-bound).  With them the reductions are fused into the
+ * producing / consuming kernels as one-shot pushes over NVLink peer memory (fixed rank order: bitwise identical on
+ * every rank); without them ab_irlb issues ncclAllReduce between the kernels.  Protocol: every rank calls
+ * ab_peer_alloc (returns its cudaIpcMemHandle, ab_peer_handle_bytes() bytes), the caller all-gathers the handles over
+ * its own bootstrap (torch.distributed in alona_b200/engine.py) and every rank calls ab_peer_open with the
+ * world x handle_bytes array in rank order.  All ranks must be GPUs of one NVLink/NVSwitch domain (world <= 8). */
+size_t ab_peer_handle_bytes(void);
+int ab_peer_alloc(ab_ctx *ctx, void *h_handle);
+int ab_peer_open(ab_ctx *ctx, const void *h_handles);
+int ab_peer_enabled(ab_ctx *ctx);
 
 /* ---- K1: library-size normalisation + log2 + per-gene moments -------------------------
  * replaces AlonaCell.normalize raw branch  (alona/cell.py:241-243)
  *      and the per-gene reductions of hvg_seurat (alona/hvg.py:148,157).
- * libsize[i] = sum of the row's counts (exact); x = log2(fl(fl(c/S)*scale)+1) in FP64;
- * gsum[g] += x, gsumsq[g] += x*x over this shard's cells.  gsum/gsumsq must be zeroed by the
- * caller (they accumulate, so shards/tiles can be chained); all-reduce them across ranks
- * with ab_allreduce_f64. */
+ * libsize[i] = sum of the row's counts (exact); x = log2(fl(fl(c/S)*scale)+1) in FP64, the reference's arithmetic;
+ * per gene, sum x and sum x^2 over this shard's cells are ACCUMULATED into acc[n_genes][4] (uint64, zeroed by the
+ * caller, so shards / tiles can be chained) in 64-bit fixed point: acc[g] = {lo, hi of sum x in units of 2^-45,
+ * lo, hi of sum x^2 in units of 2^-46}, value = lo + hi * 2^32.  Integer sums are order independent: the result is
+ * bit-identical from run to run and for any sharding.  Across ranks the four words add with ab_allreduce_i64;
+ * ab_moments_finalize turns them into the FP64 sums gsum[g], gsumsq[g] (one rounding each; error of the fixed-point
+ * representation <= 2^-46 resp. 2^-47 per cell). */
 int ab_norm_moments(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
                     int64_t n_local, int32_t n_genes, double scale,
-                    int64_t *libsize, double *gsum, double *gsumsq, void *stream);
+                    int64_t *libsize, uint64_t *acc, void *stream);
+int ab_moments_finalize(ab_ctx *ctx, const uint64_t *acc, int32_t n_genes, double *gsum, double *gsumsq,
+                        void *stream);
 
 /* ---- K2: Seurat-style HVG selection ----------------------------------------------------
  * replaces AlonaHighlyVariableGenes.hvg_seurat (alona/hvg.py:146-165): mean, ddof-1 variance,
@@ -150,7 +166,8 @@ int ab_cluster_median_fill(ab_ctx *ctx, const int64_t *rowptr, const int32_t *co
  * Outputs: scores_local [n_local x nval] row-major = V.diag(s) (clustering.py:111),
  * v_local [n_local x nval] row-major (may be NULL), s[nval], u[H x nval] row-major (may be
  * NULL); h_info[4] (host int64) = {steps, nmult, sum of CGS panel widths, status flags:
- * bit 0 = not converged within maxit, bit 1 = the compact row operand was used}.
+ * bit 0 = not converged within maxit, bit 1 = the compact row operand was used, bit 2 = the small all-reduces
+ * ran fused over peer memory (ab_peer_open)}.
  * Synchronises the stream (one small D2H per restart decides convergence).
  * Workspace: ab_irlb_ws_bytes is the minimum; with ab_irlb_ws_bytes_compact (which also needs
  * the shard's nonzero count) ab_irlb re-encodes A_H once as 4-byte (gene | value-slot) words

@@ -129,6 +129,28 @@ def gene_moments(csr, lib=None):
     return sx, sx2, nz
 
 
+def gene_moments_fixed(csr, lib=None):
+    """The K1 accumulators of include/alona_b200.h (ab_norm_moments): per gene {lo, hi of sum x in units of 2^-45,
+    lo, hi of sum x^2 in units of 2^-46}, value = lo + hi * 2^32, as int64 [G, 4].  Python integers: exact."""
+    x = normalized_values(csr, lib)
+    fx = np.rint(x * float(1 << 45)).astype(np.uint64)
+    fxx = np.rint((x * x) * float(1 << 46)).astype(np.uint64)
+    out = np.zeros((csr.shape[1], 4), dtype=np.int64)
+    for g, a, b in zip(csr.indices.tolist(), fx.tolist(), fxx.tolist()):
+        out[g, 0] += a & 0xFFFFFFFF
+        out[g, 1] += a >> 32
+        out[g, 2] += b & 0xFFFFFFFF
+        out[g, 3] += b >> 32
+    return out
+
+
+def moments_from_fixed(acc):
+    """ab_moments_finalize: exact integer recombination, then FP64."""
+    sx = np.array([(int(a[1]) << 32) + int(a[0]) for a in acc], dtype=object)
+    sxx = np.array([(int(a[3]) << 32) + int(a[2]) for a in acc], dtype=object)
+    return (np.array([float(v) / float(1 << 45) for v in sx]), np.array([float(v) / float(1 << 46) for v in sxx]))
+
+
 def gene_mean_var(csr, lib=None):
     """mean and ddof=1 variance per gene the way pandas computes them (two-pass):
     var = [ sum_nz (x-mean)^2 + (N-nnz)*mean^2 ] / (N-1)."""

@@ -64,3 +64,81 @@ def gaussian_mixture_embedding(n, d=50, n_clusters=30, seed=2, dtype=np.float64)
     cl = rng.randint(0, n_clusters, n)
     x = centres[cl] + rng.normal(0.0, 1.0, (n, d)) * scale
     return np.ascontiguousarray(x.astype(dtype))
+
+
+# ----------------------------------------------------------------------------------------
+# numpy twin of the DEVICE generator (alona_b200/csrc/ab_synth.cu): same counter-based hash, same cell draw,
+# same NB CDF inversion, so the CPU arm of bench.py can build "the first n cells of the workload matrix" without
+# loading the CUDA library.  Identical to the device matrix up to the last-bit differences between the host's and
+# the device's float32 log1p/expm1/exp (an entry changes only if its uniform falls within that rounding of a CDF step).
+# ----------------------------------------------------------------------------------------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(x):
+    x = x.astype(np.uint64, copy=True)
+    x ^= x >> np.uint64(30)
+    x *= np.uint64(0xbf58476d1ce4e5b9)
+    x ^= x >> np.uint64(27)
+    x *= np.uint64(0x94d049bb133111eb)
+    x ^= x >> np.uint64(31)
+    return x
+
+
+def device_twin_counts(prof, cell_begin, n_cells, lbar, depth_sigma=0.35, r_disp=5.0, seed=20251019, chunk=256):
+    """Rows [cell_begin, cell_begin + n_cells) of the matrix ab_synth_nb_* generates from `prof`
+    (float32 [clusters, genes], alona_b200.synth.make_profiles).  Returns scipy CSR int32 (cells x genes)."""
+    prof = np.ascontiguousarray(prof, dtype=np.float32)
+    n_clusters, n_genes = prof.shape
+    old = np.seterr(over='ignore')
+    try:
+        cells = np.arange(cell_begin, cell_begin + n_cells, dtype=np.uint64)
+        h = _mix64(np.uint64(seed) * np.uint64(0x9e3779b97f4a7c15) + cells * np.uint64(0xd1b54a32d192ed03) + np.uint64(0x1234567))
+        key = _mix64(h ^ np.uint64(0xabcdef12345))
+        cluster = (h % np.uint64(n_clusters)).astype(np.int64)
+        h2 = _mix64(h + np.uint64(0x632be59bd9b4e019))
+        u1 = ((h2 >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+        u2 = ((_mix64(h2) >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+        z = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+        depth = np.exp(np.log(lbar) + depth_sigma * z).astype(np.float32)
+        r = np.float32(r_disp)
+        genes = np.arange(n_genes, dtype=np.uint64) * np.uint64(0x9e3779b97f4a7c15)
+        rows = []
+        for a in range(0, n_cells, chunk):
+            b = min(n_cells, a + chunk)
+            hh = _mix64(key[a:b, None] + genes[None, :])
+            u = (hh >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+            mu = depth[a:b, None] * prof[cluster[a:b]]
+            lg = np.log1p(mu / r, dtype=np.float32)
+            qnz = -np.expm1(-r * lg, dtype=np.float32)
+            cnt = np.zeros(mu.shape, dtype=np.int32)
+            ii, jj = np.nonzero(u < qnz.astype(np.float64))
+            uu = u[ii, jj]
+            m = mu[ii, jj]
+            p = np.exp(-r * lg[ii, jj], dtype=np.float32)
+            ratio = (m / (m + r)).astype(np.float32)
+            cdf = np.zeros(uu.shape, dtype=np.float64)
+            c = np.zeros(uu.shape, dtype=np.int32)
+            live = np.ones(uu.shape, dtype=bool)
+            step = 0
+            while live.any() and step < 100000:
+                idx = np.nonzero(live)[0]
+                pp = p[idx]
+                pp = pp * (np.float32(step) + r)
+                pp = pp / np.float32(step + 1)
+                pp = pp * ratio[idx]
+                p[idx] = pp
+                c[idx] = step + 1
+                cdf[idx] += pp.astype(np.float64)
+                live[idx] = ~(uu[idx] < cdf[idx])
+                step += 1
+            cnt[ii, jj] = c
+            empty = np.nonzero(cnt.sum(axis=1) == 0)[0]
+            for e in empty:                                  # every cell must have S_c >= 1
+                cnt[e, int(key[a + e] % np.uint64(n_genes))] = 1
+            rows.append(sp.csr_matrix(cnt))
+        out = sp.vstack(rows).tocsr()
+        out.sort_indices()
+        return out.astype(np.int32)
+    finally:
+        np.seterr(**old)

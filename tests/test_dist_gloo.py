@@ -53,6 +53,14 @@ def _worker(rank, world, port, out_dir):
         assert np.allclose(both.numpy()[:m.shape[1]], fx, rtol=1e-13, atol=0)
         assert np.allclose(both.numpy()[m.shape[1]:], fx2, rtol=1e-13, atol=0)
         assert np.array_equal(R.libsize(shard), R.libsize(m)[lo:hi])                     # library sizes are local
+        # the product all-reduces the fixed-point accumulators as int64 (ab_allreduce_i64): exactly additive, so the
+        # sharded sum has the SAME BITS as the single-shard one, for any world size
+        acc = torch.from_numpy(R.gene_moments_fixed(shard))
+        dist.all_reduce(acc)
+        assert np.array_equal(acc.numpy(), R.gene_moments_fixed(m))
+        gx, gx2 = R.moments_from_fixed(acc.numpy())
+        ok = fx > 0
+        assert np.max(np.abs(gx[ok] - fx[ok]) / fx[ok]) < 1e-13 and np.max(np.abs(gx2[ok] - fx2[ok]) / fx2[ok]) < 1e-12
 
         # K2 is replicated: every rank must select the same genes from the reduced moments
         mean = both.numpy()[:m.shape[1]] / n

@@ -56,6 +56,15 @@ def test_moments_and_hvg_vs_oracle_at_20k(eng, synth):
     _, g1, q1 = eng.norm_moments(top)
     _, g2, q2 = eng.norm_moments(bot)
     assert torch.allclose(g1 + g2, gsum, rtol=1e-13, atol=0)
+    # the fixed-point accumulators make the sums EXACTLY additive: chaining the two tiles into one accumulator
+    # (= what the int64 all-reduce does across ranks) and a second run give the same bits as the single pass
+    _, acc = eng.norm_moments(top, finalize=False)
+    _, acc = eng.norm_moments(bot, acc=acc, finalize=False)
+    gc, qc = eng.moments_finalize(acc)
+    assert torch.equal(gc, gsum) and torch.equal(qc, gsumsq)
+    _, g_again, q_again = eng.norm_moments(synth)
+    assert torch.equal(g_again, gsum) and torch.equal(q_again, gsumsq)
+    assert np.max(np.abs(gsumsq.cpu().numpy()[ok] - sx2[ok]) / sx2[ok]) < 1e-12
     mean, var = R.gene_mean_var(m)
     keep = nz > 0
     ranked, z, g2h, st = eng.hvg_seurat(gsum, gsumsq, synth.n_local, 500)

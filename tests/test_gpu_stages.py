@@ -89,6 +89,41 @@ def test_k3_hvg_extract(eng, case):
     assert _ulp_diff(AH.val.cpu().numpy(), ref.data).max() <= VALUE_ULPS
 
 
+def test_explicit_zero_counts_are_inert(eng):
+    """Explicitly stored zeros: the kernels' own guards make them contribute nothing to the library
+    sizes, the moments and A_H's values, and the host-side upload drops them anyway."""
+    g = load_golden('pipe_small')
+    m = golden_csr(g)
+    rng = np.random.RandomState(3)
+    dirty = m.tolil(copy=True)
+    rr, cc = rng.randint(0, m.shape[0], 4000), rng.randint(0, m.shape[1], 4000)
+    free = np.asarray(m[rr, cc]).ravel() == 0
+    import scipy.sparse as sp
+    extra = sp.coo_matrix((np.ones(free.sum(), dtype=np.int32), (rr[free], cc[free])), shape=m.shape).tocsr()
+    extra.sum_duplicates()
+    extra.data[:] = 1
+    both = (m + extra).tocsr()
+    both.sort_indices()
+    both.data[np.asarray(extra[both.nonzero()]).ravel() > 0] = 0          # those positions become STORED zeros
+    assert both.nnz > m.nnz and (both.data == 0).sum() == both.nnz - m.nnz
+    clean = eng.norm_moments(eng.upload_csr(m))
+    for A in (eng.upload_csr(both, canonical=False), eng.upload_csr(both)):
+        lib, gsum, gsumsq = eng.norm_moments(A)
+        assert torch.equal(lib, clean[0])
+        assert torch.allclose(gsum, clean[1], rtol=1e-13, atol=0) and torch.allclose(gsumsq, clean[2], rtol=1e-13, atol=0)
+    # A_H built from the dirty matrix holds 0.0 at the stored zeros and the clean values elsewhere
+    g2h = np.full(m.shape[1], -1, dtype=np.int32)
+    cols = np.sort(g['hvg_ranked'])
+    g2h[cols] = np.arange(cols.size)
+    g2h_d = torch.from_numpy(g2h).to(eng.device)
+    A = eng.upload_csr(both, canonical=False)
+    AHd = eng.hvg_extract(A, clean[0], g2h_d, cols.size)
+    AHc = eng.hvg_extract(eng.upload_csr(m), clean[0], g2h_d, cols.size)
+    dd = sp.csr_matrix((AHd.val.cpu().numpy(), AHd.col.cpu().numpy(), AHd.rowptr.cpu().numpy()), shape=(m.shape[0], cols.size))
+    dc = sp.csr_matrix((AHc.val.cpu().numpy(), AHc.col.cpu().numpy(), AHc.rowptr.cpu().numpy()), shape=(m.shape[0], cols.size))
+    assert abs(dd - dc).max() == 0.0
+
+
 def _golden_AH(eng, g):
     m = golden_csr(g)
     A = eng.upload_csr(m)
