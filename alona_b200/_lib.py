@@ -40,6 +40,8 @@ SIGNATURES = {
     'ab_norm_moments': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_f64,
                                        c_void_p, c_void_p, c_void_p]),
     'ab_moments_finalize': (ctypes.c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p]),
+    'ab_norm_moments_linear': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_f64,
+                                              c_void_p, c_void_p, c_void_p]),
     'ab_hvg_seurat': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'ab_hvg_extract_ws_bytes': (c_size, [c_i64]),

@@ -994,62 +994,59 @@ __global__ void reset_b_kernel(double *__restrict__ B, int work, const double *_
 // X column-major (ld even, >= n), M row-major work x work (columns 0..ncols-1 used).
 // out column-major (ldo even, >= n) or, if rowmajor_out, row-major [n x ncols] scaled by colscale[c].
 //
-// The one GEMM-shaped step of IRLBA (n x work times work x keep, FP64, 1.3 GB / 6e9 FMA per restart at C3).  The
-// products run on the FP64 tensor path (same 36 TFLOP/s peak as the FP64 CUDA cores on this part, measured with
-// benchmarks/micro_atomics.cu, but a quarter of the instructions)
-// (mma.sync.m8n8k4.f64, DMMA); what the first version got wrong was feeding the A fragments straight from the
-// column-major panel in global memory (four 64-byte pieces per load).  Here a producer warp streams the panel through
-// shared memory with 1-D bulk copies (one 1 KB column segment per copy, one copy per lane, completion on an
-// mbarrier, a ring of RZ_ST stages of RZ_KC columns each) and the eight consumer warps read conflict-free fragments:
-// the column stride of the staged tile is RZ_TR + 4 doubles, so the four k-rows of a fragment land 8 banks apart.
-// The result tile is staged in shared memory and leaves through bulk stores (1 KB contiguous per output column).
-// A warp owns 16 rows x 64 output columns (16 DMMA per k-step from 2 A + 8 B fragment loads).
+// The one GEMM-shaped step of IRLBA (n x work times work x keep, FP64, 1.3 GB / 5e9 FMA per restart at C3).
+// Measured on this part (benchmarks/micro_atomics.cu, profiles/r2_ritz_svd_norm_ncu.txt): the FP64 CUDA cores sustain
+// 61 FMA/clk/SM (35.6 TFLOP/s), the FP64 tensor instruction mma.sync.m8n8k4 only ~28 (its sub-pipe was 69 % busy at
+// 10.9 TFLOP/s in the DMMA version of this kernel), so the products are register-tiled DFMA: a warp owns 32 rows x
+// (8 x CT) columns, a thread 4 rows x 2 x CT... see below.  What bounds a naive version is operand delivery, not
+// arithmetic: a producer warp streams the column-major panel through shared memory with 1-D bulk copies (one 1 KB
+// column segment per copy, one copy per lane, completion on an mbarrier, a ring of stages of KC panel columns) and
+// the result tile leaves through shared memory and bulk stores (1 KB contiguous per output column).
+// Thread tile: rows 4*tr .. 4*tr+3 (tr = lane % 8) of the warp's 32-row block, columns CT*tc .. CT*tc+CT-1
+// (tc = lane / 8) of the warp's 4*CT-column block: per k-row 2 LDS.128 of A (256 contiguous bytes per warp) and CT
+// doubles of B (broadcast), 4*CT FMAs.  Eight consumer warps = 4 row blocks x 2 column blocks = 128 rows x 8*CT columns.
 // ---------------------------------------------------------------------------------------
 static constexpr int RZ_TR = 128;                // rows per tile
-static constexpr int RZ_NC = 64;                 // output columns per CTA (grid.y tiles wider products)
-static constexpr int RZ_KC = 24;                 // k-rows (panel columns) per pipeline stage
-static constexpr int RZ_ST = 3;                  // stages
-static constexpr int RZ_XS = RZ_TR + 4;          // staged-tile column stride (doubles): k-rows 8 banks apart
-static constexpr int RZ_MS = RZ_NC + 4;          // M row stride (doubles)
-static constexpr int RZ_CS = RZ_TR + 2;          // result-tile column stride (doubles): conflict-free fragment stores
+static constexpr int RZ_XS = RZ_TR + 4;          // staged-tile column stride (doubles)
+static constexpr int RZ_CS = RZ_TR + 2;          // result-tile column stride (doubles)
+static constexpr int RZ_CSTAGE = 64;             // result columns staged per store round
 static constexpr int RZ_CONSUMERS = 8;           // consumer warps; warp RZ_CONSUMERS is the producer
 static constexpr int RZ_THREADS = (RZ_CONSUMERS + 1) * 32;
+static constexpr int RZ_MAXST = 4;
 
-__device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+struct RitzCfg { int kc, st, ct; size_t smem; };
+static RitzCfg ritz_cfg(int work, int ncols) {
+    RitzCfg c;
+    c.ct = std::max(1, (ncols + 7) / 8);                          // columns per thread
+    c.kc = work <= 72 ? 24 : 16;
+    c.st = work <= 72 ? 3 : 2;
+    c.smem = ((size_t)work * 8 * c.ct + (size_t)c.st * c.kc * RZ_XS + (size_t)RZ_CSTAGE * RZ_CS) * 8 + 2 * RZ_MAXST * 8 + 64;
+    return c;
 }
 
-static size_t ritz_smem_bytes(int work) {
-    const int kpad = (work + 3) & ~3;
-    return ((size_t)kpad * RZ_MS + (size_t)RZ_ST * RZ_KC * RZ_XS + (size_t)RZ_NC * RZ_CS) * 8 + 2 * RZ_ST * 8 + 64;
-}
-
+template <int CT>
 __global__ void __launch_bounds__(RZ_THREADS, 1)
 ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const double *__restrict__ M, int ncols,
             double *__restrict__ out, int64_t ldo, int rowmajor_out, const double *__restrict__ colscale,
-            double *__restrict__ out2 /* optional second row-major output without scaling */) {
+            double *__restrict__ out2 /* optional second row-major output without scaling */, int KC, int ST) {
     extern __shared__ __align__(128) unsigned char rz_raw[];
-    const int kpad = (work + 3) & ~3;
-    double *Ms = reinterpret_cast<double *>(rz_raw);                  // [kpad][RZ_MS]
-    double *Xs = Ms + (size_t)kpad * RZ_MS;                           // [RZ_ST][RZ_KC][RZ_XS]
-    double *Cs = Xs + (size_t)RZ_ST * RZ_KC * RZ_XS;                  // [RZ_NC][RZ_CS]
-    uint64_t *full = reinterpret_cast<uint64_t *>(Cs + (size_t)RZ_NC * RZ_CS);
-    uint64_t *empty = full + RZ_ST;
+    constexpr int MS = 8 * CT;                                        // M row stride = padded column count
+    double *Ms = reinterpret_cast<double *>(rz_raw);                  // [work][MS]
+    double *Xs = Ms + (size_t)work * MS;                              // [ST][KC][RZ_XS]
+    double *Cs = Xs + (size_t)ST * KC * RZ_XS;                        // [RZ_CSTAGE][RZ_CS]
+    uint64_t *full = reinterpret_cast<uint64_t *>(Cs + (size_t)RZ_CSTAGE * RZ_CS);
+    uint64_t *empty = full + RZ_MAXST;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = blockIdx.y * RZ_NC;                                // first output column of this CTA
-    const int nc = min(RZ_NC, ncols - c0);
-    const int nchunks = (work + RZ_KC - 1) / RZ_KC;
+    const int nchunks = (work + KC - 1) / KC;
     const int64_t ntiles = (n + RZ_TR - 1) / RZ_TR;
 
-    for (int e = threadIdx.x; e < kpad * RZ_MS; e += blockDim.x) {
-        const int l = e / RZ_MS, c = e - l * RZ_MS;
-        Ms[e] = (l < work && c < nc) ? M[l * work + c0 + c] : 0.0;
+    for (int e = threadIdx.x; e < work * MS; e += blockDim.x) {
+        const int l = e / MS, c = e - l * MS;
+        Ms[e] = c < ncols ? M[l * work + c] : 0.0;
     }
-    for (int e = threadIdx.x; e < RZ_ST * RZ_KC * RZ_XS; e += blockDim.x) Xs[e] = 0.0;   // pad rows stay finite
+    for (int e = threadIdx.x; e < ST * KC * RZ_XS; e += blockDim.x) Xs[e] = 0.0;      // rows past a clipped tile stay finite
     if (threadIdx.x == 0) {
-        for (int s2 = 0; s2 < RZ_ST; ++s2) { ab_mbar_init(full + s2, 1); ab_mbar_init(empty + s2, RZ_CONSUMERS); }
+        for (int s2 = 0; s2 < ST; ++s2) { ab_mbar_init(full + s2, 1); ab_mbar_init(empty + s2, RZ_CONSUMERS); }
         ab_mbar_init_fence();
     }
     ab_fence_proxy_async();
@@ -1062,94 +1059,111 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
             const double *xt = X + tile * RZ_TR;
             const uint32_t cb = (uint32_t)min((int64_t)RZ_TR, ld - tile * RZ_TR) * 8;     // last tile: clipped to ld
             for (int ch = 0; ch < nchunks; ++ch, ++it) {
-                const int st = it % RZ_ST;
-                if (it >= RZ_ST) ab_mbar_wait(empty + st, ((it / RZ_ST) - 1) & 1);
-                const int k0 = ch * RZ_KC, nk = min(RZ_KC, work - k0);
+                const int st = it % ST;
+                if (it >= (uint32_t)ST) ab_mbar_wait(empty + st, ((it / ST) - 1) & 1);
+                const int k0 = ch * KC, nk = min(KC, work - k0);
                 if (lane == 0) ab_mbar_expect_tx(full + st, (uint32_t)nk * cb);
                 __syncwarp();
                 if (lane < nk)
-                    ab_bulk_g2s(Xs + ((size_t)st * RZ_KC + lane) * RZ_XS, xt + (int64_t)(k0 + lane) * ld, cb, full + st);
+                    ab_bulk_g2s(Xs + ((size_t)st * KC + lane) * RZ_XS, xt + (int64_t)(k0 + lane) * ld, cb, full + st);
             }
         }
         return;
     }
 
-    // ---------------- consumers: warp w owns rows [16w, 16w+16) of the tile and all RZ_NC columns -----------------
-    const int ar = lane >> 2, ak = lane & 3;              // A fragment: row ar, k ak;  B fragment: k ak, col ar
-    const int nb = (nc + 7) >> 3;                         // live 8-column blocks
+    // ---------------- consumers -----------------------------------------------------------------------------
+    const int tr = lane & 7, tc = lane >> 3;
+    const int wr = warp & 3, wc = warp >> 2;
+    const int rloc = 32 * wr + 4 * tr;                    // first of this thread's 4 rows inside the tile
+    const int cloc = (4 * wc + tc) * CT;                  // first of this thread's CT columns
     uint32_t it = 0;
     bool stored = false;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        double acc[2][8][2];
+        double acc[4][CT];
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[g][j][0] = 0.0; acc[g][j][1] = 0.0; }
+            for (int j = 0; j < CT; ++j) acc[i][j] = 0.0;
         for (int ch = 0; ch < nchunks; ++ch, ++it) {
-            const int st = it % RZ_ST;
-            ab_mbar_wait(full + st, (it / RZ_ST) & 1);
-            const int k0 = ch * RZ_KC;
-            const int ksteps = (min(RZ_KC, work - k0) + 3) >> 2;
-            const double *xs = Xs + (size_t)st * RZ_KC * RZ_XS + (size_t)ak * RZ_XS + 16 * warp + ar;
-            const double *ms = Ms + (size_t)(k0 + ak) * RZ_MS + ar;
-#pragma unroll 2
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const double a0 = xs[(size_t)ks * 4 * RZ_XS], a1 = xs[(size_t)ks * 4 * RZ_XS + 8];
+            const int st = it % ST;
+            ab_mbar_wait(full + st, (it / ST) & 1);
+            const int k0 = ch * KC, nk = min(KC, work - k0);
+            const double *xs = Xs + (size_t)st * KC * RZ_XS + rloc;
+            const double *ms = Ms + (size_t)k0 * MS + cloc;
+#pragma unroll 4
+            for (int k = 0; k < nk; ++k) {
+                const double2 a01 = *reinterpret_cast<const double2 *>(xs + (size_t)k * RZ_XS);
+                const double2 a23 = *reinterpret_cast<const double2 *>(xs + (size_t)k * RZ_XS + 2);
+                double b[CT];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j < nb) {
-                        const double b = ms[(size_t)ks * 4 * RZ_MS + 8 * j];
-                        dmma8x8x4(acc[0][j][0], acc[0][j][1], a0, b);
-                        dmma8x8x4(acc[1][j][0], acc[1][j][1], a1, b);
-                    }
+                for (int j = 0; j < CT; ++j) b[j] = ms[(size_t)k * MS + j];
+#pragma unroll
+                for (int j = 0; j < CT; ++j) {
+                    acc[0][j] = fma(a01.x, b[j], acc[0][j]);
+                    acc[1][j] = fma(a01.y, b[j], acc[1][j]);
+                    acc[2][j] = fma(a23.x, b[j], acc[2][j]);
+                    acc[3][j] = fma(a23.y, b[j], acc[3][j]);
                 }
             }
             __syncwarp();
             if (lane == 0) ab_mbar_arrive(empty + st);
         }
-        // C fragment: row lane/4, columns (lane%4)*2 + {0,1} of each 8-column block
         const int64_t row0 = tile * RZ_TR;
         if (rowmajor_out) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int64_t r = row0 + 16 * warp + 8 * g + ar;
+            for (int i = 0; i < 4; ++i) {
+                const int64_t r = row0 + rloc + i;
                 if (r >= n) continue;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int col = c0 + 8 * j + 2 * ak + e;
-                        if (j < nb && col < ncols) {
-                            const double v = acc[g][j][e];
-                            out[r * (int64_t)ncols + col] = __dmul_rn(v, colscale ? colscale[col] : 1.0);
-                            if (out2) out2[r * (int64_t)ncols + col] = v;
-                        }
+                for (int j = 0; j < CT; ++j) {
+                    const int col = cloc + j;
+                    if (col < ncols) {
+                        out[r * (int64_t)ncols + col] = __dmul_rn(acc[i][j], colscale ? colscale[col] : 1.0);
+                        if (out2) out2[r * (int64_t)ncols + col] = acc[i][j];
                     }
+                }
             }
         } else {
-            // the previous tile's bulk stores must have finished reading Cs
-            if (warp == 0 && stored) ab_bulk_wait_read0();
-            asm volatile("bar.sync 1, %0;" ::"n"(RZ_CONSUMERS * 32) : "memory");
+            // the tile leaves in rounds of RZ_CSTAGE columns: fragments -> Cs -> one bulk store per column
+            const uint32_t cb = (uint32_t)min((int64_t)RZ_TR, ldo - row0) * 8;
+            for (int cbase = 0; cbase < ncols; cbase += RZ_CSTAGE) {
+                if (warp == 0 && stored) ab_bulk_wait_read0();        // the previous round's stores have read Cs
+                asm volatile("bar.sync 1, %0;" ::"n"(RZ_CONSUMERS * 32) : "memory");
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        if (j < nb) Cs[(size_t)(8 * j + 2 * ak + e) * RZ_CS + 16 * warp + 8 * g + ar] = acc[g][j][e];
-            ab_fence_proxy_async();
-            asm volatile("bar.sync 1, %0;" ::"n"(RZ_CONSUMERS * 32) : "memory");
-            // one bulk store per output column, issued by the lanes of warp 0 (each tracks its own bulk group)
-            if (warp == 0) {
-                const uint32_t cb = (uint32_t)min((int64_t)RZ_TR, ldo - row0) * 8;
-                for (int c = lane; c < nc; c += 32)
-                    ab_bulk_s2g(out + (int64_t)(c0 + c) * ldo + row0, Cs + (size_t)c * RZ_CS, cb);
-                ab_bulk_commit();
-                stored = true;
+                for (int j = 0; j < CT; ++j) {
+                    const int col = cloc + j - cbase;
+                    if (col >= 0 && col < RZ_CSTAGE && cloc + j < ncols) {
+                        double *cd = Cs + (size_t)col * RZ_CS + rloc;
+                        *reinterpret_cast<double2 *>(cd) = make_double2(acc[0][j], acc[1][j]);
+                        *reinterpret_cast<double2 *>(cd + 2) = make_double2(acc[2][j], acc[3][j]);
+                    }
+                }
+                ab_fence_proxy_async();
+                asm volatile("bar.sync 1, %0;" ::"n"(RZ_CONSUMERS * 32) : "memory");
+                if (warp == 0) {
+                    const int nst = min(RZ_CSTAGE, ncols - cbase);
+                    for (int c = lane; c < nst; c += 32)
+                        ab_bulk_s2g(out + (int64_t)(cbase + c) * ldo + row0, Cs + (size_t)c * RZ_CS, cb);
+                    ab_bulk_commit();
+                    stored = true;
+                }
             }
         }
     }
     if (warp == 0 && stored) ab_bulk_wait0();                 // global writes complete before the CTA retires
+}
+
+typedef void (*ritz_fn)(const double *, int64_t, int64_t, int, const double *, int, double *, int64_t, int, const double *,
+                        double *, int, int);
+static ritz_fn ritz_pick(int ct) {
+    switch (ct) {
+        case 1: return ritz_kernel<1>;   case 2: return ritz_kernel<2>;   case 3: return ritz_kernel<3>;
+        case 4: return ritz_kernel<4>;   case 5: return ritz_kernel<5>;   case 6: return ritz_kernel<6>;
+        case 7: return ritz_kernel<7>;   case 8: return ritz_kernel<8>;   case 9: return ritz_kernel<9>;
+        case 10: return ritz_kernel<10>; case 11: return ritz_kernel<11>; case 12: return ritz_kernel<12>;
+        case 13: return ritz_kernel<13>; case 14: return ritz_kernel<14>; case 15: return ritz_kernel<15>;
+        default: return ritz_kernel<16>;
+    }
 }
 
 __global__ void copy_vec_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n) {
@@ -1334,15 +1348,17 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     const size_t svd_smem = (size_t)(q_in_smem ? 2 : 1) * work * work * 8;
     AB_CUDA(cudaFuncSetAttribute(svd_restart_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
     const bool svd_one_cta = getenv("AB_IRLB_SVD1") != nullptr;       // A/B switch: the one-CTA Jacobi (round 1)
-    const size_t rz_smem = ritz_smem_bytes(work);
-    AB_REQUIRE(rz_smem <= ctx->smem_optin, "ab_irlb: work dimension %d needs %zu bytes of shared memory", work, rz_smem);
-    AB_CUDA(cudaFuncSetAttribute(ritz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rz_smem));
     auto ritz = [&](const double *X, int64_t ldx, int64_t rows, const double *M, int ncols, double *out, int64_t ldo,
                     int rowmajor, const double *colscale, double *out2) -> int {
         if (rows <= 0 || ncols <= 0) return 0;
+        const RitzCfg rc = ritz_cfg(work, ncols);
+        AB_REQUIRE(rc.smem <= ctx->smem_optin, "ab_irlb: work dimension %d needs %zu bytes of shared memory", work, rc.smem);
+        ritz_fn fn = ritz_pick(rc.ct);
+        AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc.smem));
         const int64_t tiles = (rows + RZ_TR - 1) / RZ_TR;
-        const dim3 g((unsigned)std::min<int64_t>(tiles, ctx->sm_count), (unsigned)((ncols + RZ_NC - 1) / RZ_NC));
-        ritz_kernel<<<g, RZ_THREADS, rz_smem, st>>>(X, ldx, rows, work, M, ncols, out, ldo, rowmajor, colscale, out2);
+        fn<<<(unsigned)std::min<int64_t>(tiles, ctx->sm_count), RZ_THREADS, rc.smem, st>>>(X, ldx, rows, work, M, ncols, out,
+                                                                                          ldo, rowmajor, colscale, out2,
+                                                                                          rc.kc, rc.st);
         AB_LAUNCH_CHECK(ctx);
         return 0;
     };

@@ -214,6 +214,62 @@ extern "C" int ab_moments_finalize(ab_ctx *ctx, const uint64_t *acc, int32_t n_g
 }
 
 // ---------------------------------------------------------------------------------------
+// N4: per-gene moments of the LINEAR-scale values y = 2^x - 1 that hvg_brennecke reads
+// (alona/hvg.py:83-94: `2**data_norm - 1`, then mean / var per gene).  Same row walk as K1; a selector that is
+// rarely used, so the sums go to L2-resident FP64 accumulators with plain REDs (about 2e-16 relative run-to-run
+// jitter from the summation order; the HVG decision is a chi-square test against an FDR of 0.1).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+lin_moments_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ val,
+                   const int64_t *__restrict__ libsize, int64_t n_local, double scale, double *__restrict__ ysum,
+                   double *__restrict__ ysumsq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * NORM_WARPS;
+    for (int64_t row = warp_global; row < n_local; row += nwarps) {
+        const int64_t a = rowptr[row], b = rowptr[row + 1];
+        const double lib = (double)libsize[row];
+        // lane l: y of count l+1, formed the way the reference does: 2**log2(q + 1) - 1
+        const double tab = __dsub_rn(exp2(ab_norm_value((double)(lane + 1), lib, scale)), 1.0);
+        for (int64_t p0 = a + lane; p0 - lane < b; p0 += 128) {
+            int cc[4], gg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = p0 + 32 * u;
+                cc[u] = p < b ? __ldcs(val + p) : 0;
+                gg[u] = p < b ? __ldcs(col + p) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (p0 - lane + 32 * u >= b) break;                       // warp-uniform
+                const int c = cc[u], g = gg[u];
+                double y = ab_shfl_f64(tab, (c - 1) & 31);
+                if (g >= 0 && c > 0) {
+                    if (c > 32) y = __dsub_rn(exp2(ab_norm_value((double)c, lib, scale)), 1.0);
+                    atomicAdd(ysum + g, y);
+                    atomicAdd(ysumsq + g, __dmul_rn(y, y));
+                }
+            }
+        }
+    }
+}
+
+extern "C" int ab_norm_moments_linear(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                                      const int64_t *libsize, int64_t n_local, int32_t n_genes, double scale,
+                                      double *ysum, double *ysumsq, void *stream) {
+    AB_REQUIRE(ctx, "ab_norm_moments_linear: null ctx");
+    AB_REQUIRE(n_local >= 0 && n_genes > 0, "ab_norm_moments_linear: bad shape");
+    if (n_local == 0) return 0;
+    int64_t blocks = (n_local + NORM_WARPS - 1) / NORM_WARPS;
+    int64_t cap = (int64_t)ctx->sm_count * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    lin_moments_kernel<<<(unsigned)blocks, NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(rowptr, col, val, libsize, n_local,
+                                                                                       scale, ysum, ysumsq);
+    AB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
 // K3: HVG extract
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NORM_WARPS * 32)

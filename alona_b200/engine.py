@@ -285,6 +285,19 @@ class Engine:
                    'ab_moments_finalize')
         return gsum, gsumsq
 
+    def norm_moments_linear(self, A, libsize, allreduce=True):
+        """Per-gene sum / sum of squares of y = 2^x - 1 (the linear-scale values hvg_brennecke works on)."""
+        ys = self.zeros((A.n_genes,), torch.float64)
+        yq = self.zeros((A.n_genes,), torch.float64)
+        _lib.check(self.lib.ab_norm_moments_linear(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), _ptr(libsize),
+                                                   A.n_local, A.n_genes, SCALE, _ptr(ys), _ptr(yq), self.stream()),
+                   'ab_norm_moments_linear')
+        if allreduce and self.world > 1:
+            both = torch.cat([ys, yq])
+            self.allreduce_f64(both)
+            ys, yq = both[:A.n_genes].contiguous(), both[A.n_genes:].contiguous()
+        return ys, yq
+
     # -- K2 ---------------------------------------------------------------------------
     def hvg_seurat(self, gsum, gsumsq, n_total, hvg_n, nbins=20):
         g = gsum.numel()

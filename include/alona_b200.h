@@ -79,6 +79,15 @@ int ab_norm_moments(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, cons
 int ab_moments_finalize(ab_ctx *ctx, const uint64_t *acc, int32_t n_genes, double *gsum, double *gsumsq,
                         void *stream);
 
+/* ---- N4 (next row of the scope table): per-gene moments on the LINEAR scale ----------------
+ * the device part of AlonaHighlyVariableGenes.hvg_brennecke (alona/hvg.py:83-94): y = 2^x - 1 for every
+ * normalised value x, ysum[g] += y, ysumsq[g] += y*y over this shard's cells (FP64, caller-zeroed, summed across
+ * ranks with ab_allreduce_f64); libsize as produced by ab_norm_moments.  The selector's remaining steps (Gamma GLM
+ * on <= G points, chi-square test, Benjamini-Hochberg) are O(G) host statistics in alona_b200/hvg.py. */
+int ab_norm_moments_linear(ab_ctx *ctx, const int64_t *rowptr, const int32_t *col, const int32_t *val,
+                           const int64_t *libsize, int64_t n_local, int32_t n_genes, double scale,
+                           double *ysum, double *ysumsq, void *stream);
+
 /* ---- K2: Seurat-style HVG selection ----------------------------------------------------
  * replaces AlonaHighlyVariableGenes.hvg_seurat (alona/hvg.py:146-165): mean, ddof-1 variance,
  * `nbins` equal-width mean bins (pandas.cut semantics), dispersion=var/mean, per-bin z-score,

@@ -104,6 +104,43 @@ def make_c1_cases():
               ref['snn_graph'].shape[0])
 
 
+def make_hvg_methods_case(name, n, g, lbar, seed, hvg_n, n_ercc=48):
+    """N4 fixtures: AlonaHighlyVariableGenes.find() of the live reference with hvg_method Brennecke2013
+    (alona/hvg.py:65-131) and scran (:169-225) on one input; the ERCC spikes are extra count rows normalised on their
+    own, as AlonaCell.load_data does (alona/cell.py:397,410)."""
+    C, _ = ref_shim.load()
+    import alona.hvg as H
+    m, _ = synth_np.nb_counts(n, g, lbar=lbar, n_clusters=6, seed=seed)
+    rng = np.random.RandomState(seed + 1000)
+    # spikes: the same amount in every cell, abundances over four decades, Poisson noise
+    conc = np.exp(rng.uniform(np.log(0.3), np.log(300.0), n_ercc))
+    ercc = rng.poisson(conc[None, :] * np.exp(rng.normal(0.0, 0.2, (m.shape[0], 1)))).astype(np.int64)
+    ercc[:, ercc.sum(axis=0) == 0] = 1
+    df = _counts_df(m)
+    df_ercc = pd.DataFrame(ercc.T, index=['ERCC-%05d' % i for i in range(n_ercc)], columns=df.columns)
+    o = C.AlonaClustering()
+    o.params = {'qc_auto': False, 'loglevel': 'regular'}
+    o.low_quality_cells = []
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        dn = o.normalize(df, '', 'raw', False)
+        dn_ercc = o.normalize(df_ercc, '', 'raw', False)
+        gene_pos = {gname: i for i, gname in enumerate(df.index)}
+        out = {}
+        for method in ('Brennecke2013', 'scran'):
+            f = H.AlonaHighlyVariableGenes(hvg_method=method, hvg_n=hvg_n, data_norm=dn, data_ERCC=dn_ercc)
+            out[method] = np.array([gene_pos[x] for x in f.find()], dtype=np.int32)
+    import scipy.sparse as sp
+    e = sp.csr_matrix(ercc.astype(np.int32))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'),
+                        indptr=m.indptr.astype(np.int64), indices=m.indices.astype(np.int32), data=m.data.astype(np.int32),
+                        shape=np.array(m.shape, dtype=np.int64), ercc_indptr=e.indptr.astype(np.int64),
+                        ercc_indices=e.indices.astype(np.int32), ercc_data=e.data.astype(np.int32),
+                        ercc_shape=np.array(e.shape, dtype=np.int64), hvg_n=hvg_n,
+                        hvg_brennecke=out['Brennecke2013'], hvg_scran=out['scran'])
+    print(name, m.shape, 'brennecke', out['Brennecke2013'].size, 'scran', out['scran'].size)
+
+
 def make_knn_case(name, n, d, k, seed, dup=0, quantise=None):
     emb = synth_np.gaussian_mixture_embedding(n, d=d, seed=seed)
     if quantise:
@@ -185,6 +222,10 @@ def main():
         sys.exit('reference tree not present; fixtures can only be minted in the dev container')
     os.makedirs(OUT, exist_ok=True)
     warnings.simplefilter('ignore')
+    if '--hvg' in sys.argv:                     # only the N4 selector fixtures
+        make_hvg_methods_case('hvgm_900x2500', 900, 2500, 2500.0, 21, 300)
+        make_hvg_methods_case('hvgm_1500x4000', 1500, 4000, 900.0, 23, 5000)
+        return
     if '--c1' in sys.argv:                      # only the C1 family (minutes of the live reference)
         make_c1_cases()
         return
@@ -200,6 +241,8 @@ def main():
     make_cluster_exp_case('clexp_401x500', 401, 500, 150.0, 3, 17)
     make_qc_case('qc_rect_700x300', 700, 300, 10.0, 5, 4)
     make_c1_cases()
+    make_hvg_methods_case('hvgm_900x2500', 900, 2500, 2500.0, 21, 300)
+    make_hvg_methods_case('hvgm_1500x4000', 1500, 4000, 900.0, 23, 5000)
 
 
 if __name__ == '__main__':

@@ -8,7 +8,8 @@ the oracle port against the live reference when it is present.
 Shims:
   * empty stub modules for the seven packages the reference imports at module top but never
     calls on the hot path (matplotlib, seaborn, umap, leidenalg, igraph, patsy, statsmodels);
-  * numpy.float = float  (alona/irlbpy/irlb.py:85 uses the alias removed in numpy 1.24).
+  * numpy.float = float  (alona/irlbpy/irlb.py:85 uses the alias removed in numpy 1.24) and numpy.asfarray
+    (alona/stats.py:15, removed in numpy 2.0; only the Brennecke selector reaches it).
 No reference source is edited or copied.
 """
 import os
@@ -53,6 +54,8 @@ def load():
             sys.modules[name] = m
     if not hasattr(np, 'float'):
         np.float = float
+    if not hasattr(np, 'asfarray'):             # alona/stats.py:15 (p_adjust_bh), removed in numpy 2.0
+        np.asfarray = lambda a, dtype=np.float64: np.asarray(a, dtype=dtype)
     sys.dont_write_bytecode = True
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)

@@ -95,7 +95,9 @@ def test_out_of_scope_options_exit_like_log_error():
     with pytest.raises(SystemExit):
         o.normalize(pd.DataFrame(np.ones((3, 3), dtype=np.int64)), '', 'rpkm', False)
     with pytest.raises(SystemExit):
-        AlonaHighlyVariableGenes('scran', 10, None, None).find()
+        AlonaHighlyVariableGenes('scran', 10, None, None).find()             # no ERCC spikes: alona/hvg.py:187-190
+    with pytest.raises(SystemExit):
+        AlonaHighlyVariableGenes('Chen2016', 10, None, None).find()          # outside SURVEY.md 8(f) N4
     with pytest.raises(SystemExit):
         AlonaHighlyVariableGenes('nonsense', 10, None, None).find()
 
@@ -226,3 +228,38 @@ def test_cluster_with_custom_clustering_skips_the_graph(tmp_path):
     o.preclust = pd.DataFrame({'cell': cells[::-1], 'cluster': list(np.arange(n) % 3)})
     with pytest.raises(SystemExit):
         o.cluster()
+
+
+# ---- N4: the other HVG selectors through the reference's own surface (alona/hvg.py:41-57) ----------------------
+@pytest.mark.parametrize('case', ['hvgm_900x2500', 'hvgm_1500x4000'])
+def test_hvg_brennecke_and_scran_match_reference(case, tmp_path):
+    import scipy.sparse as sp
+    from alona_b200.clustering import AlonaClustering
+    from alona_b200.hvg import AlonaHighlyVariableGenes
+    g = load_golden(case)
+    m = golden_csr(g)
+    e = sp.csr_matrix((g['ercc_data'], g['ercc_indices'], g['ercc_indptr']), shape=tuple(int(v) for v in g['ercc_shape']))
+    genes = np.array(['g%d' % i for i in range(m.shape[1])])
+    o = AlonaClustering()
+    o.set_params({'output_directory': str(tmp_path), 'qc_auto': False, 'hvg_n': int(g['hvg_n'])})
+    o.low_quality_cells = []
+    o.data_norm = o.normalize(pd.DataFrame(m.T.toarray().astype(np.int64), index=genes), '', 'raw', False)
+    o.data_ERCC = o.normalize(pd.DataFrame(e.T.toarray().astype(np.int64),
+                                           index=['ERCC-%05d' % i for i in range(e.shape[1])]), '', 'raw', False)
+    f = AlonaHighlyVariableGenes('Brennecke2013', int(g['hvg_n']), o.data_norm, o.data_ERCC)
+    assert np.array_equal(f.find(), genes[g['hvg_brennecke']])                  # same genes, same (matrix) order
+    f = AlonaHighlyVariableGenes('scran', int(g['hvg_n']), o.data_norm, o.data_ERCC)
+    got = f.find()
+    assert set(got.tolist()) == set(genes[g['hvg_scran']].tolist())
+    assert (got == genes[g['hvg_scran']]).mean() > 0.99
+    # and through the mixin: find_variable_genes() -> PCA() keeps the selected genes in original matrix order
+    o.params['hvg_method'] = 'Brennecke2013'
+    o.params['pca_n'] = 10
+    o.params['seed'] = 1
+    o.find_variable_genes()
+    assert np.array_equal(o.hvg, genes[g['hvg_brennecke']])
+    o.PCA(str(tmp_path) + '/csvs/pca.csv')
+    assert o.pca_components.shape == (m.shape[0], 10)
+    assert o.report['pca']['nnz_hvg'] == int(m[:, g['hvg_brennecke']].nnz)
+    with pytest.raises(SystemExit):                                             # scran without spikes: hvg.py:187-190
+        AlonaHighlyVariableGenes('scran', 10, o.data_norm, pd.DataFrame()).find()

@@ -167,3 +167,34 @@ def test_restated_cluster_mean_median(case):
     assert np.allclose(med, g['median'], rtol=1e-13, atol=0)
     assert np.array_equal(med == 0, g['median'] == 0)
     assert np.allclose(rss / (m.shape[0] - len(g['cluster_ids'])), g['sigma2'], rtol=1e-11, atol=1e-15)
+
+
+# ---- N4: Brennecke2013 / scran selectors (alona/hvg.py:65-131, 169-225) ---------------------------------------
+HVGM_CASES = ['hvgm_900x2500', 'hvgm_1500x4000']
+
+
+@pytest.mark.parametrize('case', HVGM_CASES)
+def test_host_statistics_of_brennecke_and_scran_match_reference(case):
+    """The O(G) host half of the two selectors (alona_b200/hvg.py) fed with oracle-computed per-gene sums must pick
+    the reference's genes, in the reference's order."""
+    import scipy.sparse as sp
+    from alona_b200.hvg import brennecke_select, scran_select, mean_var_from_sums
+    g = load_golden(case)
+    m = golden_csr(g)
+    n = m.shape[0]
+    x = R.normalized_values(m)
+    y = 2 ** x - 1                                                     # alona/hvg.py:83
+    ys = np.bincount(m.indices, weights=y, minlength=m.shape[1])
+    yq = np.bincount(m.indices, weights=y * y, minlength=m.shape[1])
+    idx, diag = brennecke_select(ys, yq, n, int(g['hvg_n']))
+    assert np.array_equal(idx, g['hvg_brennecke'])
+    e = sp.csr_matrix((g['ercc_data'], g['ercc_indices'], g['ercc_indptr']), shape=tuple(int(v) for v in g['ercc_shape']))
+    xe = R.normalized_values(e)
+    es = np.bincount(e.indices, weights=xe, minlength=e.shape[1])
+    eq = np.bincount(e.indices, weights=xe * xe, minlength=e.shape[1])
+    mt, vt = mean_var_from_sums(es, eq, n)
+    sx, sx2, _ = R.gene_moments(m)
+    idx2, _ = scran_select(mt, vt, sx, sx2, n, int(g['hvg_n']))
+    assert set(idx2.tolist()) == set(g['hvg_scran'].tolist())
+    same = idx2 == g['hvg_scran']
+    assert same.mean() > 0.99                                          # order: equal up to rounding-level ties
