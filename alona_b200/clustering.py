@@ -105,6 +105,10 @@ class AlonaClustering(AlonaCell):
         idx, rdist, stats = eng.knn(emb.contiguous(), int(inp_k), lo, hi, mode=int(self.params.get('knn_mode', 0)))
         rows = [bounds[r + 1] - bounds[r] for r in range(eng.world)]
         self._knn_dev = eng.allgather_rows(idx, rows)
+        if eng.world > 1:
+            counters = stats[:4].clone()                     # tie / fallback / duplicate / certified rows: sum over ranks
+            eng.allreduce_i64(counters)
+            stats = torch.cat([counters, stats[4:]])
         st = stats.cpu().numpy()
         self.report['knn'] = {'tie_rows': int(st[0]), 'exact_fallback_rows': int(st[1]), 'duplicate_rows': int(st[2]),
                               'certified_rows': int(st[3])}
@@ -130,7 +134,6 @@ class AlonaClustering(AlonaCell):
         bounds = shard_bounds(n, eng.world)
         lo, hi = bounds[eng.rank], bounds[eng.rank + 1]
         vmin = prune_threshold(int(k), prune_snn)
-        # unpruned nonzeros of A.A^T are only needed for the ">80 % pruned" warning
         res = eng.snn(knn_dev, vmin, lo, hi, want_overlap=True)
         self._snn_dev = res
         counts = None
@@ -146,8 +149,20 @@ class AlonaClustering(AlonaCell):
         else:
             src, dst, ov = res['src'], res['dst'], res['overlap']
         self.snn_overlap = ov.cpu().numpy()
-        self.report['snn'] = {'edges': int(src.numel()), 'v_min': vmin, 'big_rows': res['big_rows'],
-                              'max_walk': res['max_walk'], 'duplicate_rows': res['dup_rows']}
+        nonzeros, dup_rows = res['nonzeros_unpruned'], res['dup_rows']
+        if eng.world > 1:
+            t = torch.tensor([nonzeros, dup_rows], dtype=torch.int64, device=eng.device)
+            eng.allreduce_i64(t)
+            nonzeros, dup_rows = int(t[0].item()), int(t[1].item())
+        self.report['snn'] = {'edges': int(src.numel()), 'v_min': vmin, 'max_walk': res['max_walk'],
+                              'duplicate_rows': dup_rows, 'nonzeros_unpruned': nonzeros}
+        # the reference's messages (clustering.py:231-235)
+        pruned_count = nonzeros - int(src.numel())
+        perc_pruned = (pruned_count / max(1, nonzeros)) * 100
+        log_debug('%.2f%% (n=%s) of links pruned' % (perc_pruned, '{:,}'.format(pruned_count)))
+        if perc_pruned > 80:
+            log_warning('more than 80% of the edges were pruned')
+        res = dict(res, dup_rows=dup_rows)
         if res['dup_rows']:
             log_warning('%d cells have an exact duplicate ranked before themselves; the reference keys such rows '
                         'on the duplicate (clustering.py:204) - reported, not emulated.' % res['dup_rows'])

@@ -294,8 +294,8 @@ def main():
     info = {'steps': out['irlb']['steps'], 'nmult': out['irlb']['nmult'], 'sum_panel': out['irlb']['sum_panel'],
             'fused_allreduce': out['irlb'].get('fused_allreduce', False), **hashes,
             'nnz': nnz_local, 'nnz_hvg': nnz_h, 'edges_local': edges_local,
-            'knn_stats': out['knn_stats'].cpu().numpy().tolist(), 'snn_big_rows': out['snn']['big_rows'],
-            'snn_max_walk': out['snn']['max_walk'], 'hvg_stats': out['hvg_stats'].cpu().numpy().tolist()}
+            'knn_stats': out['knn_stats'].cpu().numpy().tolist(), 'snn_max_walk': out['snn']['max_walk'], 'snn_nonzeros_unpruned': out['snn']['nonzeros_unpruned'],
+            'hvg_stats': out['hvg_stats'].cpu().numpy().tolist()}
 
     # ---- per-kernel table: one extra, untimed pass (ALL ranks: it contains the collectives) with an
     # event pair around every launch -----------------------------------------------------------

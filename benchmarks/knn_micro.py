@@ -58,7 +58,7 @@ def main():
             torch.cuda.synchronize(); t0 = time.perf_counter()
             res = eng.snn(idx, prune_threshold(k, 0.067), want_overlap=False)
             torch.cuda.synchronize(); rec['snn_s'] = time.perf_counter() - t0
-            rec['edges'] = int(res['src'].numel()); rec['snn_big_rows'] = res['big_rows']; rec['snn_max_walk'] = res['max_walk']
+            rec['edges'] = int(res['src'].numel()); rec['snn_max_walk'] = res['max_walk']
         print(json.dumps(rec), flush=True)
 
 

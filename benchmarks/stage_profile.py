@@ -36,7 +36,7 @@ def main():
                       'kernel_ms': {k: {'total_ms': round(v[0], 3), 'launches': v[1]} for k, v in pr.items()},
                       'irlb': {k: out['irlb'][k] for k in ('steps', 'nmult', 'sum_panel')},
                       'nnz': A.nnz, 'nnz_hvg': out['AH'].nnz, 'edges': int(out['snn']['src'].numel()),
-                      'snn': {k: out['snn'][k] for k in ('big_rows', 'max_walk', 'dense_rows', 'sum_walk', 'class_rows')}}))
+                      'snn': {k: out['snn'][k] for k in ('max_walk', 'sum_walk', 'nonzeros_unpruned')}}))
 
 
 if __name__ == '__main__':
