@@ -65,7 +65,8 @@ SIGNATURES = {
     'ab_irlb_ws_bytes': (c_size, [c_i64, c_i32, c_i32]),
     'ab_irlb_ws_bytes_compact': (c_size, [c_i64, c_i32, c_i32, c_i64]),
     'ab_irlb': (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_f64, c_i32,
-                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, p_i64, c_void_p, c_size, c_void_p]),
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, p_i64, c_void_p, c_size,
+                               c_void_p]),
     'ab_knn_ws_bytes': (c_size, [c_i64, c_i32, c_i64, c_i32]),
     'ab_knn': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i64, c_i32, c_i32, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_size, c_void_p]),

@@ -59,12 +59,16 @@ class AlonaClustering(AlonaCell):
 
     # -- PCA ------------------------------------------------------------------------------
     def PCA(self, out_path):
-        """Truncated SVD of the (uncentred) HVG x cells log-expression matrix by IRLBA,
-        scores = V.diag(s) (alona/clustering.py:103-113)."""
+        """--pca irlb: truncated SVD of the (uncentred) HVG x cells log-expression matrix by IRLBA,
+        scores = V.diag(s) (alona/clustering.py:103-113).
+        --pca regular (alona/clustering.py:114-125): the reference centres every gene, takes the full LAPACK SVD and
+        keeps the first pca_n columns of x.v = u.diag(d).  Here the same leading components come from the same
+        device iteration run on the IMPLICITLY centred operator (gene means subtracted inside the products, the
+        centred matrix is never formed) to a residual tolerance of 1e-10, i.e. the centred exact SVD to ~1e-8 per
+        component; component signs are LAPACK's convention in the reference and arbitrary here (as for irlb)."""
         log_debug('Running PCA...')
-        if self.params['pca'] != 'irlb':
-            # clustering.py:114-125 (--pca regular) is not on the hot path (SURVEY.md §8(f) N4)
-            log_error('alona_b200 implements --pca irlb only.')
+        if self.params['pca'] not in ('irlb', 'regular'):
+            log_error('--pca must be irlb or regular.')
         eng = get_engine()
         dn = self.data_norm
         n_comp = self.params['pca_n']
@@ -78,7 +82,14 @@ class AlonaClustering(AlonaCell):
             gene2hvg = torch.from_numpy(g2h).to(eng.device)
         n_hvg = int((gene2hvg >= 0).sum().item())
         self._AH = eng.hvg_extract(dn.counts, dn.libsize, gene2hvg, n_hvg)
-        lanc = irlbpy.lanczos(self._AH, nval=n_comp, maxit=1000, seed=self.params['seed'], device_result=True)
+        if self.params['pca'] == 'regular':
+            # per-gene means of the HVG columns (original gene order), from the moments of the normalisation pass
+            sel = torch.nonzero(gene2hvg >= 0).flatten()
+            center = (dn.gsum[sel] / dn.counts.n_total).contiguous()
+            lanc = irlbpy.lanczos(self._AH, nval=n_comp, tol=1e-10, maxit=1000, seed=self.params['seed'],
+                                  device_result=True, gene_center=center)
+        else:
+            lanc = irlbpy.lanczos(self._AH, nval=n_comp, maxit=1000, seed=self.params['seed'], device_result=True)
         self._lanczos = lanc
         self.report['pca'] = {'steps': lanc['steps'], 'nmult': lanc['nmult'], 'nnz_hvg': self._AH.nnz,
                               'not_converged': lanc['not_converged']}

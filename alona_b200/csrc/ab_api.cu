@@ -152,6 +152,12 @@ extern "C" int ab_peer_open(ab_ctx *ctx, const void *h_handles) {
         memcpy(&h, (const char *)h_handles + (size_t)q * sizeof(h), sizeof(h));
         AB_CUDA(cudaIpcOpenMemHandle(&ctx->peer_buf[q], h, cudaIpcMemLazyEnablePeerAccess));
     }
+    AbPeer h{};
+    h.world = ctx->world;
+    h.rank = ctx->rank;
+    for (int q = 0; q < ctx->world; ++q) h.buf[q] = (char *)ctx->peer_buf[q];
+    if (!ctx->d_peer) AB_CUDA(cudaMalloc(&ctx->d_peer, sizeof(AbPeer)));
+    AB_CUDA(cudaMemcpy(ctx->d_peer, &h, sizeof(AbPeer), cudaMemcpyHostToDevice));
     ctx->peer_ready = true;
     return 0;
 }
@@ -190,6 +196,7 @@ extern "C" int ab_ctx_destroy(ab_ctx *ctx) {
     for (int q = 0; q < ctx->world && q < AB_PEER_MAX; ++q)
         if (ctx->peer_ready && q != ctx->rank && ctx->peer_buf[q]) cudaIpcCloseMemHandle(ctx->peer_buf[q]);
     if (ctx->peer_local) cudaFree(ctx->peer_local);
+    if (ctx->d_peer) cudaFree(ctx->d_peer);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     for (int i = 0; i < AB_PROF_SLOTS; ++i) {
         for (cudaEvent_t e : ctx->prof[i].begin) cudaEventDestroy(e);

@@ -46,6 +46,7 @@ struct ab_ctx {
     void *comm = nullptr;          // ncclComm_t
     void *peer_local = nullptr;    // this rank's peer-exchange buffer (ab_peer.cuh), cudaMalloc'ed
     void *peer_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // all ranks' buffers, mapped
+    void *d_peer = nullptr;        // device copy of the AbPeer table the kernels read
     bool peer_ready = false;       // ab_peer_open succeeded on every rank
     uint32_t peer_seq[4] = {0, 0, 0, 0};   // per-channel instance counters (identical on all ranks)
     int *d_counter = nullptr;      // device scratch: "last block done" tickets (64 ints, kept 0)

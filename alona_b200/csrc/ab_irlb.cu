@@ -29,7 +29,8 @@ static constexpr int DOT_ROWS = 4;              // rows per thread
 static constexpr int DOT_TILE = DOT_THREADS * DOT_ROWS;
 
 // scalar slots (device doubles)
-enum { SC_S = 0, SC_FN2 = 1, SC_SMAX = 2, SC_V0N2 = 3, SC_COUNT = 8 };
+enum { SC_S = 0, SC_FN2 = 1, SC_SMAX = 2, SC_V0N2 = 3, SC_MUW = 4 /* mu^T w of the current left vector (0 without centring) */,
+       SC_SUMX = 5 /* sum over ALL cells of the vector the next A.x multiplies (centring only) */, SC_COUNT = 8 };
 // control ints
 enum { CT_CONV = 0, CT_KEEP = 1, CT_DONE = 2, CT_ROT = 3, CT_COUNT = 8 };
 
@@ -62,12 +63,13 @@ atw_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, 
     const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * 8;
     const double s = scal[SC_S];
+    const double muw = scal[SC_MUW];             // implicit centring: (A - mu 1^T)^T w = A^T w - (mu^T w) 1; 0.0 otherwise
     for (int64_t row = wid; row < n; row += nw) {
         const int64_t a = rowptr[row], b = rowptr[row + 1];
         double acc = 0.0;
         for (int64_t p = a + lane; p < b; p += 32) acc = fma(__ldg(val + p), __ldg(w + __ldg(col + p)), acc);
         acc = ab_warp_sum_f64(acc);
-        if (lane == 0) F[row] = __dsub_rn(acc, __dmul_rn(s, vj[row]));
+        if (lane == 0) F[row] = __dsub_rn(__dsub_rn(acc, muw), __dmul_rn(s, vj[row]));
     }
 }
 
@@ -150,6 +152,7 @@ atw_compact_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restric
     const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * 8;
     const double s = scal[SC_S];
+    const double muw = scal[SC_MUW];             // see atw_kernel
     for (int64_t row = wid; row < n; row += nw) {
         const int64_t a = rowptr[row], b = rowptr[row + 1];
         const double *__restrict__ tb = tabv + taboff[row];
@@ -159,7 +162,7 @@ atw_compact_kernel(const int64_t *__restrict__ rowptr, const uint32_t *__restric
             acc = fma(__ldg(tb + (e >> 16)), w_sm[e & 0xFFFFu], acc);
         }
         acc = ab_warp_sum_f64(acc);
-        if (lane == 0) F[row] = __dsub_rn(acc, __dmul_rn(s, vj[row]));
+        if (lane == 0) F[row] = __dsub_rn(__dsub_rn(acc, muw), __dmul_rn(s, vj[row]));
     }
 }
 
@@ -175,7 +178,7 @@ static constexpr int PD_CB = 16;
 __global__ void __launch_bounds__(DOT_THREADS)
 panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols, const double *__restrict__ F,
                  double *__restrict__ partial /*[grid][IR_MAXWORK]*/, double *__restrict__ out, int *counter,
-                 AbPeer peer, uint32_t seq_coef) {
+                 const AbPeer *__restrict__ peer_p, uint32_t seq_coef) {
     __shared__ double wsum[DOT_THREADS / 32][PD_CB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * DOT_THREADS;
@@ -217,13 +220,13 @@ panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols,
         for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) {
             double t = 0.0;
             for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + (int64_t)b * IR_MAXWORK + l);
-            if (peer.world > 1) ab_peer_push(peer, AB_CH_COEF, seq_coef, l, t);      // all-reduce, first half: push
+            if (ab_peer_world(peer_p) > 1) ab_peer_push(*peer_p, AB_CH_COEF, seq_coef, l, t);      // all-reduce, first half: push
             else out[l] = t;
         }
-        if (peer.world > 1) {
+        if (ab_peer_world(peer_p) > 1) {
             __threadfence_system();
             __syncthreads();
-            if (threadIdx.x == 0) ab_peer_publish(peer, AB_CH_COEF, seq_coef);
+            if (threadIdx.x == 0) ab_peer_publish(*peer_p, AB_CH_COEF, seq_coef);
         }
     }
 }
@@ -232,13 +235,13 @@ panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols,
 __global__ void __launch_bounds__(DOT_THREADS)
 panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols, const double *__restrict__ c,
                     double *__restrict__ F, double *__restrict__ partial, double *__restrict__ out_fn2, int *counter,
-                    AbPeer peer, uint32_t seq_coef, uint32_t seq_fn2) {
+                    const AbPeer *__restrict__ peer_p, uint32_t seq_coef, uint32_t seq_fn2) {
     __shared__ double cs[IR_MAXWORK];
     __shared__ double red[DOT_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (peer.world > 1) {
-        ab_peer_wait(peer, AB_CH_COEF, seq_coef);                                    // all-reduce, second half: sum
-        for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) cs[l] = ab_peer_sum(peer, AB_CH_COEF, seq_coef, l);
+    if (ab_peer_world(peer_p) > 1) {
+        ab_peer_wait(*peer_p, AB_CH_COEF, seq_coef);                                    // all-reduce, second half: sum
+        for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) cs[l] = ab_peer_sum(*peer_p, AB_CH_COEF, seq_coef, l);
     } else {
         for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) cs[l] = c[l];
     }
@@ -274,9 +277,9 @@ panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int nco
         if (threadIdx.x == 0) {
             double tt = 0.0;
             for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
-            if (peer.world > 1) {
-                ab_peer_push(peer, AB_CH_SCAL, seq_fn2, 0, tt);
-                ab_peer_publish(peer, AB_CH_SCAL, seq_fn2);
+            if (ab_peer_world(peer_p) > 1) {
+                ab_peer_push(*peer_p, AB_CH_SCAL, seq_fn2, 0, tt);
+                ab_peer_publish(*peer_p, AB_CH_SCAL, seq_fn2);
             } else {
                 *out_fn2 = tt;
             }
@@ -286,10 +289,10 @@ panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int nco
 
 // ||F||^2 summed over ranks: the consumer kernels (A.v or the final F scaling) finish the all-reduce themselves;
 // block 0 also leaves the total in scal[SC_FN2] for the kernels that follow on the stream.
-__device__ __forceinline__ double resolve_fn2(const AbPeer &peer, uint32_t seq_fn2, double *__restrict__ scal) {
-    if (peer.world == 1) return scal[SC_FN2];
-    ab_peer_wait(peer, AB_CH_SCAL, seq_fn2);
-    const double t = ab_peer_sum(peer, AB_CH_SCAL, seq_fn2, 0);
+__device__ __forceinline__ double resolve_fn2(const AbPeer *__restrict__ peer_p, uint32_t seq_fn2, double *__restrict__ scal) {
+    if (ab_peer_world(peer_p) == 1) return scal[SC_FN2];
+    ab_peer_wait(*peer_p, AB_CH_SCAL, seq_fn2);
+    const double t = ab_peer_sum(*peer_p, AB_CH_SCAL, seq_fn2, 0);
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_FN2] = t;
     return t;
 }
@@ -317,6 +320,49 @@ sumsq_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ parti
             for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
             *out = tt;
         }
+    }
+}
+
+// plain sum of a vector (centring: 1^T x), same fixed-order reduction as sumsq_kernel
+__global__ void __launch_bounds__(DOT_THREADS)
+vecsum_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ partial, double *__restrict__ out,
+              int *counter) {
+    __shared__ double red[DOT_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * DOT_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * DOT_THREADS)
+        acc += x[i];
+    acc = ab_warp_sum_f64(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tt = 0.0;
+        for (int w2 = 0; w2 < DOT_THREADS / 32; ++w2) tt += red[w2];
+        partial[blockIdx.x] = tt;
+    }
+    if (last_block_ticket(counter)) {
+        if (threadIdx.x == 0) {
+            double tt = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
+            *out = tt;
+        }
+    }
+}
+
+// mu^T w over the H genes (centring), one CTA
+__global__ void __launch_bounds__(256)
+muw_kernel(const double *__restrict__ mu, const double *__restrict__ w, int H, double *__restrict__ out) {
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (int g = threadIdx.x; g < H; g += 256) acc = fma(mu[g], w[g], acc);
+    acc = ab_warp_sum_f64(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tt = 0.0;
+        for (int w2 = 0; w2 < 8; ++w2) tt += red[w2];
+        *out = tt;
     }
 }
 
@@ -428,10 +474,10 @@ __global__ void __launch_bounds__(384, 1)
 av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
           int64_t n, int H, const double *__restrict__ src, double *__restrict__ scal_fn2 /* scal, or NULL: scale 1 */,
           double *__restrict__ vdst, int nwarps_cta, double *__restrict__ partial /*[grid][H]*/,
-          AbPeer peer, uint32_t seq_fn2) {
+          const AbPeer *__restrict__ peer_p, uint32_t seq_fn2) {
     extern __shared__ double acc_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double scale = scal_fn2 ? invcheck(sqrt(resolve_fn2(peer, seq_fn2, scal_fn2))) : 1.0;
+    const double scale = scal_fn2 ? invcheck(sqrt(resolve_fn2(peer_p, seq_fn2, scal_fn2))) : 1.0;
     for (int i = threadIdx.x; i < nwarps_cta * H; i += blockDim.x) acc_sm[i] = 0.0;
     __syncthreads();
     if (warp < nwarps_cta) {
@@ -508,16 +554,22 @@ av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, c
 // NVLink; the last block raises the flags (the consumer, wstep_kernel, sums the slots in rank order).
 __global__ void __launch_bounds__(128)
 av_reduce_kernel(const double *__restrict__ partial, int nparts, int H, double *__restrict__ out, int *counter,
-                 AbPeer peer, uint32_t seq_vec) {
+                 const AbPeer *__restrict__ peer_p, uint32_t seq_vec, const double *__restrict__ mu /* NULL, or on ONE rank the gene means */,
+                 const double *__restrict__ scal, int scaled) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < H) {
         double t = 0.0;
         for (int b = 0; b < nparts; ++b) t += partial[(size_t)b * H + g];
-        if (peer.world > 1) ab_peer_push(peer, AB_CH_VEC, seq_vec, g, t);
+        // implicit centring: (A - mu 1^T) x = A x - mu (1^T x); the correction enters once (on rank 0's contribution)
+        if (mu) {
+            const double sx = (scaled ? invcheck(sqrt(scal[SC_FN2])) : 1.0) * scal[SC_SUMX];
+            t = __dsub_rn(t, __dmul_rn(mu[g], sx));
+        }
+        if (ab_peer_world(peer_p) > 1) ab_peer_push(*peer_p, AB_CH_VEC, seq_vec, g, t);
         else out[g] = t;
     }
-    if (peer.world > 1 && last_block_ticket(counter, true)) {
-        if (threadIdx.x == 0) ab_peer_publish(peer, AB_CH_VEC, seq_vec);
+    if (ab_peer_world(peer_p) > 1 && last_block_ticket(counter, true)) {
+        if (threadIdx.x == 0) ab_peer_publish(*peer_p, AB_CH_VEC, seq_vec);
     }
 }
 
@@ -538,7 +590,7 @@ static constexpr int WS_THREADS = 512;
 __global__ void __launch_bounds__(WS_THREADS, 1)
 wstep_kernel(const double *__restrict__ wraw, double *__restrict__ W, int H, int64_t ldw, int jd, int ncols, int sub_prev,
              double *__restrict__ scal, double *__restrict__ B, int work, int jb, int cache_w,
-             AbPeer peer, uint32_t seq_vec) {
+             const AbPeer *__restrict__ peer_p, uint32_t seq_vec) {
     extern __shared__ double ws_sm[];
     __shared__ double inbox_c[WS_CL][IR_MAXWORK];        // partial W^T t of every CTA of the cluster
     __shared__ double inbox_n[WS_CL];                    // partial ||t||^2
@@ -551,14 +603,14 @@ wstep_kernel(const double *__restrict__ wraw, double *__restrict__ W, int H, int
     const int nsp = (H + WS_CL - 1) / WS_CL + 1;         // slice capacity
     double *t = ws_sm;                                   // [nsp]
     double *Wc = ws_sm + nsp;                            // [ncols][ns] when cache_w
-    if (peer.world > 1) ab_peer_wait(peer, AB_CH_VEC, seq_vec);
+    if (ab_peer_world(peer_p) > 1) ab_peer_wait(*peer_p, AB_CH_VEC, seq_vec);
     const double fn = sqrt(scal[SC_FN2]);
     if (cr == 0 && threadIdx.x == 0 && jb >= 0) {
         B[jb * work + jb] = scal[SC_S];
         if (jb + 1 < work) B[jb * work + jb + 1] = fn;
     }
     for (int g = threadIdx.x; g < ns; g += WS_THREADS) {
-        double v = peer.world > 1 ? ab_peer_sum(peer, AB_CH_VEC, seq_vec, g0 + g) : wraw[g0 + g];
+        double v = ab_peer_world(peer_p) > 1 ? ab_peer_sum(*peer_p, AB_CH_VEC, seq_vec, g0 + g) : wraw[g0 + g];
         if (sub_prev) v = __dsub_rn(v, __dmul_rn(fn, W[(size_t)(jd - 1) * ldw + g0 + g]));
         t[g] = v;
     }
@@ -626,8 +678,8 @@ wstep_kernel(const double *__restrict__ wraw, double *__restrict__ W, int H, int
 
 // last Lanczos step of a pass (j = work-1): F *= invcheck(fn); B[j,j] = s  (irlb.py:193,221)
 __global__ void fscale_kernel(double *__restrict__ F, int64_t n, double *__restrict__ scal,
-                              double *__restrict__ B, int work, int jb, AbPeer peer, uint32_t seq_fn2) {
-    const double inv = invcheck(sqrt(resolve_fn2(peer, seq_fn2, scal)));
+                              double *__restrict__ B, int work, int jb, const AbPeer *__restrict__ peer_p, uint32_t seq_fn2) {
+    const double inv = invcheck(sqrt(resolve_fn2(peer_p, seq_fn2, scal)));
     if (blockIdx.x == 0 && threadIdx.x == 0) B[jb * work + jb] = scal[SC_S];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         F[i] = __dmul_rn(inv, F[i]);
@@ -1278,7 +1330,7 @@ extern "C" size_t ab_irlb_ws_bytes_compact(int64_t n_local, int32_t n_hvg, int32
 
 extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_h, const double *val_h,
                        int64_t n_local, int64_t n_total, int32_t n_hvg, int32_t nval, double tol, int32_t maxit,
-                       const double *v0_local, double *scores_local, double *v_local, double *s_out, double *u_out,
+                       const double *v0_local, const double *center, double *scores_local, double *v_local, double *s_out, double *u_out,
                        int64_t *h_info, void *ws, size_t ws_bytes, void *stream) {
     AB_REQUIRE(ctx, "ab_irlb: null ctx");
     AB_REQUIRE(n_hvg >= 2 && n_total >= 2, "ab_irlb: the input matrix must be at least 2x2 (irlb.py:119-120)");
@@ -1296,15 +1348,8 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     int *cnt = ctx->d_counter;
     // small all-reduces: fused one-shot pushes over NVLink peer memory when the exchange buffers are mapped
     // (ab_peer_open), ncclAllReduce between the kernels otherwise
-    AbPeer peer{};
-    peer.world = 1;
-    peer.rank = 0;
     const bool fused = ctx->world > 1 && ctx->peer_ready && H <= AB_PEER_VEC && !getenv("AB_IRLB_NCCL");
-    if (fused) {
-        peer.world = ctx->world;
-        peer.rank = ctx->rank;
-        for (int q = 0; q < ctx->world; ++q) peer.buf[q] = (char *)ctx->peer_buf[q];
-    }
+    const AbPeer *peer = fused ? (const AbPeer *)ctx->d_peer : nullptr;      // device copy of the peer table; NULL: no exchange
     uint32_t *seq = ctx->peer_seq;
 
     ab_prof_begin(ctx, AB_PROF_IRLB_TOTAL, st);
@@ -1385,6 +1430,10 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         AB_CUDA(cudaLaunchKernelEx(&cfg, wstep_kernel, (const double *)w.wraw, w.W, H, ldw, jd, ncols, sub_prev, w.scal, w.B,
                                    work, jb, cache_w, peer, seq_vec));
         AB_LAUNCH_CHECK(ctx);
+        if (center) {                                       // mu^T w of the new left vector, read by the next A^T.w
+            muw_kernel<<<1, 256, 0, st>>>(center, w.W + (size_t)jd * ldw, H, w.scal + SC_MUW);
+            AB_LAUNCH_CHECK(ctx);
+        }
         ab_prof_end(ctx, AB_PROF_IRLB_SMALL, st);
         return 0;
     };
@@ -1400,6 +1449,13 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     // A.x, summed over the CTAs (and, sharded, pushed to every rank); returns the instance id the consumer waits for
     uint32_t seq_fn2 = 0;                                    // instance of the last ||F||^2 exchange
     auto av = [&](const double *src, bool scaled, double *vdst, uint32_t *seq_vec_out) -> int {
+        if (center) {
+            // implicit centring needs 1^T x over all cells (x = src, scaled inside av_reduce_kernel)
+            vecsum_kernel<<<(unsigned)std::min<int64_t>(1024, std::max<int64_t>(1, (n + 255) / 256)), DOT_THREADS, 0, st>>>(
+                src, n, w.nrm_partial, w.scal + SC_SUMX, cnt + 4);
+            AB_LAUNCH_CHECK(ctx);
+            if (ab_allreduce_f64(ctx, w.scal + SC_SUMX, 1, st)) return 1;
+        }
         ab_prof_begin(ctx, AB_PROF_IRLB_AV, st);
         // (A.x keeps the plain operand: its 12 warps per SM leave ~30 KB of L1, a table look-up per nonzero at consume
         // time misses it, and the compact variant measured 344 ms against 195)
@@ -1407,7 +1463,8 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
                                                    w.av_warps, w.av_partial, peer, seq_fn2);
         AB_LAUNCH_CHECK(ctx);
         const uint32_t sv = fused ? ++seq[AB_CH_VEC] : 0;
-        av_reduce_kernel<<<(H + 127) / 128, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw, cnt + 3, peer, sv);
+        av_reduce_kernel<<<(H + 127) / 128, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw, cnt + 3, peer, sv,
+                                                          (center && ctx->rank == 0) ? center : nullptr, w.scal, scaled ? 1 : 0);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_AV, st);
         if (!fused && ab_allreduce_f64(ctx, w.wraw, H, st)) return 1;

@@ -20,7 +20,7 @@ static constexpr int AB_PEER_COEF = 128;               // channel 1: CGS coeffic
 static constexpr int AB_PEER_SCAL = 8;                 // channel 2: ||F||^2
 enum { AB_CH_VEC = 0, AB_CH_COEF = 1, AB_CH_SCAL = 2, AB_CH_COUNT = 3 };
 
-struct AbPeer {                                        // passed to kernels by value
+struct AbPeer {                                        // lives in device memory (ab_ctx::d_peer)
     int world, rank;
     char *buf[AB_PEER_MAX];                            // every rank's exchange buffer; buf[rank] is the local one
 };
@@ -35,6 +35,8 @@ __host__ __device__ constexpr size_t ab_peer_ch_off(int ch) {      // byte offse
 static constexpr size_t AB_PEER_BYTES = ab_peer_ch_off(AB_CH_SCAL) + 2 * AB_PEER_MAX * (size_t)AB_PEER_SCAL * 8;
 
 #ifdef __CUDACC__
+// kernels take the table by pointer (a device copy kept in the context); NULL = single rank / exchange off
+__device__ __forceinline__ int ab_peer_world(const AbPeer *p) { return p ? p->world : 1; }
 __device__ __forceinline__ uint32_t *ab_peer_flag(char *buf, int ch, int sender) {
     return reinterpret_cast<uint32_t *>(buf + 256 * ch) + sender * 8;          // 32 bytes apart
 }

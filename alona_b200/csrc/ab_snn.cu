@@ -186,26 +186,30 @@ __device__ __forceinline__ long long warp_load_row(const int32_t *__restrict__ k
     return run;
 }
 
-// walk position -> (index a of the neighbour whose reverse list holds it, cell id m)
-__device__ __forceinline__ int walk_fetch(const WarpRowState &st, int k, int p, const int32_t *__restrict__ rlist, int &a_out) {
-    int lo = 0, hi = k;                                   // last a with base[a] <= p
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (st.base[mid] <= p) lo = mid; else hi = mid;
-    }
-    a_out = lo;
-    return __ldg(rlist + st.start[lo] + (p - st.base[lo]));
-}
-
 __device__ __forceinline__ unsigned snn_hash(int key, int lg) { return ((unsigned)key * 2654435761u) >> (32 - lg); }
+
+// membership probe: position of cell x in the row's sorted neighbour list, or -1
+__device__ __forceinline__ int snn_probe(const int *__restrict__ hkeys, const int *__restrict__ hvals, int S, int lg, int x) {
+    unsigned s = snn_hash(x, lg);
+    int key = hkeys[s];
+    while (key != x && key != -1) { s = (s + 1) & (S - 1); key = hkeys[s]; }
+    return key == x ? hvals[s] : -1;
+}
 
 // ---------------------------------------------------------------------------------------
 // the intersection walk.  MODE 0: stage every row's edges (emission order included) into its slot of `cap`
 // entries and write the row's edge count (rows are taken from a global ticket counter: walk lengths differ by two
 // orders of magnitude).  MODE 1: write the rows listed in `rows` (those whose edges overflowed their slot) straight
 // to their final positions given by rowptr_out.
+// GL lanes share one walk entry (a, m): together they read the k ids of N(m) as 16-byte pieces - one contiguous
+// 4k-byte segment per entry instead of k scattered 4-byte reads per lane, which is what bounds a lane-per-entry
+// version (measured: 163 ms at C3, the L1 processes one 32-byte sector per cycle) - and probe the row's hash; the
+// hits are summed inside the group.  An entry is emitted iff overlap >= v_min and it is the first encounter of m
+// (the smallest hit position equals a); first encounters leave in descending walk position = scipy's order.
+// The number of nonzeros of A.A^T (the reference's "links pruned" statistic) needs no de-duplication either: an
+// (i, m) pair with overlap c is met exactly c times, so it is  #{c = 1} + #{c = 2}/2 + #{first encounters with c >= 3}.
 // ---------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, int GL>
 __global__ void __launch_bounds__(SNN_WARPS * 32)
 snn_isect_kernel(const int32_t *__restrict__ knn, int k, int lg, int64_t row_begin, int64_t n_rows,
                  const int32_t *__restrict__ rows, const int *__restrict__ n_listed, const int64_t *__restrict__ rptr,
@@ -215,13 +219,16 @@ snn_isect_kernel(const int32_t *__restrict__ knn, int k, int lg, int64_t row_beg
                  unsigned long long *__restrict__ walk_stats /* [0] max walk, [1] sum of walks, [2] nonzeros of A.A^T */,
                  int *__restrict__ n_dup) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int EP = 32 / GL;                                  // walk entries per step
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / GL, gl = lane % GL;
     WarpRowState &st = reinterpret_cast<WarpRowState *>(smem_raw)[warp];
     const int S = 1 << lg;
     int *hkeys = reinterpret_cast<int *>(smem_raw + sizeof(WarpRowState) * SNN_WARPS) + (size_t)warp * 2 * S;
     int *hvals = hkeys + S;
     const int64_t total = MODE == 0 ? n_rows : (int64_t)*n_listed;
-    unsigned long long wmax = 0, wsum = 0, nz_sum = 0;
+    const bool vec = (k & 3) == 0;                               // rows of the table are 16-byte aligned
+    unsigned long long wmax = 0, wsum = 0, n1 = 0, n2 = 0, n3 = 0;
     int dups = 0;
     while (true) {
         unsigned long long q = 0;
@@ -231,7 +238,6 @@ snn_isect_kernel(const int32_t *__restrict__ knn, int k, int lg, int64_t row_beg
         const int64_t r = MODE == 0 ? (int64_t)q : (int64_t)rows[q];
         const int64_t grow = row_begin + r;
         const long long walk_ll = warp_load_row(knn, k, grow, rptr, st, lane);
-        const int walk = (int)min(walk_ll, (long long)INT_MAX);          // (n_total * k < 2^31 is checked by the host)
         for (int s = lane; s < S; s += 32) hkeys[s] = -1;
         __syncwarp();
         for (int a = lane; a < k; a += 32) {                             // distinct ids: plain CAS insertion
@@ -248,45 +254,73 @@ snn_isect_kernel(const int32_t *__restrict__ knn, int k, int lg, int64_t row_beg
         }
         const int64_t obase = MODE == 0 ? r * (int64_t)cap : rowptr_out[r];
         int64_t out = obase;
-        for (int p0 = ((walk - 1) / 32) * 32; p0 >= 0; p0 -= 32) {
-            const int p = p0 + lane;
-            bool keep = false, firstenc = false;
-            int m = 0, cnt = 0;
-            if (p < walk) {
-                int a;
-                m = walk_fetch(st, k, p, rlist, a);
-                const int32_t *nm = knn + (int64_t)m * k;
-                int amin = INT_MAX;
-                for (int t = 0; t < k; ++t) {
-                    const int x = __ldg(nm + t);
-                    unsigned s = snn_hash(x, lg);
-                    int key = hkeys[s];
-                    while (key != x && key != -1) { s = (s + 1) & (S - 1); key = hkeys[s]; }
-                    if (key == x) { ++cnt; amin = min(amin, hvals[s]); }
+        for (int a = k - 1; a >= 0; --a) {
+            const int len = st.base[a + 1] - st.base[a];
+            const int32_t *rl = rlist + st.start[a];
+            for (int t0 = ((len - 1) / EP) * EP; t0 >= 0; t0 -= EP) {
+                const int e = t0 + g;
+                const bool valid = e < len;
+                const int m = valid ? __ldg(rl + e) : 0;
+                // this lane's up to four ids of N(m)
+                int x0 = -2, x1 = -2, x2 = -2, x3 = -2;                  // -2 is never a key
+                if (valid && 4 * gl < k) {
+                    const int32_t *nm = knn + (int64_t)m * k + 4 * gl;
+                    if (vec) {
+                        const int4 v = __ldg(reinterpret_cast<const int4 *>(nm));
+                        x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+                    } else {
+                        x0 = __ldg(nm);
+                        if (4 * gl + 1 < k) x1 = __ldg(nm + 1);
+                        if (4 * gl + 2 < k) x2 = __ldg(nm + 2);
+                        if (4 * gl + 3 < k) x3 = __ldg(nm + 3);
+                    }
                 }
-                firstenc = amin == a;
-                keep = firstenc && cnt >= v_min;
-            }
-            if (MODE == 0) nz_sum += __popc(__ballot_sync(AB_FULL, firstenc));
-            const unsigned b = __ballot_sync(AB_FULL, keep);
-            if (keep) {
-                const int64_t o = out + __popc(b & ~((2u << lane) - 1));     // higher lanes (later positions) first
-                if (MODE == 1 || o - obase < cap) {
-                    dst[o] = m;
-                    if (MODE == 1) src[o] = (int32_t)grow;
-                    if (overlap) overlap[o] = (uint8_t)min(cnt, 255);
+                const int p0 = snn_probe(hkeys, hvals, S, lg, x0), p1 = snn_probe(hkeys, hvals, S, lg, x1);
+                const int p2 = snn_probe(hkeys, hvals, S, lg, x2), p3 = snn_probe(hkeys, hvals, S, lg, x3);
+                int cnt = (p0 >= 0) + (p1 >= 0) + (p2 >= 0) + (p3 >= 0);
+#pragma unroll
+                for (int o = GL / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(AB_FULL, cnt, o);
+                bool keep = false;
+                if (__any_sync(AB_FULL, cnt >= min(v_min, 3))) {           // rare: first-encounter test
+                    int amin = INT_MAX;
+                    if (p0 >= 0) amin = p0;
+                    if (p1 >= 0) amin = min(amin, p1);
+                    if (p2 >= 0) amin = min(amin, p2);
+                    if (p3 >= 0) amin = min(amin, p3);
+#pragma unroll
+                    for (int o = GL / 2; o > 0; o >>= 1) amin = min(amin, __shfl_xor_sync(AB_FULL, amin, o));
+                    const bool first = valid && amin == a;
+                    keep = first && cnt >= v_min && gl == 0;
+                    if (MODE == 0 && first && cnt >= 3 && gl == 0) ++n3;
+                }
+                if (MODE == 0 && valid && gl == 0) { n1 += cnt == 1; n2 += cnt == 2; }
+                const unsigned b = __ballot_sync(AB_FULL, keep);
+                if (b) {
+                    if (keep) {
+                        const int64_t o = out + __popc(b & ~((2u << lane) - 1));     // later walk positions first
+                        if (MODE == 1 || o - obase < cap) {
+                            dst[o] = m;
+                            if (MODE == 1) src[o] = (int32_t)grow;
+                            if (overlap) overlap[o] = (uint8_t)min(cnt, 255);
+                        }
+                    }
+                    out += __popc(b);
                 }
             }
-            out += __popc(b);
         }
         if (MODE == 0 && lane == 0) rowcount[r] = out - obase;
         __syncwarp();
     }
-    if (MODE == 0 && lane == 0) {
-        atomicMax(walk_stats, wmax);
-        atomicAdd(walk_stats + 1, wsum);
-        atomicAdd(walk_stats + 2, nz_sum);
-        if (dups) atomicAdd(n_dup, dups);
+    if (MODE == 0) {
+        n1 = (unsigned long long)ab_warp_sum_i64((long long)n1);
+        n2 = (unsigned long long)ab_warp_sum_i64((long long)n2);
+        n3 = (unsigned long long)ab_warp_sum_i64((long long)n3);
+        if (lane == 0) {
+            atomicMax(walk_stats, wmax);
+            atomicAdd(walk_stats + 1, wsum);
+            atomicAdd(walk_stats + 2, n1 + n2 / 2 + n3);
+            if (dups) atomicAdd(n_dup, dups);
+        }
     }
 }
 
@@ -362,7 +396,7 @@ extern "C" size_t ab_snn_ws_bytes(int64_t n_total, int32_t k, int64_t n_rows) {
 
 static int snn_hash_lg(int k) {
     int lg = 5;
-    while ((1 << lg) < 2 * k) ++lg;                        // load factor <= 1/2
+    while ((1 << lg) < 8 * k) ++lg;                        // load factor <= 1/8: an absent id stops at its first slot 7 times in 8
     return lg;
 }
 static size_t snn_isect_smem(int k) {
@@ -407,13 +441,17 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
         // ONE walk per row: every row's edges (emission order included) are staged in a per-row slot;
         // ab_snn_fill then only compacts the slots into the final list
         const size_t smem = snn_isect_smem(k);
-        AB_CUDA(cudaFuncSetAttribute(snn_isect_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)200 * 1024 / smem));
         const unsigned grid = (unsigned)std::min<int64_t>((n_rows + SNN_WARPS - 1) / SNN_WARPS, (int64_t)ctx->sm_count * per_sm);
-        snn_isect_kernel<0><<<grid, SNN_WARPS * 32, smem, st>>>(knn_all, k, snn_hash_lg(k), row_begin, n_rows, nullptr, nullptr,
-                                                                w.deg, w.rlist, v_min, w.rowcount, nullptr, nullptr,
-                                                                w.stage_dst, w.stage_ov, snn_stage_cap(k), w.walk_stats + 3,
-                                                                w.walk_stats, w.counters + 2);
+#define AB_SNN_ISECT0(GL)                                                                                             \
+        do {                                                                                                          \
+            AB_CUDA(cudaFuncSetAttribute(snn_isect_kernel<0, GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            snn_isect_kernel<0, GL><<<grid, SNN_WARPS * 32, smem, st>>>(                                              \
+                knn_all, k, snn_hash_lg(k), row_begin, n_rows, nullptr, nullptr, w.deg, w.rlist, v_min, w.rowcount, nullptr, \
+                nullptr, w.stage_dst, w.stage_ov, snn_stage_cap(k), w.walk_stats + 3, w.walk_stats, w.counters + 2);  \
+        } while (0)
+        if (k <= 32) AB_SNN_ISECT0(8); else if (k <= 64) AB_SNN_ISECT0(16); else AB_SNN_ISECT0(32);
+#undef AB_SNN_ISECT0
         AB_LAUNCH_CHECK(ctx);
     }
     if (ab_exclusive_scan_i64(ctx, w.rowcount, rowptr, n_rows, w.scan_ws, w.scan_bytes, st)) return 1;
@@ -456,10 +494,15 @@ extern "C" int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total,
     AB_LAUNCH_CHECK(ctx);
     // rows whose edges overflowed their staging slot (rare) walk once more, straight into their final positions
     const size_t smem = snn_isect_smem(k);
-    AB_CUDA(cudaFuncSetAttribute(snn_isect_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    snn_isect_kernel<1><<<ctx->sm_count, SNN_WARPS * 32, smem, st>>>(knn_all, k, snn_hash_lg(k), row_begin, n_rows, w.ovf_rows,
-                                                                     w.counters + 10, w.deg, w.rlist, v_min, nullptr, rowptr, src,
-                                                                     dst, overlap, 0, w.walk_stats + 3, w.walk_stats, nullptr);
+#define AB_SNN_ISECT1(GL)                                                                                             \
+    do {                                                                                                              \
+        AB_CUDA(cudaFuncSetAttribute(snn_isect_kernel<1, GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        snn_isect_kernel<1, GL><<<ctx->sm_count, SNN_WARPS * 32, smem, st>>>(                                         \
+            knn_all, k, snn_hash_lg(k), row_begin, n_rows, w.ovf_rows, w.counters + 10, w.deg, w.rlist, v_min, nullptr, rowptr, \
+            src, dst, overlap, 0, w.walk_stats + 3, w.walk_stats, nullptr);                                            \
+    } while (0)
+    if (k <= 32) AB_SNN_ISECT1(8); else if (k <= 64) AB_SNN_ISECT1(16); else AB_SNN_ISECT1(32);
+#undef AB_SNN_ISECT1
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_SNN_FILL, st);
     return 0;

@@ -326,7 +326,7 @@ class Engine:
         return DeviceCSR(rowptr_h, col_h, val_h, n_hvg, A.row_begin, A.n_total)
 
     # -- K4-K8 ------------------------------------------------------------------------
-    def irlb(self, AH, nval, tol=1e-4, maxit=1000, v0_local=None, want_v=True, want_u=True):
+    def irlb(self, AH, nval, tol=1e-4, maxit=1000, v0_local=None, want_v=True, want_u=True, center=None):
         n, H = AH.n_local, AH.n_genes
         ws = self.workspace(self.lib.ab_irlb_ws_bytes_compact(n, H, nval, int(AH.val.numel())))
         scores = self.empty((n, nval), torch.float64)
@@ -335,7 +335,7 @@ class Engine:
         u = self.empty((H, nval), torch.float64) if want_u else None
         info = (ctypes.c_int64 * 4)()
         _lib.check(self.lib.ab_irlb(self.ctx, _ptr(AH.rowptr), _ptr(AH.col), _ptr(AH.val), n, AH.n_total, H, int(nval),
-                                    float(tol), int(maxit), _ptr(v0_local), _ptr(scores), _ptr(v), _ptr(s), _ptr(u),
+                                    float(tol), int(maxit), _ptr(v0_local), _ptr(center), _ptr(scores), _ptr(v), _ptr(s), _ptr(u),
                                     info, _ptr(ws), ws.numel(), self.stream()), 'ab_irlb')
         return {'scores': scores, 'V': v, 's': s, 'U': u, 'steps': int(info[0]), 'nmult': int(info[1]),
                 'sum_panel': int(info[2]), 'not_converged': int(info[3]) & 1, 'compact': bool(int(info[3]) & 2),

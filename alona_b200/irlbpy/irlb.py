@@ -44,11 +44,15 @@ def _device_matrix(A, eng):
                      torch.from_numpy(part.data.astype(np.float64)).to(eng.device), H, lo, n_total)
 
 
-def lanczos(A, nval, tol=0.0001, maxit=50, center=None, scale=None, L=None, seed=None, device_result=False):
+def lanczos(A, nval, tol=0.0001, maxit=50, center=None, scale=None, L=None, seed=None, device_result=False,
+            gene_center=None):
     """Truncated SVD by augmented implicitly-restarted Lanczos bidiagonalisation.
 
     Returns LanczosResult(U [H x nval], s [nval], V [N x nval], steps, nmult) such that
     A.dot(V) ~= U * s, for A given in the reference's orientation (genes x cells).
+
+    gene_center (extension, device tensor of H doubles): per-gene means for implicit centring, operator
+    A - gene_center.1^T (what AlonaClustering.PCA uses for `--pca regular`); not the reference's `center` argument.
     """
     if center is not None or scale is not None or L is not None:
         raise NotImplementedError('center/scale/L are never passed by alona (clustering.py:108-109) '
@@ -62,7 +66,7 @@ def lanczos(A, nval, tol=0.0001, maxit=50, center=None, scale=None, L=None, seed
     v0 = np.random.randn(n_total)                      # irlb.py:152
     lo, hi = AH.row_begin, AH.row_begin + AH.n_local
     v0_local = torch.from_numpy(np.ascontiguousarray(v0[lo:hi])).to(eng.device)
-    res = eng.irlb(AH, nval, tol=tol, maxit=maxit, v0_local=v0_local)
+    res = eng.irlb(AH, nval, tol=tol, maxit=maxit, v0_local=v0_local, center=gene_center)
     if device_result:
         return res
     V = res['V']

@@ -172,6 +172,10 @@ int ab_cluster_median_fill(ab_ctx *ctx, const int64_t *rowptr, const int32_t *co
  * Same work dimension (irlb.py:138), restart rule (:231-234), invcheck (:84-92), CGS order.
  * v0_local: this shard's slice of the start vector (the reference draws it on the host with
  * np.random.seed(seed); randn(N), irlb.py:151-152; normalised here).
+ * center (device, n_hvg doubles, may be NULL): per-gene means for IMPLICIT centring - the operator becomes
+ * A - center.1^T without ever forming it (A.x - center.(1^T x),  A^T.w - (center^T w).1); with a tight `tol` this
+ * yields the leading components of the centred exact SVD that `--pca regular` computes (alona/clustering.py:114-125).
+ * NULL = the uncentred operator of the irlb branch.
  * Outputs: scores_local [n_local x nval] row-major = V.diag(s) (clustering.py:111),
  * v_local [n_local x nval] row-major (may be NULL), s[nval], u[H x nval] row-major (may be
  * NULL); h_info[4] (host int64) = {steps, nmult, sum of CGS panel widths, status flags:
@@ -186,7 +190,7 @@ size_t ab_irlb_ws_bytes(int64_t n_local, int32_t n_hvg, int32_t nval);
 size_t ab_irlb_ws_bytes_compact(int64_t n_local, int32_t n_hvg, int32_t nval, int64_t nnz_local);
 int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_h, const double *val_h,
             int64_t n_local, int64_t n_total, int32_t n_hvg, int32_t nval, double tol,
-            int32_t maxit, const double *v0_local, double *scores_local, double *v_local,
+            int32_t maxit, const double *v0_local, const double *center, double *scores_local, double *v_local,
             double *s, double *u, int64_t *h_info, void *ws, size_t ws_bytes, void *stream);
 
 /* ---- K9: exact k-nearest neighbours ----------------------------------------------------

@@ -104,6 +104,34 @@ def make_c1_cases():
               ref['snn_graph'].shape[0])
 
 
+def make_pca_regular_case(name, n, g, lbar, seed, hvg_n, pca_n):
+    """N4 fixture: AlonaClustering.PCA with --pca regular (alona/clustering.py:114-125: gene-centred exact SVD)."""
+    C, _ = ref_shim.load()
+    import tempfile
+    m, _ = synth_np.nb_counts(n, g, lbar=lbar, n_clusters=6, seed=seed)
+    df = _counts_df(m)
+    o = C.AlonaClustering()
+    with tempfile.TemporaryDirectory() as wd:
+        os.makedirs(wd + '/csvs')
+        o.params = {'qc_auto': False, 'hvg_method': 'seurat', 'hvg_n': hvg_n, 'pca': 'regular', 'pca_n': pca_n, 'seed': 42,
+                    'output_directory': wd, 'loglevel': 'regular'}
+        o.low_quality_cells = []
+        o.data_ERCC = pd.DataFrame()
+        o.anno = None
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            o.data_norm = o.normalize(df, '', 'raw', False)
+            o.find_variable_genes()
+            o.PCA(wd + '/csvs/pca.csv')
+    gene_pos = {gname: i for i, gname in enumerate(df.index)}
+    np.savez_compressed(os.path.join(OUT, name + '.npz'),
+                        indptr=m.indptr.astype(np.int64), indices=m.indices.astype(np.int32), data=m.data.astype(np.int32),
+                        shape=np.array(m.shape, dtype=np.int64), hvg_n=hvg_n, pca_n=pca_n,
+                        hvg_ranked=np.array([gene_pos[x] for x in o.hvg], dtype=np.int32),
+                        pca_components=np.asarray(o.pca_components.values))
+    print(name, m.shape, 'pca regular', o.pca_components.shape)
+
+
 def make_hvg_methods_case(name, n, g, lbar, seed, hvg_n, n_ercc=48):
     """N4 fixtures: AlonaHighlyVariableGenes.find() of the live reference with hvg_method Brennecke2013
     (alona/hvg.py:65-131) and scran (:169-225) on one input; the ERCC spikes are extra count rows normalised on their
@@ -222,6 +250,9 @@ def main():
         sys.exit('reference tree not present; fixtures can only be minted in the dev container')
     os.makedirs(OUT, exist_ok=True)
     warnings.simplefilter('ignore')
+    if '--pcareg' in sys.argv:
+        make_pca_regular_case('pcareg_1200x3000', 1200, 3000, 1500.0, 31, 400, 20)
+        return
     if '--hvg' in sys.argv:                     # only the N4 selector fixtures
         make_hvg_methods_case('hvgm_900x2500', 900, 2500, 2500.0, 21, 300)
         make_hvg_methods_case('hvgm_1500x4000', 1500, 4000, 900.0, 23, 5000)
@@ -243,6 +274,7 @@ def main():
     make_c1_cases()
     make_hvg_methods_case('hvgm_900x2500', 900, 2500, 2500.0, 21, 300)
     make_hvg_methods_case('hvgm_1500x4000', 1500, 4000, 900.0, 23, 5000)
+    make_pca_regular_case('pcareg_1200x3000', 1200, 3000, 1500.0, 31, 400, 20)
 
 
 if __name__ == '__main__':

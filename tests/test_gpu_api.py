@@ -263,3 +263,28 @@ def test_hvg_brennecke_and_scran_match_reference(case, tmp_path):
     assert o.report['pca']['nnz_hvg'] == int(m[:, g['hvg_brennecke']].nnz)
     with pytest.raises(SystemExit):                                             # scran without spikes: hvg.py:187-190
         AlonaHighlyVariableGenes('scran', 10, o.data_norm, pd.DataFrame()).find()
+
+
+def test_pca_regular_matches_reference(tmp_path):
+    """--pca regular (alona/clustering.py:114-125: gene-centred exact SVD, first pca_n columns of x.v) through the
+    implicitly centred device iteration: scores equal to the reference's after sign alignment."""
+    from alona_b200.clustering import AlonaClustering
+    g = load_golden('pcareg_1200x3000')
+    m = golden_csr(g)
+    genes = np.array(['g%d' % i for i in range(m.shape[1])])
+    o = AlonaClustering()
+    o.set_params({'output_directory': str(tmp_path), 'qc_auto': False, 'hvg_n': int(g['hvg_n']), 'pca': 'regular',
+                  'pca_n': int(g['pca_n']), 'seed': 42})
+    o.low_quality_cells = []
+    o.data_ERCC = pd.DataFrame()
+    o.data_norm = o.normalize(pd.DataFrame(m.T.toarray().astype(np.int64), index=genes), '', 'raw', False)
+    o.find_variable_genes()
+    assert set(o.hvg.tolist()) == set(genes[g['hvg_ranked']].tolist())
+    o.PCA(str(tmp_path) + '/csvs/pca.csv')
+    assert o.report['pca']['not_converged'] == 0
+    err = R.column_rel_err(g['pca_components'], o.pca_components.values)
+    assert err.max() < 1e-7, err
+    # the uncentred default differs: the first component of --pca irlb is dominated by the gene means
+    o.params['pca'] = 'irlb'
+    o.PCA('')
+    assert R.column_rel_err(g['pca_components'][:, :1], o.pca_components.values[:, :1]).max() > 1e-2
