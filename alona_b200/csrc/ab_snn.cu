@@ -3,28 +3,33 @@
 //   A = kNN incidence (self included), C = A.A^T (integer overlaps, scipy csr_matmat),
 //   keep (i,m) iff C[i,m]/(k+(k-C[i,m])) > prune_snn, emit in csr_matmat's order.
 //
-// C[i,m] = |N(i) n N(m)|.  The nonzeros of row i are the cells m met on the 2-hop walk
-//   for j in sorted(N(i)):  for m in sorted(R(j)):      R(j) = { m : j in N(m) }  (reverse lists)
-// and scipy's order inside the row is the REVERSE of first-encounter order of that walk.
+// C[i,m] = |N(i) n N(m)| = #{ j in N(i) : m in R(j) },  R(j) = { m : j in N(m) } (reverse lists).
+// scipy's order inside row i is the REVERSE of first-encounter order when scanning j over
+// sorted(N(i)) and m over sorted(R(j)).  So, per row, the 2-hop walk is
+// enumerated by position p = base(j) + t; a per-warp shared-memory hash keeps for every
+// distinct m its overlap count and the position of its first encounter; a second walk emits
+// the first encounters from the last position to the first, filtered by overlap >= v_min.
+// No sort, no atomics in the common path (duplicates inside a 32-wide step are merged with
+// match.any, steps are processed in ascending position order).
 //
-// Round 1 de-duplicated the walk with per-row hash tables in shared memory (five row classes by walk length, up to
-// 128 KB of table per row; 68 ms at C3, bound by dependent shared-memory atomics and per-row latency).  This version
-// needs no table of the walk at all - it is the sorted-neighbour-list intersection the brief describes:
-//   * one warp per cell row i; the row's sorted neighbours go into a small open-addressing hash (cell id -> position
-//     a in the sorted row) in shared memory: 2k..4k slots, built once per row;
-//   * the walk is enumerated by position p (lane <-> position, coalesced reads of the reverse lists); for the entry
-//     (a, m) the lane scans N(m) (k ids, one row of the kNN table, L2 resident) through that hash: the number of hits
-//     IS the overlap |N(i) n N(m)| and the smallest hit position a* is where the walk meets m first, so the entry is
-//     a first encounter iff a* == a.  No atomics, no inter-lane dependence, any walk length, any in-degree;
-//   * positions are visited from the last to the first, so first encounters leave in scipy's order.
-// Work: one k-id row read + k hash probes per walk entry (C3: 2.4e9 entries x 80 B of L2 traffic).
+// Rows are classified by walk length: short walks take one warp with a per-warp table, longer
+// ones one CTA with a shared-memory table sized to the walk (the common case at scale: kNN graphs
+// in 50 dimensions have hubs), and anything beyond shared memory one CTA with dense count/first
+// arrays in global scratch (always correct, any in-degree).
 #include "ab_common.cuh"
 #include <limits.h>
+#include <stdlib.h>
 #include <algorithm>
 
+static constexpr int SNN_WARPS = 8;
+static constexpr int SNN_SLOTS = 512;             // per warp, power of two (walk <= 350: load factor <= 0.69)
+static constexpr int SNN_SLOTS_LG = 9;
+static constexpr int SNN_WALK_LIMIT = 350;        // rows with a longer walk take a whole CTA (measured at C3: limit 1400 -> 68.7 ms,
+                                                  // 700 -> 52.7, 350 -> 51.9, 0 -> 51.9: the one-warp kernel holds 8 warps per SM)
 static constexpr int SNN_MAXK = 128;
+static constexpr int SNN_BIG_CTAS = 148;         // one per SM (each owns 2*n_total ints of global scratch)
+static constexpr int SNN_BIG_THREADS = 256;
 static constexpr int SORT_CTA_MAX = 4096;
-static constexpr int SNN_WARPS = 16;              // warps per CTA of the intersection kernel
 // staged edges per row (single-pass protocol); rows with more take a second pass.  Edges per row grow with k
 // (C3, k = 20: 21 on average; a C5-shaped run, k = 30: 324), the slot is sized generously: it is only ever read up
 // to the row's count.
@@ -136,7 +141,54 @@ snn_sort_long_kernel(const int64_t *__restrict__ rptr, int32_t *__restrict__ rli
 }
 
 // ---------------------------------------------------------------------------------------
-// per-row state of a warp: sorted neighbours, their reverse-list extents and walk positions, membership hash
+// per-row walk length and classification
+//   class 0: walk <= SNN_WALK_LIMIT          one warp per row, 2048-slot table per warp
+//   class 1: walk <= 0.7 * SNN_MID_SLOTS     one CTA (256 threads) per row, 4096-slot table
+//   class 2: walk <= 0.7 * 8192              one CTA (512 threads) per row, 8192-slot table (3 CTAs/SM for k<=32)
+//   class 3: walk <= 0.7 * 16384 (k<=32)     one CTA (512 threads) per row, 16384-slot table
+//   class 4: anything longer                 one CTA per row, dense arrays in global scratch
+// High-dimensional kNN graphs have hubs (in-degrees in the thousands), so classes 1-2 are the
+// common case at scale, not the exception.
+// ---------------------------------------------------------------------------------------
+static constexpr int SNN_MID_SLOTS = 4096;
+static constexpr int SNN_MID_THREADS = 256;
+static constexpr int SNN_LARGE_THREADS = 512;
+static inline int snn_large_slots(int k) { return k <= 32 ? 16384 : 8192; }
+static inline int snn_walk_cap(int slots) { return slots / 10 * 7; }
+
+__global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_t n_rows,
+                                const int64_t *__restrict__ rptr, int32_t *__restrict__ cls_rows /*[5][n_rows]*/,
+                                int *__restrict__ n_cls /*[5]*/, int lim0, int lim1, int lim2, int lim3,
+                                unsigned long long *__restrict__ max_walk, unsigned long long *__restrict__ sum_walk,
+                                int *__restrict__ n_dup, uint8_t *__restrict__ row_cls) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    long long walk = 0;
+    if (r < n_rows) {
+        const int32_t *row = knn + (row_begin + r) * k;
+        for (int c = 0; c < k; ++c) {
+            int j = row[c];
+            walk += rptr[j + 1] - rptr[j];
+        }
+        if (row[0] != row_begin + r) atomicAdd(n_dup, 1);
+        const int cls = walk <= lim0 ? 0 : (walk <= lim1 ? 1 : (walk <= lim2 ? 2 : (walk <= lim3 ? 3 : 4)));
+        cls_rows[(int64_t)cls * n_rows + atomicAdd(n_cls + cls, 1)] = (int32_t)r;
+        row_cls[r] = (uint8_t)cls;
+    }
+    // block-level max / sum before touching the global atomics
+    unsigned long long wmax = (unsigned long long)walk, wsum = (unsigned long long)walk;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wmax = max(wmax, __shfl_xor_sync(AB_FULL, wmax, o));
+        wsum += __shfl_xor_sync(AB_FULL, wsum, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(max_walk, wmax);
+        atomicAdd(sum_walk, wsum);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// shared row state: sorted neighbours, their reverse-list extents and walk positions
 // ---------------------------------------------------------------------------------------
 struct WarpRowState {
     int nb[SNN_MAXK];            // sorted neighbour ids
@@ -144,9 +196,14 @@ struct WarpRowState {
     long long start[SNN_MAXK];   // rptr of each neighbour
 };
 
-// Loads and sorts row `grow`, fills st; returns the walk length.  One warp.
-__device__ __forceinline__ long long warp_load_row(const int32_t *__restrict__ knn, int k, int64_t grow,
-                                                   const int64_t *__restrict__ rptr, WarpRowState &st, int lane) {
+__device__ __forceinline__ unsigned hash_slot(int key) {
+    return ((unsigned)key * 2654435761u) >> (32 - SNN_SLOTS_LG);
+}
+__device__ __forceinline__ unsigned hash_slot_lg(int key, int lg) { return ((unsigned)key * 2654435761u) >> (32 - lg); }
+
+// Loads and sorts row `r`, fills st; returns the walk length.  One warp.
+__device__ __forceinline__ int warp_load_row(const int32_t *__restrict__ knn, int k, int64_t grow,
+                                             const int64_t *__restrict__ rptr, WarpRowState &st, int lane) {
     // sort k <= 128 ids: rank by counting through shared memory
     for (int c = lane; c < k; c += 32) st.base[c] = knn[grow * k + c];       // base[] as scratch
     __syncwarp();
@@ -161,7 +218,7 @@ __device__ __forceinline__ long long warp_load_row(const int32_t *__restrict__ k
     }
     __syncwarp();
     // degrees and exclusive prefix
-    long long run = 0;
+    int run = 0;
     for (int c0 = 0; c0 < k; c0 += 32) {
         const int c = c0 + lane;
         int d = 0;
@@ -171,169 +228,416 @@ __device__ __forceinline__ long long warp_load_row(const int32_t *__restrict__ k
             st.start[c] = s;
             d = (int)(rptr[j + 1] - s);
         }
-        long long inc = d;
+        int inc = d;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            long long t = __shfl_up_sync(AB_FULL, inc, o);
+            int t = __shfl_up_sync(AB_FULL, inc, o);
             if (lane >= o) inc += t;
         }
         __syncwarp();
-        if (c < k) st.base[c] = (int)min(run + inc - d, (long long)INT_MAX);
+        if (c < k) st.base[c] = run + inc - d;
         run += __shfl_sync(AB_FULL, inc, 31);
     }
-    if (lane == 0) st.base[k] = (int)min(run, (long long)INT_MAX);
+    if (lane == 0) st.base[k] = run;
     __syncwarp();
     return run;
 }
 
-__device__ __forceinline__ unsigned snn_hash(int key, int lg) { return ((unsigned)key * 2654435761u) >> (32 - lg); }
-
-// membership probe: position of cell x in the row's sorted neighbour list, or -1
-__device__ __forceinline__ int snn_probe(const int *__restrict__ hkeys, const int *__restrict__ hvals, int S, int lg, int x) {
-    unsigned s = snn_hash(x, lg);
-    int key = hkeys[s];
-    while (key != x && key != -1) { s = (s + 1) & (S - 1); key = hkeys[s]; }
-    return key == x ? hvals[s] : -1;
+// walk position -> cell id m
+__device__ __forceinline__ int walk_fetch(const WarpRowState &st, int k, int p, const int32_t *__restrict__ rlist) {
+    int lo = 0, hi = k;                                   // last a with base[a] <= p
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (st.base[mid] <= p) lo = mid; else hi = mid;
+    }
+    return __ldg(rlist + st.start[lo] + (p - st.base[lo]));
 }
 
 // ---------------------------------------------------------------------------------------
-// the intersection walk.  MODE 0: stage every row's edges (emission order included) into its slot of `cap`
-// entries and write the row's edge count (rows are taken from a global ticket counter: walk lengths differ by two
-// orders of magnitude).  MODE 1: write the rows listed in `rows` (those whose edges overflowed their slot) straight
-// to their final positions given by rowptr_out.
-// GL lanes share one walk entry (a, m): together they read the k ids of N(m) as 16-byte pieces - one contiguous
-// 4k-byte segment per entry instead of k scattered 4-byte reads per lane, which is what bounds a lane-per-entry
-// version (measured: 163 ms at C3, the L1 processes one 32-byte sector per cycle) - and probe the row's hash; the
-// hits are summed inside the group.  An entry is emitted iff overlap >= v_min and it is the first encounter of m
-// (the smallest hit position equals a); first encounters leave in descending walk position = scipy's order.
-// The number of nonzeros of A.A^T (the reference's "links pruned" statistic) needs no de-duplication either: an
-// (i, m) pair with overlap c is met exactly c times, so it is  #{c = 1} + #{c = 2}/2 + #{first encounters with c >= 3}.
+// class 0: one warp per row, shared-memory hash  (value = first position << 8 | count)
 // ---------------------------------------------------------------------------------------
-template <int MODE, int GL>
+template <bool FILL>
 __global__ void __launch_bounds__(SNN_WARPS * 32)
-snn_isect_kernel(const int32_t *__restrict__ knn, int k, int lg, int64_t row_begin, int64_t n_rows,
-                 const int32_t *__restrict__ rows, const int *__restrict__ n_listed, const int64_t *__restrict__ rptr,
+snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const int32_t *__restrict__ rows,
+                 const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
                  const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
                  const int64_t *__restrict__ rowptr_out, int32_t *__restrict__ src, int32_t *__restrict__ dst,
-                 uint8_t *__restrict__ overlap, int cap, unsigned long long *__restrict__ ticket,
-                 unsigned long long *__restrict__ walk_stats /* [0] max walk, [1] sum of walks, [2] nonzeros of A.A^T */,
-                 int *__restrict__ n_dup) {
+                 uint8_t *__restrict__ overlap, int cap, unsigned long long *__restrict__ nz_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int EP = 32 / GL;                                  // walk entries per step
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane / GL, gl = lane % GL;
+    unsigned long long nz = 0;                       // nonzeros of A.A^T met by this warp (first encounters)
     WarpRowState &st = reinterpret_cast<WarpRowState *>(smem_raw)[warp];
-    const int S = 1 << lg;
-    int *hkeys = reinterpret_cast<int *>(smem_raw + sizeof(WarpRowState) * SNN_WARPS) + (size_t)warp * 2 * S;
-    int *hvals = hkeys + S;
-    const int64_t total = MODE == 0 ? n_rows : (int64_t)*n_listed;
-    const bool vec = (k & 3) == 0;                               // rows of the table are 16-byte aligned
-    unsigned long long wmax = 0, wsum = 0, n1 = 0, n2 = 0, n3 = 0;
-    int dups = 0;
-    while (true) {
-        unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(ticket, 1ull);
-        q = __shfl_sync(AB_FULL, q, 0);
-        if ((int64_t)q >= total) break;
-        const int64_t r = MODE == 0 ? (int64_t)q : (int64_t)rows[q];
-        const int64_t grow = row_begin + r;
-        const long long walk_ll = warp_load_row(knn, k, grow, rptr, st, lane);
-        for (int s = lane; s < S; s += 32) hkeys[s] = -1;
+    int *keys = reinterpret_cast<int *>(smem_raw + sizeof(WarpRowState) * SNN_WARPS) + warp * SNN_SLOTS * 2;
+    int *vals = keys + SNN_SLOTS;
+    const int64_t w = (int64_t)blockIdx.x * SNN_WARPS + warp;
+    const int64_t nw = (int64_t)gridDim.x * SNN_WARPS;
+    const int64_t n_rows = *n_rows_ptr;
+    for (int64_t q = w; q < n_rows; q += nw) {
+        const int64_t r = rows[q];
+        const int walk = warp_load_row(knn, k, row_begin + r, rptr, st, lane);
+        for (int s = lane; s < SNN_SLOTS; s += 32) keys[s] = -1;
         __syncwarp();
-        for (int a = lane; a < k; a += 32) {                             // distinct ids: plain CAS insertion
-            const int key = st.nb[a];
-            unsigned s = snn_hash(key, lg);
-            while (atomicCAS(hkeys + s, -1, key) != -1) s = (s + 1) & (S - 1);
-            hvals[s] = a;
-        }
-        __syncwarp();
-        if (MODE == 0) {
-            wmax = max(wmax, (unsigned long long)walk_ll);
-            wsum += (unsigned long long)walk_ll;
-            if (lane == 0 && knn[grow * k] != (int32_t)grow) ++dups;
-        }
-        const int64_t obase = MODE == 0 ? r * (int64_t)cap : rowptr_out[r];
-        int64_t out = obase;
-        for (int a = k - 1; a >= 0; --a) {
-            const int len = st.base[a + 1] - st.base[a];
-            const int32_t *rl = rlist + st.start[a];
-            for (int t0 = ((len - 1) / EP) * EP; t0 >= 0; t0 -= EP) {
-                const int e = t0 + g;
-                const bool valid = e < len;
-                const int m = valid ? __ldg(rl + e) : 0;
-                // this lane's up to four ids of N(m)
-                int x0 = -2, x1 = -2, x2 = -2, x3 = -2;                  // -2 is never a key
-                if (valid && 4 * gl < k) {
-                    const int32_t *nm = knn + (int64_t)m * k + 4 * gl;
-                    if (vec) {
-                        const int4 v = __ldg(reinterpret_cast<const int4 *>(nm));
-                        x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
-                    } else {
-                        x0 = __ldg(nm);
-                        if (4 * gl + 1 < k) x1 = __ldg(nm + 1);
-                        if (4 * gl + 2 < k) x2 = __ldg(nm + 2);
-                        if (4 * gl + 3 < k) x3 = __ldg(nm + 3);
-                    }
+        // walk 1: ascending positions; merge duplicates inside a step with match.any
+        for (int p0 = 0; p0 < walk; p0 += 32) {
+            const int p = p0 + lane;
+            const bool live = p < walk;
+            const int m = live ? walk_fetch(st, k, p, rlist) : -1 - lane;
+            const unsigned grp = __match_any_sync(AB_FULL, m);
+            const bool leader = live && (__ffs(grp) - 1 == lane);
+            if (leader) {
+                const int add = __popc(grp);
+                unsigned s = hash_slot(m);
+                while (true) {
+                    const int prev = atomicCAS(keys + s, -1, m);
+                    if (prev == -1) { vals[s] = (p << 8) | add; break; }
+                    if (prev == m) { vals[s] += add; break; }
+                    s = (s + 1) & (SNN_SLOTS - 1);
                 }
-                const int p0 = snn_probe(hkeys, hvals, S, lg, x0), p1 = snn_probe(hkeys, hvals, S, lg, x1);
-                const int p2 = snn_probe(hkeys, hvals, S, lg, x2), p3 = snn_probe(hkeys, hvals, S, lg, x3);
-                int cnt = (p0 >= 0) + (p1 >= 0) + (p2 >= 0) + (p3 >= 0);
-#pragma unroll
-                for (int o = GL / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(AB_FULL, cnt, o);
+            }
+            __syncwarp();
+        }
+        if (!FILL) {
+            int c = 0;
+            for (int s = lane; s < SNN_SLOTS; s += 32) c += (keys[s] != -1) && ((vals[s] & 255) >= v_min);
+            c = ab_warp_sum_i32(c);
+            if (lane == 0) rowcount[r] = c;
+        } else {
+            // cap > 0: "staging" mode of the single-pass protocol: the row's edges go to its own slot of `cap`
+            // entries (dst/overlap are the staging arrays, src is implied) and the row count is written as well
+            const int64_t obase = cap ? r * (int64_t)cap : rowptr_out[r];
+            int64_t out = obase;
+            const int grow = (int)(row_begin + r);
+            for (int p0 = ((walk - 1) / 32) * 32; p0 >= 0; p0 -= 32) {
+                const int p = p0 + lane;
                 bool keep = false;
-                if (__any_sync(AB_FULL, cnt >= min(v_min, 3))) {           // rare: first-encounter test
-                    int amin = INT_MAX;
-                    if (p0 >= 0) amin = p0;
-                    if (p1 >= 0) amin = min(amin, p1);
-                    if (p2 >= 0) amin = min(amin, p2);
-                    if (p3 >= 0) amin = min(amin, p3);
-#pragma unroll
-                    for (int o = GL / 2; o > 0; o >>= 1) amin = min(amin, __shfl_xor_sync(AB_FULL, amin, o));
-                    const bool first = valid && amin == a;
-                    keep = first && cnt >= v_min && gl == 0;
-                    if (MODE == 0 && first && cnt >= 3 && gl == 0) ++n3;
+                int m = 0, cnt = 0;
+                if (p < walk) {
+                    m = walk_fetch(st, k, p, rlist);
+                    unsigned s = hash_slot(m);
+                    while (keys[s] != m) s = (s + 1) & (SNN_SLOTS - 1);
+                    const int v = vals[s];
+                    cnt = v & 255;
+                    keep = ((v >> 8) == p) && cnt >= v_min;
+                    nz += (v >> 8) == p;
                 }
-                if (MODE == 0 && valid && gl == 0) { n1 += cnt == 1; n2 += cnt == 2; }
                 const unsigned b = __ballot_sync(AB_FULL, keep);
-                if (b) {
-                    if (keep) {
-                        const int64_t o = out + __popc(b & ~((2u << lane) - 1));     // later walk positions first
-                        if (MODE == 1 || o - obase < cap) {
-                            dst[o] = m;
-                            if (MODE == 1) src[o] = (int32_t)grow;
-                            if (overlap) overlap[o] = (uint8_t)min(cnt, 255);
-                        }
+                if (keep) {
+                    const int64_t o = out + __popc(b & ~((2u << lane) - 1));     // higher lanes first
+                    if (!cap || o - obase < cap) {
+                        dst[o] = m;
+                        if (!cap) src[o] = grow;
+                        if (overlap) overlap[o] = (uint8_t)cnt;
                     }
-                    out += __popc(b);
+                }
+                out += __popc(b);
+            }
+            if (cap && lane == 0) rowcount[r] = out - obase;
+        }
+        __syncwarp();
+    }
+    if (FILL && nz_out) {
+        nz = (unsigned long long)ab_warp_sum_i64((long long)nz);
+        if (lane == 0 && nz) atomicAdd(nz_out, nz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// classes 1-2: one CTA per row.  The walk is cut into chunks of <= 32 consecutive entries of ONE
+// reverse list (coalesced 128-byte reads, no binary search, no duplicate cell inside a chunk) that
+// the warps take round-robin.  Table value = bitmask over the row's sorted neighbours a that
+// contain the cell: overlap = popcount, first encounter = lowest set bit (the walk visits the
+// lists in ascending a and each list in ascending cell id, so the first encounter of m is at
+// (lowest a, rank of m in R(nb[a]))); atomicOr makes the insertion order irrelevant.
+// ---------------------------------------------------------------------------------------
+struct CtaRowState {
+    WarpRowState w;
+    int chunk0[SNN_MAXK + 1];    // first chunk of each neighbour's list
+    int walk, chunks;
+};
+
+template <int SLOTS, int W, int THREADS, bool FILL>
+__global__ void __launch_bounds__(THREADS)
+snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const int32_t *__restrict__ rows,
+               const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
+               const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
+               const int64_t *__restrict__ rowptr_out, int32_t *__restrict__ src, int32_t *__restrict__ dst,
+               uint8_t *__restrict__ overlap, int cap, unsigned long long *__restrict__ nz_out) {
+    static_assert(SLOTS / 10 * 7 / 32 + SNN_MAXK + 1 <= THREADS, "chunk table must fit one scan pass");
+    unsigned long long nz = 0;                       // nonzeros of A.A^T met by this thread (first encounters)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *keys = reinterpret_cast<int *>(smem_raw);
+    unsigned *masks = reinterpret_cast<unsigned *>(keys + SLOTS);
+    CtaRowState &st = *reinterpret_cast<CtaRowState *>(masks + (size_t)SLOTS * W);
+    int *chunk_tab = reinterpret_cast<int *>(&st + 1);                 // [THREADS]
+    unsigned *ballots = reinterpret_cast<unsigned *>(chunk_tab + THREADS);   // [THREADS]
+    int *choff = reinterpret_cast<int *>(ballots + THREADS);           // [THREADS]
+    __shared__ int red[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = THREADS / 32;
+    const int n_rows = *n_rows_ptr;
+    for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
+        const int64_t r = rows[q];
+        __syncthreads();                                               // previous row fully retired
+        if (warp == 0) {
+            const int walk = warp_load_row(knn, k, row_begin + r, rptr, st.w, lane);
+            int run = 0;
+            for (int c0 = 0; c0 < k; c0 += 32) {
+                const int c = c0 + lane;
+                const int nch = c < k ? (st.w.base[c + 1] - st.w.base[c] + 31) >> 5 : 0;
+                int inc = nch;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(AB_FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (c < k) st.chunk0[c] = run + inc - nch;
+                run += __shfl_sync(AB_FULL, inc, 31);
+            }
+            if (lane == 0) { st.chunk0[k] = run; st.walk = walk; st.chunks = run; }
+        }
+        __syncthreads();
+        const int walk = st.walk, C = st.chunks;
+        int lg = 6;
+        while ((1 << lg) < 2 * walk && (1 << lg) < SLOTS) ++lg;
+        const int S = 1 << lg;
+        for (int s = threadIdx.x; s < S; s += THREADS) keys[s] = -1;
+        for (int s = threadIdx.x; s < S * W; s += THREADS) masks[s] = 0u;
+        for (int a = warp; a < k; a += NW) {
+            const int c0 = st.chunk0[a], nch = st.chunk0[a + 1] - c0;
+            for (int c = lane; c < nch; c += 32) chunk_tab[c0 + c] = (a << 24) | c;
+        }
+        __syncthreads();
+        // ---- walk: insert ----
+        for (int c = warp; c < C; c += NW) {
+            const int e = chunk_tab[c];
+            const int a = e >> 24, t = ((e & 0xFFFFFF) << 5) + lane;
+            const int len = st.w.base[a + 1] - st.w.base[a];
+            if (t < len) {
+                const int m = __ldg(rlist + st.w.start[a] + t);
+                unsigned s = hash_slot_lg(m, lg);
+                while (true) {
+                    const int prev = atomicCAS(keys + s, -1, m);
+                    if (prev == -1 || prev == m) break;
+                    s = (s + 1) & (S - 1);
+                }
+                atomicOr(masks + (size_t)s * W + (a >> 5), 1u << (a & 31));
+            }
+        }
+        __syncthreads();
+        if (!FILL) {
+            int c = 0;
+            for (int s = threadIdx.x; s < S; s += THREADS) {
+                if (keys[s] != -1) {
+                    int pc = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; ++w2) pc += __popc(masks[(size_t)s * W + w2]);
+                    c += pc >= v_min;
+                }
+            }
+            c = ab_warp_sum_i32(c);
+            if (lane == 0) red[warp] = c;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int tot = 0;
+                for (int w2 = 0; w2 < NW; ++w2) tot += red[w2];
+                rowcount[r] = tot;
+            }
+        } else {
+            // ---- pass A: which entries of each chunk are kept first encounters ----
+            for (int c = warp; c < C; c += NW) {
+                const int e = chunk_tab[c];
+                const int a = e >> 24, t = ((e & 0xFFFFFF) << 5) + lane;
+                const int len = st.w.base[a + 1] - st.w.base[a];
+                bool keep = false;
+                if (t < len) {
+                    const int m = __ldg(rlist + st.w.start[a] + t);
+                    unsigned s = hash_slot_lg(m, lg);
+                    while (keys[s] != m) s = (s + 1) & (S - 1);
+                    int pc = 0, first = -1;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; ++w2) {
+                        const unsigned mk = masks[(size_t)s * W + w2];
+                        if (first < 0 && mk) first = 32 * w2 + __ffs(mk) - 1;
+                        pc += __popc(mk);
+                    }
+                    keep = (first == a) && pc >= v_min;
+                    nz += first == a;
+                }
+                const unsigned b = __ballot_sync(AB_FULL, keep);
+                if (lane == 0) ballots[c] = b;
+            }
+            __syncthreads();
+            // ---- suffix sums over chunks: output runs from the LAST walk position to the first ----
+            {
+                const int cidx = C - 1 - (int)threadIdx.x;                 // thread i owns chunk C-1-i
+                const int v = cidx >= 0 ? __popc(ballots[cidx]) : 0;
+                int inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(AB_FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) red[warp] = inc;
+                __syncthreads();
+                if (warp == 0) {
+                    int x = lane < NW ? red[lane] : 0;
+                    int xi = x;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int t = __shfl_up_sync(AB_FULL, xi, o);
+                        if (lane >= o) xi += t;
+                    }
+                    red[lane] = xi - x;
+                }
+                __syncthreads();
+                if (cidx >= 0) choff[cidx] = red[warp] + inc - v;      // entries emitted before this chunk
+                if (cap && cidx == 0) rowcount[r] = red[warp] + inc;   // staging mode: the row's edge count
+            }
+            __syncthreads();
+            // ---- pass B: emit (cap > 0: into the row's staging slot of `cap` entries, see snn_small_kernel) ----
+            const int64_t out = cap ? r * (int64_t)cap : rowptr_out[r];
+            const int grow = (int)(row_begin + r);
+            for (int c = warp; c < C; c += NW) {
+                const unsigned b = ballots[c];
+                if ((b >> lane) & 1u) {
+                    const int e = chunk_tab[c];
+                    const int a = e >> 24, t = ((e & 0xFFFFFF) << 5) + lane;
+                    const int m = __ldg(rlist + st.w.start[a] + t);
+                    unsigned s = hash_slot_lg(m, lg);
+                    while (keys[s] != m) s = (s + 1) & (S - 1);
+                    int pc = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; ++w2) pc += __popc(masks[(size_t)s * W + w2]);
+                    const int rel = choff[c] + __popc(b & ~((2u << lane) - 1));            // higher lanes first
+                    if (!cap || rel < cap) {
+                        const int64_t o = out + rel;
+                        dst[o] = m;
+                        if (!cap) src[o] = grow;
+                        if (overlap) overlap[o] = (uint8_t)pc;
+                    }
                 }
             }
         }
-        if (MODE == 0 && lane == 0) rowcount[r] = out - obase;
-        __syncwarp();
     }
-    if (MODE == 0) {
-        n1 = (unsigned long long)ab_warp_sum_i64((long long)n1);
-        n2 = (unsigned long long)ab_warp_sum_i64((long long)n2);
-        n3 = (unsigned long long)ab_warp_sum_i64((long long)n3);
-        if (lane == 0) {
-            atomicMax(walk_stats, wmax);
-            atomicAdd(walk_stats + 1, wsum);
-            atomicAdd(walk_stats + 2, n1 + n2 / 2 + n3);
-            if (dups) atomicAdd(n_dup, dups);
+    if (FILL && nz_out) {
+        nz = (unsigned long long)ab_warp_sum_i64((long long)nz);
+        if (lane == 0 && nz) atomicAdd(nz_out, nz);
+    }
+}
+
+template <int SLOTS, int W, int THREADS>
+static size_t snn_cta_smem() {
+    return (size_t)SLOTS * 4 * (1 + W) + sizeof(CtaRowState) + (size_t)THREADS * 12 + 64;
+}
+
+// ---------------------------------------------------------------------------------------
+// class 3: one CTA per row, dense per-CTA arrays in global scratch (cnt, first); any in-degree
+// ---------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(SNN_BIG_THREADS)
+snn_big_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_t n_total,
+               const int64_t *__restrict__ rptr, const int32_t *__restrict__ rlist, int v_min,
+               const int32_t *__restrict__ big_rows, const int *__restrict__ n_big,
+               int *__restrict__ dense /* SNN_BIG_CTAS x 2 x n_total, cnt=0 / first=INT_MAX */,
+               int64_t *__restrict__ rowcount, const int64_t *__restrict__ rowptr_out,
+               int32_t *__restrict__ src, int32_t *__restrict__ dst, uint8_t *__restrict__ overlap,
+               unsigned long long *__restrict__ nz_out) {
+    __shared__ WarpRowState st;
+    unsigned long long nz = 0;
+    __shared__ int warp_tot[SNN_BIG_THREADS / 32];
+    __shared__ int walk_sm;
+    __shared__ int total_sm;
+    int *cnt = dense + (int64_t)blockIdx.x * 2 * n_total;
+    int *first = cnt + n_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = *n_big;
+    for (int q = blockIdx.x; q < nb; q += gridDim.x) {
+        const int64_t r = big_rows[q];
+        __syncthreads();
+        if (warp == 0) {
+            int wl = warp_load_row(knn, k, row_begin + r, rptr, st, lane);
+            if (lane == 0) { walk_sm = wl; total_sm = 0; }
+        }
+        __syncthreads();
+        const int walk = walk_sm;
+        for (int p = threadIdx.x; p < walk; p += SNN_BIG_THREADS) {
+            const int m = walk_fetch(st, k, p, rlist);
+            atomicAdd(cnt + m, 1);
+            atomicMin(first + m, p);
+        }
+        __syncthreads();
+        if (!FILL) {
+            int c = 0;
+            for (int p = threadIdx.x; p < walk; p += SNN_BIG_THREADS) {
+                const int m = walk_fetch(st, k, p, rlist);
+                c += (first[m] == p) && (cnt[m] >= v_min);
+                nz += first[m] == p;
+            }
+            c = ab_warp_sum_i32(c);
+            if (lane == 0) atomicAdd(&total_sm, c);
+            __syncthreads();
+            if (threadIdx.x == 0) rowcount[r] = total_sm;
+        } else {
+            int64_t out = rowptr_out[r];
+            const int grow = (int)(row_begin + r);
+            for (int p0 = ((walk - 1) / SNN_BIG_THREADS) * SNN_BIG_THREADS; p0 >= 0; p0 -= SNN_BIG_THREADS) {
+                const int p = p0 + threadIdx.x;
+                bool keep = false;
+                int m = 0, c = 0;
+                if (p < walk) {
+                    m = walk_fetch(st, k, p, rlist);
+                    c = cnt[m];
+                    keep = (first[m] == p) && c >= v_min;
+                }
+                const unsigned b = __ballot_sync(AB_FULL, keep);
+                if (lane == 0) warp_tot[warp] = __popc(b);
+                __syncthreads();
+                int higher = 0, tot = 0;
+                for (int w2 = 0; w2 < SNN_BIG_THREADS / 32; ++w2) {
+                    tot += warp_tot[w2];
+                    if (w2 > warp) higher += warp_tot[w2];
+                }
+                if (keep) {
+                    const int64_t pos = out + higher + __popc(b & ~((2u << lane) - 1));
+                    dst[pos] = m;
+                    src[pos] = grow;
+                    if (overlap) overlap[pos] = (uint8_t)min(c, 255);
+                }
+                out += tot;
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+        // restore the dense arrays
+        for (int p = threadIdx.x; p < walk; p += SNN_BIG_THREADS) {
+            const int m = walk_fetch(st, k, p, rlist);
+            cnt[m] = 0;
+            first[m] = INT_MAX;
         }
     }
+    if (!FILL && nz_out) {
+        nz = (unsigned long long)ab_warp_sum_i64((long long)nz);
+        if (lane == 0 && nz) atomicAdd(nz_out, nz);
+    }
+}
+
+__global__ void snn_init_dense_kernel(int *dense, int64_t n_total, int nctas) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = 2 * n_total;
+    if (i < per * nctas) dense[i] = ((i % per) < n_total) ? 0 : INT_MAX;
 }
 
 // staging -> final edge list: one warp per row; rows whose edges did not fit their staging slot are queued
 __global__ void __launch_bounds__(256)
 snn_compact_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ stage_dst,
                    const uint8_t *__restrict__ stage_ov, int cap, int64_t n_rows, int64_t row_begin,
-                   int32_t *__restrict__ src, int32_t *__restrict__ dst, uint8_t *__restrict__ overlap,
-                   int32_t *__restrict__ ovf_rows, int *__restrict__ n_ovf) {
+                   const uint8_t *__restrict__ row_cls, int32_t *__restrict__ src, int32_t *__restrict__ dst,
+                   uint8_t *__restrict__ overlap, int32_t *__restrict__ ovf_rows, int *__restrict__ n_ovf) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * 8;
     for (int64_t r = w; r < n_rows; r += nw) {
+        if (row_cls[r] == 4) continue;                       // dense-path rows are filled by snn_big_kernel<true>
         const int64_t a = rowptr[r];
         const int64_t cnt = rowptr[r + 1] - a;
         if (cnt > cap) {
@@ -358,11 +662,14 @@ struct SnnWs {
     int32_t *rlist;      // n_total*k
     int32_t *tmp;        // n_total*k
     int32_t *long_ids;   // n_total
+    int32_t *cls_rows;   // 5*n_rows
+    uint8_t *row_cls;    // n_rows: class of every row
     int32_t *stage_dst;  // n_rows * snn_stage_cap(k): edges of each row, staged by the (single) walk pass
     uint8_t *stage_ov;   // n_rows * snn_stage_cap(k)
     int32_t *ovf_rows;   // n_rows: rows whose edges did not fit their staging slot
-    int *counters;       // 16 ints: [0] n_long, [2] n_dup, [3] bad, [10] overflow rows
-    unsigned long long *walk_stats;   // [0] max walk, [1] sum of walks, [2] nonzeros of A.A^T, [3] row ticket
+    int *dense;          // SNN_BIG_CTAS*2*n_total
+    int *counters;       // 16 ints: [0] n_long, [2] n_dup, [3] bad, [4..7] rows per class
+    unsigned long long *walk_stats;   // [0] max walk, [1] sum of walks, [2] nonzeros of A.A^T (first encounters)
     int64_t *rowcount;   // n_rows+1
     void *scan_ws;
     size_t scan_bytes;
@@ -371,15 +678,17 @@ struct SnnWs {
 static size_t snn_layout(int64_t n_total, int32_t k, int64_t n_rows, void *ws, size_t ws_bytes, SnnWs *out) {
     ab_arena a(ws ? ws : (void *)256, ws ? ws_bytes : (size_t)-1 / 2);
     SnnWs w;
-    const size_t nr = (size_t)(n_rows > 0 ? n_rows : 1);
     w.deg = a.take<int64_t>(n_total + 1);
     w.cursor = a.take<int>(n_total);
     w.rlist = a.take<int32_t>((size_t)n_total * k);
     w.tmp = a.take<int32_t>((size_t)n_total * k);
     w.long_ids = a.take<int32_t>(n_total);
-    w.stage_dst = a.take<int32_t>(nr * snn_stage_cap(k));
-    w.stage_ov = a.take<uint8_t>(nr * snn_stage_cap(k));
-    w.ovf_rows = a.take<int32_t>(nr);
+    w.cls_rows = a.take<int32_t>((size_t)5 * (n_rows > 0 ? n_rows : 1));
+    w.row_cls = a.take<uint8_t>((size_t)(n_rows > 0 ? n_rows : 1));
+    w.stage_dst = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1) * snn_stage_cap(k));
+    w.stage_ov = a.take<uint8_t>((size_t)(n_rows > 0 ? n_rows : 1) * snn_stage_cap(k));
+    w.ovf_rows = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1));
+    w.dense = a.take<int>((size_t)SNN_BIG_CTAS * 2 * n_total);
     w.counters = a.take<int>(16);
     w.walk_stats = a.take<unsigned long long>(4);
     w.rowcount = a.take<int64_t>(n_rows + 1);
@@ -394,13 +703,61 @@ extern "C" size_t ab_snn_ws_bytes(int64_t n_total, int32_t k, int64_t n_rows) {
     return snn_layout(n_total, k, n_rows, nullptr, 0, nullptr) + 256;
 }
 
-static int snn_hash_lg(int k) {
-    int lg = 5;
-    while ((1 << lg) < 8 * k) ++lg;                        // load factor <= 1/8: an absent id stops at its first slot 7 times in 8
-    return lg;
+static size_t snn_small_smem() { return sizeof(WarpRowState) * SNN_WARPS + (size_t)SNN_WARPS * SNN_SLOTS * 2 * sizeof(int); }
+
+// launches the shared-memory-table kernels of classes 0-3 in FILL mode: cap > 0 stages every row's edges into its own
+// slot (dst/overlap = staging arrays, rowcount written), cap == 0 writes final positions given by rowptr
+static int snn_launch_tables(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, int k, int64_t row_begin, int64_t n_rows,
+                             int v_min, int64_t *rowcount, const int64_t *rowptr, int32_t *src, int32_t *dst,
+                             uint8_t *overlap, int cap, cudaStream_t st) {
+    unsigned long long *nz = cap ? w.walk_stats + 2 : nullptr;       // counted once, in the staging pass
+    const int32_t *rows0 = w.cls_rows, *rows1 = w.cls_rows + n_rows, *rows2 = w.cls_rows + 2 * n_rows,
+                  *rows3 = w.cls_rows + 3 * n_rows;
+    const int *ncls = w.counters + 4;
+    {
+        const size_t smem = snn_small_smem();
+        AB_CUDA(cudaFuncSetAttribute(snn_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t blocks = std::min<int64_t>((n_rows + SNN_WARPS - 1) / SNN_WARPS, (int64_t)ctx->sm_count * 4);
+        snn_small_kernel<true><<<(unsigned)blocks, SNN_WARPS * 32, smem, st>>>(
+            knn_all, k, row_begin, rows0, ncls + 0, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap, cap, nz);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    const int64_t gcap = std::max<int64_t>(1, n_rows);
+#define AB_SNN_CTA(SLOTS, W, THREADS, ROWS, NPTR, PER_SM)                                                        \
+    do {                                                                                                       \
+        const size_t smem = snn_cta_smem<SLOTS, W, THREADS>();                                                 \
+        AB_CUDA(cudaFuncSetAttribute(snn_cta_kernel<SLOTS, W, THREADS, true>,                                  \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        const unsigned grid = (unsigned)std::min<int64_t>(gcap, (int64_t)ctx->sm_count * (PER_SM));            \
+        snn_cta_kernel<SLOTS, W, THREADS, true><<<grid, THREADS, smem, st>>>(                                  \
+            knn_all, k, row_begin, ROWS, NPTR, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap, cap, nz); \
+        AB_LAUNCH_CHECK(ctx);                                                                                  \
+    } while (0)
+    if (k <= 32) {
+        AB_SNN_CTA(SNN_MID_SLOTS, 1, SNN_MID_THREADS, rows1, ncls + 1, 6);
+        AB_SNN_CTA(8192, 1, SNN_LARGE_THREADS, rows2, ncls + 2, 3);
+        AB_SNN_CTA(16384, 1, SNN_LARGE_THREADS, rows3, ncls + 3, 1);
+    } else {
+        AB_SNN_CTA(SNN_MID_SLOTS, 4, SNN_MID_THREADS, rows1, ncls + 1, 2);
+        AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows2, ncls + 2, 1);     // (class 3 stays empty: lim3 == lim2)
+    }
+    return 0;
 }
-static size_t snn_isect_smem(int k) {
-    return sizeof(WarpRowState) * SNN_WARPS + (size_t)SNN_WARPS * 2 * ((size_t)1 << snn_hash_lg(k)) * sizeof(int);
+
+// second pass for the rows whose edges did not fit their staging slot: the largest table kernel takes any class-0..3 row
+static int snn_launch_overflow(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, int k, int64_t row_begin, int64_t n_rows,
+                               int v_min, const int64_t *rowptr, int32_t *src, int32_t *dst, uint8_t *overlap,
+                               cudaStream_t st) {
+    const int64_t gcap = std::max<int64_t>(1, n_rows);
+    const int32_t *rows = w.ovf_rows;
+    const int *nptr = w.counters + 10;
+    int64_t *rowcount = nullptr;
+    const int cap = 0;
+    unsigned long long *nz = nullptr;
+    if (k <= 32) AB_SNN_CTA(16384, 1, SNN_LARGE_THREADS, rows, nptr, 1);
+    else AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows, nptr, 1);
+#undef AB_SNN_CTA
+    return 0;
 }
 
 extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k, int64_t row_begin,
@@ -408,7 +765,7 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
                             void *ws, size_t ws_bytes, void *stream) {
     AB_REQUIRE(ctx, "ab_snn_count: null ctx");
     AB_REQUIRE(k >= 1 && k <= SNN_MAXK, "ab_snn_count: k must be in 1..%d", SNN_MAXK);
-    AB_REQUIRE(n_total >= 1 && n_total * (int64_t)k < INT_MAX, "ab_snn_count: n_total * k must stay below 2^31");
+    AB_REQUIRE(n_total >= 1 && n_total < INT_MAX, "ab_snn_count: bad n_total");
     AB_REQUIRE(row_begin >= 0 && row_end >= row_begin && row_end <= n_total, "ab_snn_count: bad row range");
     const int64_t n_rows = row_end - row_begin;
     SnnWs w;
@@ -437,21 +794,24 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_SNN_BUILD, st);
     ab_prof_begin(ctx, AB_PROF_SNN_COUNT, st);
+    // rows with a 2-hop walk of at most lim0 entries take the one-warp kernel, longer ones a whole CTA
+    const int lim0 = getenv("AB_SNN_WALK_LIMIT") ? std::min(SNN_WALK_LIMIT, atoi(getenv("AB_SNN_WALK_LIMIT"))) : SNN_WALK_LIMIT;
     if (n_rows > 0) {
-        // ONE walk per row: every row's edges (emission order included) are staged in a per-row slot;
-        // ab_snn_fill then only compacts the slots into the final list
-        const size_t smem = snn_isect_smem(k);
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)200 * 1024 / smem));
-        const unsigned grid = (unsigned)std::min<int64_t>((n_rows + SNN_WARPS - 1) / SNN_WARPS, (int64_t)ctx->sm_count * per_sm);
-#define AB_SNN_ISECT0(GL)                                                                                             \
-        do {                                                                                                          \
-            AB_CUDA(cudaFuncSetAttribute(snn_isect_kernel<0, GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            snn_isect_kernel<0, GL><<<grid, SNN_WARPS * 32, smem, st>>>(                                              \
-                knn_all, k, snn_hash_lg(k), row_begin, n_rows, nullptr, nullptr, w.deg, w.rlist, v_min, w.rowcount, nullptr, \
-                nullptr, w.stage_dst, w.stage_ov, snn_stage_cap(k), w.walk_stats + 3, w.walk_stats, w.counters + 2);  \
-        } while (0)
-        if (k <= 32) AB_SNN_ISECT0(8); else if (k <= 64) AB_SNN_ISECT0(16); else AB_SNN_ISECT0(32);
-#undef AB_SNN_ISECT0
+        snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
+            knn_all, k, row_begin, n_rows, w.deg, w.cls_rows, w.counters + 4, lim0, snn_walk_cap(SNN_MID_SLOTS),
+            snn_walk_cap(8192), snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2, w.row_cls);
+        AB_LAUNCH_CHECK(ctx);
+        snn_init_dense_kernel<<<(unsigned)(((int64_t)SNN_BIG_CTAS * 2 * n_total + 255) / 256), 256, 0, st>>>(
+            w.dense, n_total, SNN_BIG_CTAS);
+        AB_LAUNCH_CHECK(ctx);
+        // ONE walk per row: the table kernels run in fill mode and stage each row's edges (emission order
+        // included) in a per-row slot; ab_snn_fill then only compacts the slots into the final list
+        if (snn_launch_tables(ctx, w, knn_all, k, row_begin, n_rows, v_min, w.rowcount, nullptr, nullptr, w.stage_dst,
+                              w.stage_ov, snn_stage_cap(k), st))
+            return 1;
+        snn_big_kernel<false><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
+            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.cls_rows + 4 * n_rows, w.counters + 8, w.dense,
+            w.rowcount, nullptr, nullptr, nullptr, nullptr, w.walk_stats + 2);
         AB_LAUNCH_CHECK(ctx);
     }
     if (ab_exclusive_scan_i64(ctx, w.rowcount, rowptr, n_rows, w.scan_ws, w.scan_bytes, st)) return 1;
@@ -463,15 +823,17 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     if (h_edges) AB_CUDA(cudaMemcpyAsync(h_edges, rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaStreamSynchronize(st));
     if (stats) {
-        // host array, see include/alona_b200.h
-        stats[0] = 0;
+        // host array: {rows beyond the one-warp path (classes 1-3), longest 2-hop walk, rows whose first
+        // neighbour is not the cell itself (duplicate points; alona/clustering.py:204 assumes it is),
+        // rows on the dense global path (class 3), sum of all walk lengths (the gather traffic / 4 B)}
+        stats[0] = (int64_t)h_cnt[5] + h_cnt[6] + h_cnt[7] + h_cnt[8];
         stats[1] = (int64_t)h_walk[0];
         stats[2] = h_cnt[2];
-        stats[3] = 0;
+        stats[3] = h_cnt[8];
         stats[4] = (int64_t)h_walk[1];
-        stats[5] = (int64_t)h_walk[2];
-        stats[6] = 0;
-        stats[7] = 0;
+        stats[5] = (int64_t)h_walk[2];                                     // nonzeros of A.A^T in the row range
+        stats[6] = h_cnt[5] + h_cnt[6];                                    // rows of the 4096- / 8192-slot CTA classes
+        stats[7] = h_cnt[7];                                               // rows of the 16384-slot class
     }
     return 0;
 }
@@ -487,23 +849,19 @@ extern "C" int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total,
     if (n_rows == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     ab_prof_begin(ctx, AB_PROF_SNN_FILL, st);
+    int rc = 0;
     AB_CUDA(cudaMemsetAsync(w.counters + 10, 0, sizeof(int), st));
-    AB_CUDA(cudaMemsetAsync(w.walk_stats + 3, 0, sizeof(unsigned long long), st));
     snn_compact_kernel<<<(unsigned)std::min<int64_t>((n_rows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, st>>>(
-        rowptr, w.stage_dst, w.stage_ov, snn_stage_cap(k), n_rows, row_begin, src, dst, overlap, w.ovf_rows, w.counters + 10);
+        rowptr, w.stage_dst, w.stage_ov, snn_stage_cap(k), n_rows, row_begin, w.row_cls, src, dst, overlap, w.ovf_rows,
+        w.counters + 10);
     AB_LAUNCH_CHECK(ctx);
-    // rows whose edges overflowed their staging slot (rare) walk once more, straight into their final positions
-    const size_t smem = snn_isect_smem(k);
-#define AB_SNN_ISECT1(GL)                                                                                             \
-    do {                                                                                                              \
-        AB_CUDA(cudaFuncSetAttribute(snn_isect_kernel<1, GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        snn_isect_kernel<1, GL><<<ctx->sm_count, SNN_WARPS * 32, smem, st>>>(                                         \
-            knn_all, k, snn_hash_lg(k), row_begin, n_rows, w.ovf_rows, w.counters + 10, w.deg, w.rlist, v_min, nullptr, rowptr, \
-            src, dst, overlap, 0, w.walk_stats + 3, w.walk_stats, nullptr);                                            \
-    } while (0)
-    if (k <= 32) AB_SNN_ISECT1(8); else if (k <= 64) AB_SNN_ISECT1(16); else AB_SNN_ISECT1(32);
-#undef AB_SNN_ISECT1
-    AB_LAUNCH_CHECK(ctx);
-    ab_prof_end(ctx, AB_PROF_SNN_FILL, st);
-    return 0;
+    rc = snn_launch_overflow(ctx, w, knn_all, k, row_begin, n_rows, v_min, rowptr, src, dst, overlap, st);
+    if (!rc) {
+        snn_big_kernel<true><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
+            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.cls_rows + 4 * n_rows, w.counters + 8, w.dense, nullptr,
+            rowptr, src, dst, overlap, nullptr);
+        AB_LAUNCH_CHECK(ctx);
+    }
+    ab_prof_end(ctx, AB_PROF_SNN_FILL, (cudaStream_t)stream);
+    return rc;
 }

@@ -377,8 +377,9 @@ class Engine:
                                         _ptr(src), _ptr(dst), _ptr(ov), _ptr(ws), ws.numel(), self.stream()),
                    'ab_snn_fill')
         return {'rowptr': rowptr, 'src': src, 'dst': dst, 'overlap': ov,
-                'max_walk': int(stats[1]), 'dup_rows': int(stats[2]), 'sum_walk': int(stats[4]),
-                'nonzeros_unpruned': int(stats[5])}
+                'big_rows': int(stats[0]), 'max_walk': int(stats[1]), 'dup_rows': int(stats[2]),
+                'dense_rows': int(stats[3]), 'sum_walk': int(stats[4]), 'nonzeros_unpruned': int(stats[5]),
+                'class_rows': [int(stats[6]), int(stats[7])]}
 
     # -- hand-off ---------------------------------------------------------------------
     def edges_csv_bytes(self, src, dst):

@@ -220,11 +220,12 @@ int ab_knn(ab_ctx *ctx, const double *emb_all, int64_t n_total, int32_t d, int64
  * are kept, as in the reference.
  * knn_all: N x k int32 0-based table of ALL cells; rows [row_begin,row_end) are emitted.
  * count: rowptr [nrows+1] int64 (exclusive scan), returns edges in *h_edges (synchronises);
- * stats (HOST int64[8], may be NULL) = {0, longest 2-hop walk, rows whose first neighbour is not the cell itself
- * (duplicate points), 0, sum of all 2-hop walk lengths (x k x 4 B = the gather traffic), number of nonzeros of A.A^T
- * in the row range BEFORE pruning (the denominator of the reference's "links pruned" message, clustering.py:231-235),
- * 0, 0};
- * fill: src/dst int32 [E], overlap uint8 [E] (may be NULL).  Requires n_total * k < 2^31. */
+ * stats (HOST int64[8], may be NULL) = {rows beyond the one-warp path, longest 2-hop walk, rows whose first
+ * neighbour is not the cell itself (duplicate points), rows on the dense global path, sum of all 2-hop walk lengths
+ * (x4 B = the gather traffic), number of nonzeros of A.A^T in the row range BEFORE pruning (the denominator of the
+ * reference's "links pruned" message, clustering.py:231-235), rows in the 4096- / 8192-slot CTA classes, rows in
+ * the 16384-slot class};
+ * fill: src/dst int32 [E], overlap uint8 [E] (may be NULL). */
 size_t ab_snn_ws_bytes(int64_t n_total, int32_t k, int64_t n_rows);
 int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k,
                  int64_t row_begin, int64_t row_end, int32_t v_min, int64_t *rowptr,
