@@ -1,0 +1,115 @@
+"""C4 of BASELINE.json: kNN + SNN microbench on a 1.3M x 50 mixture embedding, k sweep, 1-8 GPUs.
+
+    python benchmarks/c4_knn_snn.py [--n 1306127] [--d 50] [--ks 10,20,50,100] [--reps 2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 benchmarks/c4_knn_snn.py
+
+Queries are sharded by rows; every rank scans the whole embedding (generated identically on every rank), the kNN
+tables are all-gathered (ab_allgather_bytes) and every rank emits the SNN rows of its shard.  Device times are CUDA
+events on the launching stream, max over ranks; one JSON line per k on rank 0 with the roofline of the distance GEMM
+(2 N_q N d flops per rank / event time of knn_tc_kernel / measured bf16 peak) and the clocks seen during the run.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from alona_b200.engine import get_engine
+from alona_b200.pipeline import prune_threshold, shard_bounds
+from bench import ClockSampler
+from benchmarks.knn_micro import mixture
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--n', type=int, default=1306127)
+    ap.add_argument('--d', type=int, default=50)
+    ap.add_argument('--ks', default='10,20,50,100')
+    ap.add_argument('--reps', type=int, default=2)
+    a = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    eng = get_engine()
+    dev = eng.device
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    emb = mixture(a.n, a.d, dev)
+    b = shard_bounds(a.n, world)
+    lo, hi = b[rank], b[rank + 1]
+    rows = [b[r + 1] - b[r] for r in range(world)]
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for k in [int(x) for x in a.ks.split(',')]:
+        vmin = prune_threshold(k, 0.067)
+        eng.prof_set_level(1)
+        sampler = ClockSampler(local_rank)
+        best = None
+        for rep in range(a.reps + 1):                           # first pass = warm-up
+            if rep == 1 and rank == 0:
+                sampler.start()
+            sync()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            eng.prof_read()
+            e0.record()
+            idx, rd, st = eng.knn(emb, k, q_begin=lo, q_end=hi)
+            knn_all = eng.allgather_rows(idx, rows)
+            e1.record()
+            res = eng.snn(knn_all, vmin, row_begin=lo, row_end=hi, want_overlap=False)
+            e2.record()
+            sync()
+            prof = eng.prof_read()
+            cur = {'knn_ms': maxr(e0.elapsed_time(e1)), 'snn_ms': maxr(e1.elapsed_time(e2)),
+                   'knn_main_ms': maxr(prof['knn_main'][0] / prof['knn_main'][1]) if 'knn_main' in prof else None,
+                   'knn_rerank_ms': maxr(prof['knn_rerank'][0] / prof['knn_rerank'][1]) if 'knn_rerank' in prof else None}
+            if rep >= 1 and (best is None or cur['knn_ms'] + cur['snn_ms'] < best['knn_ms'] + best['snn_ms']):
+                best = cur
+        clocks = sampler.stop() if rank == 0 else None
+        s = st.clone()
+        e = torch.tensor([res['src'].numel()], dtype=torch.int64, device=dev)
+        if world > 1:
+            cnt = s[:4].clone()
+            dist.all_reduce(cnt)
+            s = torch.cat([cnt, s[4:]])
+            dist.all_reduce(e)
+        s = s.cpu().numpy()
+        if rank == 0:
+            total_ms = best['knn_ms'] + best['snn_ms']
+            peak = peaks.get('bf16_tflops_sustained') or 1400.0
+            frac = None
+            if best['knn_main_ms']:
+                frac = 2.0 * (a.n / world) * a.n * a.d / (best['knn_main_ms'] / 1e3) / 1e12 / peak
+            print(json.dumps({'workload': 'c4: kNN+SNN on a %d x %d mixture embedding' % (a.n, a.d), 'k': k, 'n_gpus': world,
+                              'cells_per_s': a.n / (total_ms / 1e3), **best, 'edges_total': int(e.item()),
+                              'tie_rows': int(s[0]), 'exact_fallback_rows': int(s[1]), 'certified_rows': int(s[3]),
+                              'roofline': {'bound': 'tensor', 'kernel': 'knn_tc_kernel', 'frac': frac, 'peak': peak,
+                                           'unit': 'TFLOP/s', 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained'},
+                              'clocks': clocks}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
