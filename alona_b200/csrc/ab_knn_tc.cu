@@ -51,13 +51,18 @@ static constexpr int TC_KCH = 32;            // halves per K chunk = one 64-byte
 static constexpr int TC_SLAB = TC_TILE * 64; // bytes of one 128-row x 64-byte operand slab (8 KB)
 static constexpr int TC_MAX_STAGES = 16;
 static constexpr int TC_MAX_CHUNKS = 10;     // 3d+3 <= 320  ->  d <= 105
-static constexpr double TC_KAPPA = 1.52587890625e-05;   // 2^-16
-// FP16 products kept per coordinate pair (AB_KNN_NPROD experiment): dropping q_lo.x_hi leaves an error of at most
-// 2.|q_lo.x| <= 2^-11.|q|.R <= 2^-13.(|q|+R)^2 (FP16 rounds a coordinate to 2^-12 relative); dropping x_lo as well
-// doubles it.  The certificate and the exact fall-back keep the result exact either way; only the number of
-// uncertified queries can grow.
-__host__ __device__ inline double tc_kappa(int np) {
-    return np >= 3 ? TC_KAPPA : np == 2 ? TC_KAPPA + 1.220703125e-04 : TC_KAPPA + 2.44140625e-04;
+// Error bound of an approximate score, relative to (|q| + R)^2, that the certificate of the re-rank uses:
+//   * accumulation: the K products of a score are exact in FP32 (two 11-bit significands) and are added in FP32:
+//     at most K roundings of 2^-24 relative to sum |a_i b_i| <= 2|q|R + R^2 <= (|q| + R)^2 (any summation order,
+//     so it also covers the tensor pipe's internal one);
+//   * split: each coordinate carries 22 significant bits (hi + lo), the dropped q_lo.x_lo products and the FP16
+//     rounding of -2x and of the three norm pieces add less than 2^-20 (|q| + R)^2.
+// kappa = 1.25 K 2^-24 + 2^-19 (a quarter of margin on the first term; K = 160 at d = 50 gives 1.38e-5, the
+// 2^-16 of round 1).  The largest observed error is reported (stats[4]: 7e-7 at C3) and ab_knn_tc_run refuses to
+// certify anything if it ever exceeds kappa / 2.  Dropping products (np < 3) adds their worst case.
+__host__ __device__ inline double tc_kappa(int np, int kt) {
+    const double base = 1.25 * (double)kt * 5.9604644775390625e-08 + 1.9073486328125e-06;
+    return np >= 3 ? base : np == 2 ? base + 1.220703125e-04 : base + 2.44140625e-04;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -328,8 +333,6 @@ struct TcParams {
     int ksteps;            // UMMA K steps (16 halves) that carry data: ceil((3d+3)/16)
     int stages;            // B ring depth, in slots of `group` chunks
     int group;             // K chunks per ring slot = per bulk copy and per barrier round
-    int merged;            // 1: one slot per tile and the epilogue releases its accumulator buffer straight onto the
-                           //    `full` barrier of the tile that will reuse it (one wait per tile for the issuer)
     int split;             // 1: the two 128-column halves of an accumulator buffer are committed and released
                            //    separately (needs one ring slot per tile): the epilogue of half 0 starts while the
                            //    MMAs of half 1 run, and a half is reusable as soon as ITS four warps are done
@@ -339,8 +342,6 @@ struct TcParams {
     const unsigned char *bop;   // tiled, pre-swizzled B operand (knn_b_pos)
     unsigned long long *bufg;   // [grid][TC_BUF][256] append buffers
     int *cursor;                // tile CTA 0 is currently loading: the other CTAs start their sweeps there
-    const float *tau0;          // optional per-query starting threshold (scaled score units); NULL = +inf
-    int dbg;               // experiments only (AB_KNN_DBG): 1 = epilogue skips the score scan, 2 = no MMA issue
 };
 
 // 32-wide bitonic sort across the warp, descending (lane 0 ends with the largest key)
@@ -470,7 +471,7 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, boo
 #pragma unroll
     for (int g = 1; g + 1 < NG; g += 2) mn = fmin3(mn, gmin[g], gmin[g + 1]);
     mn = fminf(mn, gmin[NG - 1]);
-    if (!__any_sync(AB_FULL, live && mn < tau) || (P.dbg & 256)) return;      // (256: experiment, common path only)
+    if (!__any_sync(AB_FULL, live && mn < tau)) return;
     // Rare path.  A candidate is a GROUP of TC_GRP consecutive points keyed by its smallest score: appending it is one
     // compare and one store per group, with no search inside the 32 registers (measured: that search, executed by
     // the whole warp for the ~1.7 lanes that hit, was everything the kernel cost above its MMA/copy floor).  The
@@ -522,7 +523,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
     const int64_t my_tiles = my_blocks * n_tiles;   // global tile counter `it` runs over [0, my_tiles)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, P.merged ? 1 + TC_EPI_WARPS : 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int b = 0; b < 2; ++b) { mbar_init(t_full + b, 1); mbar_init(t_empty + b, TC_EPI_WARPS); }
@@ -572,23 +573,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 // or MMAs, set the floor of this kernel)
                 for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
                     const int gsz = min(P.group, P.chunks - c0);
-                    const bool ptrace = (P.dbg & 64) && blockIdx.x == 0 && qb == blockIdx.x && ti >= 200 && ti < 264 && lane == 0;
-                    if (ptrace) P.bufg[1024 + (ti - 200) * 2] = (unsigned long long)clock64();
                     mbar_wait(empty + stage, phase ^ 1);
-                    if (ptrace) P.bufg[1024 + (ti - 200) * 2 + 1] = (unsigned long long)clock64();
                     if (elect_one()) {
                         const uint32_t bytes = (uint32_t)gsz * TC_SLAB;
                         unsigned char *dst = sB + (size_t)stage * P.group * b_stage_bytes;
-                        if (P.dbg & 32) {                           // experiment: 1 KB per slot
-                            mbar_expect_tx(full + stage, 1024u);
-                            bulk_load(dst, slab0 + (size_t)c0 * TC_SLAB, 1024u, full + stage);
-                        } else {
-                            mbar_expect_tx(full + stage, bytes * (uint32_t)(3 - P.mt));
-                            bulk_load(dst, slab0 + (size_t)c0 * TC_SLAB, bytes, full + stage);
-                            if (P.mt == 1)                          // second 128-point slab of the 256-point tile
-                                bulk_load(dst + (size_t)P.group * TC_SLAB, slab0 + (size_t)(P.chunks + c0) * TC_SLAB, bytes,
-                                          full + stage);
-                        }
+                        mbar_expect_tx(full + stage, bytes * (uint32_t)(3 - P.mt));
+                        bulk_load(dst, slab0 + (size_t)c0 * TC_SLAB, bytes, full + stage);
+                        if (P.mt == 1)                              // second 128-point slab of the 256-point tile
+                            bulk_load(dst + (size_t)P.group * TC_SLAB, slab0 + (size_t)(P.chunks + c0) * TC_SLAB, bytes,
+                                      full + stage);
                     }
                     __syncwarp();
                     if (++stage == P.stages) { stage = 0; phase ^= 1; }
@@ -650,58 +643,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 __syncwarp();
                 ++nblocks_done;
             }
-        } else if (P.merged) {
-            // One ring slot and one barrier per tile.  The wait for tile it+1 is taken BEFORE the last K chunk of
-            // tile it is issued: it then overlaps the MMAs still queued in the tensor pipe instead of leaving the
-            // pipe idle between tiles (measured: 1490 cycles of issue per tile, then 180-300 for the wait).
-            bool ready = false;
-            for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
-                mbar_wait(a_full, aphase);
-                aphase ^= 1;
-                const bool last_block = qb + gridDim.x >= n_qblocks;
-                for (int64_t t = 0; t < n_tiles; ++t, ++it) {
-                    const int buf = (int)(it & 1);
-                    const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
-                    if (!ready) mbar_wait(full + stage, phase);
-                    tc_fence_after();
-                    const uint64_t b_slot = b_desc0 + (uint64_t)((uint32_t)stage * slot_step);
-                    const bool has_next = !(last_block && t + 1 == n_tiles);
-                    int nstage = stage + 1;
-                    uint32_t nphase = phase;
-                    if (nstage == P.stages) { nstage = 0; nphase ^= 1; }
-                    for (int half_pass = 0; half_pass < 2; ++half_pass) {
-                        const int l0 = half_pass == 0 ? 0 : P.chunks - 1, l1 = half_pass == 0 ? P.chunks - 1 : P.chunks;
-                        if (elect_one()) {
-                            for (int l = l0; l < l1; ++l) {
-                                const uint64_t a_c = a_desc0 + (uint64_t)((uint32_t)l * a_step);
-                                const uint64_t b_s = b_slot + (uint64_t)((uint32_t)l * (TC_SLAB >> 4));
-                                const bool two = P.ksteps - 2 * l >= 2 && !(P.dbg & 2);
-                                if (!(P.dbg & 16)) {
-                                    tc_mma_f16(tmem_d, a_c, b_s, idesc, (uint32_t)(l != 0));
-                                    if (two) tc_mma_f16(tmem_d, a_c + 2, b_s + 2, idesc, 1u);
-                                    tc_mma_f16(tmem_d + TC_TILE, a_c + a_half, b_s + b_half, idesc, (uint32_t)(l != 0));
-                                    if (two) tc_mma_f16(tmem_d + TC_TILE, a_c + a_half + 2, b_s + b_half + 2, idesc, 1u);
-                                }
-                            }
-                            if (half_pass == 1) {
-                                tc_commit(empty + stage);           // ring slot free once these MMAs retire
-                                tc_commit(t_full + buf);            // accumulators ready for the epilogue
-                            }
-                        }
-                        __syncwarp();
-                        if (half_pass == 0) {
-                            ready = false;
-                            // (the A tiles of the next query block are a different barrier: only look ahead inside a block)
-                            if (has_next && t + 1 < n_tiles) { mbar_wait(full + nstage, nphase); ready = true; }
-                        }
-                    }
-                    stage = nstage;
-                    phase = nphase;
-                }
-                if (elect_one()) tc_commit(a_empty);            // A tiles may be overwritten
-                __syncwarp();
-                ++nblocks_done;
-            }
         } else
         for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
             mbar_wait(a_full, aphase);
@@ -712,13 +653,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
                     const int gsz = min(P.group, P.chunks - c0);
                     // lane 0 waits for the operands, lane 31 for the accumulator buffer
-                    const bool trace = (P.dbg & 64) && blockIdx.x == 0 && it >= 200 && it < 264;
-                    long long tr0 = 0, tr1 = 0;
-                    if (trace) tr0 = clock64();
-                    // merged protocol: ONE barrier per tile (operands landed AND accumulator buffer released); an
-                    // mbarrier wait costs 180-300 cycles even when already complete, with the tensor pipe idle
-                    if (lane == 0) { mbar_wait(full + stage, phase); if (trace) tr1 = clock64(); }
-                    else if (lane == 31 && c0 == 0 && !P.merged) { mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1)); if (trace) tr1 = clock64(); }
+                    if (lane == 0) mbar_wait(full + stage, phase);
+                    else if (lane == 31 && c0 == 0) mbar_wait(t_empty + buf, (uint32_t)(((it >> 1) & 1) ^ 1));
                     __syncwarp();
                     tc_fence_after();
                     if (elect_one()) {
@@ -727,23 +663,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                             const int c = c0 + l;
                             const uint64_t a_c = a_desc0 + (uint64_t)((uint32_t)c * a_step);
                             const uint64_t b_s = b_slot + (uint64_t)((uint32_t)l * (TC_SLAB >> 4));
-                            const bool two = P.ksteps - 2 * c >= 2 && !(P.dbg & 2);
-                            if (!(P.dbg & 16)) {
-                                tc_mma_f16(tmem_d, a_c, b_s, idesc, (uint32_t)(c != 0));
-                                if (two) tc_mma_f16(tmem_d, a_c + 2, b_s + 2, idesc, 1u);
-                                tc_mma_f16(tmem_d + TC_TILE, a_c + a_half, b_s + b_half, idesc, (uint32_t)(c != 0));
-                                if (two) tc_mma_f16(tmem_d + TC_TILE, a_c + a_half + 2, b_s + b_half + 2, idesc, 1u);
-                            }
+                            const bool two = P.ksteps - 2 * c >= 2;
+                            tc_mma_f16(tmem_d, a_c, b_s, idesc, (uint32_t)(c != 0));
+                            if (two) tc_mma_f16(tmem_d, a_c + 2, b_s + 2, idesc, 1u);
+                            tc_mma_f16(tmem_d + TC_TILE, a_c + a_half, b_s + b_half, idesc, (uint32_t)(c != 0));
+                            if (two) tc_mma_f16(tmem_d + TC_TILE, a_c + a_half + 2, b_s + b_half + 2, idesc, 1u);
                         }
                         tc_commit(empty + stage);                   // ring slot free once these MMAs retire
                         if (c0 + gsz == P.chunks) tc_commit(t_full + buf);   // accumulators ready for the epilogue
                     }
                     __syncwarp();
-                    if (trace && (lane == 0 || lane == 31)) {       // experiment: per-tile timeline of the issuer
-                        unsigned long long *o = P.bufg + ((it - 200) * 2 + (lane == 31)) * 4;
-                        o[0] = (unsigned long long)tr0; o[1] = (unsigned long long)tr1;
-                        o[3] = (unsigned long long)clock64();
-                    }
                     if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -763,10 +692,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         const int list_id = P.mt == 1 ? half : 0;
         unsigned long long *bufp = P.bufg + (size_t)blockIdx.x * TC_BUF * TC_EPI_THREADS + etid;   // entry e at bufp[e * 256]
         const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)half * TC_TILE;
-        if (P.merged && lane == 0) {                            // tiles 0 and 1 find their accumulator buffers free
-            mbar_arrive(full + 0);
-            mbar_arrive(full + (1 % P.stages));
-        }
         int64_t cur_block = -1;
         int sweep0 = 0;
         long long q = 0;
@@ -782,13 +707,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 cur_block = blk;
                 q = (blockIdx.x + blk * gridDim.x) * q_per_block + (P.mt == 2 ? half * TC_TILE : 0) + row;
                 live = q < P.nq;
-                tau = (P.tau0 && live) ? __ldg(P.tau0 + q) : INFINITY;
+                tau = INFINITY;
                 cnt = 0;
             }
-            const bool etrace = (P.dbg & 64) && blockIdx.x == 0 && it >= 200 && it < 264 && ew == 0 && lane == 0;
-            if (etrace) P.bufg[2048 + (it - 200) * 3] = (unsigned long long)clock64();
             mbar_wait(P.split ? h_full + buf * 2 + half : t_full + buf, (uint32_t)((it >> 1) & 1));   // (one poller per warp + __syncwarp measured slower)
-            if (etrace) P.bufg[2048 + (it - 200) * 3 + 1] = (unsigned long long)clock64();
             tc_fence_after();
             if (new_block) sweep0 = sweep_start[blk & 7];           // published by the producer before this block's first load
             int64_t t = sweep0 + ti;
@@ -797,20 +719,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             const uint32_t taddr = taddr0 + (uint32_t)buf * 256;
             uint32_t ra[32];
 #pragma unroll 1
-            for (int cc = 0; cc < ((P.dbg & 4) ? 0 : TC_TILE / 32); ++cc) {
+            for (int cc = 0; cc < TC_TILE / 32; ++cc) {
                 // one unit per load/wait: a single instantiation of the scan keeps the hot loop small enough for
                 // the instruction cache (two inlined copies cost 19 % of the cycles in no-instruction stalls);
                 // the other epilogue warp of the scheduler covers the tcgen05.ld latency
                 tc_ld32(taddr + cc * 32, ra);
                 tc_wait_ld();
                 tc_touch32(ra);
-                if (P.dbg & 1) continue;
                 epi_unit(ra, (int)col0 + cc * 32, live, P, list_id, q, cnt, tau, bufp, lane);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(P.split ? h_empty + buf * 2 + half : P.merged ? full + (int)((it + 2) % P.stages) : t_empty + buf);
-            if (etrace) P.bufg[2048 + (it - 200) * 3 + 2] = (unsigned long long)clock64();
+            if (lane == 0) mbar_arrive(P.split ? h_empty + buf * 2 + half : t_empty + buf);
             // prune AFTER handing the accumulator back: the merge (two L2 round trips + a bitonic network)
             // then overlaps the MMAs of the next tiles instead of sitting on the MMA->epilogue handoff
             const unsigned due = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
@@ -836,7 +756,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                   int lists, const unsigned long long *__restrict__ cand, const double *__restrict__ qn,
                   const unsigned int *__restrict__ rmax_bits, int32_t *__restrict__ idx, double *__restrict__ rdist,
                   int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits,
-                  const float *__restrict__ tau0, double kappa) {
+                  double kappa) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int mg = lists * m;                              // candidate groups of the query (all lists)
@@ -895,9 +815,23 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                 if (cnd < n_total) {                          // (padding columns: ids past the end)
                     const double *xv = emb + cnd * d;
                     double acc = 0.0;
-                    for (int j = 0; j < d; ++j) {             // the reference's arithmetic, no FMA
-                        const double df = __dsub_rn(qv[j], xv[j]);
-                        acc = __dadd_rn(acc, __dmul_rn(df, df));
+                    if ((d & 1) == 0) {
+                        // same sequential, non-fused sum; 16-byte loads: every lane walks its own row, so the L1 sees
+                        // one request per lane and load - half as many as with 8-byte loads (it was the re-rank's bound)
+                        const double2 *xv2 = reinterpret_cast<const double2 *>(xv);
+                        const double2 *qv2 = reinterpret_cast<const double2 *>(qv);
+                        for (int j = 0; j < d / 2; ++j) {
+                            const double2 x = __ldg(xv2 + j), qq = qv2[j];
+                            const double d0 = __dsub_rn(qq.x, x.x);
+                            acc = __dadd_rn(acc, __dmul_rn(d0, d0));
+                            const double d1 = __dsub_rn(qq.y, x.y);
+                            acc = __dadd_rn(acc, __dmul_rn(d1, d1));
+                        }
+                    } else {
+                        for (int j = 0; j < d; ++j) {         // the reference's arithmetic, no FMA
+                            const double df = __dsub_rn(qv[j], xv[j]);
+                            acc = __dadd_rn(acc, __dmul_rn(df, df));
+                        }
                     }
                     dist = acc;
                     id = (int)cnd;
@@ -936,8 +870,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         if (lane == 0) {
             const double dk = sd[k - 1];
             // a list that is not full holds every group it saw -> no outside point there
-            // (with a starting threshold, groups at or above it were never listed)
-            double tau = tau0 ? (double)tau0[q] * inv_sc2 : INFINITY;
+            double tau = INFINITY;
             for (int g = 0; g < lists; ++g) {
                 const unsigned long long last = cand[((size_t)g * nq + q) * m + (m - 1)];
                 if (last != TC_KEY_MAX) tau = fmin(tau, (double)key_score(last) * inv_sc2);
@@ -959,15 +892,6 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         if (lane == 0) atomicMax(relerr_bits, __float_as_uint((float)worst_rel));
         __syncwarp();
     }
-}
-
-// experiment (AB_KNN_DBG & 512): the final threshold of a finished run, nudged up, as the starting threshold of a
-// second run - the best case any threshold-seeding scheme could reach
-__global__ void knn_final_tau_kernel(const unsigned long long *__restrict__ cand, int64_t nq, int m, float *__restrict__ tau0) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    const float t = key_score(cand[(size_t)q * m + (m - 1)]);
-    tau0[q] = t + 1e-3f * fabsf(t) + 1e-6f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1044,7 +968,7 @@ static int make_map(CUtensorMap *map, __half *base, int64_t rows, int kt, int bo
 
 int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k,
                   int32_t *idx, double *rdist, unsigned long long *stats, void *ws, size_t ws_bytes, cudaStream_t st) {
-    const int np = getenv("AB_KNN_NPROD") ? std::max(1, std::min(3, atoi(getenv("AB_KNN_NPROD")))) : 3;
+    const int np = 3;            // FP16 products per coordinate pair (2 and 1 were measured: profiles/r1_knn_notes.md)
     const int kt = tc_kt(d, np), chunks = kt / TC_KCH, m = tc_candidates(k);
     if (chunks > TC_MAX_CHUNKS || n_total < m || n_total >= ((int64_t)1 << 31) - 512) {
         // outside the tensor path's envelope (very wide embeddings, tiny inputs): exact scan
@@ -1090,49 +1014,15 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     TcParams P{};
     P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (np * d + 3 + 15) / 16;
     P.stages = stages; P.group = group; P.bufg = w.bufg;
-    // one barrier round per tile instead of two: measured floor -10 %, full kernel +9 % -> experiment knob only
-    P.merged = (group == chunks && stages >= 3 && getenv("AB_KNN_MERGED")) ? 1 : 0;
-    P.split = (group == chunks && !P.merged && !getenv("AB_KNN_NOSPLIT")) ? 1 : 0;
+    // a tile that is one ring slot: per-half accumulator hand-off; otherwise (wide embeddings) one hand-off per tile
+    P.split = group == chunks ? 1 : 0;
     P.cursor = (int *)(w.scal + 2); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
-    P.dbg = getenv("AB_KNN_DBG") ? atoi(getenv("AB_KNN_DBG")) : 0;
     const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
     const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
     ab_prof_begin(ctx, AB_PROF_KNN_MAIN, st);
     knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, P);
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_MAIN, st);
-    if ((P.dbg & 512) && lists == 1) {
-        float *t0 = reinterpret_cast<float *>(w.fb_list);          // scratch until the re-rank
-        knn_final_tau_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(w.cand, nq, m, t0);
-        AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)nq * m * sizeof(unsigned long long), st));
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        P.tau0 = t0;
-        cudaEventRecord(e0, st);
-        knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, P);
-        cudaEventRecord(e1, st);
-        AB_CUDA(cudaStreamSynchronize(st));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        fprintf(stderr, "[knn dbg] second run seeded with the first run's final thresholds: %.3f ms\n", ms);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        // the re-rank below sees the second run's lists; fb_list is overwritten there, so certify without tau0
-        P.tau0 = nullptr;
-    }
-    if (P.dbg & 64) {                                               // experiment: print the three roles' timelines
-        static unsigned long long h[4096];
-        AB_CUDA(cudaStreamSynchronize(st));
-        AB_CUDA(cudaMemcpy(h, w.bufg, sizeof(h), cudaMemcpyDeviceToHost));
-        const unsigned long long t0 = h[8 * 20];
-        for (int i = 20; i < 28; ++i) {
-            const unsigned long long *a = h + i * 8, *b = a + 4, *pp = h + 1024 + i * 2, *e = h + 2048 + i * 3;
-            fprintf(stderr, "[knn trace] tile %3d  mma: start %6lld full_ready %6lld tempty_ready %6lld issue_end %6lld | producer: start %6lld "
-                            "empty_ready %6lld | epilogue: start %6lld tfull_ready %6lld arrived %6lld\n",
-                    i, (long long)(a[0] - t0), (long long)(a[1] - t0), (long long)(b[1] - t0), (long long)(a[3] - t0),
-                    (long long)(pp[0] - t0), (long long)(pp[1] - t0), (long long)(e[0] - t0), (long long)(e[1] - t0),
-                    (long long)(e[2] - t0));
-        }
-    }
     // ---- exact re-rank + certificate ----
     ab_prof_begin(ctx, AB_PROF_KNN_RERANK, st);
     const int mp = lists * m * TC_GRP;                              // candidate points per query (m groups per list)
@@ -1142,7 +1032,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     const unsigned g_rr = (unsigned)std::min<int64_t>((nq + rr_warps - 1) / rr_warps, (int64_t)ctx->sm_count * 16);
     knn_rerank_kernel<<<g_rr, rr_warps * 32, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
-                                                           idx, rdist, w.fb_list, stats, w.scal + 1, P.tau0, tc_kappa(np));
+                                                           idx, rdist, w.fb_list, stats, w.scal + 1, tc_kappa(np, kt));
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_RERANK, st);
     // ---- uncertified queries: exact scan ----
@@ -1152,6 +1042,20 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaMemcpyAsync(h_scal, w.scal, sizeof(h_scal), cudaMemcpyDeviceToHost, st));
     AB_CUDA(cudaStreamSynchronize(st));
     const int64_t n_fb = (int64_t)h_stats[1];
+    {
+        // guard of the certificate's error model: the largest error seen on the candidates (hundreds per query) must
+        // stay far inside kappa; if it ever does not, nothing of this pass is trusted and every query is recomputed
+        // by the exact FP64 scan
+        float seen;
+        memcpy(&seen, &h_scal[1], sizeof(float));
+        if ((double)seen > 0.5 * tc_kappa(np, kt)) {
+            fprintf(stderr, "alona_b200: kNN candidate scores off by %.3g of (|q|+R)^2 (model bound %.3g): exact scan for all queries\n",
+                    (double)seen, tc_kappa(np, kt));
+            AB_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), st));
+            return ab_knn_exact_run(ctx, emb, n_total, d, nullptr, q_begin, nq, k, ab_knn_exact_pick_splits(ctx, nq), nullptr,
+                                    idx, rdist, stats, ws, ws_bytes, st);
+        }
+    }
     // stats[4] = max observed |approx - exact| / (||q||+R)^2 as float bits, stats[5] = candidates per list,
     // stats[6] = query tiles per CTA (2: 256-query blocks, 1: wide embeddings)
     unsigned long long extra[3] = {(unsigned long long)h_scal[1], (unsigned long long)m, (unsigned long long)mt};

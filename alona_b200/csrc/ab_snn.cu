@@ -27,8 +27,8 @@ static constexpr int SNN_SLOTS_LG = 9;
 static constexpr int SNN_WALK_LIMIT = 350;        // rows with a longer walk take a whole CTA (measured at C3: limit 1400 -> 68.7 ms,
                                                   // 700 -> 52.7, 350 -> 51.9, 0 -> 51.9: the one-warp kernel holds 8 warps per SM)
 static constexpr int SNN_MAXK = 128;
-static constexpr int SNN_BIG_CTAS = 148;         // one per SM (each owns 2*n_total ints of global scratch)
-static constexpr int SNN_BIG_THREADS = 256;
+static constexpr int SNN_BIG_CTAS = 296;         // two per SM (each owns 2*n_total ints of global scratch)
+static constexpr int SNN_BIG_THREADS = 1024;     // (148 x 256 threads left the dense path latency-bound: k = 100 at 1.3M cells took 14 s)
 static constexpr int SORT_CTA_MAX = 4096;
 // staged edges per row (single-pass protocol); rows with more take a second pass.  Edges per row grow with k
 // (C3, k = 20: 21 on average; a C5-shaped run, k = 30: 324), the slot is sized generously: it is only ever read up
@@ -551,6 +551,11 @@ snn_big_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_
     int *first = cnt + n_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nb = *n_big;
+    if (!FILL && (int)blockIdx.x < nb) {
+        // a CTA that has rows initialises its own dense arrays (count mode runs first and restores them after
+        // every row, so fill mode finds them clean); nothing is touched when no row needs the dense path
+        for (int64_t i = threadIdx.x; i < n_total; i += SNN_BIG_THREADS) { cnt[i] = 0; first[i] = INT_MAX; }
+    }
     for (int q = blockIdx.x; q < nb; q += gridDim.x) {
         const int64_t r = big_rows[q];
         __syncthreads();
@@ -619,12 +624,6 @@ snn_big_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, int64_
         nz = (unsigned long long)ab_warp_sum_i64((long long)nz);
         if (lane == 0 && nz) atomicAdd(nz_out, nz);
     }
-}
-
-__global__ void snn_init_dense_kernel(int *dense, int64_t n_total, int nctas) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t per = 2 * n_total;
-    if (i < per * nctas) dense[i] = ((i % per) < n_total) ? 0 : INT_MAX;
 }
 
 // staging -> final edge list: one warp per row; rows whose edges did not fit their staging slot are queued
@@ -800,9 +799,6 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
         snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
             knn_all, k, row_begin, n_rows, w.deg, w.cls_rows, w.counters + 4, lim0, snn_walk_cap(SNN_MID_SLOTS),
             snn_walk_cap(8192), snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2, w.row_cls);
-        AB_LAUNCH_CHECK(ctx);
-        snn_init_dense_kernel<<<(unsigned)(((int64_t)SNN_BIG_CTAS * 2 * n_total + 255) / 256), 256, 0, st>>>(
-            w.dense, n_total, SNN_BIG_CTAS);
         AB_LAUNCH_CHECK(ctx);
         // ONE walk per row: the table kernels run in fill mode and stage each row's edges (emission order
         // included) in a per-row slot; ab_snn_fill then only compacts the slots into the final list

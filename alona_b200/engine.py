@@ -261,11 +261,11 @@ class Engine:
         return med, {'gathered': int(per.sum()), 'batch': batch}
 
     # -- K1 ---------------------------------------------------------------------------
-    def norm_moments(self, A, acc=None, allreduce=True, finalize=True):
+    def norm_moments(self, A, acc=None, allreduce=True, finalize=True, libsize_out=None):
         """Library sizes + per-gene sum x / sum x^2 of the normalised values.  `acc` ([G, 4] int64 fixed-point
         accumulators, include/alona_b200.h) lets the caller chain row tiles; with finalize=False the raw accumulators
         are returned instead of the FP64 sums."""
-        lib = self.empty((A.n_local,), torch.int64)
+        lib = libsize_out if libsize_out is not None else self.empty((A.n_local,), torch.int64)
         if acc is None:
             acc = self.zeros((A.n_genes, 4), torch.int64)
         _lib.check(self.lib.ab_norm_moments(self.ctx, _ptr(A.rowptr), _ptr(A.col), _ptr(A.val), A.n_local,

@@ -128,8 +128,44 @@ class StageTimer:
         return out
 
 
+def upload_and_normalize(eng, h_rowptr, h_col, h_val, n_genes, row_begin, n_total, tiles=16):
+    """Host (pinned) CSR shard -> device, with K1 running on row tile i while tile i+1 is still crossing PCIe: the
+    library sizes and the fixed-point moment accumulators (chainable across tiles, include/alona_b200.h) are complete
+    a kernel's length after the last byte lands.  Returns (DeviceCSR, libsize, gsum, gsumsq)."""
+    from .engine import DeviceCSR
+    dev = eng.device
+    n = int(h_rowptr.numel() - 1)
+    nnz = int(h_col.numel())
+    rowptr = h_rowptr.to(dev, non_blocking=True)
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    val = torch.empty(nnz, dtype=torch.int32, device=dev)
+    libsize = torch.empty(n, dtype=torch.int64, device=dev)
+    acc = torch.zeros((n_genes, 4), dtype=torch.int64, device=dev)
+    compute = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(device=dev)
+    copy.wait_stream(compute)
+    rp = h_rowptr                                              # host view: tile boundaries in nonzeros
+    tiles = max(1, min(int(tiles), n))
+    bounds = [(n * t) // tiles for t in range(tiles + 1)]
+    for t in range(tiles):
+        r0, r1 = bounds[t], bounds[t + 1]
+        a, b = int(rp[r0]), int(rp[r1])
+        with torch.cuda.stream(copy):
+            col[a:b].copy_(h_col[a:b], non_blocking=True)
+            val[a:b].copy_(h_val[a:b], non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(copy)
+        compute.wait_event(landed)
+        tile = DeviceCSR((rowptr[r0:r1 + 1] - rowptr[r0]).contiguous(), col[a:b], val[a:b], n_genes)
+        lib_t, _ = eng.norm_moments(tile, acc=acc, finalize=False, libsize_out=libsize[r0:r1])
+    if eng.world > 1:
+        eng.allreduce_i64(acc)
+    gsum, gsumsq = eng.moments_finalize(acc)
+    return DeviceCSR(rowptr, col, val, n_genes, row_begin, n_total), libsize, gsum, gsumsq
+
+
 def frontend(eng, counts, hvg_n, pca_n, nn_k, prune_snn=0.067, seed=42, knn_mode=0, v0=None,
-             timer=None, want_overlap=False, tol=1e-4, maxit=1000):
+             timer=None, want_overlap=False, tol=1e-4, maxit=1000, normalized=None):
     """Runs the whole path on `counts` (DeviceCSR shard).  Everything returned is on the device.
     Returns a dict with libsize, gsum, gsumsq, hvg_ranked, z, gene2hvg, AH, irlb (dict),
     emb_all [N x d], knn_idx (this shard, 0-based), knn_all, snn (dict) and statistics."""
@@ -137,7 +173,10 @@ def frontend(eng, counts, hvg_n, pca_n, nn_k, prune_snn=0.067, seed=42, knn_mode
     bounds = shard_bounds(counts.n_total, eng.world)
     rows = [bounds[r + 1] - bounds[r] for r in range(eng.world)]
     t.mark('start')
-    libsize, gsum, gsumsq = eng.norm_moments(counts)
+    if normalized is not None:                     # (libsize, gsum, gsumsq) from upload_and_normalize
+        libsize, gsum, gsumsq = normalized
+    else:
+        libsize, gsum, gsumsq = eng.norm_moments(counts)
     t.mark('normalize')
     ranked, z, gene2hvg, hstats = eng.hvg_seurat(gsum, gsumsq, counts.n_total, hvg_n)
     n_hvg = min(int(hvg_n), counts.n_genes)

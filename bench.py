@@ -229,7 +229,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from alona_b200.engine import get_engine
-    from alona_b200.pipeline import frontend, StageTimer, shard_bounds, start_vector
+    from alona_b200.pipeline import frontend, StageTimer, shard_bounds, start_vector, upload_and_normalize
     from alona_b200.synth import make_profiles
     note('process group up')
     eng = get_engine()
@@ -319,9 +319,10 @@ def main():
         from alona_b200.engine import DeviceCSR
 
         def e2e_step():
-            d = DeviceCSR(h_rowptr.to(dev, non_blocking=True), h_col.to(dev, non_blocking=True),
-                          h_val.to(dev, non_blocking=True), wl['genes'], lo, wl['cells'])
-            o = frontend(eng, d, wl['hvg_n'], wl['pca_n'], wl['k'], 0.067, args.seed, knn_mode=args.knn_mode, v0=v0)
+            # upload in row tiles, K1 on tile i while tile i+1 is still crossing PCIe
+            d, lib, gs, gq = upload_and_normalize(eng, h_rowptr, h_col, h_val, wl['genes'], lo, wl['cells'])
+            o = frontend(eng, d, wl['hvg_n'], wl['pca_n'], wl['k'], 0.067, args.seed, knn_mode=args.knn_mode, v0=v0,
+                         normalized=(lib, gs, gq))
             src = o['snn']['src'].to('cpu', non_blocking=True)
             dst = o['snn']['dst'].to('cpu', non_blocking=True)
             torch.cuda.synchronize()
@@ -346,7 +347,9 @@ def main():
             dist.all_reduce(tot)
         e2e = {'value': wl['cells'] / float(tt.item()), 'unit': UNIT, 'h2d_bytes_per_step': int(tot[0].item()),
                'd2h_bytes_per_step': int(tot[1].item()), 'ms_per_step': 1e3 * float(tt.item()),
-               'path': 'pinned host CSR -> alona_b200.pipeline.frontend (C-ABI stages) -> host edge list'}
+               'h2d_gb_per_s': float(tot[0].item()) / world / 1e9 / max(1e-9, float(tt.item())),
+               'path': 'pinned host CSR -> alona_b200.pipeline.upload_and_normalize (row tiles, K1 overlapped with the '
+                       'upload) -> frontend (C-ABI stages) -> host edge list'}
 
     if rank != 0:
         if world > 1:
