@@ -126,15 +126,56 @@ snn_sort_long_kernel(const int64_t *__restrict__ rptr, int32_t *__restrict__ rli
             for (int i = threadIdx.x; i < len; i += 256) rlist[a + i] = sm[i];
             __syncthreads();
         } else {
-            // entries of one reverse list are distinct cells -> rank = #smaller
-            for (int64_t i = threadIdx.x; i < len; i += 256) {
-                const int v = rlist[a + i];
-                int64_t r = 0;
-                for (int64_t t = 0; t < len; ++t) r += rlist[a + t] < v;
-                tmp[a + r] = v;
+            // longer lists (hubs: in-degrees reach 1e5 at k = 100): sort runs of SORT_CTA_MAX entries in shared memory,
+            // then merge runs pairwise by rank - the entries of one reverse list are distinct cells, so an element's
+            // place in the merged run is its index in its own run plus the number of smaller elements in the partner
+            // run (binary search); rlist and tmp alternate as source and destination.  (The first version ranked every
+            // element against the whole list, O(len^2): 15 s for the k = 100 sweep of C4.)
+            for (int64_t c0 = 0; c0 < len; c0 += SORT_CTA_MAX) {
+                const int cl = (int)min((int64_t)SORT_CTA_MAX, len - c0);
+                int n2 = 64;
+                while (n2 < cl) n2 <<= 1;
+                for (int i = threadIdx.x; i < n2; i += 256) sm[i] = i < cl ? rlist[a + c0 + i] : INT_MAX;
+                __syncthreads();
+                for (int size = 2; size <= n2; size <<= 1) {
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        for (int i = threadIdx.x; i < (n2 >> 1); i += 256) {
+                            int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+                            int hi = lo | stride;
+                            bool up = ((lo & size) == 0);
+                            int x = sm[lo], y = sm[hi];
+                            if ((x > y) == up) { sm[lo] = y; sm[hi] = x; }
+                        }
+                        __syncthreads();
+                    }
+                }
+                for (int i = threadIdx.x; i < cl; i += 256) rlist[a + c0 + i] = sm[i];
+                __syncthreads();
             }
-            __syncthreads();
-            for (int64_t i = threadIdx.x; i < len; i += 256) rlist[a + i] = tmp[a + i];
+            int32_t *src = rlist + a, *dst = tmp + a;
+            for (int64_t width = SORT_CTA_MAX; width < len; width <<= 1) {
+                for (int64_t i = threadIdx.x; i < len; i += 256) {
+                    const int64_t run = i / width, mine0 = run * width;
+                    const int64_t other0 = (run ^ 1) * width;
+                    const int v = src[i];
+                    int64_t pos = i;
+                    if (other0 < len) {
+                        const int64_t other1 = min(len, other0 + width);
+                        int64_t lo = other0, hi = other1;                      // first partner element > v
+                        while (lo < hi) {
+                            const int64_t mid = (lo + hi) >> 1;
+                            if (src[mid] < v) lo = mid + 1; else hi = mid;
+                        }
+                        pos = min(mine0, other0) + (i - mine0) + (lo - other0);
+                    }
+                    dst[pos] = v;
+                }
+                __syncthreads();
+                int32_t *t = src; src = dst; dst = t;
+            }
+            if (src != rlist + a) {
+                for (int64_t i = threadIdx.x; i < len; i += 256) rlist[a + i] = src[i];
+            }
             __syncthreads();
         }
     }
@@ -160,7 +201,7 @@ __global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t 
                                 const int64_t *__restrict__ rptr, int32_t *__restrict__ cls_rows /*[5][n_rows]*/,
                                 int *__restrict__ n_cls /*[5]*/, int lim0, int lim1, int lim2, int lim3,
                                 unsigned long long *__restrict__ max_walk, unsigned long long *__restrict__ sum_walk,
-                                int *__restrict__ n_dup, uint8_t *__restrict__ row_cls) {
+                                int *__restrict__ n_dup, uint8_t *__restrict__ row_cls, int cls4_mark) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     long long walk = 0;
     if (r < n_rows) {
@@ -172,7 +213,7 @@ __global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t 
         if (row[0] != row_begin + r) atomicAdd(n_dup, 1);
         const int cls = walk <= lim0 ? 0 : (walk <= lim1 ? 1 : (walk <= lim2 ? 2 : (walk <= lim3 ? 3 : 4)));
         cls_rows[(int64_t)cls * n_rows + atomicAdd(n_cls + cls, 1)] = (int32_t)r;
-        row_cls[r] = (uint8_t)cls;
+        row_cls[r] = (uint8_t)(cls == 4 ? cls4_mark : cls);        // 5: the row is filled by the dense kernel
     }
     // block-level max / sum before touching the global atomics
     unsigned long long wmax = (unsigned long long)walk, wsum = (unsigned long long)walk;
@@ -531,6 +572,189 @@ static size_t snn_cta_smem() {
 }
 
 // ---------------------------------------------------------------------------------------
+// class 4: rows whose walk does not fit the largest shared-memory table (hubs; every row at k = 50..100: the walk
+// grows with k^2).  Same bitmask table as above, but the candidates are split by a second hash into P partitions
+// and the walk is repeated once per partition, so any walk length runs out of shared memory (round 1 used dense
+// per-CTA arrays of n_total counters in global memory: 3 GB of scratch, every atomic a DRAM round trip - 15 s for
+// the k = 100 sweep of C4).  Kept first encounters (a few hundred per row at most) are collected with their walk
+// position in a shared-memory list, sorted by position (descending = scipy's order) and emitted.
+// cap > 0: staging mode (row's slot, rowcount written); cap == 0: final positions from rowptr_out.
+// Rows with more than PT_LIST kept edges or a partition that overflows its table are handed to the dense kernel
+// (queued in `fallback_rows`), which stays as the any-input safety net.
+// ---------------------------------------------------------------------------------------
+static constexpr int PT_THREADS = 512;
+static constexpr int PT_LIST = 4096;             // kept edges per row the list can hold
+
+template <int SLOTS, int W>
+__global__ void __launch_bounds__(PT_THREADS)
+snn_part_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const int32_t *__restrict__ rows,
+                const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
+                const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
+                const int64_t *__restrict__ rowptr_out, int32_t *__restrict__ src, int32_t *__restrict__ dst,
+                uint8_t *__restrict__ overlap, int cap, unsigned long long *__restrict__ nz_out,
+                int32_t *__restrict__ fallback_rows, int *__restrict__ n_fallback, uint8_t *__restrict__ row_cls) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *keys = reinterpret_cast<int *>(smem_raw);
+    unsigned *masks = reinterpret_cast<unsigned *>(keys + SLOTS);
+    unsigned long long *list = reinterpret_cast<unsigned long long *>(masks + (size_t)SLOTS * W);   // (position << 32) | m
+    uint8_t *list_ov = reinterpret_cast<uint8_t *>(list + PT_LIST);
+    CtaRowState &st = *reinterpret_cast<CtaRowState *>(list_ov + PT_LIST);
+    __shared__ int nkept_sm, nins_sm, bad_sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = PT_THREADS / 32;
+    constexpr int LG = SLOTS == 16384 ? 14 : 13;
+    static_assert(SLOTS == (1 << LG), "table size");
+    unsigned long long nz = 0;
+    const int n_rows = *n_rows_ptr;
+    for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
+        const int64_t r = rows[q];
+        __syncthreads();
+        if (warp == 0) {
+            const int walk = warp_load_row(knn, k, row_begin + r, rptr, st.w, lane);
+            int run = 0;
+            for (int c0 = 0; c0 < k; c0 += 32) {
+                const int c = c0 + lane;
+                const int nch = c < k ? (st.w.base[c + 1] - st.w.base[c] + 31) >> 5 : 0;
+                int inc = nch;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int t = __shfl_up_sync(AB_FULL, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (c < k) st.chunk0[c] = run + inc - nch;
+                run += __shfl_sync(AB_FULL, inc, 31);
+            }
+            if (lane == 0) { st.chunk0[k] = run; st.walk = walk; st.chunks = run; nkept_sm = 0; bad_sm = 0; }
+        }
+        __syncthreads();
+        const int walk = st.walk, C = st.chunks;
+        unsigned long long nz_row = 0;
+        const int P = (walk + SLOTS / 2 - 1) / (SLOTS / 2);           // expected load factor <= 1/2 per partition
+        for (int part = 0; part < P; ++part) {
+            for (int s2 = threadIdx.x; s2 < SLOTS; s2 += PT_THREADS) keys[s2] = -1;
+            for (int s2 = threadIdx.x; s2 < SLOTS * W; s2 += PT_THREADS) masks[s2] = 0u;
+            if (threadIdx.x == 0) nins_sm = 0;
+            __syncthreads();
+            // ---- insert the walk entries of this partition ----
+            for (int c = warp; c < C; c += NW) {
+                int lo = 0, hi = k;                                    // list a with chunk0[a] <= c
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (st.chunk0[mid] <= c) lo = mid; else hi = mid;
+                }
+                const int a = lo, t = ((c - st.chunk0[a]) << 5) + lane;
+                const int len = st.w.base[a + 1] - st.w.base[a];
+                if (t < len) {
+                    const int m = __ldg(rlist + st.w.start[a] + t);
+                    const unsigned h = (unsigned)m * 2654435761u;
+                    if ((int)((h >> 7) % (unsigned)P) == part) {
+                        unsigned s2 = h >> (32 - LG);
+                        int probes = 0;
+                        while (true) {
+                            const int prev = atomicCAS(keys + s2, -1, m);
+                            if (prev == -1) { atomicAdd(&nins_sm, 1); break; }
+                            if (prev == m) break;
+                            s2 = (s2 + 1) & (SLOTS - 1);
+                            if (++probes >= SLOTS) { bad_sm = 1; break; }      // table full: hand the row over
+                        }
+                        if (probes < SLOTS) atomicOr(masks + (size_t)s2 * W + (a >> 5), 1u << (a & 31));
+                    }
+                }
+            }
+            __syncthreads();
+            if (bad_sm || nins_sm > SLOTS - SLOTS / 8) { if (threadIdx.x == 0) bad_sm = 1; __syncthreads(); break; }
+            // ---- first encounters of this partition: count, and list the kept ones with their walk position ----
+            for (int c = warp; c < C; c += NW) {
+                int lo = 0, hi = k;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (st.chunk0[mid] <= c) lo = mid; else hi = mid;
+                }
+                const int a = lo, t = ((c - st.chunk0[a]) << 5) + lane;
+                const int len = st.w.base[a + 1] - st.w.base[a];
+                if (t < len) {
+                    const int m = __ldg(rlist + st.w.start[a] + t);
+                    const unsigned h = (unsigned)m * 2654435761u;
+                    if ((int)((h >> 7) % (unsigned)P) == part) {
+                        unsigned s2 = h >> (32 - LG);
+                        while (keys[s2] != m) s2 = (s2 + 1) & (SLOTS - 1);
+                        int pc = 0, first = -1;
+#pragma unroll
+                        for (int w2 = 0; w2 < W; ++w2) {
+                            const unsigned mk = masks[(size_t)s2 * W + w2];
+                            if (first < 0 && mk) first = 32 * w2 + __ffs(mk) - 1;
+                            pc += __popc(mk);
+                        }
+                        if (first == a) {
+                            ++nz_row;
+                            if (pc >= v_min) {
+                                const int slot = atomicAdd(&nkept_sm, 1);
+                                if (slot < PT_LIST) {
+                                    // key = (walk position + 1, cell): positions are distinct, padding keys are 0
+                                    list[slot] = ((unsigned long long)(unsigned)(st.w.base[a] + t + 1) << 32) | (unsigned)m;
+                                    list_ov[slot] = (uint8_t)min(pc, 255);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int nkept = nkept_sm;
+        if (bad_sm || nkept > PT_LIST) {
+            // safety net: the dense kernel recounts and emits this row (count mode runs right after this kernel)
+            if (threadIdx.x == 0 && cap) {
+                fallback_rows[atomicAdd(n_fallback, 1)] = (int32_t)r;
+                rowcount[r] = 0;
+                row_cls[r] = 5;                                        // filled by snn_big_kernel<true>, not from staging
+            }
+            continue;
+        }
+        nz += nz_row;
+        // ---- order: descending walk position.  Bitonic sort of (position, m) keys, overlap carried along ----
+        int n2 = 32;
+        while (n2 < nkept) n2 <<= 1;
+        for (int i = nkept + threadIdx.x; i < n2; i += PT_THREADS) { list[i] = 0ull; list_ov[i] = 0; }
+        __syncthreads();
+        for (int size = 2; size <= n2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = threadIdx.x; i < (n2 >> 1); i += PT_THREADS) {
+                    const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
+                    const int hi = lo | stride;
+                    const bool down = ((lo & size) == 0);              // this block sorts descending
+                    const unsigned long long x = list[lo], y = list[hi];
+                    if ((x < y) == down) {
+                        list[lo] = y; list[hi] = x;
+                        const uint8_t ox = list_ov[lo]; list_ov[lo] = list_ov[hi]; list_ov[hi] = ox;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const int64_t obase = cap ? r * (int64_t)cap : rowptr_out[r];
+        const int grow = (int)(row_begin + r);
+        for (int i = threadIdx.x; i < nkept; i += PT_THREADS) {
+            if (!cap || i < cap) {
+                dst[obase + i] = (int32_t)(unsigned)(list[i] & 0xFFFFFFFFull);
+                if (!cap) src[obase + i] = grow;
+                if (overlap) overlap[obase + i] = list_ov[i];
+            }
+        }
+        if (cap && threadIdx.x == 0) rowcount[r] = nkept;
+    }
+    if (nz_out && cap) {
+        nz = (unsigned long long)ab_warp_sum_i64((long long)nz);
+        if (lane == 0 && nz) atomicAdd(nz_out, nz);
+    }
+}
+
+template <int SLOTS, int W>
+static size_t snn_part_smem() {
+    return (size_t)SLOTS * 4 * (1 + W) + (size_t)PT_LIST * 9 + sizeof(CtaRowState) + 64;
+}
+
+// ---------------------------------------------------------------------------------------
 // class 3: one CTA per row, dense per-CTA arrays in global scratch (cnt, first); any in-degree
 // ---------------------------------------------------------------------------------------
 template <bool FILL>
@@ -631,16 +855,20 @@ __global__ void __launch_bounds__(256)
 snn_compact_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ stage_dst,
                    const uint8_t *__restrict__ stage_ov, int cap, int64_t n_rows, int64_t row_begin,
                    const uint8_t *__restrict__ row_cls, int32_t *__restrict__ src, int32_t *__restrict__ dst,
-                   uint8_t *__restrict__ overlap, int32_t *__restrict__ ovf_rows, int *__restrict__ n_ovf) {
+                   uint8_t *__restrict__ overlap, int32_t *__restrict__ ovf_rows, int32_t *__restrict__ ovf_part,
+                   int *__restrict__ n_ovf /* [0] table rows, [2] partitioned rows */) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * 8;
     for (int64_t r = w; r < n_rows; r += nw) {
-        if (row_cls[r] == 4) continue;                       // dense-path rows are filled by snn_big_kernel<true>
+        if (row_cls[r] == 5) continue;                       // dense-path rows are filled by snn_big_kernel<true>
         const int64_t a = rowptr[r];
         const int64_t cnt = rowptr[r + 1] - a;
-        if (cnt > cap) {
-            if (lane == 0) ovf_rows[atomicAdd(n_ovf, 1)] = (int32_t)r;
+        if (cnt > cap) {                                     // second pass: table kernel, or the partitioned kernel for class 4
+            if (lane == 0) {
+                if (row_cls[r] == 4) ovf_part[atomicAdd(n_ovf + 2, 1)] = (int32_t)r;
+                else ovf_rows[atomicAdd(n_ovf, 1)] = (int32_t)r;
+            }
             continue;
         }
         const int grow = (int)(row_begin + r);
@@ -666,8 +894,11 @@ struct SnnWs {
     int32_t *stage_dst;  // n_rows * snn_stage_cap(k): edges of each row, staged by the (single) walk pass
     uint8_t *stage_ov;   // n_rows * snn_stage_cap(k)
     int32_t *ovf_rows;   // n_rows: rows whose edges did not fit their staging slot
+    int32_t *ovf_part;   // n_rows: same, rows of the partitioned class
+    int32_t *fb_rows;    // n_rows: rows the partitioned kernel handed to the dense kernel
     int *dense;          // SNN_BIG_CTAS*2*n_total
-    int *counters;       // 16 ints: [0] n_long, [2] n_dup, [3] bad, [4..7] rows per class
+    int *counters;       // 16 ints: [0] n_long, [2] n_dup, [3] bad, [4..8] rows per class, [10] overflow rows (tables),
+                         // [11] rows handed to the dense kernel, [12] overflow rows (partitioned class)
     unsigned long long *walk_stats;   // [0] max walk, [1] sum of walks, [2] nonzeros of A.A^T (first encounters)
     int64_t *rowcount;   // n_rows+1
     void *scan_ws;
@@ -687,6 +918,8 @@ static size_t snn_layout(int64_t n_total, int32_t k, int64_t n_rows, void *ws, s
     w.stage_dst = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1) * snn_stage_cap(k));
     w.stage_ov = a.take<uint8_t>((size_t)(n_rows > 0 ? n_rows : 1) * snn_stage_cap(k));
     w.ovf_rows = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1));
+    w.ovf_part = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1));
+    w.fb_rows = a.take<int32_t>((size_t)(n_rows > 0 ? n_rows : 1));
     w.dense = a.take<int>((size_t)SNN_BIG_CTAS * 2 * n_total);
     w.counters = a.take<int>(16);
     w.walk_stats = a.take<unsigned long long>(4);
@@ -759,6 +992,29 @@ static int snn_launch_overflow(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_a
     return 0;
 }
 
+// class 4 rows (`rows`, `n_listed` on the device) through the partitioned-table kernel; cap as in snn_launch_tables
+static int snn_launch_part(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all, int k, int64_t row_begin, int64_t n_rows,
+                           int v_min, const int32_t *rows, const int *n_listed, int64_t *rowcount, const int64_t *rowptr,
+                           int32_t *src, int32_t *dst, uint8_t *overlap, int cap, cudaStream_t st) {
+    unsigned long long *nz = cap ? w.walk_stats + 2 : nullptr;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_rows, ctx->sm_count));
+    if (k <= 32) {
+        const size_t smem = snn_part_smem<16384, 1>();
+        AB_CUDA(cudaFuncSetAttribute(snn_part_kernel<16384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        snn_part_kernel<16384, 1><<<grid, PT_THREADS, smem, st>>>(knn_all, k, row_begin, rows, n_listed, w.deg, w.rlist, v_min,
+                                                                  rowcount, rowptr, src, dst, overlap, cap, nz, w.fb_rows,
+                                                                  w.counters + 11, w.row_cls);
+    } else {
+        const size_t smem = snn_part_smem<8192, 4>();
+        AB_CUDA(cudaFuncSetAttribute(snn_part_kernel<8192, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        snn_part_kernel<8192, 4><<<grid, PT_THREADS, smem, st>>>(knn_all, k, row_begin, rows, n_listed, w.deg, w.rlist, v_min,
+                                                                 rowcount, rowptr, src, dst, overlap, cap, nz, w.fb_rows,
+                                                                 w.counters + 11, w.row_cls);
+    }
+    AB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total, int32_t k, int64_t row_begin,
                             int64_t row_end, int32_t v_min, int64_t *rowptr, int64_t *h_edges, int64_t *stats,
                             void *ws, size_t ws_bytes, void *stream) {
@@ -794,19 +1050,27 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
     ab_prof_end(ctx, AB_PROF_SNN_BUILD, st);
     ab_prof_begin(ctx, AB_PROF_SNN_COUNT, st);
     // rows with a 2-hop walk of at most lim0 entries take the one-warp kernel, longer ones a whole CTA
+    const bool force_dense = getenv("AB_SNN_DENSE") != nullptr;        // test knob: class 4 straight to the safety net
     const int lim0 = getenv("AB_SNN_WALK_LIMIT") ? std::min(SNN_WALK_LIMIT, atoi(getenv("AB_SNN_WALK_LIMIT"))) : SNN_WALK_LIMIT;
     if (n_rows > 0) {
         snn_walk_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(
             knn_all, k, row_begin, n_rows, w.deg, w.cls_rows, w.counters + 4, lim0, snn_walk_cap(SNN_MID_SLOTS),
-            snn_walk_cap(8192), snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2, w.row_cls);
+            snn_walk_cap(8192), snn_walk_cap(snn_large_slots(k)), w.walk_stats, w.walk_stats + 1, w.counters + 2, w.row_cls,
+            force_dense ? 5 : 4);
         AB_LAUNCH_CHECK(ctx);
         // ONE walk per row: the table kernels run in fill mode and stage each row's edges (emission order
         // included) in a per-row slot; ab_snn_fill then only compacts the slots into the final list
         if (snn_launch_tables(ctx, w, knn_all, k, row_begin, n_rows, v_min, w.rowcount, nullptr, nullptr, w.stage_dst,
                               w.stage_ov, snn_stage_cap(k), st))
             return 1;
+        // class 4 (walks beyond the largest table): partitioned tables; what even they cannot take -> dense kernel
+        if (!force_dense && snn_launch_part(ctx, w, knn_all, k, row_begin, n_rows, v_min, w.cls_rows + 4 * n_rows,
+                                            w.counters + 8, w.rowcount, nullptr, nullptr, w.stage_dst, w.stage_ov,
+                                            snn_stage_cap(k), st))
+            return 1;
         snn_big_kernel<false><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
-            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.cls_rows + 4 * n_rows, w.counters + 8, w.dense,
+            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, force_dense ? w.cls_rows + 4 * n_rows : w.fb_rows,
+            force_dense ? w.counters + 8 : w.counters + 11, w.dense,
             w.rowcount, nullptr, nullptr, nullptr, nullptr, w.walk_stats + 2);
         AB_LAUNCH_CHECK(ctx);
     }
@@ -825,7 +1089,7 @@ extern "C" int ab_snn_count(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total
         stats[0] = (int64_t)h_cnt[5] + h_cnt[6] + h_cnt[7] + h_cnt[8];
         stats[1] = (int64_t)h_walk[0];
         stats[2] = h_cnt[2];
-        stats[3] = h_cnt[8];
+        stats[3] = force_dense ? h_cnt[8] : h_cnt[11];                     // rows the dense kernel had to take
         stats[4] = (int64_t)h_walk[1];
         stats[5] = (int64_t)h_walk[2];                                     // nonzeros of A.A^T in the row range
         stats[6] = h_cnt[5] + h_cnt[6];                                    // rows of the 4096- / 8192-slot CTA classes
@@ -847,15 +1111,19 @@ extern "C" int ab_snn_fill(ab_ctx *ctx, const int32_t *knn_all, int64_t n_total,
     ab_prof_begin(ctx, AB_PROF_SNN_FILL, st);
     int rc = 0;
     AB_CUDA(cudaMemsetAsync(w.counters + 10, 0, sizeof(int), st));
+    AB_CUDA(cudaMemsetAsync(w.counters + 12, 0, sizeof(int), st));
     snn_compact_kernel<<<(unsigned)std::min<int64_t>((n_rows + 7) / 8, (int64_t)ctx->sm_count * 16), 256, 0, st>>>(
         rowptr, w.stage_dst, w.stage_ov, snn_stage_cap(k), n_rows, row_begin, w.row_cls, src, dst, overlap, w.ovf_rows,
-        w.counters + 10);
+        w.ovf_part, w.counters + 10);
     AB_LAUNCH_CHECK(ctx);
     rc = snn_launch_overflow(ctx, w, knn_all, k, row_begin, n_rows, v_min, rowptr, src, dst, overlap, st);
+    if (!rc) rc = snn_launch_part(ctx, w, knn_all, k, row_begin, n_rows, v_min, w.ovf_part, w.counters + 12, nullptr, rowptr,
+                                  src, dst, overlap, 0, st);
     if (!rc) {
+        const bool force_dense = getenv("AB_SNN_DENSE") != nullptr;
         snn_big_kernel<true><<<SNN_BIG_CTAS, SNN_BIG_THREADS, 0, st>>>(
-            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, w.cls_rows + 4 * n_rows, w.counters + 8, w.dense, nullptr,
-            rowptr, src, dst, overlap, nullptr);
+            knn_all, k, row_begin, n_total, w.deg, w.rlist, v_min, force_dense ? w.cls_rows + 4 * n_rows : w.fb_rows,
+            force_dense ? w.counters + 8 : w.counters + 11, w.dense, nullptr, rowptr, src, dst, overlap, nullptr);
         AB_LAUNCH_CHECK(ctx);
     }
     ab_prof_end(ctx, AB_PROF_SNN_FILL, (cudaStream_t)stream);

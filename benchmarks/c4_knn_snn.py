@@ -83,7 +83,11 @@ def main():
             prof = eng.prof_read()
             cur = {'knn_ms': maxr(e0.elapsed_time(e1)), 'snn_ms': maxr(e1.elapsed_time(e2)),
                    'knn_main_ms': maxr(prof['knn_main'][0] / prof['knn_main'][1]) if 'knn_main' in prof else None,
-                   'knn_rerank_ms': maxr(prof['knn_rerank'][0] / prof['knn_rerank'][1]) if 'knn_rerank' in prof else None}
+                   'knn_rerank_ms': maxr(prof['knn_rerank'][0] / prof['knn_rerank'][1]) if 'knn_rerank' in prof else None,
+                   'snn_build_ms': maxr(prof['snn_build'][0]) if 'snn_build' in prof else None,
+                   'snn_count_ms': maxr(prof['snn_count'][0]) if 'snn_count' in prof else None,
+                   'snn_fill_ms': maxr(prof['snn_fill'][0]) if 'snn_fill' in prof else None,
+                   'snn_max_walk': res['max_walk'], 'snn_dense_rows': res['dense_rows'], 'snn_big_rows': res['big_rows']}
             if rep >= 1 and (best is None or cur['knn_ms'] + cur['snn_ms'] < best['knn_ms'] + best['snn_ms']):
                 best = cur
         clocks = sampler.stop() if rank == 0 else None

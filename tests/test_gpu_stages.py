@@ -300,20 +300,26 @@ def _hub_table(n, k, plan, seed=0):
     # k > 32 uses the multi-word bitmask tables (8192/4096 slots): ~7.5k dense, ~4.5k large, ~1.5k mid
     (6000, 40, [(0, 1, 2), (0,), (), ()], 0.03),
 ])
-def test_snn_hub_rows_cover_every_walk_class(eng, n, k, plan, prune):
-    """Hub-heavy tables (every row class: one-warp, mid CTA table, large CTA table, dense global path)."""
+def test_snn_hub_rows_cover_every_walk_class(eng, n, k, plan, prune, monkeypatch):
+    """Hub-heavy tables (every row class: one-warp, mid / large CTA table, partitioned tables for walks beyond the
+    largest table), then once more with the longest walks forced onto the dense safety-net kernel."""
     nn = _hub_table(n, k, plan)
     ref_e, ref_c = R.snn_restated(nn, k, prune)
+    ref_all = R.snn_restated(nn, k, 0.0, return_all=True)[0].shape[0]
     t = torch.from_numpy(nn.astype(np.int32)).to(eng.device)
-    res = eng.snn(t, R.prune_threshold(k, prune))
-    assert 0 < res['dense_rows'] < res['big_rows'] <= n and res['max_walk'] > 5000
-    assert res['nonzeros_unpruned'] == R.snn_restated(nn, k, 0.0, return_all=True)[0].shape[0]
-    assert np.array_equal(np.stack([res['src'].cpu().numpy(), res['dst'].cpu().numpy()], 1), ref_e)
-    assert np.array_equal(res['overlap'].cpu().numpy().astype(np.int64), ref_c)
-    # row sharding must not change anything
-    a = eng.snn(t, R.prune_threshold(k, prune), 0, n // 3)
-    b = eng.snn(t, R.prune_threshold(k, prune), n // 3, n)
-    assert np.array_equal(np.concatenate([a['dst'].cpu().numpy(), b['dst'].cpu().numpy()]), ref_e[:, 1])
+    for dense in (False, True):
+        if dense:
+            monkeypatch.setenv('AB_SNN_DENSE', '1')
+        res = eng.snn(t, R.prune_threshold(k, prune))
+        assert 0 < res['big_rows'] <= n and res['max_walk'] > 5000
+        assert (res['dense_rows'] > 0) == dense
+        assert res['nonzeros_unpruned'] == ref_all
+        assert np.array_equal(np.stack([res['src'].cpu().numpy(), res['dst'].cpu().numpy()], 1), ref_e)
+        assert np.array_equal(res['overlap'].cpu().numpy().astype(np.int64), ref_c)
+        # row sharding must not change anything
+        a = eng.snn(t, R.prune_threshold(k, prune), 0, n // 3)
+        b = eng.snn(t, R.prune_threshold(k, prune), n // 3, n)
+        assert np.array_equal(np.concatenate([a['dst'].cpu().numpy(), b['dst'].cpu().numpy()]), ref_e[:, 1])
 
 
 def check_free_running_against_reference(out, g):
