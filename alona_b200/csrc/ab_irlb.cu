@@ -52,6 +52,23 @@ __device__ __forceinline__ bool last_block_ticket(int *counter, bool sys = false
     return ticket_sm != 0;
 }
 
+// Sum of `nparts` per-block partial values in the last block of a reduction kernel: every thread adds a strided
+// subset (independent loads), then a fixed butterfly / warp-order combine - a fixed order for a given grid, and a
+// dozen dependent steps instead of one thread walking all partials (that serial tail was ~45 us per launch: invisible
+// at 1.3 M rows per GPU, a third of the kernel at 163 k).  Every thread of the block must call it.
+__device__ __forceinline__ double block_sum_partials(const double *__restrict__ partial, int nparts, double *red /* smem [32] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double t = 0.0;
+    for (int b = threadIdx.x; b < nparts; b += blockDim.x) t += __ldcg(partial + b);
+    t = ab_warp_sum_f64(t);
+    __syncthreads();
+    if (lane == 0) red[warp] = t;
+    __syncthreads();
+    double tt = 0.0;
+    for (int w2 = 0; w2 < nwarp; ++w2) tt += red[w2];
+    return tt;
+}
+
 // ---------------------------------------------------------------------------------------
 // A^T.w - s.V_j   (irlb.py:182,189)
 // ---------------------------------------------------------------------------------------
@@ -217,11 +234,15 @@ panel_dot_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int ncols,
         __syncthreads();
     }
     if (last_block_ticket(counter)) {
-        for (int l = threadIdx.x; l < ncols; l += DOT_THREADS) {
+        // a warp per column, lanes over the per-block partials (independent loads), fixed butterfly
+        for (int l = warp; l < ncols; l += DOT_THREADS / 32) {
             double t = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + (int64_t)b * IR_MAXWORK + l);
-            if (ab_peer_world(peer_p) > 1) ab_peer_push(*peer_p, AB_CH_COEF, seq_coef, l, t);      // all-reduce, first half: push
-            else out[l] = t;
+            for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(partial + (int64_t)b * IR_MAXWORK + l);
+            t = ab_warp_sum_f64(t);
+            if (lane == 0) {
+                if (ab_peer_world(peer_p) > 1) ab_peer_push(*peer_p, AB_CH_COEF, seq_coef, l, t);      // all-reduce, first half: push
+                else out[l] = t;
+            }
         }
         if (ab_peer_world(peer_p) > 1) {
             __threadfence_system();
@@ -274,9 +295,8 @@ panel_update_kernel(const double *__restrict__ V, int64_t ld, int64_t n, int nco
         partial[blockIdx.x] = tt;
     }
     if (last_block_ticket(counter)) {
+        const double tt = block_sum_partials(partial, (int)gridDim.x, red);
         if (threadIdx.x == 0) {
-            double tt = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
             if (ab_peer_world(peer_p) > 1) {
                 ab_peer_push(*peer_p, AB_CH_SCAL, seq_fn2, 0, tt);
                 ab_peer_publish(*peer_p, AB_CH_SCAL, seq_fn2);
@@ -315,11 +335,8 @@ sumsq_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ parti
         partial[blockIdx.x] = tt;
     }
     if (last_block_ticket(counter)) {
-        if (threadIdx.x == 0) {
-            double tt = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
-            *out = tt;
-        }
+        const double tt = block_sum_partials(partial, (int)gridDim.x, red);
+        if (threadIdx.x == 0) *out = tt;
     }
 }
 
@@ -341,11 +358,8 @@ vecsum_kernel(const double *__restrict__ x, int64_t n, double *__restrict__ part
         partial[blockIdx.x] = tt;
     }
     if (last_block_ticket(counter)) {
-        if (threadIdx.x == 0) {
-            double tt = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) tt += __ldcg(partial + b);
-            *out = tt;
-        }
+        const double tt = block_sum_partials(partial, (int)gridDim.x, red);
+        if (threadIdx.x == 0) *out = tt;
     }
 }
 
@@ -556,10 +570,15 @@ __global__ void __launch_bounds__(128)
 av_reduce_kernel(const double *__restrict__ partial, int nparts, int H, double *__restrict__ out, int *counter,
                  const AbPeer *__restrict__ peer_p, uint32_t seq_vec, const double *__restrict__ mu /* NULL, or on ONE rank the gene means */,
                  const double *__restrict__ scal, int scaled) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < H) {
-        double t = 0.0;
-        for (int b = 0; b < nparts; ++b) t += partial[(size_t)b * H + g];
+    // four threads per gene (a quarter of the CTA partials each, combined in a fixed order): the chain of 148
+    // dependent loads of one thread per gene was 11 us of every A.x at any GPU count
+    const int g = blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2), part = threadIdx.x & 3;
+    double t = 0.0;
+    if (g < H)
+        for (int b = part; b < nparts; b += 4) t += partial[(size_t)b * H + g];
+    t += ab_shfl_xor_f64(t, 1);
+    t += ab_shfl_xor_f64(t, 2);
+    if (g < H && part == 0) {
         // implicit centring: (A - mu 1^T) x = A x - mu (1^T x); the correction enters once (on rank 0's contribution)
         if (mu) {
             const double sx = (scaled ? invcheck(sqrt(scal[SC_FN2])) : 1.0) * scal[SC_SUMX];
@@ -898,16 +917,24 @@ svd_cluster_kernel(const double *__restrict__ B, int work, double *__restrict__ 
 
     const int mp = (m + 1) & ~1;
     const int pr = threadIdx.x / SV_LP, hl = threadIdx.x % SV_LP;
+    // this thread's column pair of every round of a sweep (circle method: player mp-1 fixed, the others rotate), packed
+    // p | q << 8, computed once: the two integer modulo sequences sat on the critical path of each of the ~520 rounds
+    extern __shared__ unsigned short sched[];            // [(mp - 1) * (mp / 2)], dynamic
+    for (int e = threadIdx.x; e < (mp - 1) * (mp / 2); e += SV_THREADS) {
+        const int round = e / (mp / 2), pp = e - round * (mp / 2);
+        const int a = (pp == 0) ? mp - 1 : (round + pp) % (mp - 1);
+        const int b = (round + mp - 1 - pp) % (mp - 1);
+        sched[e] = (unsigned short)(min(a, b) | (max(a, b) << 8));
+    }
+    __syncthreads();
     uint32_t round_id = 0;
     int sweeps = 0;
     for (int sweep = 0; sweep < 60; ++sweep) {
         if (threadIdx.x == 0) rot_sm = 0;
         refresh_norms();
         for (int round = 0; round < mp - 1; ++round, ++round_id) {
-            // circle method: player mp-1 fixed, the others rotate
-            const int a = (pr == 0) ? mp - 1 : (round + pr) % (mp - 1);
-            const int b = (round + mp - 1 - pr) % (mp - 1);
-            const int p = min(a, b), q = max(a, b);
+            const unsigned pq = pr < mp / 2 ? sched[round * (mp / 2) + pr] : 0xFFFFu;
+            const int p = pq & 255, q = pq >> 8;
             const bool valid = pr < mp / 2 && q < m;
             double *gp = Gs + (valid ? p : 0) * SV_RS, *gq = Gs + (valid ? q : 0) * SV_RS;
             double ga = 0.0;
@@ -1399,6 +1426,8 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     const size_t svd_smem = (size_t)(q_in_smem ? 2 : 1) * work * work * 8;
     AB_CUDA(cudaFuncSetAttribute(svd_restart_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
     const bool svd_one_cta = getenv("AB_IRLB_SVD1") != nullptr;       // A/B switch: the one-CTA Jacobi (round 1)
+    const size_t svc_smem = (size_t)(((work + 1) & ~1) - 1) * (((work + 1) & ~1) / 2) * sizeof(unsigned short);   // pair schedule
+    AB_CUDA(cudaFuncSetAttribute(svd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svc_smem));
     auto ritz = [&](const double *X, int64_t ldx, int64_t rows, const double *M, int ncols, double *out, int64_t ldo,
                     int rowmajor, const double *colscale, double *out2) -> int {
         if (rows <= 0 || ncols <= 0) return 0;
@@ -1463,7 +1492,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
                                                    w.av_warps, w.av_partial, peer, seq_fn2);
         AB_LAUNCH_CHECK(ctx);
         const uint32_t sv = fused ? ++seq[AB_CH_VEC] : 0;
-        av_reduce_kernel<<<(H + 127) / 128, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw, cnt + 3, peer, sv,
+        av_reduce_kernel<<<(H + 31) / 32, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw, cnt + 3, peer, sv,
                                                           (center && ctx->rank == 0) ? center : nullptr, w.scal, scaled ? 1 : 0);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_AV, st);
@@ -1531,6 +1560,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(SV_CL);
             cfg.blockDim = dim3(SV_THREADS);
+            cfg.dynamicSmemBytes = svc_smem;
             cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
