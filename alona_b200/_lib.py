@@ -26,6 +26,7 @@ p_i64 = ctypes.POINTER(ctypes.c_int64)
 SIGNATURES = {
     'ab_version': (ctypes.c_int, []),
     'ab_last_error': (ctypes.c_char_p, []),
+    'ab_source_digest': (ctypes.c_char_p, []),
     'ab_ctx_create': (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'ab_ctx_destroy': (ctypes.c_int, [c_void_p]),
     'ab_nccl_unique_id': (ctypes.c_int, [ctypes.c_char_p, c_void_p]),
@@ -100,9 +101,17 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(_LIB_PATH):
+        if not os.environ.get('ALONA_B200_LIB'):
+            # build() is a no-op when the library carries the digest of the sources next to it; a stale library
+            # (sources changed since it was built) is rebuilt when nvcc is there, else refused below
             from . import build as _build
-            _build.build()
+            if not _build.is_fresh():
+                import shutil
+                if shutil.which(os.environ.get('NVCC', 'nvcc')):
+                    _build.build()
+                elif os.path.exists(_LIB_PATH):
+                    raise RuntimeError('alona_b200: %s was built from other sources (digest %s, tree %s) and nvcc is not '
+                                       'available to rebuild it' % (_LIB_PATH, _build.lib_digest(), _build._digest()[:16]))
         try:
             lib = ctypes.CDLL(_LIB_PATH)
         except OSError as e:

@@ -30,11 +30,27 @@ def _digest():
     return h.hexdigest()
 
 
+def lib_digest(path=LIB):
+    """The source digest the library at `path` was built from (embedded as the string 'AB_SOURCE_DIGEST=<hex>'),
+    or None.  The digest travels inside the binary, so a stale .so next to newer sources is always detected - a
+    side-car stamp file could not tell."""
+    try:
+        data = open(path, 'rb').read()
+    except OSError:
+        return None
+    key = b'AB_SOURCE_DIGEST='
+    i = data.find(key)
+    return data[i + len(key):i + len(key) + 64].decode('ascii', 'replace') if i >= 0 else None
+
+
+def is_fresh():
+    return os.path.exists(LIB) and lib_digest() == _digest()
+
+
 def build(force=False, verbose=False):
     """Compiles every .cu for sm_100a and links the shared library. Returns its path."""
-    stamp = LIB + '.stamp'
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and os.path.exists(LIB) and lib_digest() == dig:
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
     objdir = os.path.join(HERE, 'build')
@@ -43,6 +59,8 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         obj = os.path.join(objdir, s.replace('.cu', '.o'))
         cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, s), '-o', obj]
+        if s == 'ab_api.cu':
+            cmd += ['-DAB_SOURCE_DIGEST="%s"' % dig]
         procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     log = []
@@ -59,8 +77,6 @@ def build(force=False, verbose=False):
         print('\n'.join(log))
     cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart', '-ldl']
     subprocess.check_call(cmd)
-    with open(stamp, 'w') as fh:
-        fh.write(dig)
     return LIB
 
 

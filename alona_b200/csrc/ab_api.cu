@@ -20,6 +20,15 @@ int ab_fail(const char *fmt, ...) {
 }
 
 extern "C" const char *ab_last_error(void) { return g_err; }
+
+// digest of the sources this library was built from (alona_b200/build.py embeds and checks it)
+#ifndef AB_SOURCE_DIGEST
+#define AB_SOURCE_DIGEST "unknown"
+#endif
+extern "C" const char *ab_source_digest(void) {
+    static const char tag[] = "AB_SOURCE_DIGEST=" AB_SOURCE_DIGEST;
+    return tag + sizeof("AB_SOURCE_DIGEST=") - 1;
+}
 extern "C" int ab_version(void) { return AB_VERSION; }
 
 // ---------------------------------------------------------------------------------------

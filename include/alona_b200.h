@@ -38,6 +38,10 @@ typedef struct ab_ctx ab_ctx;
 /* ---- context ------------------------------------------------------------------------ */
 int ab_version(void);
 const char *ab_last_error(void);
+/* hex digest of the sources (csrc/, this header, compiler flags) the library was built from, "unknown" for a build
+ * outside alona_b200/build.py; the Python loader refuses a library whose digest differs from the tree next to it
+ * when the sources are present. */
+const char *ab_source_digest(void);
 /* Binds to CUDA device `device`; fails if it is not an sm_100 part. rank/world describe the
  * row sharding (world==1: single GPU). */
 int ab_ctx_create(ab_ctx **out, int device, int rank, int world);

@@ -264,6 +264,33 @@ def test_snn_edge_list_identical(eng, case):
     assert np.array_equal(np.repeat(np.arange(len(rp) - 1), np.diff(rp)), edges[:, 0])
 
 
+def test_snn_with_duplicate_points_matches_reference_outside_the_duplicates(eng):
+    """Exact duplicate cells: the reference keys a cell's incidence row on its FIRST neighbour (clustering.py:204
+    melts on column 0), so a cell whose twin is ranked first donates its row to the twin (entries add up, weights of
+    2 appear).  That quirk is reported (`dup_rows`), not emulated; this test pins the extent of the deviation: every
+    edge between two cells that are neither such a cell nor its twin is the reference's, order and overlap included."""
+    g = load_golden('knn_dup_800x50_k10')
+    k = int(g['k'])
+    nn = g['nn_idx'].astype(np.int64) - 1
+    n = nn.shape[0]
+    dup = np.where(nn[:, 0] != np.arange(n))[0]
+    assert dup.size == 5
+    bad = np.zeros(n, dtype=bool)
+    bad[dup] = True
+    bad[nn[dup, 0]] = True
+    res = eng.snn(torch.from_numpy(nn.astype(np.int32)).to(eng.device).contiguous(), R.prune_threshold(k, float(g['prune'])))
+    assert res['dup_rows'] == dup.size
+    e = np.stack([res['src'].cpu().numpy(), res['dst'].cpu().numpy()], 1)
+    c = res['overlap'].cpu().numpy().astype(np.int16)
+
+    def clean(E, C):
+        keep = ~bad[E[:, 0]] & ~bad[E[:, 1]]
+        return E[keep], C[keep]
+    a, ac = clean(e, c)
+    b, bc = clean(g['snn_graph'], g['snn_overlap'])
+    assert a.shape[0] > 20000 and np.array_equal(a, b) and np.array_equal(ac, bc)
+
+
 def test_snn_row_sharding_and_prune_levels(eng):
     g = load_golden('knn_mix_2000x50_k10')
     nn0 = torch.from_numpy((g['nn_idx'].astype(np.int64) - 1).astype(np.int32)).to(eng.device).contiguous()
