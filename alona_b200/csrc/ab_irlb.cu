@@ -1076,30 +1076,31 @@ __global__ void reset_b_kernel(double *__restrict__ B, int work, const double *_
 // The one GEMM-shaped step of IRLBA (n x work times work x keep, FP64, 1.3 GB / 5e9 FMA per restart at C3).
 // Measured on this part (benchmarks/micro_atomics.cu, profiles/r2_ritz_svd_norm_ncu.txt): the FP64 CUDA cores sustain
 // 61 FMA/clk/SM (35.6 TFLOP/s), the FP64 tensor instruction mma.sync.m8n8k4 only ~28 (its sub-pipe was 69 % busy at
-// 10.9 TFLOP/s in the DMMA version of this kernel), so the products are register-tiled DFMA: a warp owns 32 rows x
-// (8 x CT) columns, a thread 4 rows x 2 x CT... see below.  What bounds a naive version is operand delivery, not
+// 10.9 TFLOP/s in the DMMA version of this kernel), so the products are register-tiled DFMA (thread tile below).
+// What bounds a naive version is operand delivery, not
 // arithmetic: a producer warp streams the column-major panel through shared memory with 1-D bulk copies (one 1 KB
-// column segment per copy, one copy per lane, completion on an mbarrier, a ring of stages of KC panel columns) and
-// the result tile leaves through shared memory and bulk stores (1 KB contiguous per output column).
+// column segment per copy, one copy per lane, completion on an mbarrier, a ring of stages of KC panel columns); the
+// result leaves straight from the registers (32 contiguous bytes per thread and column).
 // Thread tile: rows 4*tr .. 4*tr+3 (tr = lane % 8) of the warp's 32-row block, columns CT*tc .. CT*tc+CT-1
 // (tc = lane / 8) of the warp's 4*CT-column block: per k-row 2 LDS.128 of A (256 contiguous bytes per warp) and CT
 // doubles of B (broadcast), 4*CT FMAs.  Eight consumer warps = 4 row blocks x 2 column blocks = 128 rows x 8*CT columns.
 // ---------------------------------------------------------------------------------------
 static constexpr int RZ_TR = 128;                // rows per tile
 static constexpr int RZ_XS = RZ_TR + 4;          // staged-tile column stride (doubles)
-static constexpr int RZ_CS = RZ_TR + 2;          // result-tile column stride (doubles)
-static constexpr int RZ_CSTAGE = 64;             // result columns staged per store round
 static constexpr int RZ_CONSUMERS = 8;           // consumer warps; warp RZ_CONSUMERS is the producer
 static constexpr int RZ_THREADS = (RZ_CONSUMERS + 1) * 32;
-static constexpr int RZ_MAXST = 4;
+static constexpr int RZ_MAXST = 6;
 
 struct RitzCfg { int kc, st, ct; size_t smem; };
-static RitzCfg ritz_cfg(int work, int ncols) {
+static RitzCfg ritz_cfg(int work, int ncols, size_t smem_optin) {
     RitzCfg c;
     c.ct = std::max(1, (ncols + 7) / 8);                          // columns per thread
-    c.kc = work <= 72 ? 24 : 16;
-    c.st = work <= 72 ? 3 : 2;
-    c.smem = ((size_t)work * 8 * c.ct + (size_t)c.st * c.kc * RZ_XS + (size_t)RZ_CSTAGE * RZ_CS) * 8 + 2 * RZ_MAXST * 8 + 64;
+    const int ctp = (c.ct + 1) & ~1;                              // padded to even: B rows are read with 16-byte loads
+    c.kc = 24;
+    const size_t fixed = (size_t)work * 8 * ctp * 8 + 2 * RZ_MAXST * 8 + 64;
+    const size_t stage = (size_t)c.kc * RZ_XS * 8;
+    c.st = (int)std::min<size_t>(RZ_MAXST, (std::min<size_t>(smem_optin, 227 * 1024) - 1024 - fixed) / stage);
+    c.smem = fixed + (size_t)std::max(c.st, 1) * stage;
     return c;
 }
 
@@ -1109,19 +1110,22 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
             double *__restrict__ out, int64_t ldo, int rowmajor_out, const double *__restrict__ colscale,
             double *__restrict__ out2 /* optional second row-major output without scaling */, int KC, int ST) {
     extern __shared__ __align__(128) unsigned char rz_raw[];
-    constexpr int MS = 8 * CT;                                        // M row stride = padded column count
-    double *Ms = reinterpret_cast<double *>(rz_raw);                  // [work][MS]
+    constexpr int CTP = (CT + 1) & ~1;                                // thread's B slice, padded to an even length
+    constexpr int MS = 8 * CTP;                                       // M row stride in shared memory
+    double *Ms = reinterpret_cast<double *>(rz_raw);                  // [work][8 thread-columns][CTP]
     double *Xs = Ms + (size_t)work * MS;                              // [ST][KC][RZ_XS]
-    double *Cs = Xs + (size_t)ST * KC * RZ_XS;                        // [RZ_CSTAGE][RZ_CS]
-    uint64_t *full = reinterpret_cast<uint64_t *>(Cs + (size_t)RZ_CSTAGE * RZ_CS);
+    uint64_t *full = reinterpret_cast<uint64_t *>(Xs + (size_t)ST * KC * RZ_XS);
     uint64_t *empty = full + RZ_MAXST;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunks = (work + KC - 1) / KC;
     const int64_t ntiles = (n + RZ_TR - 1) / RZ_TR;
 
+    // M in the order the threads consume it: thread-column group t (= 4*wc + tc) holds output columns t*CT .. t*CT+CT-1
     for (int e = threadIdx.x; e < work * MS; e += blockDim.x) {
-        const int l = e / MS, c = e - l * MS;
-        Ms[e] = c < ncols ? M[l * work + c] : 0.0;
+        const int l = e / MS, r = e - l * MS;
+        const int t = r / CTP, j = r - t * CTP;
+        const int c = t * CT + j;
+        Ms[e] = (j < CT && c < ncols) ? M[l * work + c] : 0.0;
     }
     for (int e = threadIdx.x; e < ST * KC * RZ_XS; e += blockDim.x) Xs[e] = 0.0;      // rows past a clipped tile stay finite
     if (threadIdx.x == 0) {
@@ -1154,9 +1158,9 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
     const int tr = lane & 7, tc = lane >> 3;
     const int wr = warp & 3, wc = warp >> 2;
     const int rloc = 32 * wr + 4 * tr;                    // first of this thread's 4 rows inside the tile
-    const int cloc = (4 * wc + tc) * CT;                  // first of this thread's CT columns
+    const int tg = 4 * wc + tc;                           // thread-column group
+    const int cglob = tg * CT;                            // first of this thread's CT output columns
     uint32_t it = 0;
-    bool stored = false;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         double acc[4][CT];
 #pragma unroll
@@ -1168,14 +1172,17 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
             ab_mbar_wait(full + st, (it / ST) & 1);
             const int k0 = ch * KC, nk = min(KC, work - k0);
             const double *xs = Xs + (size_t)st * KC * RZ_XS + rloc;
-            const double *ms = Ms + (size_t)k0 * MS + cloc;
+            const double *ms = Ms + (size_t)k0 * MS + tg * CTP;
 #pragma unroll 4
             for (int k = 0; k < nk; ++k) {
                 const double2 a01 = *reinterpret_cast<const double2 *>(xs + (size_t)k * RZ_XS);
                 const double2 a23 = *reinterpret_cast<const double2 *>(xs + (size_t)k * RZ_XS + 2);
-                double b[CT];
+                double b[CTP];
 #pragma unroll
-                for (int j = 0; j < CT; ++j) b[j] = ms[(size_t)k * MS + j];
+                for (int j = 0; j < CTP; j += 2) {
+                    const double2 bb = *reinterpret_cast<const double2 *>(ms + (size_t)k * MS + j);
+                    b[j] = bb.x; b[j + 1] = bb.y;
+                }
 #pragma unroll
                 for (int j = 0; j < CT; ++j) {
                     acc[0][j] = fma(a01.x, b[j], acc[0][j]);
@@ -1187,15 +1194,15 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
             __syncwarp();
             if (lane == 0) ab_mbar_arrive(empty + st);
         }
-        const int64_t row0 = tile * RZ_TR;
+        const int64_t row0 = tile * RZ_TR + rloc;
         if (rowmajor_out) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int64_t r = row0 + rloc + i;
+                const int64_t r = row0 + i;
                 if (r >= n) continue;
 #pragma unroll
                 for (int j = 0; j < CT; ++j) {
-                    const int col = cloc + j;
+                    const int col = cglob + j;
                     if (col < ncols) {
                         out[r * (int64_t)ncols + col] = __dmul_rn(acc[i][j], colscale ? colscale[col] : 1.0);
                         if (out2) out2[r * (int64_t)ncols + col] = acc[i][j];
@@ -1203,33 +1210,20 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
                 }
             }
         } else {
-            // the tile leaves in rounds of RZ_CSTAGE columns: fragments -> Cs -> one bulk store per column
-            const uint32_t cb = (uint32_t)min((int64_t)RZ_TR, ldo - row0) * 8;
-            for (int cbase = 0; cbase < ncols; cbase += RZ_CSTAGE) {
-                if (warp == 0 && stored) ab_bulk_wait_read0();        // the previous round's stores have read Cs
-                asm volatile("bar.sync 1, %0;" ::"n"(RZ_CONSUMERS * 32) : "memory");
+            // straight from the registers: a thread owns 4 consecutive rows (32 bytes) of each of its columns, the
+            // eight tr-lanes of a warp 256 contiguous bytes.  (A shared-memory staged tile + bulk stores cost two
+            // block barriers per tile: 18 % of the kernel's stall samples.)  Rows in [n, ldo) are padding.
 #pragma unroll
-                for (int j = 0; j < CT; ++j) {
-                    const int col = cloc + j - cbase;
-                    if (col >= 0 && col < RZ_CSTAGE && cloc + j < ncols) {
-                        double *cd = Cs + (size_t)col * RZ_CS + rloc;
-                        *reinterpret_cast<double2 *>(cd) = make_double2(acc[0][j], acc[1][j]);
-                        *reinterpret_cast<double2 *>(cd + 2) = make_double2(acc[2][j], acc[3][j]);
-                    }
-                }
-                ab_fence_proxy_async();
-                asm volatile("bar.sync 1, %0;" ::"n"(RZ_CONSUMERS * 32) : "memory");
-                if (warp == 0) {
-                    const int nst = min(RZ_CSTAGE, ncols - cbase);
-                    for (int c = lane; c < nst; c += 32)
-                        ab_bulk_s2g(out + (int64_t)(cbase + c) * ldo + row0, Cs + (size_t)c * RZ_CS, cb);
-                    ab_bulk_commit();
-                    stored = true;
+            for (int j = 0; j < CT; ++j) {
+                const int col = cglob + j;
+                if (col < ncols) {
+                    double *o = out + (int64_t)col * ldo + row0;
+                    if (row0 + 2 <= ldo) *reinterpret_cast<double2 *>(o) = make_double2(acc[0][j], acc[1][j]);
+                    if (row0 + 4 <= ldo) *reinterpret_cast<double2 *>(o + 2) = make_double2(acc[2][j], acc[3][j]);
                 }
             }
         }
     }
-    if (warp == 0 && stored) ab_bulk_wait0();                 // global writes complete before the CTA retires
 }
 
 typedef void (*ritz_fn)(const double *, int64_t, int64_t, int, const double *, int, double *, int64_t, int, const double *,
@@ -1431,7 +1425,8 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     auto ritz = [&](const double *X, int64_t ldx, int64_t rows, const double *M, int ncols, double *out, int64_t ldo,
                     int rowmajor, const double *colscale, double *out2) -> int {
         if (rows <= 0 || ncols <= 0) return 0;
-        const RitzCfg rc = ritz_cfg(work, ncols);
+        const RitzCfg rc = ritz_cfg(work, ncols, ctx->smem_optin);
+        AB_REQUIRE(rc.st >= 2, "ab_irlb: work dimension %d leaves no room for the Ritz pipeline", work);
         AB_REQUIRE(rc.smem <= ctx->smem_optin, "ab_irlb: work dimension %d needs %zu bytes of shared memory", work, rc.smem);
         ritz_fn fn = ritz_pick(rc.ct);
         AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc.smem));
