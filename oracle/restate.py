@@ -375,7 +375,7 @@ def prune_threshold(k, prune_snn):
     return k + 1
 
 
-def snn_restated(nn_idx0, k, prune_snn, return_all=False):
+def snn_restated(nn_idx0, k, prune_snn, return_all=False, rows=None):
     """nn_idx0: 0-based (N,k) table with column 0 == the row's own cell.
     Returns (edges [E,2] int64, overlap [E] int64) in the reference's order:
     rows ascending; within row i, REVERSE first-encounter order when scanning
@@ -390,7 +390,7 @@ def snn_restated(nn_idx0, k, prune_snn, return_all=False):
     dst_s, src_s = dst[order], src[order]
     start = np.searchsorted(dst_s, np.arange(n + 1))
     e_src, e_dst, e_cnt = [], [], []
-    for i in range(n):
+    for i in (range(n) if rows is None else rows):          # rows: only these rows of the graph (large inputs)
         seq = np.concatenate([src_s[start[j]:start[j + 1]] for j in nbr[i]])
         uniq, first, cnt = np.unique(seq, return_index=True, return_counts=True)
         o = np.argsort(-first, kind='stable')
