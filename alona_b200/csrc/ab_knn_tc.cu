@@ -7,11 +7,14 @@
 //  prep      centre the embedding (translation invariant, shrinks norms), scale by a power of two
 //            so that the largest norm lies in [32,64) (keeps every operand inside FP16 range,
 //            exact), round to FP32 and split every coordinate into two FP16 pieces
-//            (hi = rn(x), lo = rn(x-hi): 22 significant bits, the same split a 3xTF32 scheme
-//            carries, at twice the tensor rate).  The operand rows are laid out so that ONE GEMM
-//            emits finished scores, norms folded into three extra K columns:
-//               A[q] = [  q_hi |  q_hi |  q_lo | 1 1 1 | 0.. ]
-//               B[x] = [-2x_hi |-2x_lo |-2x_hi | n0 n1 n2 | 0.. ],  n0+n1+n2 = ||x||^2
+//            (hi = rn(x), lo = rn(x-hi): 22 significant bits).  The DATABASE side carries both pieces, the
+//            QUERY side only q_hi: the GEMM then measures exact distances to the perturbed query q_hi
+//            (an FP16 vector, so nothing is lost on that side), and |q - q_hi| - known per query - enters the
+//            certificate through the triangle inequality.  Two FP16 products per coordinate pair instead of
+//            the three a 3xTF32-style split needs (K = 2d+3 instead of 3d+3).  ONE GEMM emits finished
+//            scores, norms folded into three extra K columns:
+//               A[q] = [  q_hi |  q_hi | 1 1 1 | 0.. ]
+//               B[x] = [-2x_hi |-2x_lo | n0 n1 n2 | 0.. ],  n0+n1+n2 = ||x||^2
 //  main      persistent warp-specialised kernel, one CTA per SM:
 //              warp 0   TMA producer: B arrives as contiguous 8 KB bulk copies (one 128-point x 32-half K chunk,
 //                       stored pre-swizzled in HBM) through an mbarrier ring; A by 2-D tensor-map loads;
@@ -28,8 +31,9 @@
 //            query tile against 256-point B tiles (two lists per query, merged by the re-rank).
 //  re-rank   one warp per query: exact distances of the candidates with the reference's
 //            arithmetic, sort by (distance, index), certificate
-//                 tau + ||q||^2 - eps  >  D_k      (tau = m-th smallest approximate score)
-//            which proves that no point outside the candidate list can enter the top k;
+//                 sqrt(tau + ||q_hi||^2 - eps) - |q - q_hi|  >  sqrt(D_k)      (tau = m-th smallest approximate score)
+//            which proves that no point outside the candidate list can enter the top k: such a point has
+//            |x - q_hi|^2 >= tau + ||q_hi||^2 - eps and |x - q| >= |x - q_hi| - |q - q_hi|;
 //            eps = KAPPA (||q|| + R)^2 bounds FP32 rounding + split + accumulation error.
 //            Uncertified queries are recomputed by the exact FP64 scan (ab_knn_exact.cu).
 #include "ab_common.cuh"
@@ -50,19 +54,22 @@ static constexpr int TC_TILE = 128;          // UMMA M and N
 static constexpr int TC_KCH = 32;            // halves per K chunk = one 64-byte swizzle row
 static constexpr int TC_SLAB = TC_TILE * 64; // bytes of one 128-row x 64-byte operand slab (8 KB)
 static constexpr int TC_MAX_STAGES = 16;
-static constexpr int TC_MAX_CHUNKS = 10;     // 3d+3 <= 320  ->  d <= 105
-// Error bound of an approximate score, relative to (|q| + R)^2, that the certificate of the re-rank uses:
+static constexpr int TC_MAX_CHUNKS = 10;     // 2d+3 <= 320  ->  d <= 158
+static constexpr int TC_NPROD = 2;           // FP16 products per coordinate pair: q_hi.x_hi + q_hi.x_lo
+// Error bound of an approximate score as a distance to q_hi, relative to (|q| + R)^2, that the certificate uses:
 //   * accumulation: the K products of a score are exact in FP32 (two 11-bit significands) and are added in FP32:
 //     at most K roundings of 2^-24 relative to sum |a_i b_i| <= 2|q|R + R^2 <= (|q| + R)^2 (any summation order,
 //     so it also covers the tensor pipe's internal one);
-//   * split: each coordinate carries 22 significant bits (hi + lo), the dropped q_lo.x_lo products and the FP16
-//     rounding of -2x and of the three norm pieces add less than 2^-20 (|q| + R)^2.
-// kappa = 1.25 K 2^-24 + 2^-19 (a quarter of margin on the first term; K = 160 at d = 50 gives 1.38e-5, the
-// 2^-16 of round 1).  The largest observed error is reported (stats[4]: 7e-7 at C3) and ab_knn_tc_run refuses to
-// certify anything if it ever exceeds kappa / 2.  Dropping products (np < 3) adds their worst case.
-__host__ __device__ inline double tc_kappa(int np, int kt) {
-    const double base = 1.25 * (double)kt * 5.9604644775390625e-08 + 1.9073486328125e-06;
-    return np >= 3 ? base : np == 2 ? base + 1.220703125e-04 : base + 2.44140625e-04;
+//   * database side: each coordinate carries 22 significant bits (hi + lo); what x_hi + x_lo misses of x, the FP32
+//     rounding of the coordinates and the FP16 rounding of the three norm pieces add less than 2^-20 (|q| + R)^2.
+// kappa = 1.25 K 2^-24 + 2^-19 (a quarter of margin on the first term; K = 112 at d = 50 gives 1.03e-5).  The query
+// side has no term here: q_hi is exact in FP16 and the distance between q and q_hi is handled exactly (see above).
+// The largest error observed on the candidates is reported (stats[4]) and ab_knn_tc_run refuses to certify anything
+// if it ever exceeds kappa / 2.
+// (Round 1 multiplied three products - q_lo.x_hi as well - at K = 3d+3: 507 ms against 421 ms at C3 for the same table.
+// One product, q_hi.x_hi, would need max |x - x_hi| in the certificate as well and no longer certifies.)
+__host__ __device__ inline double tc_kappa(int kt) {
+    return 1.25 * (double)kt * 5.9604644775390625e-08 + 1.9073486328125e-06;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -247,9 +254,9 @@ __host__ __device__ __forceinline__ size_t knn_b_pos(int64_t i, int j, int chunk
 // B has n_pad >= n rows (a whole number of tiles): padding rows are all zero except a norm of
 // 60000, larger than any real score (<= (2*64)^2), so padded columns never pass a threshold.
 __global__ void __launch_bounds__(256)
-knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d, int kt, int np, const double *__restrict__ mean,
+knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d, int kt, const double *__restrict__ mean,
                 const unsigned int *__restrict__ rmax_bits, __half *__restrict__ aop, __half *__restrict__ bop,
-                double *__restrict__ qn) {
+                double *__restrict__ qn, double *__restrict__ qh2 /* |q_hi|^2 */, double *__restrict__ qdel /* |q - q_hi| */) {
     const int lane = threadIdx.x & 31;
     const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * 8;
@@ -258,26 +265,34 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d,
     const int chunks = kt / TC_KCH;
     for (int64_t i = w; i < n; i += nw) {
         __half *a = aop + i * kt;
-        double n2 = 0.0;
-        const int nd = np * d;                                   // first norm column
+        double n2 = 0.0, h2 = 0.0, dl2 = 0.0;
+        const int nd = TC_NPROD * d;                             // first norm column
         for (int j = nd + lane; j < kt; j += 32) {               // clear the tail (norm slots are rewritten below)
             a[j] = zero; bop[knn_b_pos(i, j, chunks)] = zero;
         }
         for (int j = lane; j < d; j += 32) {
-            const float x = (float)((emb[i * d + j] - mean[j]) * sc);
+            const double xs = (emb[i * d + j] - mean[j]) * sc;
+            const float x = (float)xs;
             const __half hi = __float2half_rn(x);
+            const double hd = (double)__half2float(hi);
+            h2 += hd * hd;
+            dl2 += (xs - hd) * (xs - hd);
             const __half lo = __float2half_rn(x - __half2float(hi));
             const __half mhi = __float2half_rn(-2.f * __half2float(hi)), mlo = __float2half_rn(-2.f * __half2float(lo));
-            // np = 3: q_hi.x_hi + q_hi.x_lo + q_lo.x_hi;  np = 2: q_hi.(x_hi + x_lo);  np = 1: q_hi.x_hi
+            // q_hi.(x_hi + x_lo)
             a[j] = hi;
             bop[knn_b_pos(i, j, chunks)] = mhi;
-            if (np >= 2) { a[d + j] = hi; bop[knn_b_pos(i, d + j, chunks)] = mlo; }
-            if (np >= 3) { a[2 * d + j] = lo; bop[knn_b_pos(i, 2 * d + j, chunks)] = mhi; }
+            a[d + j] = hi;
+            bop[knn_b_pos(i, d + j, chunks)] = mlo;
             n2 += (double)x * (double)x;
         }
         n2 = ab_warp_sum_f64(n2);
+        h2 = ab_warp_sum_f64(h2);
+        dl2 = ab_warp_sum_f64(dl2);
         __syncwarp();
         if (lane == 0) {
+            qh2[i] = h2 / (sc * sc);
+            qdel[i] = sqrt(dl2) / sc * (1.0 + 1e-12);
             const __half n0 = __double2half(n2);
             const double r1 = n2 - (double)__half2float(n0);
             const __half n1 = __double2half(r1);
@@ -290,7 +305,7 @@ knn_prep_kernel(const double *__restrict__ emb, int64_t n, int64_t n_pad, int d,
         }
     }
     for (int64_t i = n + w; i < n_pad; i += nw) {
-        for (int j = lane; j < kt; j += 32) bop[knn_b_pos(i, j, chunks)] = (j == np * d) ? __float2half_rn(60000.f) : zero;
+        for (int j = lane; j < kt; j += 32) bop[knn_b_pos(i, j, chunks)] = (j == TC_NPROD * d) ? __float2half_rn(60000.f) : zero;
     }
 }
 
@@ -756,7 +771,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                   int lists, const unsigned long long *__restrict__ cand, const double *__restrict__ qn,
                   const unsigned int *__restrict__ rmax_bits, int32_t *__restrict__ idx, double *__restrict__ rdist,
                   int64_t *__restrict__ fb_list, unsigned long long *__restrict__ stats, unsigned int *__restrict__ relerr_bits,
-                  double kappa) {
+                  double kappa, const double *__restrict__ qh2, const double *__restrict__ qdel) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const int mg = lists * m;                              // candidate groups of the query (all lists)
@@ -771,7 +786,11 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         const int64_t qid = q_begin + q;
         const double *qv = emb + qid * d;
         const double qnorm2 = qn[qid];
-        const double scale = sqrt(qnorm2) + (double)R;
+        // The query the GEMM saw is q_hi, exactly.  A score plus |q_hi|^2 is the squared distance to q_hi within eps,
+        // and | |x - q| - |x - q_hi| | <= del = |q - q_hi| for every x.
+        const double qbase = qh2[qid];
+        const double del = qdel[qid];
+        const double scale = sqrt(qnorm2) * 1.0009765625 + (double)R;      // |q_hi| <= (1 + 2^-11) |q|
         const double eps = kappa * scale * scale;
         // Only groups that can hold one of the k nearest are expanded.  With the lists sorted by key, the k-th
         // smallest approximate group minimum a_k of any one list bounds D_k <= a_k + eps (k distinct groups, each
@@ -780,7 +799,15 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
         double thr = INFINITY;
         if (lane < lists) {
             const unsigned long long kk = cand[((size_t)lane * nq + q) * m + (k - 1 < m ? k - 1 : m - 1)];
-            if (kk != TC_KEY_MAX && k <= m) thr = (double)key_score(kk) * inv_sc2 + qnorm2 + 2.0 * eps;
+            if (kk != TC_KEY_MAX && k <= m) {
+                const double ak = (double)key_score(kk) * inv_sc2 + qbase;
+                if (del > 0.0) {
+                    // D_k <= (sqrt(a_k + eps) + del)^2; a group with approximate minimum a has every point at
+                    // distance >= sqrt(a - eps) - del from q
+                    const double t = sqrt(fmax(ak + eps, 0.0)) + 2.0 * del;
+                    thr = t * t * (1.0 + 1e-14) + eps;
+                } else thr = ak + 2.0 * eps;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) thr = fmin(thr, ab_shfl_xor_f64(thr, o));
@@ -791,7 +818,7 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
             if (gi < mg) {
                 const int g = gi / m, e = gi - g * m;
                 const unsigned long long key = cand[((size_t)g * nq + q) * m + e];
-                take = key != TC_KEY_MAX && ((double)key_score(key) * inv_sc2 + qnorm2 <= thr);
+                take = key != TC_KEY_MAX && ((double)key_score(key) * inv_sc2 + qbase <= thr);
             }
             const unsigned bal = __ballot_sync(AB_FULL, take);
             if (take) sel[n_exp + __popc(bal & ((1u << lane) - 1))] = gi;
@@ -842,8 +869,13 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
 #pragma unroll
             for (int o = TC_GRP / 2; o > 0; o >>= 1) gmin = fmin(gmin, ab_shfl_xor_f64(gmin, o));
             if (key != TC_KEY_MAX && gmin < INFINITY) {
-                const double approx = (double)key_score(key) * inv_sc2 + qnorm2;
-                worst_rel = fmax(worst_rel, fabs(approx - gmin) / (scale * scale));
+                const double approx = (double)key_score(key) * inv_sc2 + qbase;
+                double err = fabs(approx - gmin);
+                if (del > 0.0) {                              // what lies outside the band the perturbed query allows
+                    const double sg = sqrt(gmin), up = (sg + del) * (sg + del), lo = sg > del ? (sg - del) * (sg - del) : 0.0;
+                    err = fmax(0.0, fmax(approx - up, lo - approx));
+                }
+                worst_rel = fmax(worst_rel, err / (scale * scale));
             }
             sd[c] = dist;
             si[c] = id;
@@ -876,7 +908,12 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                 if (last != TC_KEY_MAX) tau = fmin(tau, (double)key_score(last) * inv_sc2);
             }
             // every point outside the listed groups has  D >= tau + ||q||^2 - eps ; strict '>' also settles ties
-            const bool certified = (tau + qnorm2 - eps > dk);
+            const double t2 = tau + qbase - eps;
+            bool certified = t2 > dk;
+            if (del > 0.0 && certified) {                      // |x - q| >= |x - q_hi| - del > sqrt(t2) - del
+                const double t = sqrt(t2) - del;
+                certified = t > 0.0 && t * t * (1.0 - 1e-14) > dk;
+            }
             if (certified) {
                 atomicAdd(stats + 3, 1ull);
                 if (k < p2 && sd[k] == dk) atomicAdd(stats + 0, 1ull);
@@ -904,12 +941,14 @@ static int tc_candidates(int k) {
     return std::min(m, 256);
 }
 static int64_t tc_pad(int64_t n) { return (n + 255) / 256 * 256; }
-static int tc_kt(int d, int np = 3) { return (np * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
+static int tc_kt(int d) { return (TC_NPROD * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
 // two resident query tiles when their A operand (256 rows x kt halves) leaves room for the B ring
-static int tc_mt(int d, int np = 3) { return tc_kt(d, np) * 2 * 256 <= 96 * 1024 ? 2 : 1; }
+// (at d = 100 the two tiles take 112 KB and leave three ring slots of 32 KB: measured on 200,000 cells x 100 dims, k = 30:
+// GEMM 25.4 -> 21.5 ms and, with one candidate list per query instead of two, re-rank 58 -> 32 ms)
+static int tc_mt(int d) { return tc_kt(d) * 2 * 256 <= 112 * 1024 ? 2 : 1; }
 
 struct TcWs {
-    double *mean, *partial, *qn;
+    double *mean, *partial, *qn, *qh2, *qdel;
     __half *aop, *bop;
     unsigned long long *cand;
     int64_t *fb_list;
@@ -928,6 +967,8 @@ static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t by
     w.mean = a.take<double>(d);
     w.partial = a.take<double>((size_t)1024 * d);
     w.qn = a.take<double>(n);
+    w.qh2 = a.take<double>(n);
+    w.qdel = a.take<double>(n);
     w.cand = a.take<unsigned long long>((size_t)2 * nq * m);
     w.fb_list = a.take<int64_t>((size_t)2 * nq);
     w.scal = a.take<unsigned int>(4);
@@ -968,8 +1009,8 @@ static int make_map(CUtensorMap *map, __half *base, int64_t rows, int kt, int bo
 
 int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_t q_begin, int64_t nq, int k,
                   int32_t *idx, double *rdist, unsigned long long *stats, void *ws, size_t ws_bytes, cudaStream_t st) {
-    const int np = 3;            // FP16 products per coordinate pair (2 and 1 were measured: profiles/r1_knn_notes.md)
-    const int kt = tc_kt(d, np), chunks = kt / TC_KCH, m = tc_candidates(k);
+    const int m = tc_candidates(k);
+    const int kt = tc_kt(d), chunks = kt / TC_KCH;
     if (chunks > TC_MAX_CHUNKS || n_total < m || n_total >= ((int64_t)1 << 31) - 512) {
         // outside the tensor path's envelope (very wide embeddings, tiny inputs): exact scan
         return ab_knn_exact_run(ctx, emb, n_total, d, nullptr, q_begin, nq, k, ab_knn_exact_pick_splits(ctx, nq), nullptr,
@@ -978,7 +1019,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     TcWs w;
     AB_REQUIRE(tc_layout(n_total, d, nq, k, ws, ws_bytes, &w) != 0, "ab_knn: workspace too small");
     AB_CUDA(cudaMemsetAsync(w.scal, 0, 4 * sizeof(unsigned int), st));
-    const int mt = tc_mt(d, np), lists = 3 - mt;
+    const int mt = tc_mt(d), lists = 3 - mt;
     // ---- prep ----
     ab_prof_begin(ctx, AB_PROF_KNN_PREP, st);
     const int parts = (int)std::min<int64_t>(1024, std::max<int64_t>(1, n_total / 64));
@@ -989,7 +1030,8 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     const unsigned g_prep = (unsigned)std::min<int64_t>((n_total + 7) / 8, (int64_t)ctx->sm_count * 16);
     knn_rmax_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, w.mean, w.scal);
     AB_LAUNCH_CHECK(ctx);
-    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, tc_pad(n_total), d, kt, np, w.mean, w.scal, w.aop, w.bop, w.qn);
+    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, tc_pad(n_total), d, kt, w.mean, w.scal, w.aop, w.bop, w.qn,
+                                            w.qh2, w.qdel);
     AB_LAUNCH_CHECK(ctx);
     AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)lists * nq * m * sizeof(unsigned long long), st));
     ab_prof_end(ctx, AB_PROF_KNN_PREP, st);
@@ -1012,7 +1054,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     const size_t smem = 1024 + a_bytes + (size_t)stages * group * b_stage + bar_bytes;
     AB_CUDA(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TcParams P{};
-    P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (np * d + 3 + 15) / 16;
+    P.n_total = n_total; P.q_begin = q_begin; P.nq = nq; P.chunks = chunks; P.ksteps = (TC_NPROD * d + 3 + 15) / 16;
     P.stages = stages; P.group = group; P.bufg = w.bufg;
     // a tile that is one ring slot: per-half accumulator hand-off; otherwise (wide embeddings) one hand-off per tile
     P.split = group == chunks ? 1 : 0;
@@ -1032,7 +1074,8 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     const unsigned g_rr = (unsigned)std::min<int64_t>((nq + rr_warps - 1) / rr_warps, (int64_t)ctx->sm_count * 16);
     knn_rerank_kernel<<<g_rr, rr_warps * 32, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
-                                                           idx, rdist, w.fb_list, stats, w.scal + 1, tc_kappa(np, kt));
+                                                           idx, rdist, w.fb_list, stats, w.scal + 1, tc_kappa(kt), w.qh2,
+                                                           w.qdel);
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_KNN_RERANK, st);
     // ---- uncertified queries: exact scan ----
@@ -1048,9 +1091,9 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
         // by the exact FP64 scan
         float seen;
         memcpy(&seen, &h_scal[1], sizeof(float));
-        if ((double)seen > 0.5 * tc_kappa(np, kt)) {
+        if ((double)seen > 0.5 * tc_kappa(kt)) {
             fprintf(stderr, "alona_b200: kNN candidate scores off by %.3g of (|q|+R)^2 (model bound %.3g): exact scan for all queries\n",
-                    (double)seen, tc_kappa(np, kt));
+                    (double)seen, tc_kappa(kt));
             AB_CUDA(cudaMemsetAsync(stats, 0, 8 * sizeof(unsigned long long), st));
             return ab_knn_exact_run(ctx, emb, n_total, d, nullptr, q_begin, nq, k, ab_knn_exact_pick_splits(ctx, nq), nullptr,
                                     idx, rdist, stats, ws, ws_bytes, st);

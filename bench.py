@@ -379,7 +379,7 @@ def main():
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f64 (normalise/HVG/IRLBA/re-rank), fp16x3 with fp32 accumulate (distance GEMM candidates), int32 (SNN)',
+            'dtype': 'f64 (normalise/HVG/IRLBA/re-rank), fp16 hi/lo operands with fp32 accumulate (distance GEMM candidates), int32 (SNN)',
             'data': 'synthetic', 'config': config, 'clocks': clocks, 'gpu_launches': launches // max(1, args.steps),
             'stage_ms': stage_ms, 'kernel_ms': kernel_ms,
             'kernel_ms_fine_pass': {k: {'ms_total': v[0], 'launches': v[1]} for k, v in fine.items()},
@@ -391,7 +391,7 @@ def main():
 
 
 def roofline(wl, world, kernel_ms, peaks):
-    """Dominant kernel = knn_tc_kernel (the FP16x3 distance GEMM + top-m epilogue).
+    """Dominant kernel = knn_tc_kernel (the FP16 hi/lo distance GEMM + top-m epilogue).
     Algorithmic work per launch: 2 * N_q * N * d flops (true d); duration = the CUDA-event
     pair the library records around the launch on its stream, averaged over the timed steps."""
     n, d = wl['cells'], wl['pca_n']
@@ -412,8 +412,8 @@ def roofline(wl, world, kernel_ms, peaks):
     return {'bound': 'tensor', 'kernel': 'knn_tc_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': achieved / peak, 'traffic': traffic, 'ms_per_launch': ms, 'flops_per_launch': flops,
             'peak_source': ('MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step; FP16 and '
-                            'bf16 share the tensor rate); 3 FP16 products per useful flop + K padding 153->160 cap '
-                            'this fraction at 0.3125') if peaks else 'fallback 1.4 PFLOP/s sustained'}
+                            'bf16 share the tensor rate); 2 FP16 products per useful flop + K padding 103->112 cap '
+                            'this fraction at 0.446') if peaks else 'fallback 1.4 PFLOP/s sustained'}
 
 
 def stage_rooflines(wl, world, fine, info, out, peaks):

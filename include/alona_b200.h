@@ -200,9 +200,10 @@ int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_h, const do
 /* ---- K9: exact k-nearest neighbours ----------------------------------------------------
  * replaces AlonaClustering.knn (alona/clustering.py:184-186; scikit-learn BallTree).
  * emb_all: N x d row-major FP64 embedding of ALL cells; queries are rows [q_begin,q_end).
- * Candidate generation: tcgen05 distance GEMM on FP16 operand pairs (each coordinate split into
- * hi + lo halves, three products: the accuracy of a 3xTF32 scheme at the FP16 rate) with per-query
- * top-m selection of candidate groups;
+ * Candidate generation: tcgen05 distance GEMM on FP16 operands (database coordinates split into
+ * hi + lo halves, queries rounded to FP16: exact distances to the rounded query, whose offset from
+ * the true query enters the certificate by the triangle inequality) with per-query top-m selection
+ * of candidate groups;
  * then exact re-rank with the reference's own arithmetic (sequential non-fused FP64
  * sum of squared differences) and a certificate that no non-candidate can belong to the
  * top k; uncertified queries are recomputed by an exact FP64 scan.
