@@ -400,8 +400,21 @@ __global__ void scale_by_invnorm_kernel(const double *__restrict__ src, double *
 // and plain load/FMA/store is race-free and order-deterministic; __syncwarp separates rows.
 // Row metadata (row end, x) travels in registers, 32 rows per refill, read by shuffle.
 // ---------------------------------------------------------------------------------------
-static constexpr int AV_U = 8;       // steps per register batch (measured at C3: 4 -> 210 ms, 6 -> 187, 8 -> 179, 12 -> 196, 16 -> 193:
-                                     // fewer bytes in flight below 8, instruction-cache misses of the unrolled consume loop above)
+// steps per register batch, one CTA of 12 warps per SM (measured at C3: 4 -> 210 ms, 6 -> 187, 8 -> 179, 12 -> 196, 16 -> 193:
+// fewer bytes in flight below 8, instruction-cache misses of the unrolled consume loop above)
+static constexpr int AV_U_WIDE = 8;
+// Gene-split form (see ah_split_kernel): the genes are cut in two halves, each warp owns rows x ONE half, so its
+// accumulator is H/2 doubles and twice as many warps fit an SM (24 x 8 KB at H = 2000).  The register file then allows
+// fewer steps in flight per warp; the bytes in flight per SM stay the same, the warps hiding the shared-memory and
+// fixed latencies of the consume loop double.
+static constexpr int AV_U_SPLIT = 4;
+
+struct AvOperand {                   // halves == 1: [0] is the caller's CSR; halves == 2: the two gene halves of it
+    const int64_t *rowptr[2];
+    const int32_t *col[2];           // half 1: gene ids rebased by hs
+    const double *val[2];
+    int halves, hs;                  // hs: first gene of half 1
+};
 
 struct AvRowState {           // row metadata of one warp: 32 rows per refill, read by shuffle
     int64_t blk;              // first row of the register block
@@ -472,7 +485,7 @@ __device__ __forceinline__ void av_step(AvRowState &r, double *acc, int cgu, dou
 // consumes one batch of AV_U steps of 32 nonzeros.  FULL: every step of the batch is complete (no bounds checks).
 // (Issuing two in-row steps interleaved - their 64 genes are distinct - was measured slower: the kernel is
 // sensitive to its own code size, 17 % of its stalls are instruction fetch.)
-template <bool FULL>
+template <bool FULL, int AV_U>
 __device__ __forceinline__ void av_consume(AvRowState &r, double *acc, const int (&cg)[AV_U], const double (&vv)[AV_U],
                                            int base, int len, const int64_t *__restrict__ rowptr, int64_t p0, int64_t r1,
                                            const double *__restrict__ src, double scale, double *__restrict__ vdst, int lane) {
@@ -484,19 +497,27 @@ __device__ __forceinline__ void av_consume(AvRowState &r, double *acc, const int
     }
 }
 
-__global__ void __launch_bounds__(384, 1)
-av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
-          int64_t n, int H, const double *__restrict__ src, double *__restrict__ scal_fn2 /* scal, or NULL: scale 1 */,
-          double *__restrict__ vdst, int nwarps_cta, double *__restrict__ partial /*[grid][H]*/,
+template <int AV_U, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+av_kernel(const AvOperand op, int64_t n, int H, const double *__restrict__ src,
+          double *__restrict__ scal_fn2 /* scal, or NULL: scale 1 */, double *__restrict__ vdst_all,
+          int nwarps_cta /* per gene half */, double *__restrict__ partial /*[grid][H]*/,
           const AbPeer *__restrict__ peer_p, uint32_t seq_fn2) {
     extern __shared__ double acc_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double scale = scal_fn2 ? invcheck(sqrt(resolve_fn2(peer_p, seq_fn2, scal_fn2))) : 1.0;
-    for (int i = threadIdx.x; i < nwarps_cta * H; i += blockDim.x) acc_sm[i] = 0.0;
+    const int Hw = op.halves == 2 ? max(op.hs, H - op.hs) : H;         // accumulator width of one warp
+    for (int i = threadIdx.x; i < op.halves * nwarps_cta * Hw; i += blockDim.x) acc_sm[i] = 0.0;
     __syncthreads();
-    if (warp < nwarps_cta) {
-        double *acc = acc_sm + (size_t)warp * H;
-        const int64_t wid = (int64_t)blockIdx.x * nwarps_cta + warp;
+    if (warp < op.halves * nwarps_cta) {
+        const int half = warp / nwarps_cta, slot = warp - half * nwarps_cta;
+        // (selects, not op.x[half]: a dynamically indexed kernel parameter is copied to local memory first)
+        const int64_t *__restrict__ rowptr = half ? op.rowptr[1] : op.rowptr[0];
+        const int32_t *__restrict__ col = half ? op.col[1] : op.col[0];
+        const double *__restrict__ val = half ? op.val[1] : op.val[0];
+        double *__restrict__ vdst = half == 0 ? vdst_all : nullptr;   // the new Lanczos vector is stored once
+        double *acc = acc_sm + (size_t)warp * Hw;
+        const int64_t wid = (int64_t)blockIdx.x * nwarps_cta + slot;
         const int64_t nw = (int64_t)gridDim.x * nwarps_cta;
         const int64_t per = (n + nw - 1) / nw;
         const int64_t r0 = min(n, wid * per), r1 = min(n, r0 + per);
@@ -542,8 +563,8 @@ av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, c
                             vv[bb ^ 1][u] = ok ? __ldg(valw + p) : 0.0;
                         }
                     }
-                    if (base + B <= len) av_consume<true>(r, acc, cg[bb], vv[bb], base, len, rowptr, p0, r1, src, scale, vdst, lane);
-                    else av_consume<false>(r, acc, cg[bb], vv[bb], base, len, rowptr, p0, r1, src, scale, vdst, lane);
+                    if (base + B <= len) av_consume<true, AV_U>(r, acc, cg[bb], vv[bb], base, len, rowptr, p0, r1, src, scale, vdst, lane);
+                    else av_consume<false, AV_U>(r, acc, cg[bb], vv[bb], base, len, rowptr, p0, r1, src, scale, vdst, lane);
                 }
             }
             // rows after the last nonzero (empty tail rows) still need their x stored
@@ -557,9 +578,55 @@ av_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, c
     }
     __syncthreads();
     for (int g = threadIdx.x; g < H; g += blockDim.x) {
+        const int half = (op.halves == 2 && g >= op.hs) ? 1 : 0;
+        const double *a0 = acc_sm + (size_t)half * nwarps_cta * Hw + (g - half * op.hs);
         double t = 0.0;
-        for (int w2 = 0; w2 < nwarps_cta; ++w2) t += acc_sm[(size_t)w2 * H + g];
+        for (int w2 = 0; w2 < nwarps_cta; ++w2) t += a0[(size_t)w2 * Hw];
         partial[(size_t)blockIdx.x * H + g] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Gene-split copy of A_H for A.x, built once per ab_irlb call: row r's nonzeros with gene < hs go to stream 0, the
+// others (gene ids rebased by hs) to stream 1, each a CSR of its own (rows stay in order, so a warp's flat walk over
+// its row range works unchanged).  rp0 = exclusive scan of the per-row counts of half 0.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ah_split_count_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t n, int hs,
+                      int64_t *__restrict__ cnt0) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    int64_t lo = rowptr[row], hi = rowptr[row + 1];
+    const int64_t a = lo;
+    while (lo < hi) {                                   // first entry with gene >= hs (columns ascend inside a row)
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(col + mid) < hs) lo = mid + 1; else hi = mid;
+    }
+    cnt0[row] = lo - a;
+}
+
+__global__ void __launch_bounds__(256)
+ah_split_fill_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
+                     int64_t n, int hs, const int64_t *__restrict__ rp0 /* n+1, scanned */, int64_t *__restrict__ rp1 /* n+1 */,
+                     int32_t *__restrict__ col2, double *__restrict__ val2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nw = (int64_t)gridDim.x * 8;
+    const int64_t base0 = rowptr[0], nnz0 = rp0[n];
+    for (int64_t row = wid; row <= n; row += nw) {
+        const int64_t a = rowptr[row];
+        // stream 1 starts at nnz0: what precedes row `row` there = all earlier nonzeros minus those of half 0
+        const int64_t o1 = nnz0 + (a - base0) - rp0[row];
+        if (lane == 0) rp1[row] = o1;
+        if (row == n) break;
+        const int64_t b = rowptr[row + 1], o0 = rp0[row], c0 = rp0[row + 1] - o0;
+        for (int64_t p = a + lane; p < b; p += 32) {
+            const int c = __ldg(col + p);
+            const int64_t i = p - a;
+            const int64_t dst = i < c0 ? o0 + i : o1 + (i - c0);
+            col2[dst] = i < c0 ? c : c - hs;
+            val2[dst] = __ldg(val + p);
+        }
     }
 }
 
@@ -1283,6 +1350,13 @@ static int av_warps_for(int H) {
     if (w > 12) w = 12;
     return w;
 }
+// gene-split form: warps per gene half (two halves of (H+1)/2 accumulators each)
+static int av_split_hs(int H) { return (H + 1) / 2; }
+static int av_warps_split(int H) {
+    int w = (int)((216 * 1024) / ((size_t)2 * av_split_hs(H) * 8));
+    if (w > 12) w = 12;
+    return w;
+}
 
 static size_t irlb_layout(int64_t n, int H, int nval, int64_t n_total_hint, int sm_count, void *ws, size_t bytes,
                           IrlbWs *out) {
@@ -1328,6 +1402,12 @@ struct IrlbCompact {
     uint32_t *ent, *taboff;
     double *tabv;
     unsigned int *cursor;
+    // gene-split copy of A_H for A.x (ah_split_*_kernel)
+    int32_t *col2;
+    double *val2;
+    int64_t *rp0, *rp1;
+    void *scan;
+    size_t scan_bytes;
 };
 static size_t irlb_compact_layout(int64_t n, int64_t nnz, void *base, size_t bytes, IrlbCompact *out) {
     ab_arena a(base ? base : (void *)256, base ? bytes : (size_t)-1 / 2);
@@ -1336,6 +1416,12 @@ static size_t irlb_compact_layout(int64_t n, int64_t nnz, void *base, size_t byt
     c.ent = a.take<uint32_t>((size_t)std::max<int64_t>(nnz, 1));
     c.taboff = a.take<uint32_t>((size_t)std::max<int64_t>(n, 1));
     c.cursor = a.take<unsigned int>(4);
+    c.col2 = a.take<int32_t>((size_t)std::max<int64_t>(nnz, 1));
+    c.val2 = a.take<double>((size_t)std::max<int64_t>(nnz, 1));
+    c.rp0 = a.take<int64_t>((size_t)n + 1);
+    c.rp1 = a.take<int64_t>((size_t)n + 1);
+    c.scan_bytes = ab_scan_ws_bytes(n);
+    c.scan = a.take<char>(c.scan_bytes);
     if (out) *out = c;
     return a.ok ? a.off : 0;
 }
@@ -1408,9 +1494,29 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
             }
         }
     }
-
-    const size_t av_smem = (size_t)w.av_warps * H * 8;
-    AB_CUDA(cudaFuncSetAttribute(av_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
+    // A.x operand: the gene-split copy when the workspace tail holds it, the caller's CSR otherwise
+    AvOperand avop{};
+    avop.rowptr[0] = rowptr_h; avop.col[0] = col_h; avop.val[0] = val_h; avop.halves = 1; avop.hs = H;
+    int av_nw = w.av_warps;
+    if (cp.col2 && H >= 64 && av_warps_split(H) >= 1 && !getenv("AB_IRLB_NOSPLIT")) {
+        const int hs = av_split_hs(H);
+        ab_prof_begin(ctx, AB_PROF_IRLB_AV, st);
+        ah_split_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowptr_h, col_h, n, hs, cp.rp0);
+        AB_LAUNCH_CHECK(ctx);
+        if (ab_exclusive_scan_i64(ctx, cp.rp0, cp.rp0, n, cp.scan, cp.scan_bytes, st)) return 1;
+        const unsigned g_sp = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 8) / 8, (int64_t)ctx->sm_count * 32));
+        ah_split_fill_kernel<<<g_sp, 256, 0, st>>>(rowptr_h, col_h, val_h, n, hs, cp.rp0, cp.rp1, cp.col2, cp.val2);
+        AB_LAUNCH_CHECK(ctx);
+        ab_prof_end(ctx, AB_PROF_IRLB_AV, st);
+        avop.rowptr[0] = cp.rp0; avop.rowptr[1] = cp.rp1;
+        avop.col[0] = avop.col[1] = cp.col2;
+        avop.val[0] = avop.val[1] = cp.val2;
+        avop.halves = 2; avop.hs = hs;
+        av_nw = av_warps_split(H);
+    }
+    const size_t av_smem = avop.halves == 2 ? (size_t)2 * av_nw * avop.hs * 8 : (size_t)av_nw * H * 8;
+    AB_CUDA(cudaFuncSetAttribute(av_kernel<AV_U_WIDE, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
+    AB_CUDA(cudaFuncSetAttribute(av_kernel<AV_U_SPLIT, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
     // wstep: one cluster of WS_CL CTAs; the W slice is cached in shared memory when it fits
     const int ws_nsp = (H + WS_CL - 1) / WS_CL + 1;
     const int cache_w = ((size_t)ws_nsp * (work + 1)) * 8 <= (size_t)200 * 1024 ? 1 : 0;
@@ -1483,8 +1589,12 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         ab_prof_begin(ctx, AB_PROF_IRLB_AV, st);
         // (A.x keeps the plain operand: its 12 warps per SM leave ~30 KB of L1, a table look-up per nonzero at consume
         // time misses it, and the compact variant measured 344 ms against 195)
-        av_kernel<<<w.av_grid, 384, av_smem, st>>>(rowptr_h, col_h, val_h, n, H, src, scaled ? w.scal : nullptr, vdst,
-                                                   w.av_warps, w.av_partial, peer, seq_fn2);
+        if (avop.halves == 2)
+            av_kernel<AV_U_SPLIT, 768><<<w.av_grid, 64 * av_nw, av_smem, st>>>(avop, n, H, src, scaled ? w.scal : nullptr, vdst,
+                                                                               av_nw, w.av_partial, peer, seq_fn2);
+        else
+            av_kernel<AV_U_WIDE, 384><<<w.av_grid, 384, av_smem, st>>>(avop, n, H, src, scaled ? w.scal : nullptr, vdst,
+                                                                       av_nw, w.av_partial, peer, seq_fn2);
         AB_LAUNCH_CHECK(ctx);
         const uint32_t sv = fused ? ++seq[AB_CH_VEC] : 0;
         av_reduce_kernel<<<(H + 31) / 32, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw, cnt + 3, peer, sv,
