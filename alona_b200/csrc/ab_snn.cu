@@ -231,11 +231,13 @@ __global__ void snn_walk_kernel(const int32_t *__restrict__ knn, int k, int64_t 
 // ---------------------------------------------------------------------------------------
 // shared row state: sorted neighbours, their reverse-list extents and walk positions
 // ---------------------------------------------------------------------------------------
-struct WarpRowState {
-    int nb[SNN_MAXK];            // sorted neighbour ids
-    int base[SNN_MAXK + 1];      // walk position where each neighbour's reverse list starts
-    long long start[SNN_MAXK];   // rptr of each neighbour
+template <int KM>
+struct WarpRowStateT {
+    int nb[KM];                  // sorted neighbour ids
+    int base[KM + 1];            // walk position where each neighbour's reverse list starts
+    long long start[KM];         // rptr of each neighbour
 };
+using WarpRowState = WarpRowStateT<SNN_MAXK>;
 
 __device__ __forceinline__ unsigned hash_slot(int key) {
     return ((unsigned)key * 2654435761u) >> (32 - SNN_SLOTS_LG);
@@ -269,6 +271,55 @@ __device__ __forceinline__ int warp_load_row(const int32_t *__restrict__ knn, in
             st.start[c] = s;
             d = (int)(rptr[j + 1] - s);
         }
+        int inc = d;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(AB_FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __syncwarp();
+        if (c < k) st.base[c] = run + inc - d;
+        run += __shfl_sync(AB_FULL, inc, 31);
+    }
+    if (lane == 0) st.base[k] = run;
+    __syncwarp();
+    return run;
+}
+
+// The same row state from values already in registers (one row ahead, see snn_cta_kernel): lane l holds neighbour
+// c = l + 32 i of the UNSORTED row, with its reverse-list start and length.  Shared-memory work only.
+template <int KM>
+__device__ __forceinline__ int warp_build_row(const int (&nb)[KM / 32], const long long (&rs)[KM / 32], const int (&rd)[KM / 32],
+                                              int k, WarpRowStateT<KM> &st, int lane) {
+    constexpr int SNN_KR = KM / 32;
+#pragma unroll
+    for (int i = 0; i < SNN_KR; ++i)
+        if (lane + 32 * i < k) st.base[lane + 32 * i] = nb[i];                // base[] as scratch
+    __syncwarp();
+    int rk[SNN_KR];
+#pragma unroll
+    for (int i = 0; i < SNN_KR; ++i) {
+        const int c = lane + 32 * i;
+        rk[i] = 0;
+        if (c < k) {
+            const int v = nb[i];
+            int rank = 0;
+            for (int t = 0; t < k; ++t) {
+                const int u = st.base[t];
+                rank += (u < v) || (u == v && t < c);
+            }
+            rk[i] = rank;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < SNN_KR; ++i)
+        if (lane + 32 * i < k) { st.nb[rk[i]] = nb[i]; st.start[rk[i]] = rs[i]; st.base[rk[i]] = rd[i]; }
+    __syncwarp();
+    int run = 0;
+    for (int c0 = 0; c0 < k; c0 += 32) {
+        const int c = c0 + lane;
+        const int d = c < k ? st.base[c] : 0;
         int inc = d;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -390,37 +441,72 @@ snn_small_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, cons
 // lists in ascending a and each list in ascending cell id, so the first encounter of m is at
 // (lowest a, rank of m in R(nb[a]))); atomicOr makes the insertion order irrelevant.
 // ---------------------------------------------------------------------------------------
-struct CtaRowState {
-    WarpRowState w;
-    int chunk0[SNN_MAXK + 1];    // first chunk of each neighbour's list
+template <int KM>
+struct CtaRowStateT {            // KM = 32 W in the table kernels (k <= 32 takes 0.7 KB instead of 2.6: six CTAs per SM, not five)
+    WarpRowStateT<KM> w;
+    int chunk0[KM + 1];          // first chunk of each neighbour's list
     int walk, chunks;
 };
+using CtaRowState = CtaRowStateT<SNN_MAXK>;
 
 template <int SLOTS, int W, int THREADS, bool FILL>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (W == 1 ? 6 : 2) : (W == 1 ? 3 : 1))
 snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const int32_t *__restrict__ rows,
                const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
                const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
                const int64_t *__restrict__ rowptr_out, int32_t *__restrict__ src, int32_t *__restrict__ dst,
                uint8_t *__restrict__ overlap, int cap, unsigned long long *__restrict__ nz_out) {
-    static_assert(SLOTS / 10 * 7 / 32 + SNN_MAXK + 1 <= THREADS, "chunk table must fit one scan pass");
+    static_assert(SLOTS / 10 * 7 / 32 + 32 * W + 1 <= THREADS, "chunk table must fit one scan pass");
     unsigned long long nz = 0;                       // nonzeros of A.A^T met by this thread (first encounters)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *keys = reinterpret_cast<int *>(smem_raw);
     unsigned *masks = reinterpret_cast<unsigned *>(keys + SLOTS);
-    CtaRowState &st = *reinterpret_cast<CtaRowState *>(masks + (size_t)SLOTS * W);
+    constexpr int SNN_KR = W;                                          // k <= 32 W
+    using RowState = CtaRowStateT<32 * W>;
+    RowState &st = *reinterpret_cast<RowState *>(masks + (size_t)SLOTS * W);
     int *chunk_tab = reinterpret_cast<int *>(&st + 1);                 // [THREADS]
     unsigned *ballots = reinterpret_cast<unsigned *>(chunk_tab + THREADS);   // [THREADS]
     int *choff = reinterpret_cast<int *>(ballots + THREADS);           // [THREADS]
     __shared__ int red[32];
+    __shared__ int sv_n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = THREADS / 32;
     const int n_rows = *n_rows_ptr;
+    // Warp 0 keeps the NEXT row's neighbour ids and reverse-list extents in registers: the two dependent global round
+    // trips behind them (row -> ids -> extents) are issued while the current row is processed, so building the row
+    // state at the top of a row is shared-memory work only (it was ~10 % of the kernel with seven warps waiting).
+    int nx_nb[SNN_KR];
+    long long nx_s[SNN_KR];
+    int nx_d[SNN_KR];
+    auto fetch_ids = [&](int qq) {
+#pragma unroll
+        for (int i = 0; i < SNN_KR; ++i) nx_nb[i] = 0;
+        if (qq < n_rows) {
+            const int64_t r2 = rows[qq];
+#pragma unroll
+            for (int i = 0; i < SNN_KR; ++i)
+                if (lane + 32 * i < k) nx_nb[i] = knn[(row_begin + r2) * k + lane + 32 * i];
+        }
+    };
+    auto fetch_extents = [&]() {
+#pragma unroll
+        for (int i = 0; i < SNN_KR; ++i) {
+            nx_s[i] = 0; nx_d[i] = 0;
+            if (lane + 32 * i < k) {
+                const long long s0 = rptr[nx_nb[i]];
+                nx_s[i] = s0;
+                nx_d[i] = (int)(rptr[nx_nb[i] + 1] - s0);
+            }
+        }
+    };
+    if (warp == 0) { fetch_ids(blockIdx.x); fetch_extents(); }
     for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
         const int64_t r = rows[q];
         __syncthreads();                                               // previous row fully retired
+        if (threadIdx.x == 0) sv_n = 0;
         if (warp == 0) {
-            const int walk = warp_load_row(knn, k, row_begin + r, rptr, st.w, lane);
+            const int walk = warp_build_row<32 * W>(nx_nb, nx_s, nx_d, k, st.w, lane);
+            fetch_ids(q + (int)gridDim.x);                             // next row: ids now, extents after the insert phase
             int run = 0;
             for (int c0 = 0; c0 < k; c0 += 32) {
                 const int c = c0 + lane;
@@ -448,22 +534,37 @@ snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const 
             for (int c = lane; c < nch; c += 32) chunk_tab[c0 + c] = (a << 24) | c;
         }
         __syncthreads();
-        // ---- walk: insert ----
-        for (int c = warp; c < C; c += NW) {
-            const int e = chunk_tab[c];
-            const int a = e >> 24, t = ((e & 0xFFFFFF) << 5) + lane;
-            const int len = st.w.base[a + 1] - st.w.base[a];
-            if (t < len) {
-                const int m = __ldg(rlist + st.w.start[a] + t);
-                unsigned s = hash_slot_lg(m, lg);
-                while (true) {
-                    const int prev = atomicCAS(keys + s, -1, m);
-                    if (prev == -1 || prev == m) break;
-                    s = (s + 1) & (S - 1);
+        // ---- walk: insert (four chunks of reverse-list reads in flight per warp: the loop was a chain of exposed
+        // global latencies, one per chunk) ----
+        constexpr int PF = 4;
+        for (int c0 = warp; c0 < C; c0 += NW * PF) {
+            int mm[PF], aa[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int c = c0 + u * NW;
+                mm[u] = -1; aa[u] = 0;
+                if (c < C) {
+                    const int e = chunk_tab[c];
+                    const int a = e >> 24, t = ((e & 0xFFFFFF) << 5) + lane;
+                    aa[u] = a;
+                    if (t < st.w.base[a + 1] - st.w.base[a]) mm[u] = __ldg(rlist + st.w.start[a] + t);
                 }
-                atomicOr(masks + (size_t)s * W + (a >> 5), 1u << (a & 31));
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int m = mm[u], a = aa[u];
+                if (m >= 0) {
+                    unsigned s = hash_slot_lg(m, lg);
+                    while (true) {
+                        const int prev = atomicCAS(keys + s, -1, m);
+                        if (prev == -1 || prev == m) break;
+                        s = (s + 1) & (S - 1);
+                    }
+                    atomicOr(masks + (size_t)s * W + (a >> 5), 1u << (a & 31));
+                }
             }
         }
+        if (warp == 0) fetch_extents();                                 // next row's ids have arrived by now
         __syncthreads();
         if (!FILL) {
             int c = 0;
@@ -482,6 +583,56 @@ snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const 
                 int tot = 0;
                 for (int w2 = 0; w2 < NW; ++w2) tot += red[w2];
                 rowcount[r] = tot;
+            }
+        } else if (cap) {
+            // ---- staging mode (the common path): the kept edges are read off the TABLE, not off a second and third walk.
+            // A slot knows its overlap (popcount) and the neighbour a of its first encounter (lowest set bit); the
+            // position inside R(nb[a]) - the lists are sorted - is a binary search, done for the ~1 % of the
+            // candidates that survive the pruning only.  Emission order = descending walk position (rank by counting).
+            int *sv_m = reinterpret_cast<int *>(ballots);                      // [cap] cell ids   (aliases the cap == 0 scratch)
+            unsigned *sv_key = reinterpret_cast<unsigned *>(sv_m + cap);       // [cap] walk position << 8 | overlap
+            for (int s = threadIdx.x; s < S; s += THREADS) {
+                const int m = keys[s];
+                if (m != -1) {
+                    ++nz;
+                    int pc = 0, first = -1;
+#pragma unroll
+                    for (int w2 = 0; w2 < W; ++w2) {
+                        const unsigned mk = masks[(size_t)s * W + w2];
+                        if (first < 0 && mk) first = 32 * w2 + __ffs(mk) - 1;
+                        pc += __popc(mk);
+                    }
+                    if (pc >= v_min) {
+                        const int i = atomicAdd(&sv_n, 1);
+                        if (i < cap) { sv_m[i] = m; sv_key[i] = ((unsigned)first << 8) | (unsigned)pc; }
+                    }
+                }
+            }
+            __syncthreads();
+            const int total = sv_n;
+            if (threadIdx.x == 0) rowcount[r] = total;                         // > cap: the overflow pass redoes the row
+            if (total <= cap) {
+                for (int i = threadIdx.x; i < total; i += THREADS) {
+                    const int m = sv_m[i];
+                    const unsigned kx = sv_key[i];
+                    const int a = (int)(kx >> 8);
+                    const int32_t *__restrict__ L = rlist + st.w.start[a];
+                    int lo = 0, hi = st.w.base[a + 1] - st.w.base[a];
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (__ldg(L + mid) < m) lo = mid + 1; else hi = mid;
+                    }
+                    sv_key[i] = ((unsigned)(st.w.base[a] + lo) << 8) | (kx & 255u);
+                }
+                __syncthreads();
+                const int64_t out = r * (int64_t)cap;
+                for (int i = threadIdx.x; i < total; i += THREADS) {
+                    const unsigned kx = sv_key[i];
+                    int rel = 0;
+                    for (int j = 0; j < total; ++j) rel += sv_key[j] > kx;      // walk positions are distinct
+                    dst[out + rel] = sv_m[i];
+                    if (overlap) overlap[out + rel] = (uint8_t)(kx & 255u);
+                }
             }
         } else {
             // ---- pass A: which entries of each chunk are kept first encounters ----
@@ -567,8 +718,10 @@ snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const 
 }
 
 template <int SLOTS, int W, int THREADS>
-static size_t snn_cta_smem() {
-    return (size_t)SLOTS * 4 * (1 + W) + sizeof(CtaRowState) + (size_t)THREADS * 12 + 64;
+static size_t snn_cta_smem(int cap) {
+    // [keys][masks][row state][chunk table][scratch: ballots + chunk offsets (cap == 0) or the survivor list (2 * cap ints)]
+    return (size_t)SLOTS * 4 * (1 + W) + sizeof(CtaRowStateT<32 * W>) + (size_t)THREADS * 4 +
+           (size_t)std::max(2 * THREADS, 2 * cap) * 4 + 64;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -957,10 +1110,16 @@ static int snn_launch_tables(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all
     const int64_t gcap = std::max<int64_t>(1, n_rows);
 #define AB_SNN_CTA(SLOTS, W, THREADS, ROWS, NPTR, PER_SM)                                                        \
     do {                                                                                                       \
-        const size_t smem = snn_cta_smem<SLOTS, W, THREADS>();                                                 \
+        const size_t smem = snn_cta_smem<SLOTS, W, THREADS>(cap);                                              \
         AB_CUDA(cudaFuncSetAttribute(snn_cta_kernel<SLOTS, W, THREADS, true>,                                  \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
-        const unsigned grid = (unsigned)std::min<int64_t>(gcap, (int64_t)ctx->sm_count * (PER_SM));            \
+        /* rows are dealt round-robin over the CTAs: the grid must be ONE resident wave (a grid of 6 per SM with 5   \
+           resident left 148 CTAs for a second, nearly empty wave as long as the first) */                           \
+        int resident = 0;                                                                                      \
+        AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, snn_cta_kernel<SLOTS, W, THREADS, true>, \
+                                                              THREADS, smem));                                 \
+        resident = std::max(1, std::min(resident, (PER_SM)));                                                  \
+        const unsigned grid = (unsigned)std::min<int64_t>(gcap, (int64_t)ctx->sm_count * resident);            \
         snn_cta_kernel<SLOTS, W, THREADS, true><<<grid, THREADS, smem, st>>>(                                  \
             knn_all, k, row_begin, ROWS, NPTR, w.deg, w.rlist, v_min, rowcount, rowptr, src, dst, overlap, cap, nz); \
         AB_LAUNCH_CHECK(ctx);                                                                                  \
