@@ -55,6 +55,18 @@ struct ab_ctx {
     std::vector<cudaEvent_t> prof_pool;
 };
 
+// Grid of a grid-stride kernel: whole resident waves.  A fixed "N CTAs per SM" that exceeds what registers / shared memory
+// let reside leaves a partial last wave running at a fraction of the machine (measured on the SNN table kernels: 6 per
+// SM launched, 5 resident, the leftover 148 CTAs as long as the first 740).
+template <class K>
+static inline unsigned ab_wave_grid(const ab_ctx *ctx, K kernel, int threads, size_t smem, int64_t useful_blocks) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int64_t g = (int64_t)ctx->sm_count * per_sm;
+    if (g > useful_blocks) g = useful_blocks;
+    return (unsigned)(g < 1 ? 1 : g);
+}
+
 void ab_prof_begin(ab_ctx *ctx, int slot, cudaStream_t st);
 void ab_prof_end(ab_ctx *ctx, int slot, cudaStream_t st);
 

@@ -1481,8 +1481,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
             if (got != 0) {
                 ab_prof_begin(ctx, AB_PROF_IRLB_ATW, st);
                 AB_CUDA(cudaMemsetAsync(cp.cursor, 0, 4 * sizeof(unsigned int), st));
-                const unsigned g_cb = (unsigned)std::max<int64_t>(
-                    1, std::min<int64_t>((n + CB_WARPS - 1) / CB_WARPS, (int64_t)ctx->sm_count * 32));
+                const unsigned g_cb = ab_wave_grid(ctx, ah_compact_kernel, CB_WARPS * 32, 0, (n + CB_WARPS - 1) / CB_WARPS);
                 ah_compact_kernel<<<g_cb, CB_WARPS * 32, 0, st>>>(rowptr_h, col_h, val_h, n, cp.ent, cp.tabv, cp.taboff,
                                                                   cp.cursor);
                 AB_LAUNCH_CHECK(ctx);
@@ -1504,7 +1503,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         ah_split_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowptr_h, col_h, n, hs, cp.rp0);
         AB_LAUNCH_CHECK(ctx);
         if (ab_exclusive_scan_i64(ctx, cp.rp0, cp.rp0, n, cp.scan, cp.scan_bytes, st)) return 1;
-        const unsigned g_sp = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 8) / 8, (int64_t)ctx->sm_count * 32));
+        const unsigned g_sp = ab_wave_grid(ctx, ah_split_fill_kernel, 256, 0, (n + 8) / 8);
         ah_split_fill_kernel<<<g_sp, 256, 0, st>>>(rowptr_h, col_h, val_h, n, hs, cp.rp0, cp.rp1, cp.col2, cp.val2);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_AV, st);
@@ -1572,8 +1571,8 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     const unsigned g_dot = (unsigned)w.dot_grid;
 
     // compact A^T.w: 8 resident CTAs per SM, each with its own copy of w in shared memory
-    const unsigned g_atw = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8));
     AB_CUDA(cudaFuncSetAttribute(atw_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)H * 8)));
+    const unsigned g_atw = ab_wave_grid(ctx, atw_compact_kernel, 256, (size_t)H * 8, (n + 7) / 8);
     int64_t nmult = 0, sum_panel = 0;
 
     // A.x, summed over the CTAs (and, sharded, pushed to every rank); returns the instance id the consumer waits for

@@ -1027,10 +1027,9 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     AB_LAUNCH_CHECK(ctx);
     knn_colmean_kernel<<<(d + 127) / 128, 128, 0, st>>>(w.partial, parts, d, n_total, w.mean);
     AB_LAUNCH_CHECK(ctx);
-    const unsigned g_prep = (unsigned)std::min<int64_t>((n_total + 7) / 8, (int64_t)ctx->sm_count * 16);
-    knn_rmax_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, d, w.mean, w.scal);
+    knn_rmax_kernel<<<ab_wave_grid(ctx, knn_rmax_kernel, 256, 0, (n_total + 7) / 8), 256, 0, st>>>(emb, n_total, d, w.mean, w.scal);
     AB_LAUNCH_CHECK(ctx);
-    knn_prep_kernel<<<g_prep, 256, 0, st>>>(emb, n_total, tc_pad(n_total), d, kt, w.mean, w.scal, w.aop, w.bop, w.qn,
+    knn_prep_kernel<<<ab_wave_grid(ctx, knn_prep_kernel, 256, 0, (n_total + 7) / 8), 256, 0, st>>>(emb, n_total, tc_pad(n_total), d, kt, w.mean, w.scal, w.aop, w.bop, w.qn,
                                             w.qh2, w.qdel);
     AB_LAUNCH_CHECK(ctx);
     AB_CUDA(cudaMemsetAsync(w.cand, 0xFF, (size_t)lists * nq * m * sizeof(unsigned long long), st));
@@ -1072,7 +1071,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     while (rr_warps > 1 && (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) > (size_t)160 * 1024) rr_warps >>= 1;
     const size_t rr_smem = (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) + (size_t)rr_warps * (mp / TC_GRP) * sizeof(int);
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
-    const unsigned g_rr = (unsigned)std::min<int64_t>((nq + rr_warps - 1) / rr_warps, (int64_t)ctx->sm_count * 16);
+    const unsigned g_rr = ab_wave_grid(ctx, knn_rerank_kernel, rr_warps * 32, rr_smem, (nq + rr_warps - 1) / rr_warps);
     knn_rerank_kernel<<<g_rr, rr_warps * 32, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
                                                            idx, rdist, w.fb_list, stats, w.scal + 1, tc_kappa(kt), w.qh2,
                                                            w.qdel);

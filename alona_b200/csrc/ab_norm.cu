@@ -176,11 +176,9 @@ extern "C" int ab_norm_moments(ab_ctx *ctx, const int64_t *rowptr, const int32_t
     const int ntiles = nm_tiles_for(n_genes, ctx->smem_optin);
     AB_REQUIRE(ntiles <= 8, "ab_norm_moments: %d genes need more than 8 shared-memory tables", n_genes);
     const int gtile = (n_genes + ntiles - 1) / ntiles;
-    int64_t blocks = (n_local + NORM_WARPS - 1) / NORM_WARPS;
-    int64_t cap = (int64_t)ctx->sm_count * 8 * 4;         // 8 CTAs/SM resident, 4 waves
-    if (blocks > cap) blocks = cap;
+    const unsigned blocks = ab_wave_grid(ctx, libsize_kernel, NORM_WARPS * 32, 0, (n_local + NORM_WARPS - 1) / NORM_WARPS);
     ab_prof_begin(ctx, AB_PROF_NORM, st);
-    libsize_kernel<<<(unsigned)blocks, NORM_WARPS * 32, 0, st>>>(rowptr, val, n_local, libsize);
+    libsize_kernel<<<blocks, NORM_WARPS * 32, 0, st>>>(rowptr, val, n_local, libsize);
     AB_LAUNCH_CHECK(ctx);
     const size_t smem = (size_t)gtile * 16;
     AB_CUDA(cudaFuncSetAttribute(norm_moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -260,10 +258,8 @@ extern "C" int ab_norm_moments_linear(ab_ctx *ctx, const int64_t *rowptr, const 
     AB_REQUIRE(ctx, "ab_norm_moments_linear: null ctx");
     AB_REQUIRE(n_local >= 0 && n_genes > 0, "ab_norm_moments_linear: bad shape");
     if (n_local == 0) return 0;
-    int64_t blocks = (n_local + NORM_WARPS - 1) / NORM_WARPS;
-    int64_t cap = (int64_t)ctx->sm_count * 8 * 4;
-    if (blocks > cap) blocks = cap;
-    lin_moments_kernel<<<(unsigned)blocks, NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(rowptr, col, val, libsize, n_local,
+    const unsigned blocks = ab_wave_grid(ctx, lin_moments_kernel, NORM_WARPS * 32, 0, (n_local + NORM_WARPS - 1) / NORM_WARPS);
+    lin_moments_kernel<<<blocks, NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(rowptr, col, val, libsize, n_local,
                                                                                        scale, ysum, ysumsq);
     AB_LAUNCH_CHECK(ctx);
     return 0;
@@ -346,11 +342,9 @@ extern "C" int ab_hvg_extract_count(ab_ctx *ctx, const int64_t *rowptr, const in
     AB_REQUIRE(ws_bytes >= ab_hvg_extract_ws_bytes(n_local), "ab_hvg_extract_count: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     if (n_local > 0) {
-        int64_t blocks = (n_local + NORM_WARPS - 1) / NORM_WARPS;
-        int64_t cap = (int64_t)ctx->sm_count * 8 * 4;
-        if (blocks > cap) blocks = cap;
+        const unsigned blocks = ab_wave_grid(ctx, hvg_count_kernel, NORM_WARPS * 32, 0, (n_local + NORM_WARPS - 1) / NORM_WARPS);
         ab_prof_begin(ctx, AB_PROF_HVG_EXTRACT, st);
-        hvg_count_kernel<<<(unsigned)blocks, NORM_WARPS * 32, 0, st>>>(rowptr, col, n_local, gene2hvg, rowptr_h);
+        hvg_count_kernel<<<blocks, NORM_WARPS * 32, 0, st>>>(rowptr, col, n_local, gene2hvg, rowptr_h);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_HVG_EXTRACT, st);
     }
@@ -368,11 +362,9 @@ extern "C" int ab_hvg_extract_fill(ab_ctx *ctx, const int64_t *rowptr, const int
                                    void *stream) {
     AB_REQUIRE(ctx, "ab_hvg_extract_fill: null ctx");
     if (n_local == 0) return 0;
-    int64_t blocks = (n_local + NORM_WARPS - 1) / NORM_WARPS;
-    int64_t cap = (int64_t)ctx->sm_count * 8 * 4;
-    if (blocks > cap) blocks = cap;
+    const unsigned blocks = ab_wave_grid(ctx, hvg_fill_kernel, NORM_WARPS * 32, 0, (n_local + NORM_WARPS - 1) / NORM_WARPS);
     ab_prof_begin(ctx, AB_PROF_HVG_EXTRACT, (cudaStream_t)stream);
-    hvg_fill_kernel<<<(unsigned)blocks, NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    hvg_fill_kernel<<<blocks, NORM_WARPS * 32, 0, (cudaStream_t)stream>>>(
         rowptr, col, val, libsize, n_local, gene2hvg, scale, rowptr_h, col_h, val_h);
     AB_LAUNCH_CHECK(ctx);
     ab_prof_end(ctx, AB_PROF_HVG_EXTRACT, (cudaStream_t)stream);
