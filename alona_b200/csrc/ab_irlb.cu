@@ -1148,9 +1148,11 @@ __global__ void reset_b_kernel(double *__restrict__ B, int work, const double *_
 // arithmetic: a producer warp streams the column-major panel through shared memory with 1-D bulk copies (one 1 KB
 // column segment per copy, one copy per lane, completion on an mbarrier, a ring of stages of KC panel columns); the
 // result leaves straight from the registers (32 contiguous bytes per thread and column).
-// Thread tile: rows 4*tr .. 4*tr+3 (tr = lane % 8) of the warp's 32-row block, columns CT*tc .. CT*tc+CT-1
-// (tc = lane / 8) of the warp's 4*CT-column block: per k-row 2 LDS.128 of A (256 contiguous bytes per warp) and CT
-// doubles of B (broadcast), 4*CT FMAs.  Eight consumer warps = 4 row blocks x 2 column blocks = 128 rows x 8*CT columns.
+// Thread tile: rows 2l, 2l+1, 64+2l, 65+2l (l = lane) of the 128-row tile, columns CT*w .. CT*w+CT-1 (w = warp): per
+// k-row 2 LDS.128 of A (each 512 contiguous bytes per warp, conflict-free) and CT doubles of B at a warp-UNIFORM
+// address (one wavefront per load), 4*CT FMAs.  The first DFMA version split a warp 8 row groups x 4 column groups:
+// its B loads then cost a wavefront per quarter warp, 24 shared-memory wavefronts per 28 FMA instructions - bound by
+// the shared-memory pipe (ncu: 65 % busy), not by the FP64 cores.  Eight consumer warps = 128 rows x 8*CT columns.
 // ---------------------------------------------------------------------------------------
 static constexpr int RZ_TR = 128;                // rows per tile
 static constexpr int RZ_XS = RZ_TR + 4;          // staged-tile column stride (doubles)
@@ -1222,10 +1224,8 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
     }
 
     // ---------------- consumers -----------------------------------------------------------------------------
-    const int tr = lane & 7, tc = lane >> 3;
-    const int wr = warp & 3, wc = warp >> 2;
-    const int rloc = 32 * wr + 4 * tr;                    // first of this thread's 4 rows inside the tile
-    const int tg = 4 * wc + tc;                           // thread-column group
+    const int rloc = 2 * lane;                            // this thread's rows inside the tile: rloc, rloc+1, 64+rloc, 65+rloc
+    const int tg = warp;                                  // thread-column group = warp
     const int cglob = tg * CT;                            // first of this thread's CT output columns
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1243,7 +1243,7 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
 #pragma unroll 4
             for (int k = 0; k < nk; ++k) {
                 const double2 a01 = *reinterpret_cast<const double2 *>(xs + (size_t)k * RZ_XS);
-                const double2 a23 = *reinterpret_cast<const double2 *>(xs + (size_t)k * RZ_XS + 2);
+                const double2 a23 = *reinterpret_cast<const double2 *>(xs + (size_t)k * RZ_XS + 64);
                 double b[CTP];
 #pragma unroll
                 for (int j = 0; j < CTP; j += 2) {
@@ -1265,7 +1265,7 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
         if (rowmajor_out) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int64_t r = row0 + i;
+                const int64_t r = row0 + (i & 1) + 64 * (i >> 1);
                 if (r >= n) continue;
 #pragma unroll
                 for (int j = 0; j < CT; ++j) {
@@ -1277,16 +1277,16 @@ ritz_kernel(const double *__restrict__ X, int64_t ld, int64_t n, int work, const
                 }
             }
         } else {
-            // straight from the registers: a thread owns 4 consecutive rows (32 bytes) of each of its columns, the
-            // eight tr-lanes of a warp 256 contiguous bytes.  (A shared-memory staged tile + bulk stores cost two
-            // block barriers per tile: 18 % of the kernel's stall samples.)  Rows in [n, ldo) are padding.
+            // straight from the registers: a thread owns two pairs of consecutive rows (16 bytes each) of each of its
+            // columns, a warp 2 x 512 contiguous bytes.  (A shared-memory staged tile + bulk stores cost two block
+            // barriers per tile: 18 % of the kernel's stall samples.)  Rows in [n, ldo) are padding.
 #pragma unroll
             for (int j = 0; j < CT; ++j) {
                 const int col = cglob + j;
                 if (col < ncols) {
                     double *o = out + (int64_t)col * ldo + row0;
                     if (row0 + 2 <= ldo) *reinterpret_cast<double2 *>(o) = make_double2(acc[0][j], acc[1][j]);
-                    if (row0 + 4 <= ldo) *reinterpret_cast<double2 *>(o + 2) = make_double2(acc[2][j], acc[3][j]);
+                    if (row0 + 66 <= ldo) *reinterpret_cast<double2 *>(o + 64) = make_double2(acc[2][j], acc[3][j]);
                 }
             }
         }
