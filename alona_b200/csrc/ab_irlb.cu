@@ -409,9 +409,10 @@ static constexpr int AV_U_WIDE = 8;
 // fixed latencies of the consume loop double.
 static constexpr int AV_U_SPLIT = 4;
 
-struct AvOperand {                   // halves == 1: [0] is the caller's CSR; halves == 2: the two gene halves of it
+template <class ColT>                // int32_t: the caller's CSR (halves == 1); uint16_t: the gene-split copy (ids < 65536
+struct AvOperand {                   // inside a half: 10 bytes per nonzero instead of 12 for a kernel at 0.78 of its HBM floor)
     const int64_t *rowptr[2];
-    const int32_t *col[2];           // half 1: gene ids rebased by hs
+    const ColT *col[2];              // half 1: gene ids rebased by hs
     const double *val[2];
     int halves, hs;                  // hs: first gene of half 1
 };
@@ -497,9 +498,9 @@ __device__ __forceinline__ void av_consume(AvRowState &r, double *acc, const int
     }
 }
 
-template <int AV_U, int THREADS>
+template <int AV_U, int THREADS, class ColT>
 __global__ void __launch_bounds__(THREADS, 1)
-av_kernel(const AvOperand op, int64_t n, int H, const double *__restrict__ src,
+av_kernel(const AvOperand<ColT> op, int64_t n, int H, const double *__restrict__ src,
           double *__restrict__ scal_fn2 /* scal, or NULL: scale 1 */, double *__restrict__ vdst_all,
           int nwarps_cta /* per gene half */, double *__restrict__ partial /*[grid][H]*/,
           const AbPeer *__restrict__ peer_p, uint32_t seq_fn2) {
@@ -513,7 +514,7 @@ av_kernel(const AvOperand op, int64_t n, int H, const double *__restrict__ src,
         const int half = warp / nwarps_cta, slot = warp - half * nwarps_cta;
         // (selects, not op.x[half]: a dynamically indexed kernel parameter is copied to local memory first)
         const int64_t *__restrict__ rowptr = half ? op.rowptr[1] : op.rowptr[0];
-        const int32_t *__restrict__ col = half ? op.col[1] : op.col[0];
+        const ColT *__restrict__ col = half ? op.col[1] : op.col[0];
         const double *__restrict__ val = half ? op.val[1] : op.val[0];
         double *__restrict__ vdst = half == 0 ? vdst_all : nullptr;   // the new Lanczos vector is stored once
         double *acc = acc_sm + (size_t)warp * Hw;
@@ -524,7 +525,7 @@ av_kernel(const AvOperand op, int64_t n, int H, const double *__restrict__ src,
         if (r0 < r1) {
             const int64_t p0 = rowptr[r0];
             const int len = (int)(rowptr[r1] - p0);              // a warp's share is far below 2^31 nonzeros
-            const int32_t *colw = col + p0;
+            const ColT *colw = col + p0;
             const double *valw = val + p0;
             AvRowState r;
             r.blk = r0;
@@ -540,7 +541,7 @@ av_kernel(const AvOperand op, int64_t n, int H, const double *__restrict__ src,
             for (int u = 0; u < AV_U; ++u) {
                 const int p = 32 * u + lane;
                 const bool ok = p < len;
-                cg[0][u] = ok ? __ldg(colw + p) : 0;
+                cg[0][u] = ok ? (int)__ldg(colw + p) : 0;
                 vv[0][u] = ok ? __ldg(valw + p) : 0.0;
             }
             for (int base2 = 0; base2 < len; base2 += 2 * B) {
@@ -551,7 +552,7 @@ av_kernel(const AvOperand op, int64_t n, int H, const double *__restrict__ src,
                     if (nb + B <= len) {
 #pragma unroll
                         for (int u = 0; u < AV_U; ++u) {
-                            cg[bb ^ 1][u] = __ldg(colw + nb + 32 * u + lane);
+                            cg[bb ^ 1][u] = (int)__ldg(colw + nb + 32 * u + lane);
                             vv[bb ^ 1][u] = __ldg(valw + nb + 32 * u + lane);
                         }
                     } else {
@@ -559,7 +560,7 @@ av_kernel(const AvOperand op, int64_t n, int H, const double *__restrict__ src,
                         for (int u = 0; u < AV_U; ++u) {
                             const int p = nb + 32 * u + lane;
                             const bool ok = p < len;
-                            cg[bb ^ 1][u] = ok ? __ldg(colw + p) : 0;
+                            cg[bb ^ 1][u] = ok ? (int)__ldg(colw + p) : 0;
                             vv[bb ^ 1][u] = ok ? __ldg(valw + p) : 0.0;
                         }
                     }
@@ -608,7 +609,7 @@ ah_split_count_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restr
 __global__ void __launch_bounds__(256)
 ah_split_fill_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const double *__restrict__ val,
                      int64_t n, int hs, const int64_t *__restrict__ rp0 /* n+1, scanned */, int64_t *__restrict__ rp1 /* n+1 */,
-                     int32_t *__restrict__ col2, double *__restrict__ val2) {
+                     uint16_t *__restrict__ col2, double *__restrict__ val2) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nw = (int64_t)gridDim.x * 8;
@@ -624,7 +625,7 @@ ah_split_fill_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restri
             const int c = __ldg(col + p);
             const int64_t i = p - a;
             const int64_t dst = i < c0 ? o0 + i : o1 + (i - c0);
-            col2[dst] = i < c0 ? c : c - hs;
+            col2[dst] = (uint16_t)(i < c0 ? c : c - hs);
             val2[dst] = __ldg(val + p);
         }
     }
@@ -1403,7 +1404,7 @@ struct IrlbCompact {
     double *tabv;
     unsigned int *cursor;
     // gene-split copy of A_H for A.x (ah_split_*_kernel)
-    int32_t *col2;
+    uint16_t *col2;
     double *val2;
     int64_t *rp0, *rp1;
     void *scan;
@@ -1416,7 +1417,7 @@ static size_t irlb_compact_layout(int64_t n, int64_t nnz, void *base, size_t byt
     c.ent = a.take<uint32_t>((size_t)std::max<int64_t>(nnz, 1));
     c.taboff = a.take<uint32_t>((size_t)std::max<int64_t>(n, 1));
     c.cursor = a.take<unsigned int>(4);
-    c.col2 = a.take<int32_t>((size_t)std::max<int64_t>(nnz, 1));
+    c.col2 = a.take<uint16_t>((size_t)std::max<int64_t>(nnz, 1) + 8);
     c.val2 = a.take<double>((size_t)std::max<int64_t>(nnz, 1));
     c.rp0 = a.take<int64_t>((size_t)n + 1);
     c.rp1 = a.take<int64_t>((size_t)n + 1);
@@ -1494,10 +1495,11 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         }
     }
     // A.x operand: the gene-split copy when the workspace tail holds it, the caller's CSR otherwise
-    AvOperand avop{};
+    AvOperand<int32_t> avop{};
     avop.rowptr[0] = rowptr_h; avop.col[0] = col_h; avop.val[0] = val_h; avop.halves = 1; avop.hs = H;
+    AvOperand<uint16_t> avop2{};
     int av_nw = w.av_warps;
-    if (cp.col2 && H >= 64 && av_warps_split(H) >= 1 && !getenv("AB_IRLB_NOSPLIT")) {
+    if (cp.col2 && H >= 64 && av_split_hs(H) <= 65536 && av_warps_split(H) >= 1) {
         const int hs = av_split_hs(H);
         ab_prof_begin(ctx, AB_PROF_IRLB_AV, st);
         ah_split_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowptr_h, col_h, n, hs, cp.rp0);
@@ -1507,15 +1509,15 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         ah_split_fill_kernel<<<g_sp, 256, 0, st>>>(rowptr_h, col_h, val_h, n, hs, cp.rp0, cp.rp1, cp.col2, cp.val2);
         AB_LAUNCH_CHECK(ctx);
         ab_prof_end(ctx, AB_PROF_IRLB_AV, st);
-        avop.rowptr[0] = cp.rp0; avop.rowptr[1] = cp.rp1;
-        avop.col[0] = avop.col[1] = cp.col2;
-        avop.val[0] = avop.val[1] = cp.val2;
-        avop.halves = 2; avop.hs = hs;
+        avop2.rowptr[0] = cp.rp0; avop2.rowptr[1] = cp.rp1;
+        avop2.col[0] = avop2.col[1] = cp.col2;
+        avop2.val[0] = avop2.val[1] = cp.val2;
+        avop2.halves = 2; avop2.hs = hs;
         av_nw = av_warps_split(H);
     }
-    const size_t av_smem = avop.halves == 2 ? (size_t)2 * av_nw * avop.hs * 8 : (size_t)av_nw * H * 8;
-    AB_CUDA(cudaFuncSetAttribute(av_kernel<AV_U_WIDE, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
-    AB_CUDA(cudaFuncSetAttribute(av_kernel<AV_U_SPLIT, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
+    const size_t av_smem = avop2.halves == 2 ? (size_t)2 * av_nw * avop2.hs * 8 : (size_t)av_nw * H * 8;
+    AB_CUDA(cudaFuncSetAttribute(av_kernel<AV_U_WIDE, 384, int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
+    AB_CUDA(cudaFuncSetAttribute(av_kernel<AV_U_SPLIT, 768, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)av_smem));
     // wstep: one cluster of WS_CL CTAs; the W slice is cached in shared memory when it fits
     const int ws_nsp = (H + WS_CL - 1) / WS_CL + 1;
     const int cache_w = ((size_t)ws_nsp * (work + 1)) * 8 <= (size_t)200 * 1024 ? 1 : 0;
@@ -1588,12 +1590,12 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         ab_prof_begin(ctx, AB_PROF_IRLB_AV, st);
         // (A.x keeps the plain operand: its 12 warps per SM leave ~30 KB of L1, a table look-up per nonzero at consume
         // time misses it, and the compact variant measured 344 ms against 195)
-        if (avop.halves == 2)
-            av_kernel<AV_U_SPLIT, 768><<<w.av_grid, 64 * av_nw, av_smem, st>>>(avop, n, H, src, scaled ? w.scal : nullptr, vdst,
-                                                                               av_nw, w.av_partial, peer, seq_fn2);
+        if (avop2.halves == 2)
+            av_kernel<AV_U_SPLIT, 768, uint16_t><<<w.av_grid, 64 * av_nw, av_smem, st>>>(
+                avop2, n, H, src, scaled ? w.scal : nullptr, vdst, av_nw, w.av_partial, peer, seq_fn2);
         else
-            av_kernel<AV_U_WIDE, 384><<<w.av_grid, 384, av_smem, st>>>(avop, n, H, src, scaled ? w.scal : nullptr, vdst,
-                                                                       av_nw, w.av_partial, peer, seq_fn2);
+            av_kernel<AV_U_WIDE, 384, int32_t><<<w.av_grid, 384, av_smem, st>>>(
+                avop, n, H, src, scaled ? w.scal : nullptr, vdst, av_nw, w.av_partial, peer, seq_fn2);
         AB_LAUNCH_CHECK(ctx);
         const uint32_t sv = fused ? ++seq[AB_CH_VEC] : 0;
         av_reduce_kernel<<<(H + 31) / 32, 128, 0, st>>>(w.av_partial, w.av_grid, H, w.wraw, cnt + 3, peer, sv,
