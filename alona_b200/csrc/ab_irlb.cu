@@ -777,7 +777,7 @@ __global__ void fscale_kernel(double *__restrict__ F, int64_t n, double *__restr
 // Outputs: Ub (columns = left vectors), sb (descending), Vb (columns = right vectors),
 // all row-major work x work.  Then residuals / convergence / restart bookkeeping (:225-234).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ Ub, double *__restrict__ sb,
                    double *__restrict__ Vb, double *__restrict__ Gws /* 2*work*work scratch */,
                    double *__restrict__ scal, int *__restrict__ ctrl, double *__restrict__ R, int nu, double tol,
@@ -787,69 +787,92 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
     // bound by one SM's FP64 pipe): V = B^T U diag(1/s) is formed once at the end.  A copy of B sits next
     // to G in shared memory when it fits (q_in_smem), else it is read from global memory.
     extern __shared__ double svd_sm[];
-    double *G = svd_sm;
-    double *Bs = q_in_smem ? svd_sm + (size_t)work * work : Gws + (size_t)work * work;   // row-major copy of B
+    const int m = work;
+    const int mp = (m + 1) & ~1;                        // round-robin needs an even player count
+    const int gs = m | 1;                               // column stride of G: odd, so the four pairs a warp hosts spread over the banks
+    double *G = svd_sm;                                 // [m][gs]
+    double *Bs = q_in_smem ? svd_sm + (size_t)m * gs : Gws + (size_t)work * work;   // row-major copy of B
+    unsigned short *sched = reinterpret_cast<unsigned short *>(svd_sm + (size_t)m * gs + (q_in_smem ? (size_t)m * m : 0));
     __shared__ double nrm[IR_MAXWORK];
     __shared__ double cn[IR_MAXWORK];                   // running squared column norms
     __shared__ int order[IR_MAXWORK];
     __shared__ int rot_sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int m = work;
     for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
         const int r = e % m, c = e / m;
         const double v = B[r * m + c];
-        G[(size_t)c * m + r] = v;
+        G[(size_t)c * gs + r] = v;
         Bs[r * m + c] = v;
     }
+    // pair schedule of a sweep (circle method: player mp-1 fixed, the others rotate), p | q << 8, computed once
+    for (int e = threadIdx.x; e < (mp - 1) * (mp / 2); e += blockDim.x) {
+        const int round = e / (mp / 2), pp = e - round * (mp / 2);
+        const int a = (pp == 0) ? mp - 1 : (round + pp) % (mp - 1);
+        const int b = (round + mp - 1 - pp) % (mp - 1);
+        sched[e] = (unsigned short)(min(a, b) | (max(a, b) << 8));
+    }
     __syncthreads();
-    const int mp = (m + 1) & ~1;                        // round-robin needs an even player count
-    // eight lanes per column pair, so that a whole round (mp/2 <= 64 pairs) is one pass of the 512-thread
-    // CTA: a round costs every warp the same ~150 instructions whatever the number of pairs it hosts, and with
-    // 32 warps (half a warp per pair) instruction issue, not latency, set the round time
+    // One-sided Jacobi is a chain of ~(m-1) x 7.5 dependent rounds; what a round costs is its latency chain
+    //   dot (m/LP FMAs per lane) -> shuffle-reduce -> rotation parameters -> shuffle -> rotate -> barrier.
+    // The CTA is exactly LP lanes per column pair (blockDim = LP * mp/2), so a round is one pass with no idle warps
+    // issuing; ONE lane per pair runs the parameter chain, which is two dependent FP64 rsqrt instead of
+    // sqrt -> divide -> rsqrt:  with r = sqrt(dd^2 + 4 g^2), cos(2 theta) = |dd| / r,  c = sqrt(h), h = (1 + cos 2theta) / 2,
+    // s = sign(dd) g / (r c),  t = s / c:   rs = rsqrt(dd^2 + 4 g^2);  rc = rsqrt(h);  c = h rc;  s = sign g rs rc;  t = s rc.
+    // Measured: 2400 cycles per round (42.6 ms per C3 pass; the form with every lane running a three-operation chain took
+    // 48) against 1900 for svd_cluster_kernel, which spreads the rows over 8 CTAs - the dependent FP64 latencies of the
+    // dot / parameter / rotate chain, not the exchange, are what a round costs, and the cluster shortens the dot and the
+    // rotation.  Kept as the A/B reference (AB_IRLB_SVD1).
     constexpr int LP = 8;                               // lanes per column pair (4 pairs per warp)
-    const int hw = threadIdx.x / LP, hl = threadIdx.x % LP, nhw = blockDim.x / LP;
+    const int pr = threadIdx.x / LP, hl = threadIdx.x % LP;
     for (int sweep = 0; sweep < 60; ++sweep) {
         if (threadIdx.x == 0) rot_sm = 0;
         // refresh the running norms once per sweep (they are updated incrementally inside it)
         for (int c = warp; c < m; c += nwarp) {
             double acc = 0.0;
-            for (int r = lane; r < m; r += 32) acc = fma(G[(size_t)c * m + r], G[(size_t)c * m + r], acc);
+            for (int r = lane; r < m; r += 32) acc = fma(G[(size_t)c * gs + r], G[(size_t)c * gs + r], acc);
             acc = ab_warp_sum_f64(acc);
             if (lane == 0) cn[c] = acc;
         }
         __syncthreads();
         for (int round = 0; round < mp - 1; ++round) {
-            for (int pr0 = 0; pr0 < mp / 2; pr0 += nhw) {
-                const int pr = pr0 + hw;
-                // circle method: player mp-1 fixed, the others rotate
-                const int a = (pr == 0) ? mp - 1 : (round + pr) % (mp - 1);
-                const int b = (round + mp - 1 - pr) % (mp - 1);
-                const int p = min(a, b), q = max(a, b);
-                const bool valid = pr < mp / 2 && q < m;
-                double *gp = G + (size_t)(valid ? p : 0) * m, *gq = G + (size_t)(valid ? q : 0) * m;
-                double ga = 0.0;
-                if (valid)
-                    for (int r = hl; r < m; r += LP) ga = fma(gp[r], gq[r], ga);
+            const unsigned pq = pr < mp / 2 ? sched[round * (mp / 2) + pr] : 0xFFFFu;
+            const int p = pq & 255, q = pq >> 8;
+            const bool valid = pr < mp / 2 && q < m;
+            double *gp = G + (size_t)(valid ? p : 0) * gs, *gq = G + (size_t)(valid ? q : 0) * gs;
+            double g0 = 0.0, g1 = 0.0;
+            if (valid) {
+                int r = hl;
+                for (; r + LP < m; r += 2 * LP) { g0 = fma(gp[r], gq[r], g0); g1 = fma(gp[r + LP], gq[r + LP], g1); }
+                if (r < m) g0 = fma(gp[r], gq[r], g0);
+            }
+            double ga = g0 + g1;
 #pragma unroll
-                for (int o = LP / 2; o > 0; o >>= 1) ga += ab_shfl_xor_f64(ga, o);    // stays inside the lane group
-                const double al = valid ? cn[p] : 1.0, be = valid ? cn[q] : 1.0;
-                // rotate down to rounding level, but call the sweep "dirty" only above 1e-14: pairs
-                // hovering at 1e-15..1e-16 (pure rounding noise) would otherwise keep the loop alive
-                // for all 60 sweeps without changing any singular vector beyond 1e-14
+            for (int o = LP / 2; o > 0; o >>= 1) ga += ab_shfl_xor_f64(ga, o);    // stays inside the lane group
+            double cs = 1.0, sn = 0.0;
+            if (valid && hl == 0) {
+                const double al = cn[p], be = cn[q];
                 const double g2 = ga * ga, ab2 = al * be;
-                if (valid && g2 > 1e-30 * ab2 && fabs(ga) > 1e-300) {
-                    if (hl == 0 && g2 > 1e-28 * ab2) rot_sm = 1;
-                    // tan(theta) of the rotation that zeroes the pair's inner product
-                    // (FP32-seeded Newton variants of this scalar math were measured: same kernel time - the round
-                    // is a latency chain of dot / shuffle-reduce / this / rotate / __syncthreads, ~2700 cycles)
+                // rotate down to rounding level, but call the sweep "dirty" only above 1e-14: pairs hovering at
+                // 1e-15..1e-16 (pure rounding noise) would otherwise keep the loop alive without changing any vector
+                if (g2 > 1e-30 * ab2 && fabs(ga) > 1e-300) {
+                    if (g2 > 1e-28 * ab2) rot_sm = 1;
                     const double dd = be - al;
-                    const double tt = (2.0 * ga) / (dd + (dd >= 0.0 ? 1.0 : -1.0) * sqrt(fma(dd, dd, 4.0 * g2)));
-                    const double cs = rsqrt(fma(tt, tt, 1.0)), sn = cs * tt;
-                    for (int r = hl; r < m; r += LP) {
-                        const double x = gp[r], y = gq[r];
-                        gp[r] = cs * x - sn * y; gq[r] = sn * x + cs * y;
-                    }
-                    if (hl == 0) { cn[p] = al - tt * ga; cn[q] = be + tt * ga; }
+                    const double rs = rsqrt(fma(dd, dd, 4.0 * g2));
+                    const double h = fma(0.5 * fabs(dd), rs, 0.5);
+                    const double rc = rsqrt(h);
+                    cs = h * rc;
+                    sn = (dd >= 0.0 ? ga : -ga) * rs * rc;
+                    const double tg = sn * rc * ga;                 // tan(theta) g
+                    cn[p] = al - tg;
+                    cn[q] = be + tg;
+                }
+            }
+            cs = ab_shfl_f64(cs, (threadIdx.x & 31) & ~(LP - 1));
+            sn = ab_shfl_f64(sn, (threadIdx.x & 31) & ~(LP - 1));
+            if (valid && sn != 0.0) {
+                for (int r = hl; r < m; r += LP) {
+                    const double x = gp[r], y = gq[r];
+                    gp[r] = cs * x - sn * y; gq[r] = sn * x + cs * y;
                 }
             }
             __syncthreads();
@@ -862,7 +885,7 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
     // singular values = column norms; sort descending by counting rank (ties by index)
     for (int c = warp; c < m; c += nwarp) {
         double acc = 0.0;
-        for (int r = lane; r < m; r += 32) acc = fma(G[(size_t)c * m + r], G[(size_t)c * m + r], acc);
+        for (int r = lane; r < m; r += 32) acc = fma(G[(size_t)c * gs + r], G[(size_t)c * gs + r], acc);
         acc = ab_warp_sum_f64(acc);
         if (lane == 0) nrm[c] = sqrt(acc);
     }
@@ -877,10 +900,10 @@ svd_restart_kernel(const double *__restrict__ B, int work, double *__restrict__ 
         const int r = e / m, i = e % m;
         const int c = order[i];
         const double sv = nrm[c];
-        Ub[r * m + i] = sv > 0.0 ? G[(size_t)c * m + r] / sv : 0.0;
+        Ub[r * m + i] = sv > 0.0 ? G[(size_t)c * gs + r] / sv : 0.0;
         // right vector i = B^T u_i / s_i = B^T G[:, c] / s_i^2
         double acc = 0.0;
-        const double *gc = G + (size_t)c * m;
+        const double *gc = G + (size_t)c * gs;
         for (int l = 0; l < m; ++l) acc = fma(Bs[l * m + r], gc[l], acc);
         Vb[r * m + i] = sv > 0.0 ? acc / (sv * sv) : 0.0;
     }
@@ -1523,10 +1546,12 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     const int cache_w = ((size_t)ws_nsp * (work + 1)) * 8 <= (size_t)200 * 1024 ? 1 : 0;
     const size_t ws_smem = (size_t)ws_nsp * (cache_w ? work + 1 : 1) * 8;
     AB_CUDA(cudaFuncSetAttribute(wstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem));
-    const int q_in_smem = (size_t)2 * work * work * 8 <= (size_t)200 * 1024 ? 1 : 0;
-    const size_t svd_smem = (size_t)(q_in_smem ? 2 : 1) * work * work * 8;
+    const int svd_mp = (work + 1) & ~1;
+    const size_t svd_sched = (size_t)(svd_mp - 1) * (svd_mp / 2) * sizeof(unsigned short) + 16;      // pair schedule
+    const int q_in_smem = ((size_t)work * (work | 1) + (size_t)work * work) * 8 + svd_sched <= (size_t)200 * 1024 ? 1 : 0;
+    const size_t svd_smem = ((size_t)work * (work | 1) + (q_in_smem ? (size_t)work * work : 0)) * 8 + svd_sched;
     AB_CUDA(cudaFuncSetAttribute(svd_restart_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svd_smem));
-    const bool svd_one_cta = getenv("AB_IRLB_SVD1") != nullptr;       // A/B switch: the one-CTA Jacobi (round 1)
+    const bool svd_one_cta = getenv("AB_IRLB_SVD1") != nullptr;       // A/B switch: the one-CTA Jacobi (42.6 ms per C3 pass against 32.9)
     const size_t svc_smem = (size_t)(((work + 1) & ~1) - 1) * (((work + 1) & ~1) / 2) * sizeof(unsigned short);   // pair schedule
     AB_CUDA(cudaFuncSetAttribute(svd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)svc_smem));
     auto ritz = [&](const double *X, int64_t ldx, int64_t rows, const double *M, int ncols, double *out, int64_t ldo,
@@ -1660,7 +1685,7 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
         }
         ab_prof_begin(ctx, AB_PROF_IRLB_SVD, st);
         if (svd_one_cta) {
-            svd_restart_kernel<<<1, 512, svd_smem, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it,
+            svd_restart_kernel<<<1, (8 * (svd_mp / 2) + 31) / 32 * 32, svd_smem, st>>>(w.B, work, w.Ub, w.sb, w.Vb, w.G, w.scal, w.ctrl, w.R, nval, tol, it,
                                                          keep, q_in_smem);
         } else {
             cudaLaunchConfig_t cfg{};
