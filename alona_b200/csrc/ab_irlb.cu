@@ -1056,12 +1056,16 @@ svd_cluster_kernel(const double *__restrict__ B, int work, double *__restrict__ 
                 // same thresholds as the one-CTA kernel: rotate down to rounding level, "dirty" only above 1e-14
                 if (g2 > 1e-30 * ab2 && fabs(gs) > 1e-300) {
                     if (g2 > 1e-28 * ab2) rot_sm = 1;
+                    // two dependent rsqrt instead of sqrt -> divide -> rsqrt (see svd_restart_kernel)
                     const double dd = be - al;
-                    const double tt = (2.0 * gs) / (dd + (dd >= 0.0 ? 1.0 : -1.0) * sqrt(fma(dd, dd, 4.0 * g2)));
-                    cs = rsqrt(fma(tt, tt, 1.0));
-                    sn = cs * tt;
-                    cn[p] = al - tt * gs;
-                    cn[q] = be + tt * gs;
+                    const double rs = rsqrt(fma(dd, dd, 4.0 * g2));
+                    const double h = fma(0.5 * fabs(dd), rs, 0.5);
+                    const double rc = rsqrt(h);
+                    cs = h * rc;
+                    sn = (dd >= 0.0 ? gs : -gs) * rs * rc;
+                    const double tg = sn * rc * gs;                 // tan(theta) g
+                    cn[p] = al - tg;
+                    cn[q] = be + tg;
                 }
             }
             cs = ab_shfl_f64(cs, (threadIdx.x & 31) & ~(SV_LP - 1));
