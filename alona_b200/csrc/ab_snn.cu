@@ -735,7 +735,7 @@ static size_t snn_cta_smem(int cap) {
 // Rows with more than PT_LIST kept edges or a partition that overflows its table are handed to the dense kernel
 // (queued in `fallback_rows`), which stays as the any-input safety net.
 // ---------------------------------------------------------------------------------------
-static constexpr int PT_THREADS = 512;
+static constexpr int PT_THREADS = 1024;          // (512 until the walk was cut to one pass per partition with batched reads)
 static constexpr int PT_LIST = 4096;             // kept edges per row the list can hold
 
 template <int SLOTS, int W>
@@ -759,6 +759,8 @@ snn_part_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const
     static_assert(SLOTS == (1 << LG), "table size");
     unsigned long long nz = 0;
     const int n_rows = *n_rows_ptr;
+    for (int s2 = threadIdx.x; s2 < SLOTS; s2 += PT_THREADS) keys[s2] = -1;
+    for (int s2 = threadIdx.x; s2 < SLOTS * W; s2 += PT_THREADS) masks[s2] = 0u;
     for (int q = blockIdx.x; q < n_rows; q += gridDim.x) {
         const int64_t r = rows[q];
         __syncthreads();
@@ -782,75 +784,95 @@ snn_part_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const
         __syncthreads();
         const int walk = st.walk, C = st.chunks;
         unsigned long long nz_row = 0;
-        const int P = (walk + SLOTS / 2 - 1) / (SLOTS / 2);           // expected load factor <= 1/2 per partition
-        for (int part = 0; part < P; ++part) {
-            for (int s2 = threadIdx.x; s2 < SLOTS; s2 += PT_THREADS) keys[s2] = -1;
-            for (int s2 = threadIdx.x; s2 < SLOTS * W; s2 += PT_THREADS) masks[s2] = 0u;
+        // partitions sized for a load factor <= 0.7 even if every walk entry were a distinct cell (they are not)
+        constexpr int PCAP = SLOTS / 10 * 7;
+        const unsigned P = (unsigned)((walk + PCAP - 1) / PCAP);
+        for (unsigned part = 0; part < P; ++part) {
+            // (the table is clean here: cleared once at kernel start, then by the scan below as it reads the slots)
             if (threadIdx.x == 0) nins_sm = 0;
             __syncthreads();
-            // ---- insert the walk entries of this partition ----
-            for (int c = warp; c < C; c += NW) {
-                int lo = 0, hi = k;                                    // list a with chunk0[a] <= c
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (st.chunk0[mid] <= c) lo = mid; else hi = mid;
-                }
-                const int a = lo, t = ((c - st.chunk0[a]) << 5) + lane;
-                const int len = st.w.base[a + 1] - st.w.base[a];
-                if (t < len) {
-                    const int m = __ldg(rlist + st.w.start[a] + t);
-                    const unsigned h = (unsigned)m * 2654435761u;
-                    if ((int)((h >> 7) % (unsigned)P) == part) {
-                        unsigned s2 = h >> (32 - LG);
-                        int probes = 0;
-                        while (true) {
-                            const int prev = atomicCAS(keys + s2, -1, m);
-                            if (prev == -1) { atomicAdd(&nins_sm, 1); break; }
-                            if (prev == m) break;
-                            s2 = (s2 + 1) & (SLOTS - 1);
-                            if (++probes >= SLOTS) { bad_sm = 1; break; }      // table full: hand the row over
+            // ---- insert the walk entries of this partition: PF chunks of reverse-list reads in flight per warp ----
+            constexpr int PF = 4;
+            for (int c0 = warp; c0 < C; c0 += NW * PF) {
+                int mm[PF], aa[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const int c = c0 + u * NW;
+                    mm[u] = -1; aa[u] = 0;
+                    if (c < C) {
+                        int lo = 0, hi = k;                            // list a with chunk0[a] <= c
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (st.chunk0[mid] <= c) lo = mid; else hi = mid;
                         }
-                        if (probes < SLOTS) atomicOr(masks + (size_t)s2 * W + (a >> 5), 1u << (a & 31));
+                        const int t = ((c - st.chunk0[lo]) << 5) + lane;
+                        aa[u] = lo;
+                        if (t < st.w.base[lo + 1] - st.w.base[lo]) mm[u] = __ldg(rlist + st.w.start[lo] + t);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const int m = mm[u], a = aa[u];
+                    if (m < 0) continue;
+                    const unsigned h = (unsigned)m * 2654435761u;
+                    // partition from the LOW bits, slot from the high bits (a partition taken from the high bits would
+                    // squeeze its keys into 1/P of the slots); multiply-shift, no integer division per entry
+                    if ((((h & 0x3FFFFu) * P) >> 18) != part) continue;
+                    unsigned s2 = h >> (32 - LG);
+                    int probes = 0;
+                    while (true) {
+                        const int prev = atomicCAS(keys + s2, -1, m);
+                        if (prev == -1) { atomicAdd(&nins_sm, 1); break; }
+                        if (prev == m) break;
+                        s2 = (s2 + 1) & (SLOTS - 1);
+                        if (++probes >= SLOTS) { bad_sm = 1; break; }      // table full: hand the row over
+                    }
+                    if (probes < SLOTS) atomicOr(masks + (size_t)s2 * W + (a >> 5), 1u << (a & 31));
+                }
+            }
+            __syncthreads();
+            const bool bad = bad_sm || nins_sm > SLOTS - SLOTS / 8;
+            // ---- read the table off (and clear it): every occupied slot is a first encounter; the kept ones are listed
+            // with the neighbour index of their first encounter, the position inside that list is resolved below ----
+            for (int s2 = threadIdx.x; s2 < SLOTS; s2 += PT_THREADS) {
+                const int m = keys[s2];
+                if (m == -1) continue;
+                int pc = 0, first = -1;
+#pragma unroll
+                for (int w2 = 0; w2 < W; ++w2) {
+                    const unsigned mk = masks[(size_t)s2 * W + w2];
+                    if (first < 0 && mk) first = 32 * w2 + __ffs(mk) - 1;
+                    pc += __popc(mk);
+                    masks[(size_t)s2 * W + w2] = 0u;
+                }
+                keys[s2] = -1;
+                if (bad) continue;
+                ++nz_row;
+                if (pc >= v_min) {
+                    const int slot = atomicAdd(&nkept_sm, 1);
+                    if (slot < PT_LIST) {
+                        list[slot] = ((unsigned long long)(unsigned)first << 32) | (unsigned)m;
+                        list_ov[slot] = (uint8_t)min(pc, 255);
                     }
                 }
             }
             __syncthreads();
-            if (bad_sm || nins_sm > SLOTS - SLOTS / 8) { if (threadIdx.x == 0) bad_sm = 1; __syncthreads(); break; }
-            // ---- first encounters of this partition: count, and list the kept ones with their walk position ----
-            for (int c = warp; c < C; c += NW) {
-                int lo = 0, hi = k;
-                while (hi - lo > 1) {
+            if (bad) { if (threadIdx.x == 0) bad_sm = 1; __syncthreads(); break; }
+        }
+        if (!bad_sm && nkept_sm <= PT_LIST) {
+            // walk position of every kept cell: binary search in the (sorted) reverse list of its first neighbour;
+            // key = (walk position + 1, cell): positions are distinct, padding keys are 0
+            const int nk0 = nkept_sm;
+            for (int i = threadIdx.x; i < nk0; i += PT_THREADS) {
+                const unsigned long long e = list[i];
+                const int a = (int)(e >> 32), m = (int)(unsigned)(e & 0xFFFFFFFFull);
+                const int32_t *__restrict__ L = rlist + st.w.start[a];
+                int lo = 0, hi = st.w.base[a + 1] - st.w.base[a];
+                while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (st.chunk0[mid] <= c) lo = mid; else hi = mid;
+                    if (__ldg(L + mid) < m) lo = mid + 1; else hi = mid;
                 }
-                const int a = lo, t = ((c - st.chunk0[a]) << 5) + lane;
-                const int len = st.w.base[a + 1] - st.w.base[a];
-                if (t < len) {
-                    const int m = __ldg(rlist + st.w.start[a] + t);
-                    const unsigned h = (unsigned)m * 2654435761u;
-                    if ((int)((h >> 7) % (unsigned)P) == part) {
-                        unsigned s2 = h >> (32 - LG);
-                        while (keys[s2] != m) s2 = (s2 + 1) & (SLOTS - 1);
-                        int pc = 0, first = -1;
-#pragma unroll
-                        for (int w2 = 0; w2 < W; ++w2) {
-                            const unsigned mk = masks[(size_t)s2 * W + w2];
-                            if (first < 0 && mk) first = 32 * w2 + __ffs(mk) - 1;
-                            pc += __popc(mk);
-                        }
-                        if (first == a) {
-                            ++nz_row;
-                            if (pc >= v_min) {
-                                const int slot = atomicAdd(&nkept_sm, 1);
-                                if (slot < PT_LIST) {
-                                    // key = (walk position + 1, cell): positions are distinct, padding keys are 0
-                                    list[slot] = ((unsigned long long)(unsigned)(st.w.base[a] + t + 1) << 32) | (unsigned)m;
-                                    list_ov[slot] = (uint8_t)min(pc, 255);
-                                }
-                            }
-                        }
-                    }
-                }
+                list[i] = ((unsigned long long)(unsigned)(st.w.base[a] + lo + 1) << 32) | (unsigned)m;
             }
             __syncthreads();
         }
