@@ -450,7 +450,7 @@ struct CtaRowStateT {            // KM = 32 W in the table kernels (k <= 32 take
 using CtaRowState = CtaRowStateT<SNN_MAXK>;
 
 template <int SLOTS, int W, int THREADS, bool FILL>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? (W == 1 ? 6 : 2) : (W == 1 ? 3 : 1))
+__global__ void __launch_bounds__(THREADS, W == 1 ? (THREADS == 256 ? 6 : THREADS == 512 ? 3 : 1) : (THREADS == 256 ? 2 : 1))
 snn_cta_kernel(const int32_t *__restrict__ knn, int k, int64_t row_begin, const int32_t *__restrict__ rows,
                const int *__restrict__ n_rows_ptr, const int64_t *__restrict__ rptr,
                const int32_t *__restrict__ rlist, int v_min, int64_t *__restrict__ rowcount,
@@ -1149,7 +1149,7 @@ static int snn_launch_tables(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_all
     if (k <= 32) {
         AB_SNN_CTA(SNN_MID_SLOTS, 1, SNN_MID_THREADS, rows1, ncls + 1, 6);
         AB_SNN_CTA(8192, 1, SNN_LARGE_THREADS, rows2, ncls + 2, 3);
-        AB_SNN_CTA(16384, 1, SNN_LARGE_THREADS, rows3, ncls + 3, 1);
+        AB_SNN_CTA(16384, 1, 1024, rows3, ncls + 3, 1);             // one CTA per SM: all the warps an SM takes
     } else {
         AB_SNN_CTA(SNN_MID_SLOTS, 4, SNN_MID_THREADS, rows1, ncls + 1, 2);
         AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows2, ncls + 2, 1);     // (class 3 stays empty: lim3 == lim2)
@@ -1167,7 +1167,7 @@ static int snn_launch_overflow(ab_ctx *ctx, const SnnWs &w, const int32_t *knn_a
     int64_t *rowcount = nullptr;
     const int cap = 0;
     unsigned long long *nz = nullptr;
-    if (k <= 32) AB_SNN_CTA(16384, 1, SNN_LARGE_THREADS, rows, nptr, 1);
+    if (k <= 32) AB_SNN_CTA(16384, 1, 1024, rows, nptr, 1);
     else AB_SNN_CTA(8192, 4, SNN_LARGE_THREADS, rows, nptr, 1);
 #undef AB_SNN_CTA
     return 0;
