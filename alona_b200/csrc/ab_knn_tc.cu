@@ -357,7 +357,31 @@ struct TcParams {
     const unsigned char *bop;   // tiled, pre-swizzled B operand (knn_b_pos)
     unsigned long long *bufg;   // [grid][TC_BUF][256] append buffers
     int *cursor;                // tile CTA 0 is currently loading: the other CTAs start their sweeps there
+    // Work items of a CTA: `full` whole sweeps (query block blockIdx.x + i * gridDim.x against every tile), then at most one
+    // item of the TAIL round.  The R query blocks left over when the blocks do not divide by the grid would keep R SMs busy
+    // for a whole sweep while the others idle (163,265 queries per rank at 8 GPUs: 4.31 rounds cost 5); instead each of
+    // them is swept by S CTAs, a contiguous S-th of the tiles each, into S separate candidate lists (cand_tail) that
+    // knn_tail_merge_kernel folds into the block's ordinary list afterwards.
+    int full, R, S;
+    unsigned long long *cand_tail;   // [S * lists][R * q_per_block][m]
 };
+
+struct TcItem { int64_t qb; int tbeg, tcnt, part, tail; };
+__device__ __forceinline__ bool tc_item(const TcParams &P, int i, int n_tiles, TcItem &o) {
+    if (i < P.full) {
+        o.qb = blockIdx.x + (int64_t)i * gridDim.x; o.tbeg = 0; o.tcnt = n_tiles; o.part = 0; o.tail = 0;
+        return true;
+    }
+    if (i == P.full && (int)blockIdx.x < P.R * P.S) {
+        const int j = (int)blockIdx.x / P.S, part = (int)blockIdx.x - j * P.S;
+        o.qb = (int64_t)P.full * gridDim.x + j;
+        o.tbeg = (int)((int64_t)part * n_tiles / P.S);
+        o.tcnt = (int)((int64_t)(part + 1) * n_tiles / P.S) - o.tbeg;
+        o.part = part; o.tail = P.S > 1;
+        return true;
+    }
+    return false;
+}
 
 // 32-wide bitonic sort across the warp, descending (lane 0 ends with the largest key)
 __device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long v, int lane) {
@@ -448,9 +472,8 @@ __device__ __noinline__ float warp_prune_t(unsigned lanes, unsigned long long *c
 }
 
 // prunes the lanes in `lanes` (warp-uniform mask), updating their (cnt, tau)
-__device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, int list_id, long long q_lane, int &cnt,
+__device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, unsigned long long *cg, long long q_lane, int &cnt,
                                            float &tau, unsigned long long *bufp, int lane) {
-    unsigned long long *cg = P.cand + (size_t)list_id * P.nq * P.m;
     float t;
     switch (P.m) {
         case 32: t = warp_prune_t<1>(lanes, cg, q_lane, cnt, bufp, lane); break;
@@ -466,7 +489,7 @@ __device__ __forceinline__ void warp_prune(unsigned lanes, const TcParams &P, in
 // lane's threshold are scanned, hits go straight to the lane's append buffer (room for a whole
 // group is guaranteed beforehand; lanes short of room are pruned first, which also tightens
 // their threshold).  Padding columns carry a huge score (see knn_prep_kernel) and never pass.
-__device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, bool live, const TcParams &P, int list_id,
+__device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, bool live, const TcParams &P, unsigned long long *cg,
                                          long long q, int &cnt, float &tau, unsigned long long *bufp, int lane) {
     constexpr int NG = 32 / TC_GRP;
     float gmin[NG];
@@ -493,7 +516,7 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, boo
     // certificate is unchanged - every point outside the listed groups scores >= its group's minimum >= tau - and
     // the re-rank expands the listed groups to their points.
     const unsigned tight = __ballot_sync(AB_FULL, cnt > TC_BUF - NG);
-    if (tight) warp_prune(tight, P, list_id, q, cnt, tau, bufp, lane);
+    if (tight) warp_prune(tight, P, cg, q, cnt, tau, bufp, lane);
     if (live && mn < tau) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -532,10 +555,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_per_block = TC_TILE * P.mt;
     const int x_per_tile = TC_TILE * (3 - P.mt);
-    const int64_t n_qblocks = (P.nq + q_per_block - 1) / q_per_block;
-    const int64_t n_tiles = (P.n_total + x_per_tile - 1) / x_per_tile;
-    const int64_t my_blocks = n_qblocks > blockIdx.x ? (n_qblocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t my_tiles = my_blocks * n_tiles;   // global tile counter `it` runs over [0, my_tiles)
+    const int n_tiles = (int)((P.n_total + x_per_tile - 1) / x_per_tile);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -558,7 +578,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
         int stage = 0;
         uint32_t phase = 0, aphase = 0;
-        for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+        TcItem item;
+        for (int ii = 0; tc_item(P, ii, n_tiles, item); ++ii) {
+            const int64_t qb = item.qb;
             mbar_wait(a_empty, aphase ^ 1);
             const int qrow = (int)(P.q_begin + qb * q_per_block);
             if (elect_one()) {
@@ -572,15 +594,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             // and the other CTAs start their sweeps there.  CTAs drift apart (a few per cent per sweep); without
             // this they end up streaming different parts of an operand array that is larger than L2 (measured:
             // 370 GB of DRAM reads at C3 for 14 GB of ideal traffic), with it the pack stays inside an L2 window.
-            int s0 = blockIdx.x == 0 ? 0 : *reinterpret_cast<volatile int *>(P.cursor);
+            // (an item of the tail round covers its own part of the tiles, front to back)
+            int s0 = (blockIdx.x == 0 || item.tail) ? item.tbeg : *reinterpret_cast<volatile int *>(P.cursor);
             if (s0 < 0 || s0 >= n_tiles) s0 = 0;
             s0 = __shfl_sync(AB_FULL, s0, 0);
-            if (lane == 0) { sweep_start[((qb - blockIdx.x) / gridDim.x) & 7] = s0; __threadfence_block(); }
+            if (lane == 0) { sweep_start[ii & 7] = s0; __threadfence_block(); }
             __syncwarp();
-            for (int64_t ti = 0; ti < n_tiles; ++ti) {
+            for (int ti = 0; ti < item.tcnt; ++ti) {
                 int64_t t = s0 + ti;
                 if (t >= n_tiles) t -= n_tiles;
-                if (blockIdx.x == 0 && lane == 0 && (ti & 7) == 0) *reinterpret_cast<volatile int *>(P.cursor) = (int)t;
+                if (blockIdx.x == 0 && lane == 0 && (ti & 7) == 0 && !item.tail) *reinterpret_cast<volatile int *>(P.cursor) = (int)t;
                 // slabs of this tile: one (mt = 2) or two (mt = 1) blocks of `chunks` x 8 KB
                 const unsigned char *slab0 = P.bop + (size_t)t * (3 - P.mt) * P.chunks * TC_SLAB;
                 // one ring slot = `group` consecutive K chunks of the tile = ONE contiguous bulk copy and ONE
@@ -622,10 +645,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         if (P.split) {
             // One ring slot per tile; all K steps of half 0 (query tile 0, or the first 128 points of a wide tile),
             // commit, then all K steps of half 1, commit.  Each half has its own ready/released barrier pair.
-            for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+            TcItem item;
+            for (int ii = 0; tc_item(P, ii, n_tiles, item); ++ii) {
                 mbar_wait(a_full, aphase);
                 aphase ^= 1;
-                for (int64_t t = 0; t < n_tiles; ++t, ++it) {
+                for (int t = 0; t < item.tcnt; ++t, ++it) {
                     const int buf = (int)(it & 1);
                     const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
                     const uint32_t eph = (uint32_t)(((it >> 1) & 1) ^ 1);
@@ -658,11 +682,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
                 __syncwarp();
                 ++nblocks_done;
             }
-        } else
-        for (int64_t qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+        } else {
+        TcItem item;
+        for (int ii = 0; tc_item(P, ii, n_tiles, item); ++ii) {
             mbar_wait(a_full, aphase);
             aphase ^= 1;
-            for (int64_t t = 0; t < n_tiles; ++t, ++it) {
+            for (int t = 0; t < item.tcnt; ++t, ++it) {
                 const int buf = (int)(it & 1);
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256;
                 for (int c0 = 0; c0 < P.chunks; c0 += P.group) {
@@ -695,6 +720,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
             __syncwarp();
             ++nblocks_done;
         }
+        }
         // do not let the CTA retire with a tcgen05.commit arrive still in flight
         if (nblocks_done > 0) mbar_wait(a_empty, (uint32_t)((nblocks_done - 1) & 1));
     } else {
@@ -707,57 +733,95 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const TcParams P) {
         const int list_id = P.mt == 1 ? half : 0;
         unsigned long long *bufp = P.bufg + (size_t)blockIdx.x * TC_BUF * TC_EPI_THREADS + etid;   // entry e at bufp[e * 256]
         const uint32_t taddr0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)half * TC_TILE;
-        int64_t cur_block = -1;
-        int sweep0 = 0;
-        long long q = 0;
-        bool live = false;
-        float tau = INFINITY;
-        int cnt = 0;
-        for (int64_t it = 0; it < my_tiles; ++it) {
-            const int64_t blk = it / n_tiles, ti = it - blk * n_tiles;
-            const int buf = (int)(it & 1);
-            const bool new_block = blk != cur_block;
-            if (blk != cur_block) {
-                if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufp, lane);
-                cur_block = blk;
-                q = (blockIdx.x + blk * gridDim.x) * q_per_block + (P.mt == 2 ? half * TC_TILE : 0) + row;
-                live = q < P.nq;
-                tau = INFINITY;
-                cnt = 0;
+        int64_t it = 0;                                         // tiles of this CTA so far: accumulator buffer = it & 1
+        TcItem item;
+        for (int ii = 0; tc_item(P, ii, n_tiles, item); ++ii) {
+            const long long qg = item.qb * q_per_block + (P.mt == 2 ? half * TC_TILE : 0) + row;    // query (row of the range)
+            const bool live = qg < P.nq;
+            // candidate list of this thread: the query's ordinary list, or - tail round - the list of this item's part
+            unsigned long long *cg;
+            long long q;
+            if (item.tail) {
+                const long long tail_rows = (long long)P.R * q_per_block;
+                cg = P.cand_tail + (size_t)(item.part * (3 - P.mt) + list_id) * tail_rows * P.m;
+                q = qg - (long long)P.full * gridDim.x * q_per_block;
+            } else {
+                cg = P.cand + (size_t)list_id * P.nq * P.m;
+                q = qg;
             }
-            mbar_wait(P.split ? h_full + buf * 2 + half : t_full + buf, (uint32_t)((it >> 1) & 1));   // (one poller per warp + __syncwarp measured slower)
-            tc_fence_after();
-            if (new_block) sweep0 = sweep_start[blk & 7];           // published by the producer before this block's first load
-            int64_t t = sweep0 + ti;
-            if (t >= n_tiles) t -= n_tiles;
-            const int64_t col0 = t * x_per_tile + (P.mt == 1 ? half * TC_TILE : 0);
-            const uint32_t taddr = taddr0 + (uint32_t)buf * 256;
-            uint32_t ra[32];
+            float tau = INFINITY;
+            int cnt = 0;
+            int sweep0 = 0;
+            for (int ti = 0; ti < item.tcnt; ++ti, ++it) {
+                const int buf = (int)(it & 1);
+                mbar_wait(P.split ? h_full + buf * 2 + half : t_full + buf, (uint32_t)((it >> 1) & 1));   // (one poller per warp + __syncwarp measured slower)
+                tc_fence_after();
+                if (ti == 0) sweep0 = sweep_start[ii & 7];          // published by the producer before this item's first load
+                int64_t t = sweep0 + ti;
+                if (t >= n_tiles) t -= n_tiles;
+                const int64_t col0 = t * x_per_tile + (P.mt == 1 ? half * TC_TILE : 0);
+                const uint32_t taddr = taddr0 + (uint32_t)buf * 256;
+                uint32_t ra[32];
 #pragma unroll 1
-            for (int cc = 0; cc < TC_TILE / 32; ++cc) {
-                // one unit per load/wait: a single instantiation of the scan keeps the hot loop small enough for
-                // the instruction cache (two inlined copies cost 19 % of the cycles in no-instruction stalls);
-                // the other epilogue warp of the scheduler covers the tcgen05.ld latency
-                tc_ld32(taddr + cc * 32, ra);
-                tc_wait_ld();
-                tc_touch32(ra);
-                epi_unit(ra, (int)col0 + cc * 32, live, P, list_id, q, cnt, tau, bufp, lane);
+                for (int cc = 0; cc < TC_TILE / 32; ++cc) {
+                    // one unit per load/wait: a single instantiation of the scan keeps the hot loop small enough for
+                    // the instruction cache (two inlined copies cost 19 % of the cycles in no-instruction stalls);
+                    // the other epilogue warp of the scheduler covers the tcgen05.ld latency
+                    tc_ld32(taddr + cc * 32, ra);
+                    tc_wait_ld();
+                    tc_touch32(ra);
+                    epi_unit(ra, (int)col0 + cc * 32, live, P, cg, q, cnt, tau, bufp, lane);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(P.split ? h_empty + buf * 2 + half : t_empty + buf);
+                // prune AFTER handing the accumulator back: the merge (two L2 round trips + a bitonic network)
+                // then overlaps the MMAs of the next tiles instead of sitting on the MMA->epilogue handoff
+                const unsigned due = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
+                if (due) warp_prune(due, P, cg, q, cnt, tau, bufp, lane);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(P.split ? h_empty + buf * 2 + half : t_empty + buf);
-            // prune AFTER handing the accumulator back: the merge (two L2 round trips + a bitonic network)
-            // then overlaps the MMAs of the next tiles instead of sitting on the MMA->epilogue handoff
-            const unsigned due = __ballot_sync(AB_FULL, cnt > TC_BUF - 8);
-            if (due) warp_prune(due, P, list_id, q, cnt, tau, bufp, lane);
+            warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, cg, q, cnt, tau, bufp, lane);
         }
-        if (cur_block >= 0) warp_prune(__ballot_sync(AB_FULL, cnt > 0), P, list_id, q, cnt, tau, bufp, lane);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Tail round: fold the S part lists of a query into its ordinary list (m smallest keys of their union, sorted).
+// Valid for the certificate: a point outside every part list scores >= that part's m-th key >= the m-th key of the
+// union.  One warp per (tail query, list); every key finds its rank by binary searches in the other (sorted) parts.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+knn_tail_merge_kernel(const unsigned long long *__restrict__ cand_tail, int S, int lists, int64_t tail_rows, int m,
+                      int64_t q0, int64_t nq, unsigned long long *__restrict__ cand) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= tail_rows * lists) return;
+    const int64_t r = w / lists;
+    const int l = (int)(w - r * lists);
+    const int64_t q = q0 + r;
+    if (q >= nq) return;
+    for (int e = lane; e < S * m; e += 32) {
+        const int sp = e / m, j = e - sp * m;
+        const unsigned long long key = cand_tail[((size_t)(sp * lists + l) * tail_rows + r) * m + j];
+        int rank = j;
+        for (int o = 0; o < S; ++o) {
+            if (o == sp) continue;
+            const unsigned long long *L = cand_tail + ((size_t)(o * lists + l) * tail_rows + r) * m;
+            int lo = 0, hi = m;                        // keys of part o that sort before `key` (ties: the lower part first)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const unsigned long long v = L[mid];
+                if (v < key || (v == key && o < sp)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < m) cand[((size_t)l * nq + q) * m + rank] = key;
     }
 }
 
@@ -950,7 +1014,7 @@ static int tc_mt(int d) { return tc_kt(d) * 2 * 256 <= 112 * 1024 ? 2 : 1; }
 struct TcWs {
     double *mean, *partial, *qn, *qh2, *qdel;
     __half *aop, *bop;
-    unsigned long long *cand;
+    unsigned long long *cand, *cand_tail;
     int64_t *fb_list;
     unsigned int *scal;      // [0] rmax bits, [1] relerr bits
     unsigned long long *bufg; // append buffers of the main kernel: [<=256 CTAs][TC_BUF][256]
@@ -970,6 +1034,8 @@ static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t by
     w.qh2 = a.take<double>(n);
     w.qdel = a.take<double>(n);
     w.cand = a.take<unsigned long long>((size_t)2 * nq * m);
+    // part lists of the tail round (TcParams): at most 4 lists for at most half a grid of 256-query blocks
+    w.cand_tail = a.take<unsigned long long>((size_t)4 * std::min<int64_t>((nq + 255) / 256 * 256, 128 * 256) * m);
     w.fb_list = a.take<int64_t>((size_t)2 * nq);
     w.scal = a.take<unsigned int>(4);
     w.bufg = a.take<unsigned long long>((size_t)256 * TC_BUF * TC_EPI_THREADS);
@@ -1059,10 +1125,26 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     P.split = group == chunks ? 1 : 0;
     P.cursor = (int *)(w.scal + 2); P.mt = mt; P.m = m; P.cand = w.cand; P.bop = (const unsigned char *)w.bop;
     const int64_t n_qblocks = (nq + TC_TILE * mt - 1) / (TC_TILE * mt);
-    const unsigned grid = (unsigned)std::min<int64_t>(n_qblocks, ctx->sm_count);
+    const int64_t n_tiles = (n_total + TC_TILE * (3 - mt) - 1) / (TC_TILE * (3 - mt));
+    // work items: whole sweeps, then a tail round whose R blocks are swept by S CTAs each (see TcParams)
+    const int sms = std::min(ctx->sm_count, 256);
+    P.full = (int)(n_qblocks / sms);
+    P.R = (int)(n_qblocks - (int64_t)P.full * sms);
+    P.S = 1;
+    if (P.R > 0) P.S = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(sms / P.R, 4 / lists), n_tiles));
+    const unsigned grid = (unsigned)(P.full > 0 ? sms : P.R * P.S);
+    const int64_t tail_rows = (int64_t)P.R * TC_TILE * mt;
+    P.cand_tail = w.cand_tail;
+    if (P.S > 1)
+        AB_CUDA(cudaMemsetAsync(w.cand_tail, 0xFF, (size_t)P.S * lists * tail_rows * m * sizeof(unsigned long long), st));
     ab_prof_begin(ctx, AB_PROF_KNN_MAIN, st);
     knn_tc_kernel<<<grid, TC_NTHREADS, smem, st>>>(map_a, P);
     AB_LAUNCH_CHECK(ctx);
+    if (P.S > 1) {
+        knn_tail_merge_kernel<<<(unsigned)((tail_rows * lists + 7) / 8), 256, 0, st>>>(
+            w.cand_tail, P.S, lists, tail_rows, m, (int64_t)P.full * grid * TC_TILE * mt, nq, w.cand);
+        AB_LAUNCH_CHECK(ctx);
+    }
     ab_prof_end(ctx, AB_PROF_KNN_MAIN, st);
     // ---- exact re-rank + certificate ----
     ab_prof_begin(ctx, AB_PROF_KNN_RERANK, st);
