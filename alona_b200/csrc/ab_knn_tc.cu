@@ -357,11 +357,12 @@ struct TcParams {
     const unsigned char *bop;   // tiled, pre-swizzled B operand (knn_b_pos)
     unsigned long long *bufg;   // [grid][TC_BUF][256] append buffers
     int *cursor;                // tile CTA 0 is currently loading: the other CTAs start their sweeps there
-    // Work items of a CTA: `full` whole sweeps (query block blockIdx.x + i * gridDim.x against every tile), then at most one
-    // item of the TAIL round.  The R query blocks left over when the blocks do not divide by the grid would keep R SMs busy
+    // Work items of a CTA: `full` whole sweeps (query block blockIdx.x + i * gridDim.x against every tile), then the items
+    // of the TAIL phase.  The query blocks left over when the blocks do not divide by the grid would keep a few SMs busy
     // for a whole sweep while the others idle (163,265 queries per rank at 8 GPUs: 4.31 rounds cost 5); instead each of
-    // them is swept by S CTAs, a contiguous S-th of the tiles each, into S separate candidate lists (cand_tail) that
-    // knn_tail_merge_kernel folds into the block's ordinary list afterwards.
+    // the R tail blocks is cut into S parts, a contiguous S-th of the tiles each, the R * S parts are dealt round-robin
+    // over the CTAs, and every part fills its own candidate list (cand_tail) that knn_tail_merge_kernel folds into the
+    // block's ordinary list afterwards.  The host picks (full, R, S) for the shortest schedule (tc_schedule).
     int full, R, S;
     unsigned long long *cand_tail;   // [S * lists][R * q_per_block][m]
 };
@@ -372,8 +373,9 @@ __device__ __forceinline__ bool tc_item(const TcParams &P, int i, int n_tiles, T
         o.qb = blockIdx.x + (int64_t)i * gridDim.x; o.tbeg = 0; o.tcnt = n_tiles; o.part = 0; o.tail = 0;
         return true;
     }
-    if (i == P.full && (int)blockIdx.x < P.R * P.S) {
-        const int j = (int)blockIdx.x / P.S, part = (int)blockIdx.x - j * P.S;
+    const int64_t pi = blockIdx.x + (int64_t)(i - P.full) * gridDim.x;           // part item of the tail phase
+    if (pi < (int64_t)P.R * P.S) {
+        const int j = (int)(pi / P.S), part = (int)(pi - (int64_t)j * P.S);
         o.qb = (int64_t)P.full * gridDim.x + j;
         o.tbeg = (int)((int64_t)part * n_tiles / P.S);
         o.tcnt = (int)((int64_t)(part + 1) * n_tiles / P.S) - o.tbeg;
@@ -1005,6 +1007,24 @@ static int tc_candidates(int k) {
     return std::min(m, 256);
 }
 static int64_t tc_pad(int64_t n) { return (n + 255) / 256 * 256; }
+// Schedule of `blocks` query blocks on `sms` persistent CTAs (TcParams): `full` whole rounds, then R tail blocks in S
+// parts each, dealt round-robin.  Cost in sweeps = full + ceil(R S / grid) / S; the tail may take over the last whole
+// round (R up to 2 sms - 1) when that balances better (1,276 blocks on 148 SMs: 8.62 rounds of work cost 9 as whole
+// rounds, 8.67 with the last two rounds cut in thirds).
+static void tc_schedule(int64_t blocks, int sms, int smax, int *full, int *R, int *S) {
+    double best = 1e300;
+    *full = 0; *R = 0; *S = 1;
+    for (int pull = 0; pull < 2; ++pull) {
+        const int64_t f = blocks / sms - pull;
+        if (f < 0) break;
+        const int64_t r = blocks - f * sms;
+        for (int s = 1; s <= std::max(1, smax); ++s) {
+            const int64_t grid = f > 0 ? sms : std::min<int64_t>(sms, std::max<int64_t>(1, r * s));
+            const double cost = (double)f + (r > 0 ? (double)((r * s + grid - 1) / grid) / s : 0.0) + 1e-3 * s + 1e-3 * pull;
+            if (cost < best - 1e-9) { best = cost; *full = (int)f; *R = (int)r; *S = s; }
+        }
+    }
+}
 static int tc_kt(int d) { return (TC_NPROD * d + 3 + TC_KCH - 1) / TC_KCH * TC_KCH; }
 // two resident query tiles when their A operand (256 rows x kt halves) leaves room for the B ring
 // (at d = 100 the two tiles take 112 KB and leave three ring slots of 32 KB: measured on 200,000 cells x 100 dims, k = 30:
@@ -1034,8 +1054,8 @@ static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t by
     w.qh2 = a.take<double>(n);
     w.qdel = a.take<double>(n);
     w.cand = a.take<unsigned long long>((size_t)2 * nq * m);
-    // part lists of the tail round (TcParams): at most 4 lists for at most half a grid of 256-query blocks
-    w.cand_tail = a.take<unsigned long long>((size_t)4 * std::min<int64_t>((nq + 255) / 256 * 256, 128 * 256) * m);
+    // part lists of the tail phase (TcParams): at most 4 lists for at most two grids of 256-query blocks
+    w.cand_tail = a.take<unsigned long long>((size_t)4 * std::min<int64_t>((nq + 255) / 256 * 256, 2 * 256 * 256) * m);
     w.fb_list = a.take<int64_t>((size_t)2 * nq);
     w.scal = a.take<unsigned int>(4);
     w.bufg = a.take<unsigned long long>((size_t)256 * TC_BUF * TC_EPI_THREADS);
@@ -1128,11 +1148,8 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     const int64_t n_tiles = (n_total + TC_TILE * (3 - mt) - 1) / (TC_TILE * (3 - mt));
     // work items: whole sweeps, then a tail round whose R blocks are swept by S CTAs each (see TcParams)
     const int sms = std::min(ctx->sm_count, 256);
-    P.full = (int)(n_qblocks / sms);
-    P.R = (int)(n_qblocks - (int64_t)P.full * sms);
-    P.S = 1;
-    if (P.R > 0) P.S = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(sms / P.R, 4 / lists), n_tiles));
-    const unsigned grid = (unsigned)(P.full > 0 ? sms : P.R * P.S);
+    tc_schedule(n_qblocks, sms, (int)std::min<int64_t>(4 / lists, n_tiles), &P.full, &P.R, &P.S);
+    const unsigned grid = (unsigned)(P.full > 0 ? sms : std::min<int64_t>(sms, std::max<int64_t>(1, (int64_t)P.R * P.S)));
     const int64_t tail_rows = (int64_t)P.R * TC_TILE * mt;
     P.cand_tail = w.cand_tail;
     if (P.S > 1)
