@@ -85,6 +85,9 @@ __device__ __forceinline__ double ab_ld_cluster_f64(uint32_t addr) {
 __device__ __forceinline__ void ab_st_release_sys_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void ab_st_relaxed_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ab_ld_acquire_sys_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -1599,7 +1599,9 @@ extern "C" int ab_irlb(ab_ctx *ctx, const int64_t *rowptr_h, const int32_t *col_
     };
     const unsigned g_rows = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 32));
     const unsigned g_vec = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
-    const unsigned g_dot = (unsigned)w.dot_grid;
+    // at least two rows per thread (a 163 k-row shard on 592 CTAs left one row per thread: the per-CTA reductions and the
+    // 592-partial tail were the kernel; 17.1 -> 15.3 ms per pass at that size), never more CTAs than the layout sized
+    const unsigned g_dot = (unsigned)std::max<int64_t>(1, std::min<int64_t>(w.dot_grid, (n + 2 * DOT_THREADS - 1) / (2 * DOT_THREADS)));
 
     // compact A^T.w: 8 resident CTAs per SM, each with its own copy of w in shared memory
     AB_CUDA(cudaFuncSetAttribute(atw_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)H * 8)));

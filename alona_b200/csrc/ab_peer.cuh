@@ -49,8 +49,10 @@ __device__ __forceinline__ void ab_peer_push(const AbPeer &p, int ch, uint32_t s
 }
 // after all pushes of this rank are ordered before the calling thread (fence / ticket): raise the flags
 __device__ __forceinline__ void ab_peer_publish(const AbPeer &p, int ch, uint32_t seq) {
+    // ONE system-scope fence, then relaxed flag stores: a st.release.sys per peer is a fence per peer, i.e. `world` NVLink
+    // round trips in series in front of every exchange (777 exchanges per C3 pass)
     __threadfence_system();
-    for (int q = 0; q < p.world; ++q) ab_st_release_sys_u32(ab_peer_flag(p.buf[q], ch, p.rank), seq);
+    for (int q = 0; q < p.world; ++q) ab_st_relaxed_sys_u32(ab_peer_flag(p.buf[q], ch, p.rank), seq);
 }
 // block-wide wait for every sender's push of (ch, seq); ends with a __syncthreads
 __device__ __forceinline__ void ab_peer_wait(const AbPeer &p, int ch, uint32_t seq) {
