@@ -241,6 +241,21 @@ def test_knn_duplicates_and_ties_are_reported(eng, mode):
     _check_knn(eng, emb, 10, None, mode)
 
 
+@pytest.mark.parametrize('n,d,k', [(3000, 128, 15),      # wide embedding: one query tile x 256-point tiles, two lists per query
+                                   (40000, 24, 10),     # more query blocks than SMs: whole sweeps + a tail phase cut in parts
+                                   (777, 50, 20)])      # a handful of blocks: every block swept by several CTAs
+def test_knn_tile_shapes_and_tail_schedule(eng, n, d, k):
+    """The two operand tilings of the tensor-core pass and its work schedule (whole rounds, tail blocks swept by several
+    CTAs into part lists that are merged) against the C brute-force checker, bit for bit; no golden vector needed."""
+    rng = np.random.default_rng(n + d)
+    centres = rng.normal(0.0, 6.0, size=(12, d))
+    emb = centres[rng.integers(0, 12, size=n)] + rng.normal(0.0, 1.0, size=(n, d))
+    emb[:, 0] += 40.0                                         # an uncentred leading component, as alona's PCA has
+    idx, stats = _check_knn(eng, emb, k, None, 0)
+    assert int(stats[3]) + int(stats[1]) == n                 # certified + exact fall-backs = all queries
+    assert int(stats[1]) <= n // 100
+
+
 def test_knn_sharded_queries_equal_full(eng):
     g = load_golden('knn_mix_3000x50_k20')
     e = torch.from_numpy(g['emb']).to(eng.device)
