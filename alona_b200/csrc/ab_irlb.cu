@@ -1366,12 +1366,6 @@ static int irlb_work_dim(int nval, int64_t n_total) {
 // a stride of 64 rows x 8 B cost them 11 % against the odd stride the first version happened to have)
 static int64_t irlb_ld(int64_t rows) {
     int64_t ld = (std::max<int64_t>(rows, 2) + 1) & ~(int64_t)1;
-    static const char *mod_env = getenv("AB_IRLB_LDMOD");            // experiment: column stride (bytes) mod 4096
-    if (mod_env) {
-        const int64_t want = atoll(mod_env) & 4080;
-        while (((ld * 8) & 4095) != want) ld += 2;
-        return ld;
-    }
     const int64_t r = (ld * 8) & 4095;
     if (r < 256 || r > 3840) ld += 64;
     return ld;
