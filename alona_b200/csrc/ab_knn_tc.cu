@@ -334,6 +334,20 @@ __host__ __device__ __forceinline__ float key_score(unsigned long long key) {
     float f; memcpy(&f, &b, 4); return key == TC_KEY_MAX ? INFINITY : f;
 #endif
 }
+// Low word of a candidate key: first point of the group (a multiple of TC_GRP, below 2^31) with the pair mask in the bits
+// that leaves free - the low bits and bit 31.  (The mask only perturbs the order of keys with EQUAL scores.)
+__host__ __device__ __forceinline__ uint32_t tc_key_low(int first, unsigned pair_mask) {
+    constexpr unsigned LOWB = TC_GRP == 8 ? 3 : 2;
+    return (uint32_t)first | (pair_mask & ((1u << LOWB) - 1u)) | ((pair_mask >> LOWB) << 31);
+}
+__host__ __device__ __forceinline__ int tc_key_first(unsigned long long key) {
+    return (int)((uint32_t)key & 0x7FFFFFFFu & ~(uint32_t)(TC_GRP - 1));
+}
+__host__ __device__ __forceinline__ unsigned tc_key_pairs(unsigned long long key) {
+    constexpr unsigned LOWB = TC_GRP == 8 ? 3 : 2;
+    const uint32_t lo = (uint32_t)key;
+    return (lo & ((1u << LOWB) - 1u)) | ((lo >> 31) << LOWB);
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -519,13 +533,21 @@ __device__ __forceinline__ void epi_unit(const uint32_t (&r)[32], int cbase, boo
     // the re-rank expands the listed groups to their points.
     const unsigned tight = __ballot_sync(AB_FULL, cnt > TC_BUF - NG);
     if (tight) warp_prune(tight, P, cg, q, cnt, tau, bufp, lane);
+    // (a warp-uniform branch per group - skip the groups no lane lists - measured no better than this predicated form)
     if (live && mn < tau) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             if (gmin[g] < tau) {
+                // which PAIRS of the group hold a score below the threshold (tc_key_pairs): the re-rank only computes
+                // exact distances for those - a point at or above the threshold of its time can be left out under the
+                // same certificate as a point of an unlisted group
+                unsigned pm = 0;
+#pragma unroll
+                for (int pp = 0; pp < TC_GRP / 2; ++pp)
+                    pm |= fminf(__uint_as_float(r[TC_GRP * g + 2 * pp]), __uint_as_float(r[TC_GRP * g + 2 * pp + 1])) < tau ? (1u << pp) : 0u;
                 // append buffers live in global memory (L2): appends are rare fire-and-forget stores, and the
                 // shared memory they would take is worth more as operand ring
-                bufp[(size_t)cnt * TC_EPI_THREADS] = ((unsigned long long)__float_as_uint(gmin[g]) << 32) | (uint32_t)(cbase + TC_GRP * g);
+                bufp[(size_t)cnt * TC_EPI_THREADS] = ((unsigned long long)__float_as_uint(gmin[g]) << 32) | tc_key_low(cbase + TC_GRP * g, pm);
                 ++cnt;
             }
         }
@@ -847,7 +869,8 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
     const float R = __uint_as_float(*rmax_bits);
     const double sc = knn_scale_of(R);
     const double inv_sc2 = 1.0 / (sc * sc);                // scores are in scaled units
-    int *sel = reinterpret_cast<int *>(sm_raw + (size_t)nwarp * mp * (sizeof(double) + sizeof(int))) + (size_t)warp * mg;
+    int *sel = reinterpret_cast<int *>(sm_raw + (size_t)nwarp * mp * (sizeof(double) + sizeof(int))) + (size_t)warp * (2 * mg + 1);
+    int *goff = sel + mg;                                  // [mg + 1]
     for (int64_t q = (int64_t)blockIdx.x * nwarp + warp; q < nq; q += (int64_t)gridDim.x * nwarp) {
         const int64_t qid = q_begin + q;
         const double *qv = emb + qid * d;
@@ -891,20 +914,49 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
             n_exp += __popc(bal);
         }
         __syncwarp();
-        const int np = n_exp * TC_GRP;
+        // points to rank exactly: of every selected group the pairs its key flags (scores below the threshold of the time
+        // the group was listed).  goff[i] = first position of group sel[i] in the point list.
+        int np = 0;
+        for (int i0 = 0; i0 < n_exp; i0 += 32) {
+            const int i = i0 + lane;
+            unsigned long long key = 0ull;
+            int cntp = 0;
+            if (i < n_exp) {
+                const int gi = sel[i], g = gi / m, e = gi - g * m;
+                key = cand[((size_t)g * nq + q) * m + e];
+                cntp = 2 * __popc(tc_key_pairs(key));
+            }
+            int inc = cntp;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(AB_FULL, inc, o);
+                if (lane >= o) inc += up;
+            }
+            const int off = np + inc - cntp;
+            if (i < n_exp) {
+                goff[i] = off;
+                const int first = tc_key_first(key);
+                unsigned pm = tc_key_pairs(key);
+                int w = off;
+                while (pm) {
+                    const int pp = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    si[w++] = first + 2 * pp;
+                    si[w++] = first + 2 * pp + 1;
+                }
+            }
+            np += __shfl_sync(AB_FULL, inc, 31);
+        }
+        if (lane == 0) goff[n_exp] = np;
+        __syncwarp();
         int p2 = 32;
         while (p2 < np || p2 < k + 1) p2 <<= 1;            // sort size: power of two covering the expanded points
         if (p2 > mp) p2 = mp;
-        double worst_rel = 0.0;
-        for (int c = lane; c < p2; c += 32) {              // TC_GRP consecutive lanes = the points of one group
+        for (int c = lane; c < p2; c += 32) {
             double dist = INFINITY;
             int id = INT_MAX;
-            unsigned long long key = TC_KEY_MAX;
             if (c < np) {
-                const int gi = sel[c / TC_GRP], sub = c & (TC_GRP - 1);
-                const int g = gi / m, e = gi - g * m;
-                key = cand[((size_t)g * nq + q) * m + e];
-                const long long cnd = (long long)(uint32_t)(key & 0xFFFFFFFFull) + sub;
+                const long long cnd = si[c];
                 if (cnd < n_total) {                          // (padding columns: ids past the end)
                     const double *xv = emb + cnd * d;
                     double acc = 0.0;
@@ -930,11 +982,19 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                     id = (int)cnd;
                 }
             }
-            // the key's score approximates the SMALLEST distance of the group
-            double gmin = dist;
-#pragma unroll
-            for (int o = TC_GRP / 2; o > 0; o >>= 1) gmin = fmin(gmin, ab_shfl_xor_f64(gmin, o));
-            if (key != TC_KEY_MAX && gmin < INFINITY) {
+            sd[c] = dist;
+            si[c] = id;
+        }
+        __syncwarp();
+        // guard of the error model: the key's score approximates the SMALLEST distance of the group, and the point that
+        // attains that score is in a flagged pair
+        double worst_rel = 0.0;
+        for (int i = lane; i < n_exp; i += 32) {
+            const int gi = sel[i], g = gi / m, e = gi - g * m;
+            const unsigned long long key = cand[((size_t)g * nq + q) * m + e];
+            double gmin = INFINITY;
+            for (int c = goff[i]; c < goff[i + 1]; ++c) gmin = fmin(gmin, sd[c]);
+            if (gmin < INFINITY) {
                 const double approx = (double)key_score(key) * inv_sc2 + qbase;
                 double err = fabs(approx - gmin);
                 if (del > 0.0) {                              // what lies outside the band the perturbed query allows
@@ -943,8 +1003,6 @@ knn_rerank_kernel(const double *__restrict__ emb, int64_t n_total, int d, int64_
                 }
                 worst_rel = fmax(worst_rel, err / (scale * scale));
             }
-            sd[c] = dist;
-            si[c] = id;
         }
         __syncwarp();
         for (int size = 2; size <= p2; size <<= 1) {
@@ -1168,7 +1226,7 @@ int ab_knn_tc_run(ab_ctx *ctx, const double *emb, int64_t n_total, int d, int64_
     const int mp = lists * m * TC_GRP;                              // candidate points per query (m groups per list)
     int rr_warps = 8;
     while (rr_warps > 1 && (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) > (size_t)160 * 1024) rr_warps >>= 1;
-    const size_t rr_smem = (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) + (size_t)rr_warps * (mp / TC_GRP) * sizeof(int);
+    const size_t rr_smem = (size_t)rr_warps * mp * (sizeof(double) + sizeof(int)) + (size_t)rr_warps * (2 * (mp / TC_GRP) + 1) * sizeof(int);
     AB_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     const unsigned g_rr = ab_wave_grid(ctx, knn_rerank_kernel, rr_warps * 32, rr_smem, (nq + rr_warps - 1) / rr_warps);
     knn_rerank_kernel<<<g_rr, rr_warps * 32, rr_smem, st>>>(emb, n_total, d, q_begin, nq, k, m, lists, w.cand, w.qn, w.scal,
