@@ -69,6 +69,7 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, p_i64, c_void_p, c_size,
                                c_void_p]),
     'ab_knn_ws_bytes': (c_size, [c_i64, c_i32, c_i64, c_i32]),
+    'ab_knn_schedule': (ctypes.c_int, [c_i64, c_i32, c_i32, c_void_p]),
     'ab_knn': (ctypes.c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i64, c_i64, c_i32, c_i32, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_size, c_void_p]),
     'ab_snn_ws_bytes': (c_size, [c_i64, c_i32, c_i64]),

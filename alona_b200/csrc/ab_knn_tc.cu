@@ -1124,6 +1124,15 @@ static size_t tc_layout(int64_t n, int d, int64_t nq, int k, void *ws, size_t by
     return a.ok ? a.off : 0;
 }
 
+// host-only diagnostic (include/alona_b200.h): the schedule ab_knn's tensor pass uses for `blocks` query blocks
+extern "C" int ab_knn_schedule(int64_t blocks, int32_t n_sm, int32_t max_parts, int32_t *out3) {
+    if (blocks < 0 || n_sm < 1 || max_parts < 1 || !out3) return ab_fail("ab_knn_schedule: bad argument");
+    int full = 0, R = 0, S = 1;
+    tc_schedule(blocks, std::min(n_sm, 256), max_parts, &full, &R, &S);
+    out3[0] = full; out3[1] = R; out3[2] = S;
+    return 0;
+}
+
 size_t ab_knn_tc_ws_bytes(int64_t n_total, int d, int64_t nq, int k) {
     return tc_layout(n_total, d, nq, k, nullptr, 0, nullptr) + 2048;
 }

@@ -217,6 +217,13 @@ int ab_knn(ab_ctx *ctx, const double *emb_all, int64_t n_total, int32_t d, int64
            int64_t q_end, int32_t k, int32_t mode, int32_t *idx, double *rdist, int64_t *stats,
            void *ws, size_t ws_bytes, void *stream);
 
+/* Host-only diagnostic, no device work: the schedule of the tensor-core pass for `n_query_blocks` blocks of 256 (128 for
+ * wide embeddings) queries on `n_sm` persistent CTAs.  out3 = {whole rounds, tail blocks R, parts S per tail block}: CTA b
+ * sweeps blocks b, b + n_sm, ... for the whole rounds, then the part items b, b + grid, ... of the R * S parts of the tail
+ * phase (part p of tail block j covers tiles [p T / S, (p + 1) T / S)).  max_parts = 4 (2 for wide embeddings).
+ * Exposed so that the CPU tier can check that every (block, tile) pair is swept exactly once. */
+int ab_knn_schedule(int64_t n_query_blocks, int32_t n_sm, int32_t max_parts, int32_t *out3);
+
 /* ---- K10: shared-nearest-neighbour graph ------------------------------------------------
  * replaces AlonaClustering.snn (alona/clustering.py:204-231): overlap(i,m)=|N(i) n N(m)| over
  * self-inclusive neighbour sets, keep iff overlap >= v_min (the host evaluates the reference's
